@@ -1,0 +1,156 @@
+/*
+ * oodfq_b200.h -- C ABI of the B200 (sm_100a) fake-quantisation hot path.
+ *
+ * This is the drop-in boundary.  The reference (weesunghyun/OOD-DFQ) has no FFI
+ * of its own: its operator API is the Python package `quantization_utils`
+ * (imported at main_direct.py:21 and trainer_direct.py:19).  Each entry point
+ * below replaces the chain of ATen launches behind one reference call site; the
+ * citation after "replaces:" is file:line in the reference tree.  The Python
+ * mirror of the reference interface (ood_dfq_b200/quantization_utils/) binds
+ * these symbols with ctypes -- see INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 data unless the name ends in
+ *     `_host`; tensors are dense; `stream` is a cudaStream_t passed as void*.
+ *   - all work is enqueued on `stream`; no entry point synchronises the host.
+ *   - return value: 0 on success, a negative OODFQ_E* code otherwise; the
+ *     message of the last failure on the calling thread is oodfq_last_error().
+ *     Nothing throws across this boundary.
+ *   - memory is owned by the caller (torch allocators in the Python mirror).
+ *   - k is the bit-width: codes are integers in [-2^(k-1), 2^(k-1)-1].
+ *   - arithmetic order is the reference's, one fp32 rounding per step
+ *     (SURVEY.md section 8(a')): integer codes are bit-exact with the reference.
+ */
+#ifndef OODFQ_B200_H
+#define OODFQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OODFQ_ABI_VERSION 1
+
+#define OODFQ_OK 0
+#define OODFQ_EINVAL (-1)  /* bad argument (null pointer, k out of range, misaligned ...) */
+#define OODFQ_ECUDA (-2)   /* a CUDA runtime call or kernel launch failed                   */
+
+/* element-wise modes of oodfq_fq_forward */
+#define OODFQ_MODE_FAKEQUANT 0 /* quantise -> clamp -> dequantise                    */
+#define OODFQ_MODE_QUANTIZE 1  /* round(scale*x - zp), no clamp (linear_quantize)    */
+#define OODFQ_MODE_DEQUANTIZE 2/* (q + zp) / scale            (linear_dequantize)   */
+
+/* flags */
+#define OODFQ_SYMMETRIC 1      /* the *_DSG family: zero-point ignored               */
+#define OODFQ_PARAMS_GIVEN 2   /* p0/p1 are (scale, zero_point) instead of (min,max) */
+
+typedef void* oodfq_stream_t;  /* cudaStream_t */
+
+/* ---- library bookkeeping ------------------------------------------------- */
+int oodfq_abi_version(void);
+const char* oodfq_last_error(void);
+/* number of kernels this library has launched since load / since the last reset
+ * (bench.py reports it as "gpu_launches"). */
+unsigned long long oodfq_launch_count(void);
+void oodfq_reset_launch_count(void);
+/* bytes of zero-initialised device scratch the *_ws entry points need */
+size_t oodfq_workspace_bytes(void);
+
+/* ---- a1: scale / zero-point ---------------------------------------------
+ * replaces: asymmetric_linear_quantization_params, quant_utils.py:107-128
+ *           symmetric_linear_quantization_params_DSG, quant_utils.py:238-259
+ * lo, hi, scale, zero_point: [n]. */
+int oodfq_quant_params(const float* lo, const float* hi, float* scale, float* zero_point,
+                       long long n, int k, oodfq_stream_t stream);
+
+/* ---- a2-a5: element-wise quantise / clamp / dequantise ------------------
+ * replaces: AsymmetricQuantFunction.forward, quant_utils.py:138-157
+ *           SymmetricQuantFunction_DSG.forward, quant_utils.py:268-286
+ *           linear_quantize / linear_dequantize (+_DSG), quant_utils.py:61-104, 192-235
+ * x, y: [numel]; p0, p1: [rows] (rows == 1: one range for the whole tensor,
+ * else one range per leading-dimension row of numel/rows elements).
+ * codes (nullable, k <= 8): int8 integer codes, FAKEQUANT mode only.
+ * y may alias x (in-place variants of the reference helpers). */
+int oodfq_fq_forward(const float* x, float* y, int8_t* codes, long long numel,
+                     const float* p0, const float* p1, long long rows,
+                     int k, int mode, int flags, oodfq_stream_t stream);
+
+/* ---- a6: calibrating QuantAct forward -----------------------------------
+ * replaces: QuantAct.forward with running_stat=True, quant_modules.py:75-96
+ *           (QuantAct_DSG.forward :360-386 with OODFQ_SYMMETRIC)
+ * One call = data min/max of x, the bias-corrected running-range update of
+ * (x_min, x_max, beta_t) IN PLACE on the device, then the fake-quantised y
+ * with the UPDATED range.  y == NULL: range update only (full_precision_flag).
+ * workspace: oodfq_workspace_bytes() of device memory, zeroed once by the
+ * caller and then owned by this library between calls on one stream. */
+int oodfq_act_calib_forward(const float* x, float* y, int8_t* codes, long long numel,
+                            float* x_min, float* x_max, const float* beta, float* beta_t,
+                            int k, int flags, void* workspace, oodfq_stream_t stream);
+
+/* data min / max only (NaN-propagating like torch.min/max): out[0]=min, out[1]=max
+ * replaces: x.data.min(), x.data.max(), quant_modules.py:81-82 */
+int oodfq_minmax(const float* x, long long numel, float* out2, void* workspace,
+                 oodfq_stream_t stream);
+
+/* ---- a7/a8: weight fake-quant, many tensors in one launch ----------------
+ * replaces: Quant_Conv2d.forward :266-279, Quant_Linear.forward :215-230 and the
+ *           *_DSG twins :420-431, :465-479 (per-output-row min/max + a5), for
+ *           every layer of a model at once. */
+typedef struct {
+    const float* w;     /* [rows, row_len] dense                              */
+    float* wq;          /* same shape: fake-quantised weight                  */
+    float* lo;          /* [rows] row minimum actually used (nullable)        */
+    float* hi;          /* [rows] row maximum actually used (nullable)        */
+    int8_t* codes;      /* [rows, row_len] integer codes (nullable, k <= 8)   */
+    long long rows;
+    long long row_len;
+    int k;
+    int flags;          /* OODFQ_SYMMETRIC or 0                               */
+} oodfq_weight_desc;
+
+int oodfq_weight_fq_multi(const oodfq_weight_desc* descs_host, int n_tensors,
+                          oodfq_stream_t stream);
+
+/* ---- a11: per-channel statistics of a BN input ---------------------------
+ * replaces: hook_fn_forward, trainer_direct.py:388-393 / distill_data.py:69-73
+ * x: [N, C, HW] (NCHW).  sums: [2*C] receives S1_c = sum(x - shift_c) and
+ * S2_c = sum((x - shift_c)^2) over N and HW.  shift: [C] or NULL (zero).
+ * Optional fused fake-quant of the same read (north_star (b)): when y != NULL,
+ * y = fakequant(x) with the scalar range (fq_lo, fq_hi), k = fq_k. */
+int oodfq_bn_stats_forward(const float* x, int N, int C, long long HW, const float* shift,
+                           float* sums, float* y, const float* fq_lo, const float* fq_hi,
+                           int fq_k, void* workspace, oodfq_stream_t stream);
+
+/* mean_c = shift_c + S1_c/count, var_c = S2_c/count - (S1_c/count)^2 (biased).
+ * `sums` may have been all-reduced over ranks; count is the global N*HW. */
+int oodfq_bn_stats_finalize(const float* sums, const float* shift, int C, double count,
+                            float* mean, float* var, oodfq_stream_t stream);
+
+/* ---- a12: BN-statistics loss over L layers, packed ------------------------
+ * replaces: trainer_direct.py:473-486 and distill_data.py:252-265
+ * Layer l owns channels [ch_off_host[l], ch_off_host[l+1]) of every packed [Ctot]
+ * array.  sums is [2*Ctot] with each layer's output of oodfq_bn_stats_forward kept
+ * together: floats [2*off_l, 2*off_l + C_l) are S1, the next C_l are S2.
+ * counts_host[l] = global N*H*W of layer l.  Outputs: loss3[0] = (sum_l MSE_mean + MSE_var)/L,
+ * loss3[1] = sum_l MSE_mean / L, loss3[2] = sum_l MSE_var / L; mean, var [Ctot];
+ * gmean, gvar [Ctot] = d loss / d mean_c, d loss / d var_c. */
+int oodfq_bns_loss(const float* sums, const float* shift, const float* run_mean,
+                   const float* run_var, const int* ch_off_host, const double* counts_host,
+                   int L, float* loss3, float* mean, float* var, float* gmean, float* gvar,
+                   oodfq_stream_t stream);
+
+/* ---- a12 backward ----------------------------------------------------------
+ * grad_x[n,c,i] = (grad_in ? grad_in[n,c,i] : 0)
+ *               + g * ( gmean_c/count + gvar_c * 2*(x[n,c,i]-mean_c)/count )
+ * g = *gscale (device scalar, NULL -> 1).  grad_x may alias grad_in. */
+int oodfq_bn_stats_backward(const float* x, const float* grad_in, float* grad_x,
+                            int N, int C, long long HW, const float* mean,
+                            const float* gmean, const float* gvar, double count,
+                            const float* gscale, oodfq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OODFQ_B200_H */

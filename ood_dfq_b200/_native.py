@@ -1,0 +1,79 @@
+"""ctypes binding of include/oodfq_b200.h -- the only way Python reaches the kernels.
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is
+raised.  Build it with ``python -m ood_dfq_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liboodfq_b200.so")
+
+MODE_FAKEQUANT, MODE_QUANTIZE, MODE_DEQUANTIZE = 0, 1, 2
+SYMMETRIC, PARAMS_GIVEN = 1, 2
+ABI_VERSION = 1
+
+_vp, _ll, _i, _d = C.c_void_p, C.c_longlong, C.c_int, C.c_double
+
+
+class WeightDesc(C.Structure):
+    """oodfq_weight_desc"""
+    _fields_ = [("w", _vp), ("wq", _vp), ("lo", _vp), ("hi", _vp), ("codes", _vp),
+                ("rows", _ll), ("row_len", _ll), ("k", _i), ("flags", _i)]
+
+
+# name -> (restype, argtypes); every symbol the header declares
+SIGNATURES = {
+    "oodfq_abi_version": (_i, []),
+    "oodfq_last_error": (C.c_char_p, []),
+    "oodfq_launch_count": (C.c_ulonglong, []),
+    "oodfq_reset_launch_count": (None, []),
+    "oodfq_workspace_bytes": (C.c_size_t, []),
+    "oodfq_quant_params": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    "oodfq_fq_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _vp]),
+    "oodfq_act_calib_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "oodfq_minmax": (_i, [_vp, _ll, _vp, _vp, _vp]),
+    "oodfq_weight_fq_multi": (_i, [C.POINTER(WeightDesc), _i, _vp]),
+    "oodfq_bn_stats_forward": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "oodfq_bn_stats_finalize": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp]),
+    "oodfq_bns_loss": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(_d), _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "oodfq_bn_stats_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _d, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and type the library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"ood_dfq_b200: native library not found at {LIB_PATH}. This package has no CPU or "
+            "PyTorch fallback; build the sm_100a kernels with `python -m ood_dfq_b200.build`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.oodfq_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"ood_dfq_b200: ABI {lib.oodfq_abi_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().oodfq_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"ood_dfq_b200.{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().oodfq_launch_count())
+
+
+def reset_launch_count():
+    load().oodfq_reset_launch_count()

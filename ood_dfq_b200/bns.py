@@ -1,0 +1,232 @@
+"""BN-statistics matching loss on B200: fused statistics, loss and backward kernels.
+
+Reference behaviour being replaced (paths relative to the reference tree):
+
+* the forward hook on every BatchNorm module that takes ``mean([0,2,3])`` and
+  ``var([0,2,3], unbiased=False)`` of the module INPUT -- trainer_direct.py:388-397
+  (registered :418-423) and data_generate/distill_data.py:69-78 (registered :156-158);
+* the loss built from those lists -- trainer_direct.py:473-486
+  (``sum_l [MSE(mean_l, rm_l) + MSE(var_l, rv_l)] / L``) and distill_data.py:252-265
+  (mean term / L + var term / L: the same number, reported as two parts);
+* the autograd tape behind both (several more full passes per layer in backward).
+
+Two levels of API:
+
+``bn_channel_stats(x, shift=None)``
+    differentiable ``(mean, var)`` of one NCHW tensor: one read forward, one fused
+    read+write backward.  Drop it into the reference's hook in place of the two ATen
+    reductions.
+
+``BNStatLoss(model)``
+    hooks every BN module, accumulates the shifted sums of all layers into one packed
+    buffer (optionally all-reduced over the data-parallel group so the loss is the
+    GLOBAL-batch loss), evaluates loss and per-channel gradients in one tiny kernel, and
+    adds the loss gradient into the gradient that flows back through each BN input in
+    one fused kernel per layer.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import ops
+
+
+class _ChannelStats(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, shift):
+        n, c, h, w = x.shape
+        count = float(n * h * w)
+        xc = x.contiguous()
+        sums = ops.bn_stats_forward(xc, shift)
+        mean, var = ops.bn_stats_finalize(sums, shift, count)
+        ctx.save_for_backward(xc, mean)
+        ctx.count = count
+        ctx.set_materialize_grads(False)
+        return mean, var
+
+    @staticmethod
+    def backward(ctx, gmean, gvar):
+        xc, mean = ctx.saved_tensors
+        if gmean is None and gvar is None:
+            return None, None
+        gmean = torch.zeros_like(mean) if gmean is None else gmean.contiguous()
+        gvar = torch.zeros_like(mean) if gvar is None else gvar.contiguous()
+        return ops.bn_stats_backward(xc, None, mean, gmean, gvar, ctx.count), None
+
+
+def bn_channel_stats(x: torch.Tensor, shift: Optional[torch.Tensor] = None):
+    """Per-channel batch mean and biased variance of an NCHW tensor, differentiable.
+
+    Equivalent to ``x.mean([0,2,3]), x.var([0,2,3], unbiased=False)``
+    (trainer_direct.py:390-392).  ``shift`` ([C], e.g. the BN running mean) is only a
+    numerical pivot for the one-pass variance; the result does not depend on it.
+    """
+    return _ChannelStats.apply(x, shift)
+
+
+class _Pass:
+    """State of one hooked forward pass (several may be alive before their backward runs)."""
+
+    __slots__ = ("sums", "counts", "fired", "tokens", "world", "loss3", "mean", "var", "gmean", "gvar")
+
+    def __init__(self, n_layers, ctot, device):
+        self.sums = torch.empty(2 * ctot, dtype=torch.float32, device=device)
+        self.counts = [0.0] * n_layers
+        self.fired = [0] * n_layers
+        self.tokens = [None] * n_layers
+        self.world = 1
+        self.loss3 = self.mean = self.var = self.gmean = self.gvar = None
+
+
+class _Tap(torch.autograd.Function):
+    """Identity on a BN input that records its channel sums; backward adds the loss gradient."""
+
+    @staticmethod
+    def forward(ctx, x, mgr, idx, run):
+        n, c, h, w = x.shape
+        lay = mgr._layers[idx]
+        if c != lay.channels:
+            raise RuntimeError(f"BNStatLoss: layer {idx} saw {c} channels, expected {lay.channels}")
+        xc = x.contiguous()
+        ops.bn_stats_forward(xc, lay.module.running_mean, sums=run.sums[2 * lay.offset: 2 * (lay.offset + c)])
+        run.counts[idx] = float(n * h * w)
+        run.fired[idx] += 1
+        ctx.save_for_backward(xc)
+        ctx.lay, ctx.idx, ctx.run = lay, idx, run
+        ctx.set_materialize_grads(False)
+        token = torch.empty((), dtype=torch.float32, device=x.device)
+        return x, token
+
+    @staticmethod
+    def backward(ctx, grad_x, grad_token):
+        if grad_token is None:
+            return grad_x, None, None, None
+        (xc,) = ctx.saved_tensors
+        lay, run = ctx.lay, ctx.run
+        sl = slice(lay.offset, lay.offset + lay.channels)
+        g = ops.bn_stats_backward(xc, grad_x, run.mean[sl], run.gmean[sl], run.gvar[sl],
+                                  run.counts[ctx.idx] * run.world, gscale=grad_token.reshape(1).contiguous())
+        return g, None, None, None
+
+
+class _Loss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mgr, run, *tokens):
+        mgr._reduce_and_evaluate(run)
+        return run.loss3[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        n = len(ctx.needs_input_grad) - 2
+        return (None, None) + (grad_loss,) * n
+
+
+class _Layer:
+    __slots__ = ("module", "offset", "channels")
+
+    def __init__(self, module, offset):
+        self.module, self.offset, self.channels = module, offset, module.num_features
+
+
+class BNStatLoss:
+    """BN-statistics matching loss for a whole model.
+
+        bns = BNStatLoss(teacher)            # hooks every BatchNorm module
+        out = teacher(images)                # statistics collected during the forward
+        loss = ce(out, labels) + 0.1 * bns.loss()
+        loss.backward()                      # loss gradient fused into each BN-input gradient
+
+    ``sync=True`` (with an initialised process group): all-reduce the packed sums (one
+    NCCL call of ``2 * sum_l C_l`` floats) so that loss and gradients are those of the
+    global batch.  After ``loss()``: ``means()``, ``variances()`` give the per-layer
+    statistics the reference keeps in ``mean_list`` / ``var_list``; ``parts()`` =
+    (mean term, var term).
+    """
+
+    def __init__(self, model: nn.Module, bn_types=(nn.modules.batchnorm._BatchNorm,), sync=False,
+                 process_group=None):
+        self._layers = []
+        off = 0
+        for m in model.modules():
+            if isinstance(m, bn_types):
+                if m.running_mean is None:
+                    raise RuntimeError("BNStatLoss needs BatchNorm modules that track running statistics")
+                self._layers.append(_Layer(m, off))
+                off += m.num_features
+        if not self._layers:
+            raise RuntimeError("BNStatLoss: model has no BatchNorm module")
+        self._ctot = off
+        self._sync, self._group = sync, process_group
+        self._run = None          # the pass being collected
+        self._last = None         # the pass loss() was last called on
+        self._rm = self._rv = None
+        self._stat_versions = None
+        self._handles = [lay.module.register_forward_pre_hook(self._make_hook(i))
+                         for i, lay in enumerate(self._layers)]
+
+    # ------------------------------------------------------------------ hooks
+    def _make_hook(self, idx):
+        def hook(module, inputs):
+            x = inputs[0]
+            if self._run is None:
+                self._run = _Pass(len(self._layers), self._ctot, x.device)
+            x_out, self._run.tokens[idx] = _Tap.apply(x, self, idx, self._run)
+            return (x_out,) + tuple(inputs[1:])
+        return hook
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    def clear(self):
+        """Drop a partially collected pass (the reference's ``mean_list.clear()``)."""
+        self._run = None
+
+    # ------------------------------------------------------------------ evaluation
+    def _packed_running_stats(self, device):
+        versions = tuple((lay.module.running_mean._version, lay.module.running_var._version,
+                          lay.module.running_mean.data_ptr()) for lay in self._layers)
+        if self._rm is None or versions != self._stat_versions or self._rm.device != device:
+            self._rm = torch.cat([lay.module.running_mean.detach().reshape(-1) for lay in self._layers]).float()
+            self._rv = torch.cat([lay.module.running_var.detach().reshape(-1) for lay in self._layers]).float()
+            self._stat_versions = versions
+        return self._rm, self._rv
+
+    def _reduce_and_evaluate(self, run):
+        if self._sync:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.all_reduce(run.sums, op=dist.ReduceOp.SUM, group=self._group)
+                run.world = dist.get_world_size(self._group)
+        rm, rv = self._packed_running_stats(run.sums.device)
+        offs = [lay.offset for lay in self._layers] + [self._ctot]
+        counts = [c * run.world for c in run.counts]
+        run.loss3, run.mean, run.var, run.gmean, run.gvar = ops.bns_loss(run.sums, rm, rm, rv, offs, counts)
+
+    def loss(self) -> torch.Tensor:
+        """``sum_l [MSE(mean_l, rm_l) + MSE(var_l, rv_l)] / L`` as a differentiable 0-dim tensor."""
+        run = self._run
+        if run is None:
+            raise RuntimeError("BNStatLoss.loss(): no forward pass has been collected")
+        bad = [i for i, f in enumerate(run.fired) if f != 1]
+        if bad:
+            self._run = None
+            raise RuntimeError(f"BNStatLoss.loss(): BN layers {bad[:8]} fired {[run.fired[i] for i in bad[:8]]} "
+                               "times in this pass; each hooked module must run exactly once per loss")
+        out = _Loss.apply(self, run, *run.tokens)
+        self._run, self._last = None, run
+        return out
+
+    def parts(self):
+        """(mean term, var term) of the last loss, each already divided by L (distill_data.py:262-264)."""
+        return self._last.loss3[1], self._last.loss3[2]
+
+    def means(self):
+        return [self._last.mean[lay.offset: lay.offset + lay.channels] for lay in self._layers]
+
+    def variances(self):
+        return [self._last.var[lay.offset: lay.offset + lay.channels] for lay in self._layers]

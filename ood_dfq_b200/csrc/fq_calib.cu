@@ -1,0 +1,154 @@
+// Calibrating QuantAct forward: data min/max -> running-range update -> fake-quant.
+//
+// Replaces QuantAct.forward with running_stat=True (quantization_utils/
+// quant_modules.py:80-94): two full-tensor ATen reductions, ~10 scalar kernels for
+// the bias-corrected EMA, then the six-pass fake-quant.  Here: one reducing kernel
+// whose last CTA updates (x_min, x_max, beta_t) in place on the device, then the
+// streaming fake-quant kernel walking the tensor back to front so it starts on the
+// part of x the reduction left in L2.
+//
+// Roofline: HBM.  12 algorithmic bytes per element when 4*numel exceeds L2 (the
+// quantised range depends on the min/max of the very tensor being quantised, so x
+// must be read twice), 8 B/elem when x stays L2-resident between the passes.
+#include "common.cuh"
+
+namespace oodfq {
+
+constexpr int kRThreads = 256;
+constexpr int kRUnroll = 4;
+
+// x is read again by the quantising pass: default L2 policy here (no evict-first).
+__device__ __forceinline__ float4 ld_keep(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kRThreads)
+minmax_ema_kernel(const float* __restrict__ x, long long numel, Workspace* ws, float* out2,
+                  float* x_min, float* x_max, const float* beta, float* beta_t, int symmetric,
+                  int vec) {
+    float mn = __int_as_float(0x7f800000);   // +inf
+    float mx = __int_as_float(0xff800000);   // -inf
+    if (vec) {
+        const long long n4 = numel >> 2;
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const long long tile = (long long)kRThreads * kRUnroll;
+        for (long long base = (long long)blockIdx.x * tile; base < n4; base += (long long)gridDim.x * tile) {
+            float4 v[kRUnroll];
+#pragma unroll
+            for (int u = 0; u < kRUnroll; ++u) {
+                long long i = base + u * kRThreads + threadIdx.x;
+                // out-of-range slots re-read element 0: harmless for min/max
+                v[u] = ld_keep(x4 + (i < n4 ? i : 0));
+            }
+#pragma unroll
+            for (int u = 0; u < kRUnroll; ++u) {
+                mn = min_nan(min_nan(mn, v[u].x), min_nan(v[u].y, min_nan(v[u].z, v[u].w)));
+                mx = max_nan(max_nan(mx, v[u].x), max_nan(v[u].y, max_nan(v[u].z, v[u].w)));
+            }
+        }
+        if (blockIdx.x == 0) {
+            long long i = (n4 << 2) + threadIdx.x;
+            if (i < numel) { float t = x[i]; mn = min_nan(mn, t); mx = max_nan(mx, t); }
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * kRThreads + threadIdx.x; i < numel;
+             i += (long long)gridDim.x * kRThreads) {
+            float t = x[i];
+            mn = min_nan(mn, t);
+            mx = max_nan(mx, t);
+        }
+    }
+
+    __shared__ float s_mn[kRThreads / 32], s_mx[kRThreads / 32];
+    __shared__ int s_last;
+    mn = warp_min_nan(mn);
+    mx = warp_max_nan(mx);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kRThreads / 32; ++w) { mn = min_nan(mn, s_mn[w]); mx = max_nan(mx, s_mx[w]); }
+        ws->mm_partial[2 * blockIdx.x] = mn;
+        ws->mm_partial[2 * blockIdx.x + 1] = mx;
+        __threadfence();
+        int t = atomicAdd(&ws->ticket[0], 1);
+        s_last = (t == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    // last CTA: fold the per-CTA partials, then the scalar state update
+    __threadfence();
+    mn = __int_as_float(0x7f800000);
+    mx = __int_as_float(0xff800000);
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kRThreads) {
+        mn = min_nan(mn, __ldcg(&ws->mm_partial[2 * b]));
+        mx = max_nan(mx, __ldcg(&ws->mm_partial[2 * b + 1]));
+    }
+    mn = warp_min_nan(mn);
+    mx = warp_max_nan(mx);
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kRThreads / 32; ++w) { mn = min_nan(mn, s_mn[w]); mx = max_nan(mx, s_mx[w]); }
+        ws->ticket[0] = 0;  // ready for the next launch on this stream
+        if (out2) { out2[0] = mn; out2[1] = mx; }
+        if (x_min) {
+            if (symmetric) {   // quant_modules.py:369-374: range = +-max(|min|, |max|)
+                float m = max_nan(fabsf(mn), fabsf(mx));
+                mn = -m;
+                mx = m;
+            }
+            const float b = *beta;
+            const float bt = __fmul_rn(*beta_t, b);           // quant_modules.py:87
+            *x_min = ema_step(*x_min, mn, b, bt);             // :88
+            *x_max = ema_step(*x_max, mx, b, bt);             // :89
+            *beta_t = bt;
+        }
+    }
+}
+
+static int launch_minmax(const float* x, long long numel, void* workspace, float* out2, float* x_min,
+                         float* x_max, const float* beta, float* beta_t, int symmetric, cudaStream_t st) {
+    const int vec = (aligned16(x) && numel >= 4) ? 1 : 0;
+    long long per_block = vec ? (long long)kRThreads * kRUnroll * 4 : (long long)kRThreads;
+    long long blocks = (numel + per_block - 1) / per_block;
+    long long cap = (long long)kNumSM * 8;
+    if (cap > kMaxReduceBlocks) cap = kMaxReduceBlocks;
+    int grid = (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+    minmax_ema_kernel<<<grid, kRThreads, 0, st>>>(x, numel, reinterpret_cast<Workspace*>(workspace), out2,
+                                                   x_min, x_max, beta, beta_t, symmetric, vec);
+    count_launch();
+    return check_launch("minmax");
+}
+
+}  // namespace oodfq
+
+using namespace oodfq;
+
+extern "C" int oodfq_minmax(const float* x, long long numel, float* out2, void* workspace,
+                            oodfq_stream_t stream) {
+    if (!x || !out2 || !workspace) return fail(OODFQ_EINVAL, "minmax: null pointer");
+    if (numel <= 0) return fail(OODFQ_EINVAL, "minmax: empty tensor has no min/max");
+    return launch_minmax(x, numel, workspace, out2, nullptr, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int oodfq_act_calib_forward(const float* x, float* y, int8_t* codes, long long numel,
+                                       float* x_min, float* x_max, const float* beta, float* beta_t,
+                                       int k, int flags, void* workspace, oodfq_stream_t stream) {
+    if (!x || !x_min || !x_max || !beta || !beta_t || !workspace)
+        return fail(OODFQ_EINVAL, "act_calib_forward: null pointer");
+    if (numel <= 0) return fail(OODFQ_EINVAL, "act_calib_forward: empty tensor has no min/max");
+    if (k < 1 || k > 16) return fail(OODFQ_EINVAL, "act_calib_forward: k=%d outside [1,16]", k);
+    if (codes && k > 8) return fail(OODFQ_EINVAL, "act_calib_forward: int8 codes need k <= 8");
+    const bool sym = (flags & OODFQ_SYMMETRIC) != 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_minmax(x, numel, workspace, nullptr, x_min, x_max, beta, beta_t, sym ? 1 : 0, st);
+    if (rc != OODFQ_OK || !y) return rc;
+    return launch_fakequant_scalar(x, y, codes, numel, x_min, x_max, k, sym, /*reverse=*/true, st);
+}

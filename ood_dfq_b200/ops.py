@@ -1,0 +1,267 @@
+"""Tensor-level entry points: argument checks, output allocation, one C-ABI call each.
+
+Every function takes CUDA fp32 tensors and launches hand-written sm_100a kernels on
+the current stream through ``include/oodfq_b200.h``.  Anything else (CPU tensors,
+other dtypes) raises -- there is deliberately no PyTorch or CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _native as N
+
+_workspaces: dict = {}
+
+
+def _need(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"ood_dfq_b200: {name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"ood_dfq_b200: {name} is on {t.device}; this path only runs on CUDA "
+                           "(sm_100a kernels, no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"ood_dfq_b200: {name} must be {dtype}, got {t.dtype}")
+
+
+def _dense(t: torch.Tensor) -> torch.Tensor:
+    """A tensor whose storage can be walked flat (NCHW- or NHWC-contiguous); else a contiguous copy."""
+    if t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)):
+        return t
+    return t.contiguous()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def workspace(device) -> torch.Tensor:
+    """Zero-initialised scratch for the reducing kernels, one per (device, stream)."""
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           _stream(device))
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = torch.zeros(int(N.load().oodfq_workspace_bytes()), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ----------------------------------------------------------------------------- a1
+def quant_params(k: int, lo: torch.Tensor, hi: torch.Tensor):
+    """(scale, zero_point) of a saturation range; reference quant_utils.py:107-128 / :238-259."""
+    _need(lo, "saturation_min")
+    _need(hi, "saturation_max")
+    if lo.shape != hi.shape:
+        lo, hi = torch.broadcast_tensors(lo, hi)
+    lo_c, hi_c = lo.contiguous(), hi.contiguous()
+    scale = torch.empty_like(lo_c)
+    zp = torch.empty_like(lo_c)
+    rc = N.load().oodfq_quant_params(lo_c.data_ptr(), hi_c.data_ptr(), scale.data_ptr(), zp.data_ptr(),
+                                     lo_c.numel(), int(k), _stream(lo.device))
+    N.check(rc, "quant_params")
+    return scale, zp
+
+
+# ----------------------------------------------------------------------------- a2-a5
+def _rows_for(x: torch.Tensor, p: torch.Tensor, what: str) -> int:
+    n = p.numel()
+    if n == 1:
+        return 1
+    # the reference reshapes scale/zero-point to (-1,1,1,1) or (-1,1): one value per dim-0 row
+    if x.dim() not in (2, 4) or n != x.shape[0]:
+        raise RuntimeError(f"ood_dfq_b200: {what} has {n} entries; expected 1 or x.shape[0]={x.shape[0]} "
+                           f"for a {x.dim()}-D input")
+    return n
+
+
+def elementwise(x, p0, p1, k, mode, symmetric=False, params_given=False, out=None, codes=False):
+    """One launch of oodfq_fq_forward.  p0/p1 = (min, max) or, with params_given, (scale, zero_point)."""
+    _need(x, "input")
+    _need(p0, "range/scale")
+    _need(p1, "range/zero_point")
+    rows = _rows_for(x, p0, "range/scale")
+    if p1.numel() != p0.numel():
+        raise RuntimeError("ood_dfq_b200: mismatched parameter sizes")
+    xd = _dense(x) if rows == 1 else x.contiguous()
+    if out is None:
+        y = torch.empty_like(xd)
+    else:
+        y = out
+        if y.data_ptr() != xd.data_ptr() or y.shape != xd.shape:
+            raise RuntimeError("ood_dfq_b200: `out` must be the (dense) input itself for in-place use")
+    cd = torch.empty(xd.shape, dtype=torch.int8, device=x.device) if codes else None
+    if cd is not None and xd.stride() != cd.stride():
+        cd = torch.empty_like(xd, dtype=torch.int8)
+    flags = (N.SYMMETRIC if symmetric else 0) | (N.PARAMS_GIVEN if params_given else 0)
+    rc = N.load().oodfq_fq_forward(xd.data_ptr(), y.data_ptr(), _ptr(cd), xd.numel(),
+                                   p0.contiguous().data_ptr(), p1.contiguous().data_ptr(), rows,
+                                   int(k), mode, flags, _stream(x.device))
+    N.check(rc, "fq_forward")
+    return (y, cd) if codes else y
+
+
+def fake_quant(x, k, lo, hi, symmetric=False, codes=False):
+    """quantise -> clamp -> dequantise with the reference's rounding sequence (quant_utils.py:138-157)."""
+    return elementwise(x, lo, hi, k, N.MODE_FAKEQUANT, symmetric=symmetric, codes=codes)
+
+
+# ----------------------------------------------------------------------------- a6
+def minmax(x: torch.Tensor) -> torch.Tensor:
+    """[min, max] of x, NaN-propagating like torch.min / torch.max (quant_modules.py:81-82)."""
+    _need(x, "input")
+    xd = _dense(x)
+    out = torch.empty(2, dtype=torch.float32, device=x.device)
+    rc = N.load().oodfq_minmax(xd.data_ptr(), xd.numel(), out.data_ptr(), workspace(x.device).data_ptr(),
+                               _stream(x.device))
+    N.check(rc, "minmax")
+    return out
+
+
+def act_calib_forward(x, k, x_min, x_max, beta, beta_t, symmetric=False, quantize=True, codes=False):
+    """Calibrating QuantAct forward: updates (x_min, x_max, beta_t) in place, returns fake-quantised x.
+
+    quant_modules.py:80-94 (DSG :365-386).  ``quantize=False`` only tracks the range
+    (full_precision_flag) and returns None.
+    """
+    _need(x, "input")
+    for t, nme in ((x_min, "x_min"), (x_max, "x_max"), (beta, "beta"), (beta_t, "beta_t")):
+        _need(t, nme)
+        if t.numel() != 1 or not t.is_contiguous():
+            raise RuntimeError(f"ood_dfq_b200: {nme} must be a contiguous 1-element buffer")
+    xd = _dense(x)
+    y = torch.empty_like(xd) if quantize else None
+    cd = torch.empty_like(xd, dtype=torch.int8) if (codes and quantize) else None
+    rc = N.load().oodfq_act_calib_forward(xd.data_ptr(), _ptr(y), _ptr(cd), xd.numel(), x_min.data_ptr(),
+                                          x_max.data_ptr(), beta.data_ptr(), beta_t.data_ptr(), int(k),
+                                          N.SYMMETRIC if symmetric else 0, workspace(x.device).data_ptr(),
+                                          _stream(x.device))
+    N.check(rc, "act_calib_forward")
+    return (y, cd) if codes else y
+
+
+# ----------------------------------------------------------------------------- a7 / a8
+def weight_fq_multi(weights: Sequence[torch.Tensor], ks: Sequence[int], symmetric: Sequence[bool],
+                    outs: Optional[Sequence[torch.Tensor]] = None, want_range=False, want_codes=False):
+    """Per-output-row min/max + fake-quant of many weight tensors in ONE launch.
+
+    quant_modules.py:266-279 / :215-230 (DSG :420-431, :465-479) for every layer at once.
+    Returns a list of dicts {wq, lo, hi, codes}.
+    """
+    n = len(weights)
+    descs = (N.WeightDesc * max(n, 1))()
+    results = []
+    device = None
+    keep = []
+    for i, w in enumerate(weights):
+        _need(w, f"weight[{i}]")
+        if w.dim() < 1:
+            raise RuntimeError("ood_dfq_b200: weight must have at least one dimension")
+        device = device or w.device
+        if w.device != device:
+            raise RuntimeError("ood_dfq_b200: all weights of one launch must live on the same device")
+        wc = w.detach().contiguous()
+        keep.append(wc)
+        rows = wc.shape[0]
+        row_len = wc.numel() // rows if rows else 0
+        wq = outs[i] if outs is not None else torch.empty_like(wc)
+        lo = torch.empty(rows, dtype=torch.float32, device=device) if want_range else None
+        hi = torch.empty(rows, dtype=torch.float32, device=device) if want_range else None
+        cd = torch.empty(wc.shape, dtype=torch.int8, device=device) if want_codes else None
+        d = descs[i]
+        d.w, d.wq, d.lo, d.hi, d.codes = wc.data_ptr(), wq.data_ptr(), _ptr(lo), _ptr(hi), _ptr(cd)
+        d.rows, d.row_len, d.k = rows, row_len, int(ks[i])
+        d.flags = N.SYMMETRIC if symmetric[i] else 0
+        results.append({"wq": wq, "lo": lo, "hi": hi, "codes": cd})
+    if n:
+        rc = N.load().oodfq_weight_fq_multi(descs, n, _stream(device))
+        N.check(rc, "weight_fq_multi")
+    return results
+
+
+# ----------------------------------------------------------------------------- a11 / a12
+def _nchw(x: torch.Tensor):
+    if x.dim() != 4:
+        raise RuntimeError(f"ood_dfq_b200: BN statistics need an NCHW tensor, got {x.dim()}-D")
+    xc = x.contiguous()
+    n, c, h, w = xc.shape
+    return xc, n, c, h * w
+
+
+def bn_stats_forward(x, shift=None, sums=None, fq=None):
+    """Shifted per-channel sums of a BN input in one read (trainer_direct.py:388-393).
+
+    Returns sums [2*C] (S1 then S2), or (sums, y) when ``fq=(k, lo, hi)`` asks for the fused
+    fake-quantised output of the same read.
+    """
+    _need(x, "input")
+    xc, n, c, hw = _nchw(x)
+    if shift is not None:
+        _need(shift, "shift")
+        if shift.numel() != c or not shift.is_contiguous():
+            raise RuntimeError("ood_dfq_b200: shift must be a contiguous [C] tensor")
+    if sums is None:
+        sums = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    y = lo = hi = None
+    k = 0
+    if fq is not None:
+        k, lo, hi = fq
+        _need(lo, "fq range min")
+        _need(hi, "fq range max")
+        y = torch.empty_like(xc)
+    rc = N.load().oodfq_bn_stats_forward(xc.data_ptr(), n, c, hw, _ptr(shift), sums.data_ptr(), _ptr(y),
+                                         _ptr(lo), _ptr(hi), int(k), workspace(x.device).data_ptr(),
+                                         _stream(x.device))
+    N.check(rc, "bn_stats_forward")
+    return (sums, y) if fq is not None else sums
+
+
+def bn_stats_finalize(sums, shift, count: float):
+    c = sums.numel() // 2
+    mean = torch.empty(c, dtype=torch.float32, device=sums.device)
+    var = torch.empty(c, dtype=torch.float32, device=sums.device)
+    rc = N.load().oodfq_bn_stats_finalize(sums.data_ptr(), _ptr(shift), c, float(count), mean.data_ptr(),
+                                          var.data_ptr(), _stream(sums.device))
+    N.check(rc, "bn_stats_finalize")
+    return mean, var
+
+
+def bns_loss(sums, shift, run_mean, run_var, ch_off: Sequence[int], counts: Sequence[float]):
+    """Packed BN-statistics loss over L layers (trainer_direct.py:473-486, distill_data.py:252-265).
+
+    Returns (loss3, mean, var, gmean, gvar); loss3 = [total, mean term, var term].
+    """
+    L = len(counts)
+    ctot = ch_off[-1]
+    dev = sums.device
+    loss3 = torch.empty(3, dtype=torch.float32, device=dev)
+    mean, var, gmean, gvar = (torch.empty(ctot, dtype=torch.float32, device=dev) for _ in range(4))
+    off = (C.c_int * (L + 1))(*ch_off)
+    cnt = (C.c_double * L)(*counts)
+    rc = N.load().oodfq_bns_loss(sums.data_ptr(), _ptr(shift), run_mean.data_ptr(), run_var.data_ptr(), off, cnt,
+                                 L, loss3.data_ptr(), mean.data_ptr(), var.data_ptr(), gmean.data_ptr(),
+                                 gvar.data_ptr(), _stream(dev))
+    N.check(rc, "bns_loss")
+    return loss3, mean, var, gmean, gvar
+
+
+def bn_stats_backward(x, grad_in, mean, gmean, gvar, count: float, gscale=None, out=None):
+    """grad_x = grad_in + g*(gmean_c/M + gvar_c*2(x-mean_c)/M); one fused pass."""
+    _need(x, "input")
+    xc, n, c, hw = _nchw(x)
+    gi = None
+    if grad_in is not None:
+        _need(grad_in, "grad_in")
+        gi = grad_in.contiguous()
+    gx = out if out is not None else torch.empty_like(xc)
+    rc = N.load().oodfq_bn_stats_backward(xc.data_ptr(), _ptr(gi), gx.data_ptr(), n, c, hw, mean.data_ptr(),
+                                          gmean.data_ptr(), gvar.data_ptr(), float(count), _ptr(gscale),
+                                          _stream(x.device))
+    N.check(rc, "bn_stats_backward")
+    return gx
