@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- QAT images/sec of the OOD-DFQ quantisation path on B200 (see DESIGN.md section "Measurement").
+
+    python bench.py --gpus 1 --steps 8 --warmup 3                 # this repo's CUDA path
+    python bench.py --impl reference --steps 2 --warmup 1         # the reference algorithm on host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W    # weak scaling, one rank per GPU
+
+A "step" is one steady-state data-free QAT iteration (ood_dfq_b200/step.py, reference
+trainer_direct.py:490-518) of a W4A4 ResNet-18 on a synthetic 256 x 3 x 224 x 224 batch per GPU
+(BASELINE.json configs[3], the configuration the metric is quoted on): teacher forward, student
+forward, KD + feature-alignment loss, sign perturbation of the images, second teacher/student
+forward, backward, SGD.  Activation ranges are calibrated for 3 steps first and then frozen,
+as in the reference's epochs 0-3 / >= 4.
+
+One JSON line on stdout (rank 0).  value = images/s with the batches already in HBM; e2e = the
+same loop fed from pinned host memory with the loss read back every step.
+"""
+import argparse
+import copy
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+WORKLOADS = {
+    # name: (net factory name, num_classes, image shape, bits, default per-GPU batch, config string)
+    "imagenet_resnet18_w4a4": ("resnet18_imagenet", 1000, (3, 224, 224), 4, 256,
+                               "imagenet.hocon ResNet-18 W4A4 QAT step, 224x224, batch 256 per GPU"),
+    "cifar100_resnet20_w4a4": ("resnet20_cifar", 100, (3, 32, 32), 4, 256,
+                               "cifar100_resnet20.hocon ResNet-20 W4A4 QAT step, 32x32, batch 256 per GPU"),
+    "pathmnist_resnet18_w2a2": ("resnet18_small", 9, (3, 28, 28), 2, 64,
+                                "pathmnist_resnet18_w2a2.hocon ResNet-18 W2A2 QAT step, 28x28, batch 64 per GPU"),
+}
+METRIC = "QAT images/sec ResNet-18 W4A4 224x224 (data-free QAT step, fake-quant path on sm_100a kernels)"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- model assembly
+def build_pair(workload, namespace, device, seed=1):
+    """(teacher, student) of one workload; student = quantize_model(teacher copy) with `namespace` classes."""
+    from ood_dfq_b200 import nets, surgery
+    net, classes, _, bits, _, _ = WORKLOADS[workload]
+    torch.manual_seed(seed)                 # the reference seeds 1 on every rank (main_direct.py:349-350)
+    teacher = getattr(nets, net)(num_classes=classes) if net != "resnet18_small" else nets.resnet18_small(3, classes)
+    nets.perturb_bn_stats(teacher)
+    student = surgery.quantize_model(copy.deepcopy(teacher), bits, bits, namespace=namespace)
+    return teacher.to(device), student.to(device)
+
+
+def make_step(workload, teacher, student, namespace, group=None):
+    from ood_dfq_b200 import nets, step
+    lr = 1e-6 if workload != "cifar100_resnet20_w4a4" else 1e-5      # config/*.hocon lr_S
+    return step.QATStep(student, teacher, lr=lr, momentum=0.9, weight_decay=1e-4, temperature=20.0, alpha=20.0,
+                        lam=1000.0, eps=0.01, unit_types=(nets.ResUnit,), group=group)
+
+
+def calibrate(student, batches, namespace):
+    """Three range-tracking forwards (epochs 0-3 of the reference: trainer_direct.py:488), then freeze."""
+    from ood_dfq_b200 import surgery
+    surgery.unfreeze_model(student, namespace)
+    with torch.no_grad():
+        for b in batches:
+            student(b)
+    surgery.freeze_model(student, namespace)
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def run_cpu(workload, steps, warmup, sample_batch):
+    """The reference algorithm (oracle port: same ATen op sequence as the reference) on host cores."""
+    from oracle import fq_torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, _, shape, _, _, _ = WORKLOADS[workload]
+    teacher, student = build_pair(workload, fq_torch, "cpu")
+    g = torch.Generator().manual_seed(0)
+    batches = [torch.randn((sample_batch,) + shape, generator=g) for _ in range(2)]
+    calibrate(student, batches[:1] * 3, fq_torch)
+    qat = make_step(workload, teacher, student, fq_torch)
+    for i in range(warmup):
+        qat(batches[i % 2])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        qat(batches[i % 2])
+    dt = time.perf_counter() - t0
+    return {"value": sample_batch * steps / dt, "unit": "images/s", "cores": torch.get_num_threads(),
+            "kind": "port", "ms_per_step": 1e3 * dt / steps,
+            "sample": f"{steps} QAT steps of {sample_batch} images ({workload}) after {warmup} warm-up, "
+                      f"torch {torch.__version__} CPU eager, oracle/fq_torch.py modules"}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = run_cpu(args.workload, args.steps, args.warmup, args.cpu_batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][5], "name": args.workload,
+                   "sample_batch_per_step": args.cpu_batch,
+                   "note": "reference algorithm (torch CPU eager, same op sequence) on the host cores; "
+                           "each step is a bounded sample of the per-GPU batch"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main_ours(args):
+    from ood_dfq_b200 import _native, dist as ddist, ops
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _native.load()
+    torch.backends.cudnn.benchmark = True          # main_direct.py:351
+
+    _, _, shape, bits, default_batch, cfg = WORKLOADS[args.workload]
+    batch = args.batch or default_batch
+    teacher, student = build_pair(args.workload, qm, dev)
+    qat = make_step(args.workload, teacher, student, qm)
+
+    # synthetic inputs: seed = rank; a small pool of distinct batches
+    g = torch.Generator().manual_seed(rank)
+    pool = 3
+    host = [torch.randn((batch,) + shape, generator=g).pin_memory() for _ in range(pool)]
+    resident = [h.to(dev) for h in host]
+    calibrate(student, resident, qm)
+    if world > 1:
+        ddist.reduce_minmax(student)
+        for m in student.modules():               # ranges stay frozen from here on
+            if isinstance(m, qm.QuantAct):
+                m.fix()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: `value` and the fake-quant roofline ------------------------------
+    for i in range(args.warmup):
+        qat(resident[i % pool])
+    ops.PROFILE = []                                # event pairs around every element-wise launch
+    _native.reset_launch_count()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        qat(resident[i % pool])
+    ev1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = _native.launch_count()
+    ms = ev0.elapsed_time(ev1)
+    prof, ops.PROFILE = ops.PROFILE, None
+    fq_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    fq_bytes = sum(n for _, _, n in prof)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * batch * args.steps / (ms / 1e3)
+
+    # ---- end-to-end arm: pinned host batches in, loss out, every step --------------------------
+    copy_stream = torch.cuda.Stream(dev)
+
+    def fetch(i):
+        with torch.cuda.stream(copy_stream):
+            buf = host[i % pool].to(dev, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(copy_stream)
+        return buf, done
+
+    for i in range(min(2, args.warmup)):
+        qat(host[i % pool].to(dev, non_blocking=True)).item()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nxt = fetch(0)
+    for i in range(args.steps):
+        buf, done = nxt
+        torch.cuda.current_stream().wait_event(done)
+        buf.record_stream(torch.cuda.current_stream())
+        if i + 1 < args.steps:
+            nxt = fetch(i + 1)                    # next batch crosses PCIe while this step computes
+        loss = qat(buf)
+        _ = loss.item()                           # device -> host read of the step's result
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * batch * args.steps / (e2e_ms / 1e3)
+    h2d = batch * shape[0] * shape[1] * shape[2] * 4
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = fq_bytes / (fq_ms * 1e-3) / 1e9 if fq_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg, "name": args.workload, "batch_per_gpu": batch, "global_batch": batch * world,
+                       "bits": bits, "parallelism": f"dp{world}",
+                       "l2": "inputs larger than L2: every step streams a 154 MB batch and GBs of activations",
+                       "convolutions": "cuDNN (TF32 default, as the reference)"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "fq_flat_kernel (frozen QuantAct forward, 8 B/elem)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "launches_timed": len(prof), "peak_source": peak_src},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res = run_cpu(args.workload, args.cpu_steps, 1, args.cpu_batch)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="imagenet_resnet18_w4a4")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--cpu-batch", type=int, default=32, help="images per step of the CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == "__main__":
+    main()

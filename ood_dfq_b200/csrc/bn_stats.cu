@@ -97,8 +97,14 @@ bn_stats_kernel(const float* __restrict__ x, const BnGeom G, const float* __rest
     cta_span(G, g, ck, off, len, c0);
     const long long row = (long long)G.C * G.HW;
 
+    __shared__ float lut[QUANT ? kLutMax : 1];
     QParams qp;
-    if (QUANT) qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+    const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
+    if (QUANT) {
+        qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
+        __syncthreads();
+    }
 
     // fixed per-thread slots: element e = (threadIdx.x + u*kBThreads)*VEC + j of the span
     float a1[kSlots][VEC], a2[kSlots][VEC], sh[kSlots][VEC];
@@ -134,7 +140,7 @@ bn_stats_kernel(const float* __restrict__ x, const BnGeom G, const float* __rest
                 if (QUANT) {
                     float r[VEC];
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) r[j] = fake_quant<false>(v[u][j], qp);
+                    for (int j = 0; j < VEC; ++j) r[j] = fake_quant_lut(v[u][j], qp, lut, qh, qmask);
                     store_vec<VEC>(y + n * row + off + e, r);
                 }
             }
@@ -178,16 +184,21 @@ bn_stats_kernel(const float* __restrict__ x, const BnGeom G, const float* __rest
     if (!s_last) return;
 
     // last CTA of this channel group: fold the partials in index order
+    // (one warp per channel, lanes stride over the partials, fixed shuffle tree: deterministic)
     __threadfence();
-    for (int c = threadIdx.x; c < nch; c += kBThreads) {
+    for (int c = warp; c < nch; c += kBThreads / 32) {
         double t1 = 0.0, t2 = 0.0;
-        for (int p = 0; p < nparts; ++p) {
-            const float* q = ws->bn_partial + ((size_t)p * G.C + (c0 + c)) * 2;
-            t1 += (double)__ldcg(q);
-            t2 += (double)__ldcg(q + 1);
+        for (int p = lane; p < nparts; p += 32) {
+            const float2 q = __ldcg(reinterpret_cast<const float2*>(ws->bn_partial + ((size_t)p * G.C + (c0 + c)) * 2));
+            t1 += (double)q.x;
+            t2 += (double)q.y;
         }
-        sums[c0 + c] = (float)t1;
-        sums[G.C + c0 + c] = (float)t2;
+        t1 = warp_sum(t1);
+        t2 = warp_sum(t2);
+        if (lane == 0) {
+            sums[c0 + c] = (float)t1;
+            sums[G.C + c0 + c] = (float)t2;
+        }
     }
     if (threadIdx.x == 0) ws->bn_ticket[g] = 0;
 }
@@ -377,7 +388,7 @@ extern "C" int oodfq_bn_stats_forward(const float* x, int N, int C, long long HW
     if (!x || !sums || !workspace) return fail(OODFQ_EINVAL, "bn_stats_forward: null pointer");
     if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "bn_stats_forward: empty tensor (N=%d C=%d HW=%lld)", N, C, HW);
     if (C > kMaxBnChannels) return fail(OODFQ_EINVAL, "bn_stats_forward: C=%d exceeds %d", C, kMaxBnChannels);
-    if (y && (!fq_lo || !fq_hi || fq_k < 1 || fq_k > 16)) return fail(OODFQ_EINVAL, "bn_stats_forward: fused fake-quant needs a range and k in [1,16]");
+    if (y && (!fq_lo || !fq_hi || fq_k < 1 || fq_k > 8)) return fail(OODFQ_EINVAL, "bn_stats_forward: fused fake-quant needs a range and k in [1,8]");
     BnGeom G; int vec; char why[128];
     bool vec_ok = aligned16(x) && (!y || aligned16(y));
     if (make_geom(N, C, HW, vec_ok, G, vec, why, sizeof(why)) != OODFQ_OK) return fail(OODFQ_EINVAL, "bn_stats_forward: %s", why);

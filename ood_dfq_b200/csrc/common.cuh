@@ -154,6 +154,31 @@ __device__ __forceinline__ float fake_quant(float x, const QParams& p) {
     return value_of<SYM>(code_of<SYM>(x, p), p);
 }
 
+// ---- dequantisation by table ------------------------------------------------------------
+// A clamped code takes one of 2^k values, so (q + zp) / scale takes one of 2^k values too.
+// The generic IEEE division is the expensive part of the element loop (MUFU.RCP + FCHK +
+// 5 FFMA, and its slow path is entered whenever the numerator is zero, i.e. for every
+// post-ReLU zero).  For k <= 8 each CTA therefore evaluates the 2^k quotients once with the
+// true division -- bit-exact by construction -- and the loop does a conflict-free shared
+// memory lookup instead.
+constexpr int kLutMax = 256;
+constexpr float kRoundMagic = 12582912.0f;   // 1.5 * 2^23: float(kRoundMagic + n) has bits 0x4B400000 + n
+
+__device__ __forceinline__ void build_lut(float* lut, const QParams& p, int k, int tid, int nthreads) {
+    for (int j = tid; j < (1 << k); j += nthreads) lut[j] = value_of<false>(__fadd_rn((float)j, p.qlo), p);
+}
+
+// index of a clamped, non-NaN code q in [-h, h-1] (h = -qlo): low bits of the magic-number sum
+__device__ __forceinline__ int lut_index(float q, int h, int mask) {
+    return (__float_as_int(__fadd_rn(q, kRoundMagic)) + h) & mask;
+}
+
+__device__ __forceinline__ float fake_quant_lut(float x, const QParams& p, const float* lut, int h, int mask) {
+    float q = code_of<false>(x, p);
+    float y = lut[lut_index(q, h, mask)];
+    return (q != q) ? q : y;                 // NaN in, NaN out (as the ATen chain does)
+}
+
 template <int MODE, bool SYM>
 __device__ __forceinline__ float apply_mode(float x, const QParams& p) {
     if (MODE == OODFQ_MODE_FAKEQUANT) return fake_quant<SYM>(x, p);
@@ -195,6 +220,18 @@ __device__ __forceinline__ float ema_step(float state, float sample, float beta,
     float t3 = __fadd_rn(t1, t2);
     float d = __fsub_rn(1.0f, beta_t_new);
     return __fdiv_rn(t3, d);
+}
+
+// resident CTAs per SM of a kernel at a block size (persistent grids are sized with it);
+// answered by the occupancy calculator from the cubin, once per kernel instantiation
+template <typename K>
+inline int resident_ctas(K kernel, int threads, size_t dyn_smem = 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, dyn_smem) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = 4;
+    }
+    return n;
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -14,13 +14,21 @@ namespace oodfq {
 constexpr int kThreads = 256;
 constexpr int kUnroll = 4;  // 4 x 256-bit loads in flight per thread = 32 KB per CTA tile
 
-template <int MODE, bool SYM, bool CODES>
+// LUT = true: asymmetric FAKEQUANT with k <= 8, dequantised values come from a 2^k-entry
+// shared-memory table (see common.cuh); otherwise the generic per-element division.
+template <int MODE, bool SYM, bool CODES, bool LUT>
 __global__ void __launch_bounds__(kThreads)
 fq_flat_kernel(const float* x, float* y, int8_t* __restrict__ codes,
                long long numel, const float* __restrict__ p0, const float* __restrict__ p1,
                int k, int given, int aliased, int reverse) {
+    __shared__ float lut[LUT ? kLutMax : 1];
     const QParams p = given ? given_qparams(__ldg(p0), __ldg(p1), k)
                             : make_qparams(__ldg(p0), __ldg(p1), k);
+    const int h = 1 << (k - 1), mask = (1 << k) - 1;
+    if (LUT) {
+        build_lut(lut, p, k, threadIdx.x, kThreads);
+        __syncthreads();
+    }
     const long long n8 = numel >> 3;                    // 256-bit vectors
     const long long tile = (long long)kThreads * kUnroll;
     const long long ntiles = (n8 + tile - 1) / tile;
@@ -48,6 +56,9 @@ fq_flat_kernel(const float* x, float* y, int8_t* __restrict__ codes,
                         r.v[j] = value_of<SYM>(q, p);
                     }
                     reinterpret_cast<int2*>(codes)[i] = pk.w;
+                } else if (LUT) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r.v[j] = fake_quant_lut(v[u].v[j], p, lut, h, mask);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) r.v[j] = apply_mode<MODE, SYM>(v[u].v[j], p);
@@ -135,10 +146,21 @@ static int launch_fq(const float* x, float* y, int8_t* codes, long long numel, c
         if (vec) {
             long long n8 = numel >> 3;
             long long tiles = (n8 + (long long)kThreads * kUnroll - 1) / ((long long)kThreads * kUnroll);
-            long long cap = (long long)kNumSM * 8;
-            int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
-            fq_flat_kernel<MODE, SYM, CODES><<<grid, kThreads, 0, st>>>(x, y, codes, numel, p0, p1, k, given,
-                                                                        (const void*)x == (const void*)y, reverse);
+            const int aliased = (const void*)x == (const void*)y;
+            constexpr bool kCanLut = (MODE == OODFQ_MODE_FAKEQUANT) && !SYM && !CODES;
+            if (kCanLut && k <= 8) {
+                static const int per_sm = resident_ctas(fq_flat_kernel<MODE, SYM, CODES, kCanLut>, kThreads);
+                long long cap = (long long)kNumSM * per_sm;
+                int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
+                fq_flat_kernel<MODE, SYM, CODES, kCanLut><<<grid, kThreads, 0, st>>>(x, y, codes, numel, p0, p1, k,
+                                                                                    given, aliased, reverse);
+            } else {
+                static const int per_sm = resident_ctas(fq_flat_kernel<MODE, SYM, CODES, false>, kThreads);
+                long long cap = (long long)kNumSM * per_sm;
+                int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
+                fq_flat_kernel<MODE, SYM, CODES, false><<<grid, kThreads, 0, st>>>(x, y, codes, numel, p0, p1, k,
+                                                                                  given, aliased, reverse);
+            }
         } else {
             long long blocks = (numel + kThreads - 1) / kThreads;
             long long cap = (long long)kNumSM * 8;

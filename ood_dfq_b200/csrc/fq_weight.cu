@@ -51,7 +51,7 @@ __device__ __forceinline__ void range_from(float mn, float mx, bool sym, float& 
 }
 
 template <bool SYM>
-__device__ __forceinline__ void warp_row(const WeightJob& jb, long long row, int lane) {
+__device__ __forceinline__ void warp_row(const WeightJob& jb, long long row, int lane, float* lut) {
     const int len = (int)jb.row_len;
     const float* src = jb.w + row * jb.row_len;
     float v[kWarpRowMax / 32];
@@ -77,6 +77,17 @@ __device__ __forceinline__ void warp_row(const WeightJob& jb, long long row, int
     }
     float* dst = jb.wq + row * jb.row_len;
     int8_t* cd = jb.codes ? jb.codes + row * jb.row_len : nullptr;
+    if (!SYM && !cd && jb.k <= 8) {          // table of the 2^k dequantised values of this row
+        build_lut(lut, p, jb.k, lane, 32);
+        __syncwarp();
+        const int h = 1 << (jb.k - 1), mask = (1 << jb.k) - 1;
+#pragma unroll
+        for (int j = 0; j < kWarpRowMax / 32; ++j) {
+            int i = lane + 32 * j;
+            if (i < len) dst[i] = fake_quant_lut(v[j], p, lut, h, mask);
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < kWarpRowMax / 32; ++j) {
         int i = lane + 32 * j;
@@ -89,7 +100,7 @@ __device__ __forceinline__ void warp_row(const WeightJob& jb, long long row, int
 }
 
 template <bool SYM>
-__device__ __forceinline__ void cta_row(const WeightJob& jb, long long row, float* s_red) {
+__device__ __forceinline__ void cta_row(const WeightJob& jb, long long row, float* s_red, float* lut) {
     const long long len = jb.row_len;
     const float* src = jb.w + row * len;
     float* dst = jb.wq + row * len;
@@ -132,14 +143,26 @@ __device__ __forceinline__ void cta_row(const WeightJob& jb, long long row, floa
         if (jb.hi) jb.hi[row] = hi;
     }
     int8_t* cd = jb.codes ? jb.codes + row * len : nullptr;
+    const bool use_lut = !SYM && !cd && jb.k <= 8;
+    const int h = 1 << (jb.k - 1), mask = (1 << jb.k) - 1;
+    if (use_lut) {
+        build_lut(lut, p, jb.k, threadIdx.x, kWThreads);
+        __syncthreads();
+    }
     if (vec && !cd) {
         const float4* s4 = reinterpret_cast<const float4*>(src);
         float4* d4 = reinterpret_cast<float4*>(dst);
         for (long long i = threadIdx.x; i < (len >> 2); i += kWThreads) {
             float4 t = __ldg(s4 + i);
-            d4[i] = make_float4(fake_quant<SYM>(t.x, p), fake_quant<SYM>(t.y, p),
-                                fake_quant<SYM>(t.z, p), fake_quant<SYM>(t.w, p));
+            if (use_lut)
+                d4[i] = make_float4(fake_quant_lut(t.x, p, lut, h, mask), fake_quant_lut(t.y, p, lut, h, mask),
+                                    fake_quant_lut(t.z, p, lut, h, mask), fake_quant_lut(t.w, p, lut, h, mask));
+            else
+                d4[i] = make_float4(fake_quant<SYM>(t.x, p), fake_quant<SYM>(t.y, p),
+                                    fake_quant<SYM>(t.z, p), fake_quant<SYM>(t.w, p));
         }
+    } else if (use_lut) {
+        for (long long i = threadIdx.x; i < len; i += kWThreads) dst[i] = fake_quant_lut(__ldg(src + i), p, lut, h, mask);
     } else {
         for (long long i = threadIdx.x; i < len; i += kWThreads) {
             float q = code_of<SYM>(__ldg(src + i), p);
@@ -152,6 +175,7 @@ __device__ __forceinline__ void cta_row(const WeightJob& jb, long long row, floa
 __global__ void __launch_bounds__(kWThreads)
 weight_fq_kernel(const __grid_constant__ WeightBatch batch) {
     __shared__ float s_red[2 * kWarpsPerCta];
+    __shared__ float s_lut[kWarpsPerCta][kLutMax];
     // which job owns this CTA (jobs are few: linear scan over uniform parameter memory)
     int j = 0;
     while (j + 1 < batch.n && (int)blockIdx.x >= batch.job[j + 1].first_block) ++j;
@@ -159,11 +183,12 @@ weight_fq_kernel(const __grid_constant__ WeightBatch batch) {
     const int local = (int)blockIdx.x - jb.first_block;
     const bool sym = (jb.flags & OODFQ_SYMMETRIC) != 0;
     if (jb.rows_per_cta == 1) {
-        if (sym) cta_row<true>(jb, local, s_red); else cta_row<false>(jb, local, s_red);
+        if (sym) cta_row<true>(jb, local, s_red, s_lut[0]); else cta_row<false>(jb, local, s_red, s_lut[0]);
     } else {
         const long long row = (long long)local * kWarpsPerCta + (threadIdx.x >> 5);
         if (row < jb.rows) {
-            if (sym) warp_row<true>(jb, row, threadIdx.x & 31); else warp_row<false>(jb, row, threadIdx.x & 31);
+            float* lut = s_lut[threadIdx.x >> 5];
+            if (sym) warp_row<true>(jb, row, threadIdx.x & 31, lut); else warp_row<false>(jb, row, threadIdx.x & 31, lut);
         }
     }
 }

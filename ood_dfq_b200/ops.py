@@ -15,6 +15,10 @@ from . import _native as N
 
 _workspaces: dict = {}
 
+# bench.py sets this to a list to time every frozen fake-quant launch with CUDA events on the
+# launching stream: entries are (start_event, end_event, algorithmic_bytes).
+PROFILE = None
+
 
 def _need(t: torch.Tensor, name: str, dtype=torch.float32):
     if not isinstance(t, torch.Tensor):
@@ -100,10 +104,17 @@ def elementwise(x, p0, p1, k, mode, symmetric=False, params_given=False, out=Non
     if cd is not None and xd.stride() != cd.stride():
         cd = torch.empty_like(xd, dtype=torch.int8)
     flags = (N.SYMMETRIC if symmetric else 0) | (N.PARAMS_GIVEN if params_given else 0)
+    timed = PROFILE is not None and mode == N.MODE_FAKEQUANT and rows == 1
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = N.load().oodfq_fq_forward(xd.data_ptr(), y.data_ptr(), _ptr(cd), xd.numel(),
                                    p0.contiguous().data_ptr(), p1.contiguous().data_ptr(), rows,
                                    int(k), mode, flags, _stream(x.device))
     N.check(rc, "fq_forward")
+    if timed:
+        ev1.record()
+        PROFILE.append((ev0, ev1, 8 * xd.numel()))
     return (y, cd) if codes else y
 
 

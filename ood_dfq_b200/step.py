@@ -1,0 +1,141 @@
+"""The steady-state QAT iteration that drives the quantisation path, restated as runnable host code.
+
+This is the CALLER of the hot path, not the path: the reference's version lives in
+``Trainer.train`` (trainer_direct.py:490-518, helpers :308-340, :350-356, :379-386), a file
+that cannot even be compiled (TabError at :275) and needs pytorchcv.  Per iteration:
+
+    teacher(images)  [grad to images]  ->  student(images)  ->  KD + feature-alignment loss
+    -> sign of d loss / d images  ->  images + eps * sign  ->  teacher (no grad) + student again
+    -> backward of both losses  ->  SGD(nesterov) step
+
+so the quantisation path runs in two student forwards and is traversed by three backward
+sweeps.  The same code drives the CUDA mirror on a GPU and the CPU oracle modules (the
+``--impl reference`` arm of bench.py), only the module classes differ.
+
+Deviation from the reference, kept on purpose and identical in both arms: the teacher's
+parameters do not require grad (the reference leaves them trainable and lets DDP all-reduce
+gradients nobody uses); the student update is unaffected.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+def kd_loss(student_logits, teacher_logits, temperature: float, alpha: float):
+    """``KLDiv(log_softmax(s/T), softmax(t/T), 'batchmean') * alpha * T^2`` (trainer_direct.py:308-323)."""
+    a = F.log_softmax(student_logits / temperature, dim=1)
+    b = F.softmax(teacher_logits / temperature, dim=1)
+    return F.kl_div(a, b, reduction="batchmean") * (alpha * temperature * temperature)
+
+
+def channel_attention(x):
+    """trainer_direct.py:382-383."""
+    return F.normalize(x.pow(2).mean([2, 3]).view(x.size(0), -1))
+
+
+class FeatureTap:
+    """Forward hooks collecting channel attention of the residual bodies (trainer_direct.py:432-440)."""
+
+    def __init__(self, model: nn.Module, unit_types: tuple):
+        self.maps = []
+        self.handles = [m.body.register_forward_hook(self._hook) for m in model.modules()
+                        if isinstance(m, unit_types) and hasattr(m, "body")]
+
+    def _hook(self, module, inputs, output):
+        self.maps.append(channel_attention(output.clone()))
+
+    def clear(self):
+        self.maps.clear()
+
+
+def feature_alignment_loss(student_maps, teacher_maps, lam: float, device):
+    """``lam * sum_l mean((A_s - A_t)^2)`` (trainer_direct.py:325-330)."""
+    fa = torch.zeros(1, device=device)
+    for s, t in zip(student_maps, teacher_maps):
+        fa = fa + (s - t).pow(2).mean()
+    return lam * fa
+
+
+class FlatGrads:
+    """All gradients of a model as views into ONE buffer: one memset, one NCCL all-reduce per step.
+
+    Replaces DDP's bucketed reducer for this step (main_direct.py:484): the student is
+    traversed by ``autograd.grad`` and two forwards before its single ``backward``, a
+    pattern DDP only tolerates, and the whole payload (46.7 MB for ResNet-18) is one
+    NVLink-speed collective anyway.
+    """
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        ref = self.params[0]
+        self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))
+
+
+class QATStep:
+    """One data-free QAT iteration (see module docstring).  ``__call__`` returns the detached losses."""
+
+    def __init__(self, student, teacher, lr=1e-6, momentum=0.9, weight_decay=1e-4, temperature=20.0,
+                 alpha=20.0, lam=1000.0, eps=0.01, unit_types: tuple = (), group=None, perturb=True):
+        self.student, self.teacher = student, teacher
+        self.T, self.alpha, self.lam, self.eps = temperature, alpha, lam, eps
+        self.group, self.perturb = group, perturb
+        for p in teacher.parameters():
+            p.requires_grad_(False)
+        self.grads = FlatGrads(student.parameters())
+        self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, weight_decay=weight_decay,
+                                   nesterov=True)
+        self.tap_s = FeatureTap(student, unit_types) if unit_types else None
+        self.tap_t = FeatureTap(teacher, unit_types) if unit_types else None
+        student.eval()       # trainer_direct.py:411-412: both nets use BN running statistics
+        teacher.eval()
+
+    def _losses(self, images, teacher_logits):
+        out = self.student(images)
+        kl = kd_loss(out, teacher_logits, self.T, self.alpha)
+        if self.tap_s is not None:
+            fa = feature_alignment_loss(self.tap_s.maps, self.tap_t.maps, self.lam, images.device)
+        else:
+            fa = torch.zeros(1, device=images.device)
+        return out, kl, fa
+
+    def _clear_taps(self):
+        if self.tap_s is not None:
+            self.tap_s.clear()
+            self.tap_t.clear()
+
+    def __call__(self, images, labels=None):
+        self._clear_taps()
+        images = images.detach().requires_grad_(True)
+        t_out = self.teacher(images)
+        _, kl, fa = self._losses(images, t_out)
+        loss = kl + fa
+        total = loss
+        if self.perturb:
+            sign = torch.sgn(torch.autograd.grad(loss, images, retain_graph=True)[0])
+            self._clear_taps()
+            with torch.no_grad():
+                images_p = images + self.eps * sign
+                t_out_p = self.teacher(images_p.detach())
+            _, kl_p, fa_p = self._losses(images_p.detach(), t_out_p.detach())
+            total = loss + (kl_p + fa_p)
+        self.grads.zero()
+        total.backward()
+        self.grads.all_reduce_mean(self.group)
+        self.opt.step()
+        return total.detach()

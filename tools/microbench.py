@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Per-kernel bandwidth microbenchmark at the BASELINE tensor shapes.
+
+    python tools/microbench.py [--only fq,calib,minmax,stats,stats_fq,bwd,weights,copy] [--iters 10] [--json out.json]
+
+Timing hygiene: 3 warm-up launches, L2 flushed between timed launches (a 512 MB memset-like
+write), CUDA events on the launching stream, median over --iters.  GB/s = algorithmic bytes /
+time; fractions are of MEASURED_PEAKS.json hbm_gbs when present.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from ood_dfq_b200 import ops  # noqa: E402
+
+ACT_SHAPES = [(256, 64, 112, 112), (256, 64, 56, 56), (256, 128, 28, 28), (256, 256, 14, 14), (256, 512, 7, 7)]
+R18_WEIGHTS = [(64, 3, 7, 7)] + [(64, 64, 3, 3)] * 4 + [(128, 64, 3, 3), (128, 128, 3, 3), (128, 64, 1, 1)] + \
+              [(128, 128, 3, 3)] * 2 + [(256, 128, 3, 3), (256, 256, 3, 3), (256, 128, 1, 1)] + [(256, 256, 3, 3)] * 2 + \
+              [(512, 256, 3, 3), (512, 512, 3, 3), (512, 256, 1, 1)] + [(512, 512, 3, 3)] * 2 + [(1000, 512)]
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+class Timer:
+    def __init__(self, iters, flush=True):
+        self.iters = iters
+        self.flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda") if flush else None
+
+    def __call__(self, fn):
+        for _ in range(3):
+            fn()
+        times = []
+        for _ in range(self.iters):
+            if self.flush is not None:
+                self.flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        return statistics.median(times), min(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="copy,fq,minmax,calib,stats,stats_fq,bwd,weights")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--json", default="")
+    ap.add_argument("--shapes", default="", help="indices into the activation shape list, e.g. 0,4")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    shapes = ACT_SHAPES if not args.shapes else [ACT_SHAPES[int(i)] for i in args.shapes.split(",")]
+    pk = peak()
+    timer = Timer(args.iters, flush=not args.no_flush)
+    rows = []
+
+    def report(kernel, shape, nbytes, med, best):
+        gbs = nbytes / (med * 1e-3) / 1e9
+        rows.append({"kernel": kernel, "shape": list(shape), "bytes": nbytes, "ms_median": med, "ms_best": best,
+                     "gbs": gbs, "frac_of_peak": gbs / pk})
+        print(f"{kernel:10s} {str(tuple(shape)):24s} {nbytes / 1e6:9.1f} MB  {med * 1e3:9.1f} us  "
+              f"{gbs:7.0f} GB/s  {100 * gbs / pk:5.1f}% of {pk:.0f}", flush=True)
+
+    torch.manual_seed(0)
+    for shape in shapes:
+        x = torch.relu(torch.randn(shape, device="cuda"))
+        n = x.numel()
+        lo, hi = torch.zeros(1, device="cuda"), torch.full((1,), 2.5, device="cuda")
+        if "copy" in only:
+            y = torch.empty_like(x)
+            report("copy", shape, 8 * n, *timer(lambda: y.copy_(x)))
+            del y
+        if "fq" in only:
+            report("fq", shape, 8 * n, *timer(lambda: ops.fake_quant(x, 4, lo, hi)))
+        if "minmax" in only:
+            report("minmax", shape, 4 * n, *timer(lambda: ops.minmax(x)))
+        if "calib" in only:
+            st = [torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda"),
+                  torch.full((1,), 0.9, device="cuda"), torch.ones(1, device="cuda")]
+
+            def calib():
+                st[3].fill_(1.0)
+                ops.act_calib_forward(x, 4, st[0], st[1], st[2], st[3])
+            report("calib", shape, 12 * n, *timer(calib))
+        c = shape[1]
+        shift = torch.zeros(c, device="cuda")
+        if "stats" in only:
+            report("stats", shape, 4 * n, *timer(lambda: ops.bn_stats_forward(x, shift)))
+        if "stats_fq" in only:
+            report("stats_fq", shape, 8 * n, *timer(lambda: ops.bn_stats_forward(x, shift, fq=(4, lo, hi))))
+        if "bwd" in only:
+            g = torch.randn_like(x)
+            mean = torch.zeros(c, device="cuda")
+            gm, gv = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
+            m = float(n // c)
+            report("bwd", shape, 12 * n, *timer(lambda: ops.bn_stats_backward(x, g, mean, gm, gv, m)))
+            del g
+        del x
+        torch.cuda.empty_cache()
+    if "weights" in only:
+        ws = [torch.randn(s, device="cuda") * 0.02 for s in R18_WEIGHTS]
+        outs = [torch.empty_like(w) for w in ws]
+        n = sum(w.numel() for w in ws)
+        ks, sym = [4] * len(ws), [False] * len(ws)
+        report("weights", (len(ws), n), 8 * n, *timer(lambda: ops.weight_fq_multi(ws, ks, sym, outs=outs)))
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump({"peak_gbs": pk, "rows": rows}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
