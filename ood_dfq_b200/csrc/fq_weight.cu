@@ -7,9 +7,9 @@
 // Here each output row is read from HBM once, reduced on chip, and its
 // fake-quantised twin written once: 8 B/elem, one launch for the whole model.
 //
-// Work split: rows of <= kWarpRowMax elements are handled one per warp and held
-// in registers between the reduction and the quantise step; longer rows get a
-// whole CTA and are re-read through L1 (a 4608-element row is 18 KB).
+// Work split: rows of <= kWarpRowMax elements are handled one per warp, longer rows
+// get a whole CTA; either way the row is reduced, then re-read through L1 (a
+// 4608-element row is 18 KB) and quantised.
 //
 // Roofline: HBM, 8 algorithmic bytes per weight element.
 #include "common.cuh"
@@ -18,7 +18,7 @@ namespace oodfq {
 
 constexpr int kWThreads = 256;
 constexpr int kWarpsPerCta = kWThreads / 32;
-constexpr int kWarpRowMax = 1024;   // 32 lanes x 32 registers
+constexpr int kWarpRowMax = 1024;   // 4 KB: stays in L1 between the two passes
 constexpr int kMaxJobs = 40;        // descriptors travel in kernel-parameter space (< 4 KB)
 
 struct WeightJob {
@@ -50,21 +50,19 @@ __device__ __forceinline__ void range_from(float mn, float mx, bool sym, float& 
     }
 }
 
+// One warp per row (row_len <= kWarpRowMax = 4 KB): pass 1 reduces the row, pass 2 re-reads it
+// through L1 (the line was just brought in by this very warp) and quantises.  Keeping the row
+// in L1 instead of 32 registers per lane is what lets 6-8 CTAs stay resident per SM.
 template <bool SYM>
 __device__ __forceinline__ void warp_row(const WeightJob& jb, long long row, int lane, float* lut) {
     const int len = (int)jb.row_len;
     const float* src = jb.w + row * jb.row_len;
-    float v[kWarpRowMax / 32];
     float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-#pragma unroll
-    for (int j = 0; j < kWarpRowMax / 32; ++j) {
-        int i = lane + 32 * j;
-        if (i < len) {
-            v[j] = ld_stream(src + i);
-            float t = SYM ? fabsf(v[j]) : v[j];
-            mn = min_nan(mn, t);
-            mx = max_nan(mx, t);
-        }
+    for (int i = lane; i < len; i += 32) {
+        float t = __ldg(src + i);
+        if (SYM) t = fabsf(t);
+        mn = min_nan(mn, t);
+        mx = max_nan(mx, t);
     }
     mn = warp_min_nan(mn);
     mx = warp_max_nan(mx);
@@ -81,21 +79,13 @@ __device__ __forceinline__ void warp_row(const WeightJob& jb, long long row, int
         build_lut(lut, p, jb.k, lane, 32);
         __syncwarp();
         const int h = 1 << (jb.k - 1), mask = (1 << jb.k) - 1;
-#pragma unroll
-        for (int j = 0; j < kWarpRowMax / 32; ++j) {
-            int i = lane + 32 * j;
-            if (i < len) dst[i] = fake_quant_lut(v[j], p, lut, h, mask);
-        }
+        for (int i = lane; i < len; i += 32) dst[i] = fake_quant_lut(__ldg(src + i), p, lut, h, mask);
         return;
     }
-#pragma unroll
-    for (int j = 0; j < kWarpRowMax / 32; ++j) {
-        int i = lane + 32 * j;
-        if (i < len) {
-            float q = code_of<SYM>(v[j], p);
-            if (cd) cd[i] = (int8_t)q;
-            dst[i] = value_of<SYM>(q, p);
-        }
+    for (int i = lane; i < len; i += 32) {
+        float q = code_of<SYM>(__ldg(src + i), p);
+        if (cd) cd[i] = (int8_t)q;
+        dst[i] = value_of<SYM>(q, p);
     }
 }
 

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Per-kernel share of one QAT step (CUPTI via torch.profiler): which kernels the step spends its time in.
+
+    python tools/step_profile.py [--workload imagenet_resnet18_w4a4] [--steps 2] [--out profiles/step_share.txt]
+
+ncu serialises every launch and replays it, which on a 150 ms step with ~1500 launches and 30 GB of live
+activations does not finish; the launch list of OUR kernels comes from ncu (profiles/*launches*.csv), the
+share of the whole step from this CUPTI trace.  Numbers here are device-side kernel durations.
+"""
+import argparse
+import os
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="imagenet_resnet18_w4a4")
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.benchmark = True
+    _, _, shape, bits, default_batch, cfg = bench.WORKLOADS[args.workload]
+    batch = args.batch or default_batch
+    teacher, student = bench.build_pair(args.workload, qm, dev)
+    qat = bench.make_step(args.workload, teacher, student, qm)
+    g = torch.Generator().manual_seed(0)
+    xs = [torch.randn((batch,) + shape, generator=g).to(dev) for _ in range(2)]
+    bench.calibrate(student, xs + xs[:1], qm)
+    for i in range(3):
+        qat(xs[i % 2])
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(args.steps):
+            qat(xs[i % 2])
+        torch.cuda.synchronize()
+    agg = defaultdict(lambda: [0.0, 0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            t = getattr(ev, "device_time_total", None) or getattr(ev, "cuda_time_total", 0.0)
+            agg[ev.name][0] += t
+            agg[ev.name][1] += 1
+    total = sum(v[0] for v in agg.values())
+    lines = [f"# {cfg}; batch {batch}; {args.steps} steps; device kernel time {total / args.steps / 1e3:.2f} ms/step",
+             f"# {'share':>6s} {'ms/step':>9s} {'launches/step':>14s}  kernel"]
+    ours = 0.0
+    for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+        mine = "oodfq::" in name
+        ours += t if mine else 0.0
+        lines.append(f"  {100 * t / total:6.2f} {t / args.steps / 1e3:9.3f} {n / args.steps:14.1f}  {'*' if mine else ' '} {name[:110]}")
+    ours = sum(t for name, (t, n) in agg.items() if "oodfq::" in name)
+    lines.append(f"# kernels of liboodfq_b200.so (*): {100 * ours / total:.2f}% of device time, {ours / args.steps / 1e3:.3f} ms/step")
+    text = "\n".join(lines)
+    print(text)
+    if args.out:
+        with open(args.out, "w") as f:
+            f.write(text + "\n")
+
+
+if __name__ == "__main__":
+    main()
