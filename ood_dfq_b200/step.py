@@ -139,3 +139,44 @@ class QATStep:
         self.grads.all_reduce_mean(self.group)
         self.opt.step()
         return total.detach()
+
+
+# ------------------------------------------------------------------------------ BN-statistics distillation
+def hard_sample_loss(logits, labels, beta: float, gamma: float):
+    """Focal cross-entropy of the image-distillation loop (data_generate/distill_data.py:236-249).
+
+    ``beta * mean((1 - p_label)^gamma * CE)`` with p clamped to 1 - 1e-7; plain ``beta * mean(CE)`` for gamma = 0.
+    """
+    ce = F.cross_entropy(logits, labels, reduction="none")
+    if gamma == 0:
+        return beta * ce.mean()
+    p = F.softmax(logits, dim=1).gather(1, labels.unsqueeze(1)).squeeze(1).clamp(max=1.0 - 1e-7)
+    return beta * ((1 - p).pow(gamma) * ce).mean()
+
+
+class DistillStep:
+    """One Adam iteration on a batch of synthetic images against BN statistics (distill_data.py:229-275).
+
+    ``stat`` is either this package's ``bns.BNStatLoss`` (GPU) or the oracle's ``StatTap`` (CPU): both expose
+    ``clear()`` and ``loss()``.  The teacher may be wrapped by ``quantize_model`` first (BASELINE config 5); the
+    gradient then reaches the images through cuDNN dgrad and the identity STE of every QuantAct.
+    """
+
+    def __init__(self, teacher, stat, images, labels, lr=0.5, beta=0.1, gamma=0.5):
+        self.teacher, self.stat, self.labels, self.beta, self.gamma = teacher, stat, labels, beta, gamma
+        self.images = images.detach().clone().requires_grad_(True)
+        self.opt = torch.optim.Adam([self.images], lr=lr)           # distill_data.py:186-187
+        for p in teacher.parameters():
+            p.requires_grad_(False)
+        teacher.eval()
+
+    def __call__(self):
+        self.stat.clear()
+        out = self.teacher(self.images)
+        target = hard_sample_loss(out, self.labels, self.beta, self.gamma)
+        total = self.stat.loss() + target                            # mean/L + var/L + target, :259-265
+        self.opt.zero_grad()
+        total.backward()
+        torch.nn.utils.clip_grad_norm_([self.images], max_norm=1.0)  # :273
+        self.opt.step()
+        return total.detach()
