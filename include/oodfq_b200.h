@@ -115,28 +115,29 @@ int oodfq_weight_fq_multi(const oodfq_weight_desc* descs_host, int n_tensors,
 
 /* ---- a11: per-channel statistics of a BN input ---------------------------
  * replaces: hook_fn_forward, trainer_direct.py:388-393 / distill_data.py:69-73
- * x: [N, C, HW] (NCHW).  sums: [2*C] receives S1_c = sum(x - shift_c) and
- * S2_c = sum((x - shift_c)^2) over N and HW.  shift: [C] or NULL (zero).
+ * x: [N, C, HW] (NCHW).  sums: [2*C] fp64 receives S1_c = sum(x - shift_c) and
+ * S2_c = sum((x - shift_c)^2) over N and HW (accumulated around a local pivot and
+ * re-based in fp64, so no cancellation).  shift: [C] or NULL (zero).
  * Optional fused fake-quant of the same read (north_star (b)): when y != NULL,
  * y = fakequant(x) with the scalar range (fq_lo, fq_hi), k = fq_k. */
 int oodfq_bn_stats_forward(const float* x, int N, int C, long long HW, const float* shift,
-                           float* sums, float* y, const float* fq_lo, const float* fq_hi,
+                           double* sums, float* y, const float* fq_lo, const float* fq_hi,
                            int fq_k, void* workspace, oodfq_stream_t stream);
 
 /* mean_c = shift_c + S1_c/count, var_c = S2_c/count - (S1_c/count)^2 (biased).
  * `sums` may have been all-reduced over ranks; count is the global N*HW. */
-int oodfq_bn_stats_finalize(const float* sums, const float* shift, int C, double count,
+int oodfq_bn_stats_finalize(const double* sums, const float* shift, int C, double count,
                             float* mean, float* var, oodfq_stream_t stream);
 
 /* ---- a12: BN-statistics loss over L layers, packed ------------------------
  * replaces: trainer_direct.py:473-486 and distill_data.py:252-265
  * Layer l owns channels [ch_off_host[l], ch_off_host[l+1]) of every packed [Ctot]
- * array.  sums is [2*Ctot] with each layer's output of oodfq_bn_stats_forward kept
+ * array.  sums is [2*Ctot] fp64 with each layer's output of oodfq_bn_stats_forward kept
  * together: floats [2*off_l, 2*off_l + C_l) are S1, the next C_l are S2.
  * counts_host[l] = global N*H*W of layer l.  Outputs: loss3[0] = (sum_l MSE_mean + MSE_var)/L,
  * loss3[1] = sum_l MSE_mean / L, loss3[2] = sum_l MSE_var / L; mean, var [Ctot];
  * gmean, gvar [Ctot] = d loss / d mean_c, d loss / d var_c. */
-int oodfq_bns_loss(const float* sums, const float* shift, const float* run_mean,
+int oodfq_bns_loss(const double* sums, const float* shift, const float* run_mean,
                    const float* run_var, const int* ch_off_host, const double* counts_host,
                    int L, float* loss3, float* mean, float* var, float* gmean, float* gvar,
                    oodfq_stream_t stream);
@@ -149,6 +150,26 @@ int oodfq_bn_stats_backward(const float* x, const float* grad_in, float* grad_x,
                             int N, int C, long long HW, const float* mean,
                             const float* gmean, const float* gvar, double count,
                             const float* gscale, oodfq_stream_t stream);
+
+/* ---- eval-mode BatchNorm fused with the ReLU + QuantAct behind it ----------
+ * replaces: nn.BatchNorm2d in eval() (student and teacher always are: trainer_direct.py:411-412)
+ *           followed by the nn.Sequential(ReLU, QuantAct) of main_direct.py:464-465
+ * forward : y = [fakequant]( [relu]( a_c*x + b_c ) ),  a_c = w_c/sqrt(rv_c+eps), b_c = bias_c - rm_c*a_c
+ * backward: g' = grad_y * [a_c*x+b_c > 0];  grad_x = g'*a_c;
+ *           dwdb[c] = sum g'*(x-rm_c)/sqrt(rv_c+eps), dwdb[C+c] = sum g'   (fp64, NULL: skip)
+ * flags: OODFQ_BN_RELU | OODFQ_BN_QUANT (QUANT: scalar range fq_lo/fq_hi, k = fq_k <= 8; its
+ * backward is the identity STE).  z_debug (nullable): the fp32 value handed to the quantiser.
+ * weight / bias may be NULL (1 / 0). */
+#define OODFQ_BN_RELU 1
+#define OODFQ_BN_QUANT 2
+int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, int N, int C, long long HW,
+                          const float* weight, const float* bias, const float* running_mean,
+                          const float* running_var, float eps, int flags, const float* fq_lo,
+                          const float* fq_hi, int fq_k, oodfq_stream_t stream);
+int oodfq_bn_eval_backward(const float* x, const float* grad_y, float* grad_x, int N, int C,
+                           long long HW, const float* weight, const float* bias,
+                           const float* running_mean, const float* running_var, float eps,
+                           int flags, double* dwdb, void* workspace, oodfq_stream_t stream);
 
 #ifdef __cplusplus
 }

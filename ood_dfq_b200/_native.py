@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboodfq_b200.so")
 
 MODE_FAKEQUANT, MODE_QUANTIZE, MODE_DEQUANTIZE = 0, 1, 2
 SYMMETRIC, PARAMS_GIVEN = 1, 2
+BN_RELU, BN_QUANT = 1, 2
 ABI_VERSION = 1
 
 _vp, _ll, _i, _d = C.c_void_p, C.c_longlong, C.c_int, C.c_double
@@ -40,6 +41,8 @@ SIGNATURES = {
     "oodfq_bn_stats_finalize": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp]),
     "oodfq_bns_loss": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(_d), _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "oodfq_bn_stats_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _d, _vp, _vp]),
+    "oodfq_bn_eval_forward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
+    "oodfq_bn_eval_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

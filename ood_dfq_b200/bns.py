@@ -76,7 +76,7 @@ class _Pass:
     __slots__ = ("sums", "counts", "fired", "tokens", "world", "loss3", "mean", "var", "gmean", "gvar")
 
     def __init__(self, n_layers, ctot, device):
-        self.sums = torch.empty(2 * ctot, dtype=torch.float32, device=device)
+        self.sums = torch.empty(2 * ctot, dtype=torch.float64, device=device)
         self.counts = [0.0] * n_layers
         self.fired = [0] * n_layers
         self.tokens = [None] * n_layers

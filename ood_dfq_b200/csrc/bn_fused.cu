@@ -1,0 +1,386 @@
+// Eval-mode BatchNorm fused with the ReLU and QuantAct that follow it.
+//
+// In the reference the student always runs in eval() (trainer_direct.py:411), so every BatchNorm is
+// the per-channel affine  z = a_c*x + b_c,  a_c = w_c / sqrt(rv_c + eps),  b_c = bias_c - rm_c*a_c,
+// and the `nn.Sequential(ReLU, QuantAct)` that quantize_model puts behind it (main_direct.py:464-465)
+// re-reads and re-writes the same tensor twice more.  Measured on the ImageNet step, ATen's eval-mode
+// batch_norm_backward_kernel alone is 24 % of the step and cuDNN's inference BN another 5 %
+// (profiles/r1_step_share.txt).  Here:
+//
+//   forward   y = fakequant(relu(a_c*x + b_c))        one read, one write        (8 B/elem)
+//   backward  g' = g * [a_c*x + b_c > 0];  grad_x = g' * a_c;                    (12 B/elem)
+//             dW_c = sum g' * (x - rm_c) / sqrt(rv_c + eps);  dB_c = sum g'      (same read)
+//
+// RELU and QUANT are flags: without them this is a plain (and fast) eval-mode BN for the layers that
+// feed a residual add.  The fake-quant arithmetic is the reference's (common.cuh), applied to the
+// fp32 value z the affine produces; the QuantAct backward is the identity STE.
+//
+// Decomposition, determinism and grid sizing: bn_geom.cuh.  Roofline: HBM.
+#include "bn_geom.cuh"
+
+namespace oodfq {
+
+struct BnParams {
+    const float* w;    // [C] or NULL (1)
+    const float* b;    // [C] or NULL (0)
+    const float* rm;   // [C] running mean
+    const float* rv;   // [C] running var
+    float eps;
+};
+
+// one rounding per step, the same in every kernel (forward and the mask recomputed by backward)
+__device__ __forceinline__ void affine_of(const BnParams& P, int c, float& a, float& b, float& invstd) {
+    invstd = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(P.rv + c), P.eps)));
+    a = __fmul_rn(P.w ? __ldg(P.w + c) : 1.0f, invstd);
+    b = __fsub_rn(P.b ? __ldg(P.b + c) : 0.0f, __fmul_rn(__ldg(P.rm + c), a));
+}
+
+template <bool RELU, bool QUANT>
+__device__ __forceinline__ float head(float x, float a, float b, const QParams& qp, const float* lut, int qh,
+                                      int qmask, float& z) {
+    z = fmaf(x, a, b);
+    if (RELU) z = (z != z) ? z : fmaxf(z, 0.0f);      // clamp_min keeps NaN
+    return QUANT ? fake_quant_lut(z, qp, lut, qh, qmask) : z;
+}
+
+// =============================================================================== forward
+template <bool RELU, bool QUANT>
+__global__ void __launch_bounds__(kBThreads)
+bn_plane_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ zdbg, int N, int C,
+                    long long HW, int split, const BnParams P, const float* __restrict__ fq_lo,
+                    const float* __restrict__ fq_hi, int fq_k) {
+    __shared__ float lut[QUANT ? kLutMax : 1];
+    const int c = blockIdx.x / split, sp = blockIdx.x % split;
+    QParams qp;
+    const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
+    if (QUANT) {
+        qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
+        __syncthreads();
+    }
+    float a, b, invstd;
+    affine_of(P, c, a, b, invstd);
+    const int n4 = (int)(HW >> 2);
+    for (int n = sp; n < N; n += split) {
+        const long long base = ((long long)n * C + c) * HW;
+        const float4* p = reinterpret_cast<const float4*>(x + base);
+        float4* q = reinterpret_cast<float4*>(y + base);
+        float4* zq = zdbg ? reinterpret_cast<float4*>(zdbg + base) : nullptr;
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * kBThreads) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int i = i0 + u * kBThreads;
+                if (i < n4) v[u] = ld_stream(p + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int i = i0 + u * kBThreads;
+                if (i < n4) {
+                    float4 r, z;
+                    r.x = head<RELU, QUANT>(v[u].x, a, b, qp, lut, qh, qmask, z.x);
+                    r.y = head<RELU, QUANT>(v[u].y, a, b, qp, lut, qh, qmask, z.y);
+                    r.z = head<RELU, QUANT>(v[u].z, a, b, qp, lut, qh, qmask, z.z);
+                    r.w = head<RELU, QUANT>(v[u].w, a, b, qp, lut, qh, qmask, z.w);
+                    st_out(q + i, r);
+                    if (zq) zq[i] = z;
+                }
+            }
+        }
+    }
+}
+
+template <int VEC, bool RELU, bool QUANT>
+__global__ void __launch_bounds__(kBThreads)
+bn_group_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ zdbg, const BnGeom G,
+                    const BnParams P, const float* __restrict__ fq_lo, const float* __restrict__ fq_hi, int fq_k) {
+    __shared__ float lut[QUANT ? kLutMax : 1];
+    const int per_group = G.chunks * G.split;
+    const int g = blockIdx.x / per_group;
+    const int ck = (blockIdx.x % per_group) / G.split;
+    const int sp = blockIdx.x % G.split;
+    long long off; int len, c0;
+    cta_span(G, g, ck, off, len, c0);
+    const long long row = (long long)G.C * G.HW;
+    const int hw = (int)((G.cg > 1) ? G.HW : 0x7fffffff);
+    QParams qp;
+    const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
+    if (QUANT) {
+        qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
+        __syncthreads();
+    }
+    const int e0 = threadIdx.x * VEC;
+    if (e0 >= len) return;
+    float a[VEC], b[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        float invstd;
+        affine_of(P, c0 + (e0 + j) / hw, a[j], b[j], invstd);
+    }
+    for (int n = sp; n < G.N; n += kDepth * G.split) {
+        float v[kDepth][VEC];
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+            const int nn = n + d * G.split;
+            if (nn < G.N) load_vec<VEC>(x + nn * row + off + e0, v[d]);
+        }
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+            const int nn = n + d * G.split;
+            if (nn < G.N) {
+                float r[VEC], z[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) r[j] = head<RELU, QUANT>(v[d][j], a[j], b[j], qp, lut, qh, qmask, z[j]);
+                store_vec<VEC>(y + nn * row + off + e0, r);
+                if (zdbg) store_vec<VEC>(zdbg + nn * row + off + e0, z);
+            }
+        }
+    }
+}
+
+// =============================================================================== backward
+// REDUCE: also accumulate dB_c = sum g', dW_c = sum g' (x - rm_c) * invstd_c as fp64 into dwdb[2C]
+template <bool RELU, bool REDUCE>
+__global__ void __launch_bounds__(kBThreads)
+bn_plane_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx, int N,
+                     int C, long long HW, int split, const BnParams P, double* __restrict__ dwdb, Workspace* ws) {
+    __shared__ float r1[kBThreads / 32], r2[kBThreads / 32];
+    __shared__ int s_last;
+    const int c = blockIdx.x / split, sp = blockIdx.x % split;
+    float a, b, invstd;
+    affine_of(P, c, a, b, invstd);
+    const float rm = __ldg(P.rm + c);
+    const int n4 = (int)(HW >> 2);
+    float sb[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int n = sp; n < N; n += split) {
+        const long long base = ((long long)n * C + c) * HW;
+        const float4* p = reinterpret_cast<const float4*>(x + base);
+        const float4* pg = reinterpret_cast<const float4*>(gy + base);
+        float4* q = reinterpret_cast<float4*>(gx + base);
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * kBThreads) {
+            float4 v[4], g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int i = i0 + u * kBThreads;
+                if (i < n4) { v[u] = ld_stream(p + i); g[u] = ld_stream(pg + i); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int i = i0 + u * kBThreads;
+                if (i < n4) {
+                    const float xs[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                    float gs[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (RELU && !(fmaf(xs[j], a, b) > 0.0f)) gs[j] = 0.0f;
+                        if (REDUCE) { sb[j] += gs[j]; sw[j] = fmaf(gs[j], xs[j] - rm, sw[j]); }
+                    }
+                    st_out(q + i, make_float4(gs[0] * a, gs[1] * a, gs[2] * a, gs[3] * a));
+                }
+            }
+        }
+    }
+    if (!REDUCE) return;
+    float t1 = warp_sum((sb[0] + sb[1]) + (sb[2] + sb[3]));
+    float t2 = warp_sum((sw[0] + sw[1]) + (sw[2] + sw[3]));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { r1[warp] = t1; r2[warp] = t2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kBThreads / 32; ++w) { t1 += r1[w]; t2 += r2[w]; }
+        double* pp = ws->bn_partial + ((size_t)sp * C + c) * 2;
+        pp[0] = (double)t2 * (double)invstd;   // dW
+        pp[1] = (double)t1;                    // dB
+        __threadfence();
+        s_last = (atomicAdd(&ws->bn_ticket[c], 1) == split - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (warp == 0) fold_partials(ws->bn_partial, C, c, split, lane, dwdb);
+    if (threadIdx.x == 0) ws->bn_ticket[c] = 0;
+}
+
+template <int VEC, bool RELU, bool REDUCE>
+__global__ void __launch_bounds__(kBThreads)
+bn_group_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                     const BnGeom G, const BnParams P, double* __restrict__ dwdb, Workspace* ws) {
+    __shared__ float s1[REDUCE ? kBThreads * VEC : 1];
+    __shared__ float s2[REDUCE ? kBThreads * VEC : 1];
+    __shared__ int s_last;
+    const int per_group = G.chunks * G.split;
+    const int g = blockIdx.x / per_group;
+    const int ck = (blockIdx.x % per_group) / G.split;
+    const int sp = blockIdx.x % G.split;
+    long long off; int len, c0;
+    cta_span(G, g, ck, off, len, c0);
+    const long long row = (long long)G.C * G.HW;
+    const int hw = (int)((G.cg > 1) ? G.HW : 0x7fffffff);
+    const int e0 = threadIdx.x * VEC;
+    const bool active = e0 < len;
+    float a[VEC], b[VEC], rm[VEC], sb[VEC], sw[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        sb[j] = 0.f; sw[j] = 0.f; a[j] = 0.f; b[j] = 0.f; rm[j] = 0.f;
+        if (active) {
+            float invstd;
+            const int c = c0 + (e0 + j) / hw;
+            affine_of(P, c, a[j], b[j], invstd);
+            rm[j] = __ldg(P.rm + c);
+        }
+    }
+    if (active) {
+        for (int n = sp; n < G.N; n += kDepth * G.split) {
+            float v[kDepth][VEC], gg[kDepth][VEC];
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const int nn = n + d * G.split;
+                if (nn < G.N) {
+                    load_vec<VEC>(x + nn * row + off + e0, v[d]);
+                    load_vec<VEC>(gy + nn * row + off + e0, gg[d]);
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const int nn = n + d * G.split;
+                if (nn < G.N) {
+                    float r[VEC];
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        float t = gg[d][j];
+                        if (RELU && !(fmaf(v[d][j], a[j], b[j]) > 0.0f)) t = 0.0f;
+                        if (REDUCE) { sb[j] += t; sw[j] = fmaf(t, v[d][j] - rm[j], sw[j]); }
+                        r[j] = t * a[j];
+                    }
+                    store_vec<VEC>(gx + nn * row + off + e0, r);
+                }
+            }
+        }
+    }
+    if (!REDUCE) return;
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { s1[e0 + j] = sb[j]; s2[e0 + j] = sw[j]; }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nch = (G.cg > 1) ? min(G.cg, G.C - c0) : 1;
+    const int part = ck * G.split + sp;
+    const int nparts = per_group;
+    for (int c = warp; c < nch; c += kBThreads / 32) {
+        int eb = (G.cg > 1) ? (int)(c * G.HW) : 0;
+        int ee = (G.cg > 1) ? (int)((c + 1) * G.HW) : len;
+        float t1 = 0.f, t2 = 0.f;
+        for (int e = eb + lane; e < ee; e += 32) { t1 += s1[e]; t2 += s2[e]; }
+        t1 = warp_sum(t1);
+        t2 = warp_sum(t2);
+        if (lane == 0) {
+            float aa, bb, invstd;
+            affine_of(P, c0 + c, aa, bb, invstd);
+            double* p = ws->bn_partial + ((size_t)part * G.C + (c0 + c)) * 2;
+            p[0] = (double)t2 * (double)invstd;
+            p[1] = (double)t1;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&ws->bn_ticket[g], 1) == nparts - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = warp; c < nch; c += kBThreads / 32) fold_partials(ws->bn_partial, G.C, c0 + c, nparts, lane, dwdb);
+    if (threadIdx.x == 0) ws->bn_ticket[g] = 0;
+}
+
+}  // namespace oodfq
+
+using namespace oodfq;
+
+extern "C" int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, int N, int C, long long HW,
+                                     const float* weight, const float* bias, const float* running_mean,
+                                     const float* running_var, float eps, int flags, const float* fq_lo,
+                                     const float* fq_hi, int fq_k, oodfq_stream_t stream) {
+    if (!x || !y || !running_mean || !running_var) return fail(OODFQ_EINVAL, "bn_eval_forward: null pointer");
+    if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "bn_eval_forward: empty tensor");
+    const bool relu = flags & OODFQ_BN_RELU, quant = flags & OODFQ_BN_QUANT;
+    if (quant && (!fq_lo || !fq_hi || fq_k < 1 || fq_k > 8))
+        return fail(OODFQ_EINVAL, "bn_eval_forward: fused fake-quant needs a range and k in [1,8]");
+    cudaStream_t st = (cudaStream_t)stream;
+    const BnParams P{weight, bias, running_mean, running_var, eps};
+    const bool vec_ok = aligned16(x) && aligned16(y) && (!z_debug || aligned16(z_debug));
+    if (plane_ok(HW, vec_ok)) {
+        static const int per_sm = resident_ctas(bn_plane_fwd_kernel<true, true>, kBThreads);
+        const int split = pick_split(C, N, 1 << 20, kNumSM * per_sm);
+        const unsigned grid = (unsigned)C * split;
+        if (relu && quant) bn_plane_fwd_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, N, C, HW, split, P, fq_lo, fq_hi, fq_k);
+        else if (relu) bn_plane_fwd_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, N, C, HW, split, P, fq_lo, fq_hi, fq_k);
+        else if (quant) bn_plane_fwd_kernel<false, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, N, C, HW, split, P, fq_lo, fq_hi, fq_k);
+        else bn_plane_fwd_kernel<false, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, N, C, HW, split, P, fq_lo, fq_hi, fq_k);
+    } else {
+        BnGeom G; int vec; char why[128];
+        static const int per_sm = resident_ctas(bn_group_fwd_kernel<4, true, true>, kBThreads);
+        if (make_geom(N, C, HW, vec_ok, kNumSM * per_sm, G, vec, why, sizeof(why)) != OODFQ_OK)
+            return fail(OODFQ_EINVAL, "bn_eval_forward: %s", why);
+        const unsigned grid = (unsigned)((long long)G.groups * G.chunks * G.split);
+        if (vec == 4) {
+            if (relu && quant) bn_group_fwd_kernel<4, true, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+            else if (relu) bn_group_fwd_kernel<4, true, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+            else if (quant) bn_group_fwd_kernel<4, false, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+            else bn_group_fwd_kernel<4, false, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+        } else {
+            if (relu && quant) bn_group_fwd_kernel<1, true, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+            else if (relu) bn_group_fwd_kernel<1, true, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+            else if (quant) bn_group_fwd_kernel<1, false, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+            else bn_group_fwd_kernel<1, false, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+        }
+    }
+    count_launch();
+    return check_launch("bn_eval_forward");
+}
+
+extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float* grad_x, int N, int C,
+                                      long long HW, const float* weight, const float* bias,
+                                      const float* running_mean, const float* running_var, float eps,
+                                      int flags, double* dwdb, void* workspace, oodfq_stream_t stream) {
+    if (!x || !grad_y || !grad_x || !running_mean || !running_var) return fail(OODFQ_EINVAL, "bn_eval_backward: null pointer");
+    if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "bn_eval_backward: empty tensor");
+    if (dwdb && !workspace) return fail(OODFQ_EINVAL, "bn_eval_backward: parameter gradients need the workspace");
+    if (C > kMaxBnChannels) return fail(OODFQ_EINVAL, "bn_eval_backward: C=%d exceeds %d", C, kMaxBnChannels);
+    const bool relu = flags & OODFQ_BN_RELU, reduce = dwdb != nullptr;
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace* ws = reinterpret_cast<Workspace*>(workspace);
+    const BnParams P{weight, bias, running_mean, running_var, eps};
+    const bool vec_ok = aligned16(x) && aligned16(grad_y) && aligned16(grad_x);
+    if (plane_ok(HW, vec_ok)) {
+        static const int per_sm = resident_ctas(bn_plane_bwdx_kernel<true, true>, kBThreads);
+        const int split = pick_split(C, N, reduce ? kMaxBnSplit : (1 << 20), kNumSM * per_sm);
+        const unsigned grid = (unsigned)C * split;
+        if (relu && reduce) bn_plane_bwdx_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, N, C, HW, split, P, dwdb, ws);
+        else if (relu) bn_plane_bwdx_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, N, C, HW, split, P, dwdb, ws);
+        else if (reduce) bn_plane_bwdx_kernel<false, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, N, C, HW, split, P, dwdb, ws);
+        else bn_plane_bwdx_kernel<false, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, N, C, HW, split, P, dwdb, ws);
+    } else {
+        BnGeom G; int vec; char why[128];
+        static const int per_sm = resident_ctas(bn_group_bwdx_kernel<4, true, true>, kBThreads);
+        if (make_geom(N, C, HW, vec_ok, kNumSM * per_sm, G, vec, why, sizeof(why)) != OODFQ_OK)
+            return fail(OODFQ_EINVAL, "bn_eval_backward: %s", why);
+        const unsigned grid = (unsigned)((long long)G.groups * G.chunks * G.split);
+        if (vec == 4) {
+            if (relu && reduce) bn_group_bwdx_kernel<4, true, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, dwdb, ws);
+            else if (relu) bn_group_bwdx_kernel<4, true, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, dwdb, ws);
+            else if (reduce) bn_group_bwdx_kernel<4, false, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, dwdb, ws);
+            else bn_group_bwdx_kernel<4, false, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, dwdb, ws);
+        } else {
+            if (relu && reduce) bn_group_bwdx_kernel<1, true, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, dwdb, ws);
+            else if (relu) bn_group_bwdx_kernel<1, true, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, dwdb, ws);
+            else if (reduce) bn_group_bwdx_kernel<1, false, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, dwdb, ws);
+            else bn_group_bwdx_kernel<1, false, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, dwdb, ws);
+        }
+    }
+    count_launch();
+    return check_launch("bn_eval_backward");
+}

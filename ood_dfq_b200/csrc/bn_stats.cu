@@ -6,87 +6,166 @@
 // autograd tape behind it) and the loss around it (trainer_direct.py:473-486,
 // distill_data.py:252-265).
 //
-//   forward  : one read of x (4 B/elem) -> shifted sums S1_c = sum(x - shift_c),
-//              S2_c = sum((x - shift_c)^2).  shift = the BN running mean, which
-//              removes the cancellation of the naive sum-of-squares formula and,
-//              being identical on every rank, keeps the sums additive across GPUs.
-//              Optionally the same read also emits the fake-quantised tensor.
-//   loss     : one tiny kernel over the packed sums of all layers (after the
-//              optional NCCL all-reduce) -> loss, mean, var, dL/dmean, dL/dvar.
-//   backward : grad_x = grad_in + g*(gmean_c/M + gvar_c*2(x-mean_c)/M): one read of
-//              x (+ grad_in), one write: 8 or 12 B/elem instead of an autograd tape.
+//   forward  : one read of x (4 B/elem) -> S1_c = sum(x - shift_c), S2_c = sum((x - shift_c)^2)
+//              as fp64.  shift = the BN running mean: identical on every rank, so the sums
+//              are additive across GPUs (one packed all-reduce).  Numerically each CTA
+//              accumulates in fp32 around a LOCAL pivot (a sample of the channel it is
+//              reading, so |x - pivot| ~ sigma) and re-bases its partial onto the shift in
+//              fp64; nothing ever subtracts two large fp32 numbers.  Optionally the same
+//              read also emits the fake-quantised tensor (north_star (b)).
+//   loss     : one tiny kernel over the packed sums of all layers (after the optional NCCL
+//              all-reduce) -> loss, mean, var, dL/dmean, dL/dvar.
+//   backward : grad_x = grad_in + g*(gmean_c/M + gvar_c*2(x-mean_c)/M): one read of x
+//              (+ grad_in), one write: 8 or 12 B/elem instead of an autograd tape.
 //
-// Decomposition (all three big kernels): the NCHW tensor is [N][C*HW]; a CTA owns a
-// contiguous SPAN of that inner axis -- several whole channels when planes are
-// small (7x7, 4x4), or a chunk of one plane when they are large -- and a subset of
-// the batch index n.  A thread keeps the same offsets inside the span for every n,
-// so the channel of each of its elements is fixed and sums stay in registers.
-// The cross-thread reduction is ordered (deterministic): per-slot sums go to shared
-// memory, each channel's slice is folded by one warp, per-CTA partials are folded
-// in index order by the last CTA of each channel group.
+// Two decompositions of the NCHW tensor:
+//   plane kernels  (H*W >= 1024, 16-byte aligned): a CTA owns one channel and a subset of the
+//              batch index and simply streams its planes -- 8 accumulators per thread.
+//   group kernels  (small planes: 7x7, 14x14 ...; or unaligned): the tensor is [N][C*HW]; a CTA
+//              owns a contiguous SPAN of the inner axis covering several whole channels (or a
+//              chunk of one) and a subset of n.  A thread keeps the same offsets inside the span
+//              for every n, so the channel of each of its elements is fixed and the sums stay in
+//              registers; fully coalesced even for 49-element planes.
+// Reductions are ordered (deterministic): fixed shuffle trees, per-CTA partials folded in index
+// order by the last CTA of each channel (group); no floating-point atomics.
 //
-// Roofline: HBM for all three kernels.
-#include <cstdio>
-
-#include "common.cuh"
+// Roofline: HBM for all kernels here.
+#include "bn_geom.cuh"
 
 namespace oodfq {
 
-constexpr int kBThreads = 256;
-constexpr int kSlots = 4;                           // vector slots per thread and per n
-constexpr int kSpanMax = kBThreads * kSlots * 4;    // 4096 elements = 16 KB per n and CTA
+// re-base (count, S1, S2) taken around `pivot` onto `shift`, in fp64
+__device__ __forceinline__ void rebase(double cnt, float t1, float t2, float pivot, float shift,
+                                       double& s1, double& s2) {
+    const double d = (double)pivot - (double)shift;
+    s1 = (double)t1 + cnt * d;
+    s2 = (double)t2 + 2.0 * d * (double)t1 + cnt * d * d;
+}
 
-struct BnGeom {
-    int N, C;
-    long long HW;
-    int cg;          // channels per group (1 when a plane is split into chunks)
-    int groups;      // ceil(C / cg)
-    int chunks;      // chunks per plane (1 when cg > 1)
-    long long chunk_len;   // elements per chunk (multiple of VEC)
-    int split;       // CTAs along n
-};
+// =============================================================================== plane kernels
+template <bool QUANT>
+__global__ void __launch_bounds__(kBThreads)
+bn_plane_stats_kernel(const float* __restrict__ x, int N, int C, long long HW, int split,
+                      const float* __restrict__ shift, double* __restrict__ sums, float* __restrict__ y,
+                      const float* __restrict__ fq_lo, const float* __restrict__ fq_hi, int fq_k, Workspace* ws) {
+    __shared__ float lut[QUANT ? kLutMax : 1];
+    __shared__ float r1[kBThreads / 32], r2[kBThreads / 32];
+    __shared__ int s_last;
+    const int c = blockIdx.x / split, sp = blockIdx.x % split;
+    QParams qp;
+    const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
+    if (QUANT) {
+        qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
+        __syncthreads();
+    }
+    const float pivot = __ldg(x + ((long long)sp * C + c) * HW);
+    const int n4 = (int)(HW >> 2);
+    float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+    int iters = 0;
+    for (int n = sp; n < N; n += split, ++iters) {
+        const long long base = ((long long)n * C + c) * HW;
+        const float4* p = reinterpret_cast<const float4*>(x + base);
+        float4* q = QUANT ? reinterpret_cast<float4*>(y + base) : nullptr;
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * kBThreads) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int i = i0 + u * kBThreads;
+                if (i < n4) v[u] = ld_stream(p + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int i = i0 + u * kBThreads;
+                if (i < n4) {
+                    float d;
+                    d = v[u].x - pivot; a1[0] += d; a2[0] = fmaf(d, d, a2[0]);
+                    d = v[u].y - pivot; a1[1] += d; a2[1] = fmaf(d, d, a2[1]);
+                    d = v[u].z - pivot; a1[2] += d; a2[2] = fmaf(d, d, a2[2]);
+                    d = v[u].w - pivot; a1[3] += d; a2[3] = fmaf(d, d, a2[3]);
+                    if (QUANT)
+                        st_out(q + i, make_float4(fake_quant_lut(v[u].x, qp, lut, qh, qmask),
+                                                  fake_quant_lut(v[u].y, qp, lut, qh, qmask),
+                                                  fake_quant_lut(v[u].z, qp, lut, qh, qmask),
+                                                  fake_quant_lut(v[u].w, qp, lut, qh, qmask)));
+                }
+            }
+        }
+    }
+    float t1 = warp_sum((a1[0] + a1[1]) + (a1[2] + a1[3]));
+    float t2 = warp_sum((a2[0] + a2[1]) + (a2[2] + a2[3]));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { r1[warp] = t1; r2[warp] = t2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kBThreads / 32; ++w) { t1 += r1[w]; t2 += r2[w]; }
+        double s1, s2;
+        rebase((double)iters * (double)HW, t1, t2, pivot, shift ? __ldg(shift + c) : 0.f, s1, s2);
+        double* pp = ws->bn_partial + ((size_t)sp * C + c) * 2;
+        pp[0] = s1;
+        pp[1] = s2;
+        __threadfence();
+        s_last = (atomicAdd(&ws->bn_ticket[c], 1) == split - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (warp == 0) fold_partials(ws->bn_partial, C, c, split, lane, sums);
+    if (threadIdx.x == 0) ws->bn_ticket[c] = 0;
+}
 
-// span of CTA (g, ch): element offset inside the [C*HW] row and its length
-__device__ __forceinline__ void cta_span(const BnGeom& G, int g, int ck, long long& off, int& len, int& c0) {
-    c0 = g * G.cg;
-    if (G.cg > 1) {
-        int nch = min(G.cg, G.C - c0);
-        off = (long long)c0 * G.HW;
-        len = (int)(nch * G.HW);
-    } else {
-        long long s = (long long)ck * G.chunk_len;
-        long long e = min(G.HW, s + G.chunk_len);
-        off = (long long)c0 * G.HW + s;
-        len = (int)(e - s);
+__global__ void __launch_bounds__(kBThreads)
+bn_plane_bwd_kernel(const float* __restrict__ x, const float* grad_in, float* grad_x, int N, int C,
+                    long long HW, int split, const float* __restrict__ mean, const float* __restrict__ gmean,
+                    const float* __restrict__ gvar, float inv_count, const float* __restrict__ gscale) {
+    const int c = blockIdx.x / split, sp = blockIdx.x % split;
+    const float gs = gscale ? __ldg(gscale) : 1.0f;
+    const float ca = gs * 2.0f * __ldg(gvar + c) * inv_count;
+    const float cb = gs * __ldg(gmean + c) * inv_count;
+    const float mu = __ldg(mean + c);
+    const int n4 = (int)(HW >> 2);
+    for (int n = sp; n < N; n += split) {
+        const long long base = ((long long)n * C + c) * HW;
+        const float4* p = reinterpret_cast<const float4*>(x + base);
+        const float4* gi = grad_in ? reinterpret_cast<const float4*>(grad_in + base) : nullptr;
+        float4* go = reinterpret_cast<float4*>(grad_x + base);
+        for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * kBThreads) {
+            float4 v[4], g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int i = i0 + u * kBThreads;
+                if (i < n4) {
+                    v[u] = ld_stream(p + i);
+                    if (gi) g[u] = gi[i];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int i = i0 + u * kBThreads;
+                if (i < n4) {
+                    float4 r = make_float4(fmaf(ca, v[u].x - mu, cb), fmaf(ca, v[u].y - mu, cb),
+                                           fmaf(ca, v[u].z - mu, cb), fmaf(ca, v[u].w - mu, cb));
+                    if (gi) { r.x += g[u].x; r.y += g[u].y; r.z += g[u].z; r.w += g[u].w; }
+                    st_out(go + i, r);
+                }
+            }
+        }
     }
 }
 
-template <int VEC>
-__device__ __forceinline__ void load_vec(const float* p, float (&v)[VEC], bool keep) {
-    if (VEC == 4) {
-        float4 t;
-        if (keep) t = __ldg(reinterpret_cast<const float4*>(p));
-        else t = ld_stream(reinterpret_cast<const float4*>(p));
-        v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
-    } else {
-        v[0] = keep ? __ldg(p) : ld_stream(p);
-    }
-}
-
-template <int VEC>
-__device__ __forceinline__ void store_vec(float* p, const float (&v)[VEC]) {
-    if (VEC == 4) st_out(reinterpret_cast<float4*>(p), make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]));
-    else *p = v[0];
-}
-
-// ------------------------------------------------------------------------------ forward
+// =============================================================================== group kernels
+// One vector slot per thread (fixed offset inside the span, hence fixed channels), kDepth rows of
+// the batch in flight at once: the same bytes in flight as a wide tile, at a quarter of the
+// per-thread state (pivots / coefficients), so 5-6 CTAs stay resident per SM.
 template <int VEC, bool QUANT>
 __global__ void __launch_bounds__(kBThreads)
-bn_stats_kernel(const float* __restrict__ x, const BnGeom G, const float* __restrict__ shift,
-                float* __restrict__ sums, float* __restrict__ y, const float* __restrict__ fq_lo,
-                const float* __restrict__ fq_hi, int fq_k, Workspace* ws) {
-    __shared__ float s1[kSpanMax / 4 * VEC];
-    __shared__ float s2[kSpanMax / 4 * VEC];
+bn_group_stats_kernel(const float* __restrict__ x, const BnGeom G, const float* __restrict__ shift,
+                      double* __restrict__ sums, float* __restrict__ y, const float* __restrict__ fq_lo,
+                      const float* __restrict__ fq_hi, int fq_k, Workspace* ws) {
+    __shared__ float s1[kBThreads * VEC];
+    __shared__ float s2[kBThreads * VEC];
+    __shared__ float lut[QUANT ? kLutMax : 1];
     __shared__ int s_last;
 
     const int per_group = G.chunks * G.split;
@@ -96,8 +175,8 @@ bn_stats_kernel(const float* __restrict__ x, const BnGeom G, const float* __rest
     long long off; int len, c0;
     cta_span(G, g, ck, off, len, c0);
     const long long row = (long long)G.C * G.HW;
+    const int hw = (int)((G.cg > 1) ? G.HW : 0x7fffffff);   // group mode: planes are small
 
-    __shared__ float lut[QUANT ? kLutMax : 1];
     QParams qp;
     const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
     if (QUANT) {
@@ -106,55 +185,53 @@ bn_stats_kernel(const float* __restrict__ x, const BnGeom G, const float* __rest
         __syncthreads();
     }
 
-    // fixed per-thread slots: element e = (threadIdx.x + u*kBThreads)*VEC + j of the span
-    float a1[kSlots][VEC], a2[kSlots][VEC], sh[kSlots][VEC];
+    // this thread owns elements e0 .. e0+VEC-1 of the span, for every n of the CTA's subset.
+    // pivot of an element = first element of its channel (or chunk) in the CTA's first row.
+    const int e0 = threadIdx.x * VEC;
+    const bool active = e0 < len;
+    const float* x0 = x + sp * row + off;
+    float a1[VEC], a2[VEC], pv[VEC];
 #pragma unroll
-    for (int u = 0; u < kSlots; ++u) {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            a1[u][j] = 0.f; a2[u][j] = 0.f;
-            int e = (threadIdx.x + u * kBThreads) * VEC + j;
-            int c = (G.cg > 1) ? c0 + e / (int)G.HW : c0;
-            sh[u][j] = (shift && e < len) ? __ldg(shift + c) : 0.f;
-        }
+    for (int j = 0; j < VEC; ++j) {
+        a1[j] = 0.f; a2[j] = 0.f;
+        pv[j] = active ? __ldg(x0 + ((e0 + j) / hw) * hw) : 0.f;
     }
 
-    for (int n = sp; n < G.N; n += G.split) {
-        const float* xr = x + n * row + off;
-        float v[kSlots][VEC];
+    int iters = 0;
+    for (int n = sp; n < G.N; n += kDepth * G.split) {
+        float v[kDepth][VEC];
 #pragma unroll
-        for (int u = 0; u < kSlots; ++u) {
-            int e = (threadIdx.x + u * kBThreads) * VEC;
-            if (e < len) load_vec<VEC>(xr + e, v[u], /*keep=*/false);
+        for (int d = 0; d < kDepth; ++d) {
+            const int nn = n + d * G.split;
+            if (active && nn < G.N) load_vec<VEC>(x + nn * row + off + e0, v[d]);
         }
 #pragma unroll
-        for (int u = 0; u < kSlots; ++u) {
-            int e = (threadIdx.x + u * kBThreads) * VEC;
-            if (e < len) {
+        for (int d = 0; d < kDepth; ++d) {
+            const int nn = n + d * G.split;
+            if (nn < G.N) {
+                ++iters;
+                if (active) {
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    float d = v[u][j] - sh[u][j];
-                    a1[u][j] += d;
-                    a2[u][j] = fmaf(d, d, a2[u][j]);
-                }
-                if (QUANT) {
-                    float r[VEC];
+                    for (int j = 0; j < VEC; ++j) {
+                        float dlt = v[d][j] - pv[j];
+                        a1[j] += dlt;
+                        a2[j] = fmaf(dlt, dlt, a2[j]);
+                    }
+                    if (QUANT) {
+                        float r[VEC];
 #pragma unroll
-                    for (int j = 0; j < VEC; ++j) r[j] = fake_quant_lut(v[u][j], qp, lut, qh, qmask);
-                    store_vec<VEC>(y + n * row + off + e, r);
+                        for (int j = 0; j < VEC; ++j) r[j] = fake_quant_lut(v[d][j], qp, lut, qh, qmask);
+                        store_vec<VEC>(y + nn * row + off + e0, r);
+                    }
                 }
             }
         }
     }
 
-    // ordered reduction: slots -> shared memory -> one warp per channel
+    // ordered reduction: registers -> shared memory -> one warp per channel -> fp64 partial
+    if (active) {
 #pragma unroll
-    for (int u = 0; u < kSlots; ++u) {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            int e = (threadIdx.x + u * kBThreads) * VEC + j;
-            if (e < len) { s1[e] = a1[u][j]; s2[e] = a2[u][j]; }
-        }
+        for (int j = 0; j < VEC; ++j) { s1[e0 + j] = a1[j]; s2[e0 + j] = a2[j]; }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -169,44 +246,29 @@ bn_stats_kernel(const float* __restrict__ x, const BnGeom G, const float* __rest
         t1 = warp_sum(t1);
         t2 = warp_sum(t2);
         if (lane == 0) {
-            float* p = ws->bn_partial + ((size_t)part * G.C + (c0 + c)) * 2;
-            p[0] = t1;
-            p[1] = t2;
+            double d1, d2;
+            rebase((double)iters * (double)(ee - eb), t1, t2, __ldg(x0 + eb), shift ? __ldg(shift + c0 + c) : 0.f,
+                   d1, d2);
+            double* p = ws->bn_partial + ((size_t)part * G.C + (c0 + c)) * 2;
+            p[0] = d1;
+            p[1] = d2;
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        int t = atomicAdd(&ws->bn_ticket[g], 1);
-        s_last = (t == nparts - 1);
+        s_last = (atomicAdd(&ws->bn_ticket[g], 1) == nparts - 1);
     }
     __syncthreads();
     if (!s_last) return;
-
-    // last CTA of this channel group: fold the partials in index order
-    // (one warp per channel, lanes stride over the partials, fixed shuffle tree: deterministic)
     __threadfence();
-    for (int c = warp; c < nch; c += kBThreads / 32) {
-        double t1 = 0.0, t2 = 0.0;
-        for (int p = lane; p < nparts; p += 32) {
-            const float2 q = __ldcg(reinterpret_cast<const float2*>(ws->bn_partial + ((size_t)p * G.C + (c0 + c)) * 2));
-            t1 += (double)q.x;
-            t2 += (double)q.y;
-        }
-        t1 = warp_sum(t1);
-        t2 = warp_sum(t2);
-        if (lane == 0) {
-            sums[c0 + c] = (float)t1;
-            sums[G.C + c0 + c] = (float)t2;
-        }
-    }
+    for (int c = warp; c < nch; c += kBThreads / 32) fold_partials(ws->bn_partial, G.C, c0 + c, nparts, lane, sums);
     if (threadIdx.x == 0) ws->bn_ticket[g] = 0;
 }
 
-// ------------------------------------------------------------------------------ backward
 template <int VEC>
 __global__ void __launch_bounds__(kBThreads)
-bn_stats_bwd_kernel(const float* __restrict__ x, const float* grad_in, float* grad_x, const BnGeom G,
+bn_group_bwd_kernel(const float* __restrict__ x, const float* grad_in, float* grad_x, const BnGeom G,
                     const float* __restrict__ mean, const float* __restrict__ gmean,
                     const float* __restrict__ gvar, float inv_count, const float* __restrict__ gscale) {
     const int per_group = G.chunks * G.split;
@@ -216,62 +278,60 @@ bn_stats_bwd_kernel(const float* __restrict__ x, const float* grad_in, float* gr
     long long off; int len, c0;
     cta_span(G, g, ck, off, len, c0);
     const long long row = (long long)G.C * G.HW;
+    const int hw = (int)((G.cg > 1) ? G.HW : 0x7fffffff);
     const float gs = gscale ? __ldg(gscale) : 1.0f;
+    const int e0 = threadIdx.x * VEC;
+    if (e0 >= len) return;
 
-    float ca[kSlots][VEC], cb[kSlots][VEC], mu[kSlots][VEC];
+    float ca[VEC], cb[VEC], mu[VEC];
 #pragma unroll
-    for (int u = 0; u < kSlots; ++u) {
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            int e = (threadIdx.x + u * kBThreads) * VEC + j;
-            int c = (G.cg > 1) ? c0 + e / (int)G.HW : c0;
-            bool ok = e < len;
-            ca[u][j] = ok ? gs * 2.0f * __ldg(gvar + c) * inv_count : 0.f;
-            cb[u][j] = ok ? gs * __ldg(gmean + c) * inv_count : 0.f;
-            mu[u][j] = ok ? __ldg(mean + c) : 0.f;
-        }
+    for (int j = 0; j < VEC; ++j) {
+        int c = c0 + (e0 + j) / hw;
+        ca[j] = gs * 2.0f * __ldg(gvar + c) * inv_count;
+        cb[j] = gs * __ldg(gmean + c) * inv_count;
+        mu[j] = __ldg(mean + c);
     }
-    for (int n = sp; n < G.N; n += G.split) {
-        const long long base = n * row + off;
-        float v[kSlots][VEC], gi[kSlots][VEC];
+    for (int n = sp; n < G.N; n += kDepth * G.split) {
+        float v[kDepth][VEC], gi[kDepth][VEC];
 #pragma unroll
-        for (int u = 0; u < kSlots; ++u) {
-            int e = (threadIdx.x + u * kBThreads) * VEC;
-            if (e < len) {
-                load_vec<VEC>(x + base + e, v[u], false);
+        for (int d = 0; d < kDepth; ++d) {
+            const int nn = n + d * G.split;
+            if (nn < G.N) {
+                const long long at = nn * row + off + e0;
+                load_vec<VEC>(x + at, v[d]);
                 if (grad_in) {
                     if (VEC == 4) {
-                        float4 t = *reinterpret_cast<const float4*>(grad_in + base + e);
-                        gi[u][0] = t.x; gi[u][1 % VEC] = t.y; gi[u][2 % VEC] = t.z; gi[u][3 % VEC] = t.w;
+                        float4 t = *reinterpret_cast<const float4*>(grad_in + at);
+                        gi[d][0] = t.x; gi[d][1 % VEC] = t.y; gi[d][2 % VEC] = t.z; gi[d][3 % VEC] = t.w;
                     } else {
-                        gi[u][0] = grad_in[base + e];
+                        gi[d][0] = grad_in[at];
                     }
                 }
             }
         }
 #pragma unroll
-        for (int u = 0; u < kSlots; ++u) {
-            int e = (threadIdx.x + u * kBThreads) * VEC;
-            if (e < len) {
+        for (int d = 0; d < kDepth; ++d) {
+            const int nn = n + d * G.split;
+            if (nn < G.N) {
                 float r[VEC];
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    float t = fmaf(ca[u][j], v[u][j] - mu[u][j], cb[u][j]);
-                    r[j] = grad_in ? gi[u][j] + t : t;
+                    float t = fmaf(ca[j], v[d][j] - mu[j], cb[j]);
+                    r[j] = grad_in ? gi[d][j] + t : t;
                 }
-                store_vec<VEC>(grad_x + base + e, r);
+                store_vec<VEC>(grad_x + nn * row + off + e0, r);
             }
         }
     }
 }
 
-// ------------------------------------------------------------------------------ small kernels
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ shift, int C,
+// =============================================================================== small kernels
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ shift, int C,
                                    double inv_count, float* mean, float* var) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    double m1 = (double)sums[c] * inv_count;
-    double m2 = (double)sums[C + c] * inv_count;
+    double m1 = sums[c] * inv_count;
+    double m2 = sums[C + c] * inv_count;
     mean[c] = (float)((shift ? (double)shift[c] : 0.0) + m1);
     var[c] = (float)(m2 - m1 * m1);
 }
@@ -285,7 +345,7 @@ struct BnsLayers {
 
 // single CTA: the packed arrays hold a few thousand channels at most
 __global__ void __launch_bounds__(1024)
-bns_loss_kernel(const float* __restrict__ sums, const float* __restrict__ shift,
+bns_loss_kernel(const double* __restrict__ sums, const float* __restrict__ shift,
                 const float* __restrict__ run_mean, const float* __restrict__ run_var,
                 const __grid_constant__ BnsLayers lay, float* loss3, float* mean, float* var,
                 float* gmean, float* gvar) {
@@ -301,9 +361,9 @@ bns_loss_kernel(const float* __restrict__ sums, const float* __restrict__ shift,
         const double ic = lay.inv_count[lo];
         // layer l keeps its sums together: [2*off_l, 2*off_l + C_l) = S1, then C_l values of S2
         const int Cl = lay.off[lo + 1] - lay.off[lo];
-        const float* ls = sums + 2 * lay.off[lo];
-        double m1 = (double)ls[c - lay.off[lo]] * ic;
-        double m2 = (double)ls[Cl + c - lay.off[lo]] * ic;
+        const double* ls = sums + 2 * lay.off[lo];
+        double m1 = ls[c - lay.off[lo]] * ic;
+        double m2 = ls[Cl + c - lay.off[lo]] * ic;
         const double invC = 1.0 / (double)Cl;
         float mu = (float)((shift ? (double)shift[c] : 0.0) + m1);
         float vr = (float)(m2 - m1 * m1);
@@ -330,83 +390,47 @@ bns_loss_kernel(const float* __restrict__ sums, const float* __restrict__ shift,
     }
 }
 
-// ------------------------------------------------------------------------------ host side
-static int make_geom(int N, int C, long long HW, bool vec_ok, BnGeom& G, int& vec, char* why, size_t whyn) {
-    G.N = N; G.C = C; G.HW = HW;
-    // 128-bit access needs every span start and length to be a multiple of 4 elements
-    vec = (vec_ok && ((long long)C * HW) % 4 == 0) ? 4 : 1;
-    for (;;) {
-        const long long span_max = (vec == 4) ? kSpanMax : kSpanMax / 4;
-        if (HW <= span_max / 2) {            // several whole channels per CTA
-            long long cg = span_max / HW;
-            if (cg >= C) {
-                cg = C;                      // one group starting at channel 0
-            } else if (vec == 4 && HW % 4 != 0) {
-                cg = (cg / 4) * 4;           // group starts stay 16-byte aligned
-                if (cg == 0) { vec = 1; continue; }
-            }
-            G.cg = (int)cg;
-            G.groups = (C + G.cg - 1) / G.cg;
-            G.chunks = 1;
-            G.chunk_len = (long long)G.cg * HW;
-        } else {                             // one channel, plane cut into chunks
-            if (vec == 4 && HW % 4 != 0) { vec = 1; continue; }
-            long long chunks = (HW + span_max - 1) / span_max;
-            long long cl = (HW + chunks - 1) / chunks;
-            cl = ((cl + 3) / 4) * 4;
-            if (cl > span_max) cl = span_max;
-            chunks = (HW + cl - 1) / cl;
-            G.cg = 1;
-            G.groups = C;
-            G.chunks = (int)chunks;
-            G.chunk_len = cl;
-        }
-        break;
-    }
-    if (G.chunks > kMaxBnSplit) {
-        snprintf(why, whyn, "plane of %lld elements needs %d chunks (max %d)", HW, G.chunks, kMaxBnSplit);
-        return OODFQ_EINVAL;
-    }
-    // enough CTAs to fill the machine a few times, bounded by the partial table
-    long long base = (long long)G.groups * G.chunks;
-    long long want = ((long long)kNumSM * 8 + base - 1) / base;
-    long long cap = kMaxBnSplit / G.chunks;
-    if (want > cap) want = cap;
-    if (want > N) want = N;
-    if (want < 1) want = 1;
-    G.split = (int)want;
-    return OODFQ_OK;
-}
-
+// =============================================================================== host side
 }  // namespace oodfq
 
 using namespace oodfq;
 
 extern "C" int oodfq_bn_stats_forward(const float* x, int N, int C, long long HW, const float* shift,
-                                      float* sums, float* y, const float* fq_lo, const float* fq_hi,
+                                      double* sums, float* y, const float* fq_lo, const float* fq_hi,
                                       int fq_k, void* workspace, oodfq_stream_t stream) {
     if (!x || !sums || !workspace) return fail(OODFQ_EINVAL, "bn_stats_forward: null pointer");
     if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "bn_stats_forward: empty tensor (N=%d C=%d HW=%lld)", N, C, HW);
     if (C > kMaxBnChannels) return fail(OODFQ_EINVAL, "bn_stats_forward: C=%d exceeds %d", C, kMaxBnChannels);
     if (y && (!fq_lo || !fq_hi || fq_k < 1 || fq_k > 8)) return fail(OODFQ_EINVAL, "bn_stats_forward: fused fake-quant needs a range and k in [1,8]");
-    BnGeom G; int vec; char why[128];
-    bool vec_ok = aligned16(x) && (!y || aligned16(y));
-    if (make_geom(N, C, HW, vec_ok, G, vec, why, sizeof(why)) != OODFQ_OK) return fail(OODFQ_EINVAL, "bn_stats_forward: %s", why);
-    const unsigned grid = (unsigned)((long long)G.groups * G.chunks * G.split);
     cudaStream_t st = (cudaStream_t)stream;
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
+    const bool vec_ok = aligned16(x) && (!y || aligned16(y));
+    if (plane_ok(HW, vec_ok)) {
+        static const int per_sm_q = resident_ctas(bn_plane_stats_kernel<true>, kBThreads);
+        static const int per_sm = resident_ctas(bn_plane_stats_kernel<false>, kBThreads);
+        const int split = pick_split(C, N, kMaxBnSplit, kNumSM * (y ? per_sm_q : per_sm));
+        const unsigned grid = (unsigned)C * split;
+        if (y) bn_plane_stats_kernel<true><<<grid, kBThreads, 0, st>>>(x, N, C, HW, split, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
+        else bn_plane_stats_kernel<false><<<grid, kBThreads, 0, st>>>(x, N, C, HW, split, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
+        count_launch();
+        return check_launch("bn_stats_forward");
+    }
+    BnGeom G; int vec; char why[128];
+    static const int per_sm_g = resident_ctas(bn_group_stats_kernel<4, true>, kBThreads);
+    if (make_geom(N, C, HW, vec_ok, kNumSM * per_sm_g, G, vec, why, sizeof(why)) != OODFQ_OK) return fail(OODFQ_EINVAL, "bn_stats_forward: %s", why);
+    const unsigned grid = (unsigned)((long long)G.groups * G.chunks * G.split);
     if (vec == 4) {
-        if (y) bn_stats_kernel<4, true><<<grid, kBThreads, 0, st>>>(x, G, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
-        else bn_stats_kernel<4, false><<<grid, kBThreads, 0, st>>>(x, G, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
+        if (y) bn_group_stats_kernel<4, true><<<grid, kBThreads, 0, st>>>(x, G, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
+        else bn_group_stats_kernel<4, false><<<grid, kBThreads, 0, st>>>(x, G, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
     } else {
-        if (y) bn_stats_kernel<1, true><<<grid, kBThreads, 0, st>>>(x, G, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
-        else bn_stats_kernel<1, false><<<grid, kBThreads, 0, st>>>(x, G, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
+        if (y) bn_group_stats_kernel<1, true><<<grid, kBThreads, 0, st>>>(x, G, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
+        else bn_group_stats_kernel<1, false><<<grid, kBThreads, 0, st>>>(x, G, shift, sums, y, fq_lo, fq_hi, fq_k, ws);
     }
     count_launch();
     return check_launch("bn_stats_forward");
 }
 
-extern "C" int oodfq_bn_stats_finalize(const float* sums, const float* shift, int C, double count,
+extern "C" int oodfq_bn_stats_finalize(const double* sums, const float* shift, int C, double count,
                                        float* mean, float* var, oodfq_stream_t stream) {
     if (!sums || !mean || !var) return fail(OODFQ_EINVAL, "bn_stats_finalize: null pointer");
     if (C <= 0 || !(count > 0)) return fail(OODFQ_EINVAL, "bn_stats_finalize: C=%d count=%g", C, count);
@@ -415,7 +439,7 @@ extern "C" int oodfq_bn_stats_finalize(const float* sums, const float* shift, in
     return check_launch("bn_stats_finalize");
 }
 
-extern "C" int oodfq_bns_loss(const float* sums, const float* shift, const float* run_mean,
+extern "C" int oodfq_bns_loss(const double* sums, const float* shift, const float* run_mean,
                               const float* run_var, const int* ch_off_host, const double* counts_host,
                               int L, float* loss3, float* mean, float* var, float* gmean, float* gvar,
                               oodfq_stream_t stream) {
@@ -442,14 +466,22 @@ extern "C" int oodfq_bn_stats_backward(const float* x, const float* grad_in, flo
                                        oodfq_stream_t stream) {
     if (!x || !grad_x || !mean || !gmean || !gvar) return fail(OODFQ_EINVAL, "bn_stats_backward: null pointer");
     if (N <= 0 || C <= 0 || HW <= 0 || !(count > 0)) return fail(OODFQ_EINVAL, "bn_stats_backward: empty tensor");
-    BnGeom G; int vec; char why[128];
-    bool vec_ok = aligned16(x) && aligned16(grad_x) && (!grad_in || aligned16(grad_in));
-    if (make_geom(N, C, HW, vec_ok, G, vec, why, sizeof(why)) != OODFQ_OK) return fail(OODFQ_EINVAL, "bn_stats_backward: %s", why);
-    const unsigned grid = (unsigned)((long long)G.groups * G.chunks * G.split);
     cudaStream_t st = (cudaStream_t)stream;
     const float ic = (float)(1.0 / count);
-    if (vec == 4) bn_stats_bwd_kernel<4><<<grid, kBThreads, 0, st>>>(x, grad_in, grad_x, G, mean, gmean, gvar, ic, gscale);
-    else bn_stats_bwd_kernel<1><<<grid, kBThreads, 0, st>>>(x, grad_in, grad_x, G, mean, gmean, gvar, ic, gscale);
+    const bool vec_ok = aligned16(x) && aligned16(grad_x) && (!grad_in || aligned16(grad_in));
+    if (plane_ok(HW, vec_ok)) {
+        static const int per_sm = resident_ctas(bn_plane_bwd_kernel, kBThreads);
+        const int split = pick_split(C, N, 1 << 20, kNumSM * per_sm);
+        bn_plane_bwd_kernel<<<(unsigned)C * split, kBThreads, 0, st>>>(x, grad_in, grad_x, N, C, HW, split, mean, gmean, gvar, ic, gscale);
+        count_launch();
+        return check_launch("bn_stats_backward");
+    }
+    BnGeom G; int vec; char why[128];
+    static const int per_sm_g = resident_ctas(bn_group_bwd_kernel<4>, kBThreads);
+    if (make_geom(N, C, HW, vec_ok, kNumSM * per_sm_g, G, vec, why, sizeof(why)) != OODFQ_OK) return fail(OODFQ_EINVAL, "bn_stats_backward: %s", why);
+    const unsigned grid = (unsigned)((long long)G.groups * G.chunks * G.split);
+    if (vec == 4) bn_group_bwd_kernel<4><<<grid, kBThreads, 0, st>>>(x, grad_in, grad_x, G, mean, gmean, gvar, ic, gscale);
+    else bn_group_bwd_kernel<1><<<grid, kBThreads, 0, st>>>(x, grad_in, grad_x, G, mean, gmean, gvar, ic, gscale);
     count_launch();
     return check_launch("bn_stats_backward");
 }

@@ -27,7 +27,7 @@ struct Workspace {
     int ticket[kWsTickets];
     int bn_ticket[kMaxBnChannels];
     float mm_partial[2 * kMaxReduceBlocks];
-    float bn_partial[2 * kMaxBnSplit * kMaxBnChannels];
+    double bn_partial[2 * kMaxBnSplit * kMaxBnChannels];   // fp64 (S1, S2) per CTA and channel
 };
 constexpr size_t kWorkspaceBytes = sizeof(Workspace);
 

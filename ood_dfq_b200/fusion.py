@@ -1,0 +1,118 @@
+"""Fusion pass: eval-mode BatchNorm (+ ReLU + frozen QuantAct) as ONE kernel forward and ONE backward.
+
+SURVEY.md section 8(f) rank 1.  ``quantize_model`` (main_direct.py:444-479) leaves every BatchNorm as is and
+turns each ReLU into ``nn.Sequential(ReLU, QuantAct)``; the student then always runs in ``eval()``
+(trainer_direct.py:411), where BatchNorm is a per-channel affine.  ``fuse_eval_bn(model, example)``:
+
+* swaps the class of every ``nn.BatchNorm2d`` to ``FusedEvalBN`` (a BatchNorm2d subclass: parameters, buffers,
+  state_dict keys, hooks and ``isinstance`` checks are untouched);
+* finds, by tracing one forward of ``example``, the BatchNorms whose output is consumed directly by a
+  ``Sequential(ReLU, QuantAct)`` and lets the BatchNorm absorb that tail (the Sequential stays in the module
+  tree -- ``freeze_model`` / ``reduce_minmax`` / state_dict still see its QuantAct -- but forwards nothing).
+
+In training mode, on CPU, or while the absorbed QuantAct is still calibrating (``running_stat=True``) the
+module falls back to the ordinary BatchNorm -> ReLU -> QuantAct sequence, so ranges are tracked exactly as
+before; the fused kernels take over once ranges are frozen (146 of the reference's 150 epochs).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .quantization_utils.quant_modules import QuantAct
+
+
+class _FusedBN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn, relu, qact):
+        fq = (qact.activation_bit, qact.x_min, qact.x_max) if qact is not None else None
+        y = ops.bn_eval_forward(x, weight, bias, bn.running_mean, bn.running_var, bn.eps, relu=relu, fq=fq)
+        ctx.save_for_backward(x, weight, bias)
+        ctx.bn, ctx.relu = bn, relu
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x, weight, bias = ctx.saved_tensors
+        need_p = (weight is not None and ctx.needs_input_grad[1]) or (bias is not None and ctx.needs_input_grad[2])
+        gx, dw, db = ops.bn_eval_backward(x, grad_y, weight, bias, ctx.bn.running_mean, ctx.bn.running_var,
+                                          ctx.bn.eps, relu=ctx.relu, want_param_grads=need_p)
+        return (gx,
+                dw if (weight is not None and ctx.needs_input_grad[1]) else None,
+                db if (bias is not None and ctx.needs_input_grad[2]) else None,
+                None, None, None)
+
+
+class AbsorbedTail(nn.Sequential):
+    """The ``Sequential(ReLU, QuantAct)`` whose work the preceding FusedEvalBN has taken over."""
+
+    def forward(self, x):
+        return x
+
+    def run(self, x):
+        return nn.Sequential.forward(self, x)
+
+
+class FusedEvalBN(nn.BatchNorm2d):
+    """BatchNorm2d whose eval-mode forward/backward are single sm_100a kernels, optionally with ReLU + QuantAct."""
+
+    _tail = None          # AbsorbedTail or None (plain attribute: not a registered child)
+
+    def _tail_parts(self):
+        if self._tail is None:
+            return False, None
+        qact = self._tail[1]
+        return True, qact
+
+    def forward(self, x):
+        has_tail, qact = self._tail_parts()
+        fusable = (not self.training) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 \
+            and self.track_running_stats and self.running_mean is not None
+        if has_tail and (qact.running_stat or type(qact) is not QuantAct):
+            fusable = False                       # still calibrating (or not the asymmetric QuantAct): exact old path
+        if not fusable:
+            y = super().forward(x)
+            return self._tail.run(y) if has_tail else y
+        q = qact if (has_tail and not qact.full_precision_flag) else None
+        return _FusedBN.apply(x, self.weight, self.bias, self, has_tail, q)
+
+
+def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=True, verify=True):
+    """Apply the fusion in place and return the model.  ``example``: a (small) input batch used to trace which
+    BatchNorm feeds which ``Sequential(ReLU, QuantAct)``; without it only the BatchNorms themselves are fused."""
+    was_training = model.training
+    model.eval()
+    bns = [m for m in model.modules() if type(m) in (nn.BatchNorm2d, FusedEvalBN)]
+    tails = [m for m in model.modules() if type(m) is nn.Sequential and len(m) == 2
+             and type(m[0]) in (nn.ReLU, nn.ReLU6) and type(m[1]) is QuantAct]
+    pairs = []
+    ref_out = None
+    if example is not None and absorb_tails and tails:
+        produced = {}     # id(tensor) -> (module, tensor): the tensor is kept alive so ids cannot be recycled
+        handles = [b.register_forward_hook(lambda mod, i, o: produced.__setitem__(id(o), (mod, o))) for b in bns]
+        handles += [t.register_forward_pre_hook(
+            lambda mod, i: pairs.append((produced[id(i[0])][0], mod)) if id(i[0]) in produced else None)
+            for t in tails]
+        with torch.no_grad():
+            ref_out = model(example)
+        for h in handles:
+            h.remove()
+        produced.clear()
+    for b in bns:
+        b.__class__ = FusedEvalBN
+    for b, t in pairs:
+        if type(t[0]) is nn.ReLU6:
+            continue                              # ReLU6 clamps from above as well: leave it unfused
+        t.__class__ = AbsorbedTail
+        object.__setattr__(b, "_tail", t)
+    if verify and ref_out is not None:
+        with torch.no_grad():
+            new_out = model(example)
+        err = (new_out - ref_out).abs().max().item()
+        scale = ref_out.abs().max().item() + 1e-12
+        if not err <= 0.05 * scale:
+            raise RuntimeError(f"fuse_eval_bn: fused model deviates from the original ({err:.3e} vs scale {scale:.3e})")
+    model.train(was_training)
+    return model

@@ -208,7 +208,7 @@ def _nchw(x: torch.Tensor):
 def bn_stats_forward(x, shift=None, sums=None, fq=None):
     """Shifted per-channel sums of a BN input in one read (trainer_direct.py:388-393).
 
-    Returns sums [2*C] (S1 then S2), or (sums, y) when ``fq=(k, lo, hi)`` asks for the fused
+    Returns fp64 sums [2*C] (S1 then S2), or (sums, y) when ``fq=(k, lo, hi)`` asks for the fused
     fake-quantised output of the same read.
     """
     _need(x, "input")
@@ -218,7 +218,9 @@ def bn_stats_forward(x, shift=None, sums=None, fq=None):
         if shift.numel() != c or not shift.is_contiguous():
             raise RuntimeError("ood_dfq_b200: shift must be a contiguous [C] tensor")
     if sums is None:
-        sums = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+        sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+    elif sums.dtype != torch.float64 or sums.numel() != 2 * c or not sums.is_contiguous():
+        raise RuntimeError("ood_dfq_b200: sums must be a contiguous float64 [2*C] tensor")
     y = lo = hi = None
     k = 0
     if fq is not None:
@@ -276,3 +278,58 @@ def bn_stats_backward(x, grad_in, mean, gmean, gvar, count: float, gscale=None, 
                                           _stream(x.device))
     N.check(rc, "bn_stats_backward")
     return gx
+
+
+# ----------------------------------------------------------------------------- 8(f)-1: fused eval-mode BN
+def _bn_ptrs(weight, bias, running_mean, running_var, c):
+    for t, nme in ((running_mean, "running_mean"), (running_var, "running_var")):
+        _need(t, nme)
+    for t, nme in ((weight, "weight"), (bias, "bias"), (running_mean, "running_mean"), (running_var, "running_var")):
+        if t is not None and (t.numel() != c or not t.is_contiguous() or t.dtype != torch.float32):
+            raise RuntimeError(f"ood_dfq_b200: BN {nme} must be a contiguous fp32 [C] tensor")
+    return _ptr(weight), _ptr(bias), running_mean.data_ptr(), running_var.data_ptr()
+
+
+def bn_eval_forward(x, weight, bias, running_mean, running_var, eps, relu=False, fq=None, want_z=False):
+    """``[fakequant]([relu](BN_eval(x)))`` in one pass.  ``fq = (k, lo, hi)`` with a scalar range."""
+    _need(x, "input")
+    xc, n, c, hw = _nchw(x)
+    pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
+    y = torch.empty_like(xc)
+    z = torch.empty_like(xc) if want_z else None
+    flags, k, lo, hi = (N.BN_RELU if relu else 0), 0, None, None
+    if fq is not None:
+        k, lo, hi = fq
+        _need(lo, "fq range min")
+        _need(hi, "fq range max")
+        flags |= N.BN_QUANT
+    timed = PROFILE is not None and fq is not None
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    rc = N.load().oodfq_bn_eval_forward(xc.data_ptr(), y.data_ptr(), _ptr(z), n, c, hw, pw, pb, prm, prv, float(eps),
+                                        flags, _ptr(lo), _ptr(hi), int(k), _stream(x.device))
+    N.check(rc, "bn_eval_forward")
+    if timed:
+        ev1.record()
+        PROFILE.append((ev0, ev1, 8 * xc.numel()))
+    return (y, z) if want_z else y
+
+
+def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, relu=False, want_param_grads=True):
+    """Backward of ``bn_eval_forward`` (identity STE through the quantiser): (grad_x, dweight, dbias)."""
+    _need(x, "input")
+    _need(grad_y, "grad_output")
+    xc, n, c, hw = _nchw(x)
+    gy = grad_y.contiguous()
+    pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
+    gx = torch.empty_like(xc)
+    dwdb = torch.empty(2 * c, dtype=torch.float64, device=x.device) if want_param_grads else None
+    ws = workspace(x.device).data_ptr() if want_param_grads else None
+    rc = N.load().oodfq_bn_eval_backward(xc.data_ptr(), gy.data_ptr(), gx.data_ptr(), n, c, hw, pw, pb, prm, prv,
+                                         float(eps), N.BN_RELU if relu else 0, _ptr(dwdb), ws, _stream(x.device))
+    N.check(rc, "bn_eval_backward")
+    if not want_param_grads:
+        return gx, None, None
+    d = dwdb.float()
+    return gx, d[:c], d[c:]

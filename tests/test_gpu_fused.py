@@ -1,0 +1,127 @@
+"""Fused eval-mode BatchNorm + ReLU + QuantAct against the unfused chain."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits
+from oracle import fq_torch, fused_torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+SHAPES = [(8, 64, 56, 56), (4, 16, 112, 112), (16, 128, 28, 28), (16, 256, 14, 14), (32, 512, 7, 7), (32, 64, 4, 4),
+          (3, 5, 7, 9), (2, 3, 1, 1), (5, 130, 7, 7), (2, 6, 70, 70), (4, 2, 33, 35), (9, 16, 8, 8)]
+
+
+def make_bn(c, g, affine=True):
+    w = (torch.rand(c, generator=g) + 0.5) if affine else None
+    b = (torch.randn(c, generator=g) * 0.3) if affine else None
+    return w, b, torch.randn(c, generator=g) * 0.2, torch.rand(c, generator=g) + 0.4
+
+
+def cu(t):
+    return None if t is None else t.to(DEV)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("relu,k", [(True, 4), (True, 2), (True, 0), (False, 0), (False, 8)])
+def test_fused_forward(shape, relu, k):
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + 7 * k + relu)
+    x = torch.randn(shape, generator=g) * 1.4
+    w, b, rm, rv = make_bn(shape[1], g, affine=(k != 2))
+    eps = 1e-5
+    lo, hi = torch.tensor([0.0 if relu else -1.2]), torch.tensor([1.9])
+    fq = (k, cu(lo), cu(hi)) if k else None
+    y, z = ops.bn_eval_forward(cu(x), cu(w), cu(b), cu(rm), cu(rv), eps, relu=relu, fq=fq, want_z=True)
+    z64 = fused_torch.bn_eval_affine64(x, w, b, rm, rv, eps)
+    if relu:
+        z64 = z64.clamp_min(0)
+    # the affine is a few fp32 roundings away from the exact value (a_c, b_c are rounded, then one FMA)
+    np.testing.assert_allclose(z.cpu().double().numpy(), z64.numpy(), rtol=2e-6, atol=2e-6)
+    if k:   # the quantiser applied to THAT fp32 value is the reference's arithmetic, bit for bit
+        ref = fq_torch.fake_quant(z.cpu(), k, lo, hi)
+        assert np.array_equal(bits(y.cpu().numpy()), bits(ref.numpy()))
+    else:
+        assert torch.equal(y, z)
+    y2 = ops.bn_eval_forward(cu(x), cu(w), cu(b), cu(rm), cu(rv), eps, relu=relu, fq=fq)     # no debug output
+    assert torch.equal(y2, y)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("relu", [True, False])
+def test_fused_backward(shape, relu):
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + relu)
+    x = torch.randn(shape, generator=g) * 1.4
+    w, b, rm, rv = make_bn(shape[1], g)
+    gy = torch.randn(shape, generator=g)
+    eps = 1e-5
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    out = fused_torch.bn_relu_quant(xr, wr, br, rm, rv, eps, 4, torch.zeros(1), torch.ones(1) * 2, relu=relu)
+    out.backward(gy)
+    gx, dw, db = ops.bn_eval_backward(cu(x), cu(gy), cu(w), cu(b), cu(rm), cu(rv), eps, relu=relu)
+    # the ReLU mask is recomputed from x: elements within rounding of 0 may differ from the CPU chain
+    diff = (gx.cpu() - xr.grad).abs()
+    tol = 1e-5 * xr.grad.abs().max().item()
+    assert (diff > tol).float().mean().item() < 1e-5
+    n_red = x.numel() / shape[1]
+    np.testing.assert_allclose(dw.cpu().numpy(), wr.grad.numpy(), rtol=2e-4, atol=2e-5 * n_red ** 0.5)
+    np.testing.assert_allclose(db.cpu().numpy(), br.grad.numpy(), rtol=2e-4, atol=2e-5 * n_red ** 0.5)
+    gx2, dw2, db2 = ops.bn_eval_backward(cu(x), cu(gy), cu(w), cu(b), cu(rm), cu(rv), eps, relu=relu,
+                                         want_param_grads=False)
+    assert dw2 is None and torch.equal(gx2, gx)
+
+
+@pytest.mark.parametrize("net_name,classes,k,shape", [
+    ("resnet20_cifar", 10, 4, (32, 3, 32, 32)),
+    ("resnet18_small", 9, 2, (16, 3, 28, 28)),
+    ("resnet18_imagenet", 1000, 4, (4, 3, 224, 224)),
+])
+def test_fusion_pass_matches_unfused_model(net_name, classes, k, shape):
+    """Same student, fused vs unfused, on the GPU: logits, input gradient and every parameter gradient."""
+    from ood_dfq_b200 import fusion, nets, surgery
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(1)
+    base = nets.resnet18_small(3, classes) if net_name == "resnet18_small" else getattr(nets, net_name)(num_classes=classes)
+    nets.perturb_bn_stats(base)
+    plain = surgery.quantize_model(base, k, k).to(DEV).eval()
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(shape, generator=g).to(DEV) for _ in range(3)]
+    with torch.no_grad():
+        for x in xs:                                  # calibrate, then freeze
+            plain(x)
+    surgery.freeze_model(plain)
+    fused = copy.deepcopy(plain)
+    keys = list(fused.state_dict())
+    fusion.fuse_eval_bn(fused, xs[0][:2])
+    assert list(fused.state_dict()) == keys
+    n_bn = sum(isinstance(m, torch.nn.BatchNorm2d) for m in plain.modules())
+    assert sum(type(m) is fusion.FusedEvalBN for m in fused.modules()) == n_bn
+    assert sum(type(m) is fusion.AbsorbedTail for m in fused.modules()) >= 9
+    x = xs[2].clone().requires_grad_(True)
+    x2 = xs[2].clone().requires_grad_(True)
+    yp, yf = plain(x), fused(x2)
+    # cuDNN's inference BN and the fused affine round differently: a handful of codes move by one step
+    spread = yp.std().item()
+    assert (yf - yp).abs().max().item() < 0.2 * spread
+    yp.square().mean().backward()
+    yf.square().mean().backward()
+    cos = torch.nn.functional.cosine_similarity(x.grad.flatten(), x2.grad.flatten(), dim=0).item()
+    assert cos > 0.98, cos
+    for (n1, p1), (n2, p2) in zip(plain.named_parameters(), fused.named_parameters()):
+        assert n1 == n2 and p2.grad is not None, n1
+        c = torch.nn.functional.cosine_similarity(p1.grad.flatten(), p2.grad.flatten(), dim=0).item()
+        assert c > 0.95, (n1, c)
+    # calibrating again falls back to the exact unfused chain and tracks ranges identically
+    surgery.unfreeze_model(plain)
+    surgery.unfreeze_model(fused)
+    with torch.no_grad():
+        plain(xs[1])
+        fused(xs[1])
+    for a, b in zip([m for m in plain.modules() if type(m) is qm.QuantAct],
+                    [m for m in fused.modules() if type(m) is qm.QuantAct]):
+        assert torch.equal(a.x_max, b.x_max) and torch.equal(a.beta_t, b.beta_t)

@@ -32,9 +32,12 @@ def peak():
 
 
 class Timer:
-    def __init__(self, iters, flush=True):
-        self.iters = iters
-        self.flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda") if flush else None
+    """flush = "write": fill a 512 MB buffer (L2 left full of DIRTY lines whose write-back then competes with the
+    timed kernel -- the harsher convention); "read": sum a 512 MB buffer (L2 left full of clean foreign lines)."""
+
+    def __init__(self, iters, flush="write"):
+        self.iters, self.mode = iters, flush
+        self.flush = torch.ones(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda") if flush != "none" else None
 
     def __call__(self, fn):
         for _ in range(3):
@@ -42,7 +45,10 @@ class Timer:
         times = []
         for _ in range(self.iters):
             if self.flush is not None:
-                self.flush.fill_(1.0)
+                if self.mode == "write":
+                    self.flush.fill_(1.0)
+                else:
+                    self.flush.sum()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -58,12 +64,13 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--json", default="")
     ap.add_argument("--shapes", default="", help="indices into the activation shape list, e.g. 0,4")
-    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--flush", choices=["write", "read", "none"], default="write")
     args = ap.parse_args()
     only = set(args.only.split(","))
     shapes = ACT_SHAPES if not args.shapes else [ACT_SHAPES[int(i)] for i in args.shapes.split(",")]
     pk = peak()
-    timer = Timer(args.iters, flush=not args.no_flush)
+    timer = Timer(args.iters, flush=args.flush)
+    print(f"# L2 flush between timed launches: {args.flush}", flush=True)
     rows = []
 
     def report(kernel, shape, nbytes, med, best):
