@@ -200,6 +200,11 @@ def main_ours(args):
     host = [torch.randn((batch,) + shape, generator=g).pin_memory() for _ in range(pool)]
     resident = [h.to(dev) for h in host]
     calibrate(student, resident, qm)
+    if not args.no_fuse:
+        # eval-mode BN (+ ReLU + frozen QuantAct) as one kernel forward / one backward
+        from ood_dfq_b200 import fusion
+        fusion.fuse_eval_bn(student, resident[0][:2])
+        fusion.fuse_eval_bn(teacher, None)
     if world > 1:
         ddist.reduce_minmax(student)
         for m in student.modules():               # ranges stay frozen from here on
@@ -281,12 +286,13 @@ def main_ours(args):
             "config": {"workload": cfg, "name": args.workload, "batch_per_gpu": batch, "global_batch": batch * world,
                        "bits": bits, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2: every step streams a 154 MB batch and GBs of activations",
-                       "convolutions": "cuDNN (TF32 default, as the reference)"},
+                       "convolutions": "cuDNN (TF32 default, as the reference)",
+                       "bn_relu_quant_fusion": not args.no_fuse},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "fq_flat_kernel (frozen QuantAct forward, 8 B/elem)",
+            "roofline": {"bound": "hbm", "kernel": "frozen QuantAct forward (fq_flat_kernel + fused bn_*_fwd_kernel<relu,quant>), 8 B/elem",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "launches_timed": len(prof), "peak_source": peak_src},
@@ -310,6 +316,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=32, help="images per step of the CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="keep BatchNorm / ReLU / QuantAct as separate modules")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

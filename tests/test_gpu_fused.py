@@ -114,8 +114,11 @@ def test_fusion_pass_matches_unfused_model(net_name, classes, k, shape):
     assert cos > 0.98, cos
     for (n1, p1), (n2, p2) in zip(plain.named_parameters(), fused.named_parameters()):
         assert n1 == n2 and p2.grad is not None, n1
+        n_a, n_b = p1.grad.norm().item(), p2.grad.norm().item()
+        if n_a == 0.0 and n_b == 0.0:
+            continue                                  # dead layer in this random-init network: both agree on zero
         c = torch.nn.functional.cosine_similarity(p1.grad.flatten(), p2.grad.flatten(), dim=0).item()
-        assert c > 0.95, (n1, c)
+        assert c > 0.95 and 0.8 < n_b / n_a < 1.25, (n1, c, n_a, n_b)
     # calibrating again falls back to the exact unfused chain and tracks ranges identically
     surgery.unfreeze_model(plain)
     surgery.unfreeze_model(fused)

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--out", default="")
+    ap.add_argument("--no-fuse", action="store_true")
     args = ap.parse_args()
     from ood_dfq_b200.quantization_utils import quant_modules as qm
     dev = torch.device("cuda:0")
@@ -38,6 +39,10 @@ def main():
     g = torch.Generator().manual_seed(0)
     xs = [torch.randn((batch,) + shape, generator=g).to(dev) for _ in range(2)]
     bench.calibrate(student, xs + xs[:1], qm)
+    if not args.no_fuse:
+        from ood_dfq_b200 import fusion
+        fusion.fuse_eval_bn(student, xs[0][:2])
+        fusion.fuse_eval_bn(teacher, None)
     for i in range(3):
         qat(xs[i % 2])
     torch.cuda.synchronize()
