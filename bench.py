@@ -205,6 +205,13 @@ def main_ours(args):
         from ood_dfq_b200 import fusion
         fusion.fuse_eval_bn(student, resident[0][:2])
         fusion.fuse_eval_bn(teacher, None)
+    if args.channels_last:
+        # cuDNN's tensor-core convolutions are NHWC inside; channels_last tensors spare it the layout transposes.
+        # Every kernel of the quantisation path takes both layouts (flat walk / NHWC column mapping).
+        student.to(memory_format=torch.channels_last)
+        teacher.to(memory_format=torch.channels_last)
+        host = [h.contiguous(memory_format=torch.channels_last).pin_memory() for h in host]
+        resident = [h.to(dev) for h in host]
     if world > 1:
         ddist.reduce_minmax(student)
         for m in student.modules():               # ranges stay frozen from here on
@@ -287,7 +294,8 @@ def main_ours(args):
                        "bits": bits, "parallelism": f"dp{world}",
                        "l2": "inputs larger than L2: every step streams a 154 MB batch and GBs of activations",
                        "convolutions": "cuDNN (TF32 default, as the reference)",
-                       "bn_relu_quant_fusion": not args.no_fuse},
+                       "bn_relu_quant_fusion": not args.no_fuse,
+                       "memory_format": "channels_last" if args.channels_last else "NCHW (as the reference)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
@@ -317,6 +325,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="keep BatchNorm / ReLU / QuantAct as separate modules")
+    ap.add_argument("--channels-last", action="store_true", help="run the networks in NHWC memory format")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

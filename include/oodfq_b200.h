@@ -162,6 +162,7 @@ int oodfq_bn_stats_backward(const float* x, const float* grad_in, float* grad_x,
  * weight / bias may be NULL (1 / 0). */
 #define OODFQ_BN_RELU 1
 #define OODFQ_BN_QUANT 2
+#define OODFQ_BN_NHWC 4   /* x, y, grads are channels_last: [N*H*W rows][C]; needs C % 4 == 0 */
 int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, int N, int C, long long HW,
                           const float* weight, const float* bias, const float* running_mean,
                           const float* running_var, float eps, int flags, const float* fq_lo,

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboodfq_b200.so")
 
 MODE_FAKEQUANT, MODE_QUANTIZE, MODE_DEQUANTIZE = 0, 1, 2
 SYMMETRIC, PARAMS_GIVEN = 1, 2
-BN_RELU, BN_QUANT = 1, 2
+BN_RELU, BN_QUANT, BN_NHWC = 1, 2, 4
 ABI_VERSION = 1
 
 _vp, _ll, _i, _d = C.c_void_p, C.c_longlong, C.c_int, C.c_double

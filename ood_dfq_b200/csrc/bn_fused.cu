@@ -296,6 +296,155 @@ bn_group_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
     if (threadIdx.x == 0) ws->bn_ticket[g] = 0;
 }
 
+// =============================================================================== NHWC (channels_last)
+// x is [R = N*H*W rows][C]; channels are the fastest axis.  cuDNN's tensor-core convolutions are NHWC
+// inside: feeding them channels_last tensors removes the nchwToNhwc / nhwcToNchw transposes that are 28 %
+// of the fused NCHW step (profiles/r1_step_share_fused.txt).  Mapping: a thread owns one 128-bit column
+// (4 consecutive channels, fixed for its lifetime -> coefficients in registers) and walks down the rows;
+// the CTA's 256 threads cover `lanes_r = 256 / (C/4)` rows at a time as ONE contiguous run of memory.
+struct NhwcGeom {
+    long long R;        // rows
+    int C, cols;        // channels, 128-bit columns per row (C/4)
+    int lanes_r;        // rows covered by one pass of the CTA (>= 1); threads >= lanes_r*min(cols,256) idle
+    int col_blocks;     // ceil(cols / 256) when a row is wider than the CTA
+};
+
+__host__ __device__ inline NhwcGeom make_nhwc(long long R, int C) {
+    NhwcGeom G;
+    G.R = R; G.C = C; G.cols = C / 4;
+    G.lanes_r = G.cols <= kBThreads ? kBThreads / G.cols : 1;
+    G.col_blocks = (G.cols + kBThreads - 1) / kBThreads;
+    return G;
+}
+
+template <bool RELU, bool QUANT>
+__global__ void __launch_bounds__(kBThreads)
+bn_nhwc_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ zdbg, const NhwcGeom G,
+                   const BnParams P, const float* __restrict__ fq_lo, const float* __restrict__ fq_hi, int fq_k) {
+    __shared__ float lut[QUANT ? kLutMax : 1];
+    QParams qp;
+    const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
+    if (QUANT) {
+        qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
+        __syncthreads();
+    }
+    const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
+    if ((int)threadIdx.x >= G.lanes_r * wcols) return;
+    const int rsub = threadIdx.x / wcols;
+    for (int cb = 0; cb < G.col_blocks; ++cb) {
+        const int col = cb * kBThreads + threadIdx.x % wcols;
+        if (col >= G.cols) continue;
+        float a[4], b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float invstd; affine_of(P, 4 * col + j, a[j], b[j], invstd); }
+        const long long rstep = (long long)G.lanes_r * gridDim.x;
+        for (long long r = (long long)blockIdx.x * G.lanes_r + rsub; r < G.R; r += kDepth * rstep) {
+            float4 v[kDepth];
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const long long rr = r + d * rstep;
+                if (rr < G.R) v[d] = ld_stream(reinterpret_cast<const float4*>(x) + rr * G.cols + col);
+            }
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const long long rr = r + d * rstep;
+                if (rr < G.R) {
+                    float4 o, z;
+                    o.x = head<RELU, QUANT>(v[d].x, a[0], b[0], qp, lut, qh, qmask, z.x);
+                    o.y = head<RELU, QUANT>(v[d].y, a[1], b[1], qp, lut, qh, qmask, z.y);
+                    o.z = head<RELU, QUANT>(v[d].z, a[2], b[2], qp, lut, qh, qmask, z.z);
+                    o.w = head<RELU, QUANT>(v[d].w, a[3], b[3], qp, lut, qh, qmask, z.w);
+                    st_out(reinterpret_cast<float4*>(y) + rr * G.cols + col, o);
+                    if (zdbg) reinterpret_cast<float4*>(zdbg)[rr * G.cols + col] = z;
+                }
+            }
+        }
+    }
+}
+
+// Backward: every CTA leaves one fp64 partial (dW, dB) per channel in ws->bn_partial[cta][C][2];
+// bn_nhwc_fold_kernel then sums the partials of each channel in CTA order (deterministic).
+template <bool RELU, bool REDUCE>
+__global__ void __launch_bounds__(kBThreads)
+bn_nhwc_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                    const NhwcGeom G, const BnParams P, Workspace* ws) {
+    __shared__ float red[REDUCE ? 2 * kBThreads * 4 : 1];
+    const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
+    const bool active = (int)threadIdx.x < G.lanes_r * wcols;
+    const int rsub = threadIdx.x / wcols;
+    for (int cb = 0; cb < G.col_blocks; ++cb) {
+        const int col = cb * kBThreads + threadIdx.x % wcols;
+        const bool on = active && col < G.cols;
+        float a[4], b[4], rm[4], inv[4], sb[4], sw[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            sb[j] = 0.f; sw[j] = 0.f; a[j] = 0.f; b[j] = 0.f; rm[j] = 0.f; inv[j] = 0.f;
+            if (on) { affine_of(P, 4 * col + j, a[j], b[j], inv[j]); rm[j] = __ldg(P.rm + 4 * col + j); }
+        }
+        if (on) {
+            const long long rstep = (long long)G.lanes_r * gridDim.x;
+            for (long long r = (long long)blockIdx.x * G.lanes_r + rsub; r < G.R; r += kDepth * rstep) {
+                float4 v[kDepth], g[kDepth];
+#pragma unroll
+                for (int d = 0; d < kDepth; ++d) {
+                    const long long rr = r + d * rstep;
+                    if (rr < G.R) {
+                        v[d] = ld_stream(reinterpret_cast<const float4*>(x) + rr * G.cols + col);
+                        g[d] = ld_stream(reinterpret_cast<const float4*>(gy) + rr * G.cols + col);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < kDepth; ++d) {
+                    const long long rr = r + d * rstep;
+                    if (rr < G.R) {
+                        const float xs[4] = {v[d].x, v[d].y, v[d].z, v[d].w};
+                        float gs[4] = {g[d].x, g[d].y, g[d].z, g[d].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (RELU && !(fmaf(xs[j], a[j], b[j]) > 0.0f)) gs[j] = 0.0f;
+                            if (REDUCE) { sb[j] += gs[j]; sw[j] = fmaf(gs[j], xs[j] - rm[j], sw[j]); }
+                        }
+                        st_out(reinterpret_cast<float4*>(gx) + rr * G.cols + col,
+                               make_float4(gs[0] * a[0], gs[1] * a[1], gs[2] * a[2], gs[3] * a[3]));
+                    }
+                }
+            }
+        }
+        if (REDUCE) {
+            // fold the CTA's row-lanes in lane order, then one fp64 partial per channel
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                red[threadIdx.x * 4 + j] = on ? sb[j] : 0.f;
+                red[kBThreads * 4 + threadIdx.x * 4 + j] = on ? sw[j] : 0.f;
+            }
+            __syncthreads();
+            if (on && rsub == 0) {
+                const int lc = threadIdx.x % wcols;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float tb = 0.f, tw = 0.f;
+                    for (int l = 0; l < G.lanes_r; ++l) {
+                        tb += red[(l * wcols + lc) * 4 + j];
+                        tw += red[kBThreads * 4 + (l * wcols + lc) * 4 + j];
+                    }
+                    double* p = ws->bn_partial + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
+                    p[0] = (double)tw * (double)inv[j];
+                    p[1] = (double)tb;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBThreads)
+bn_nhwc_fold_kernel(const double* __restrict__ partial, int C, int nparts, double* __restrict__ dwdb) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (kBThreads / 32) + (threadIdx.x >> 5);
+    if (c < C) fold_partials(partial, C, c, nparts, lane, dwdb);
+}
+
 }  // namespace oodfq
 
 using namespace oodfq;
@@ -312,6 +461,20 @@ extern "C" int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, i
     cudaStream_t st = (cudaStream_t)stream;
     const BnParams P{weight, bias, running_mean, running_var, eps};
     const bool vec_ok = aligned16(x) && aligned16(y) && (!z_debug || aligned16(z_debug));
+    if (flags & OODFQ_BN_NHWC) {
+        if (!vec_ok || (C % 4) != 0) return fail(OODFQ_EINVAL, "bn_eval_forward: NHWC needs C %% 4 == 0 and 16-byte alignment");
+        const NhwcGeom G = make_nhwc((long long)N * HW, C);
+        static const int per_sm = resident_ctas(bn_nhwc_fwd_kernel<true, true>, kBThreads);
+        long long want = (G.R + (long long)G.lanes_r * kDepth - 1) / ((long long)G.lanes_r * kDepth);
+        long long cap = (long long)kNumSM * per_sm;
+        const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+        if (relu && quant) bn_nhwc_fwd_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+        else if (relu) bn_nhwc_fwd_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+        else if (quant) bn_nhwc_fwd_kernel<false, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+        else bn_nhwc_fwd_kernel<false, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+        count_launch();
+        return check_launch("bn_eval_forward");
+    }
     if (plane_ok(HW, vec_ok)) {
         static const int per_sm = resident_ctas(bn_plane_fwd_kernel<true, true>, kBThreads);
         const int split = pick_split(C, N, 1 << 20, kNumSM * per_sm);
@@ -355,6 +518,26 @@ extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
     const BnParams P{weight, bias, running_mean, running_var, eps};
     const bool vec_ok = aligned16(x) && aligned16(grad_y) && aligned16(grad_x);
+    if (flags & OODFQ_BN_NHWC) {
+        if (!vec_ok || (C % 4) != 0) return fail(OODFQ_EINVAL, "bn_eval_backward: NHWC needs C %% 4 == 0 and 16-byte alignment");
+        const NhwcGeom G = make_nhwc((long long)N * HW, C);
+        static const int per_sm = resident_ctas(bn_nhwc_bwdx_kernel<true, true>, kBThreads);
+        long long want = (G.R + (long long)G.lanes_r * kDepth - 1) / ((long long)G.lanes_r * kDepth);
+        long long cap = (long long)kNumSM * per_sm;
+        const long long table = (long long)kMaxBnSplit * kMaxBnChannels / C;     // partial slots that fit
+        if (reduce && cap > table) cap = table;
+        const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+        if (relu && reduce) bn_nhwc_bwdx_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, ws);
+        else if (relu) bn_nhwc_bwdx_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, ws);
+        else if (reduce) bn_nhwc_bwdx_kernel<false, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, ws);
+        else bn_nhwc_bwdx_kernel<false, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, ws);
+        count_launch();
+        int rc = check_launch("bn_eval_backward");
+        if (rc != OODFQ_OK || !reduce) return rc;
+        bn_nhwc_fold_kernel<<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
+        count_launch();
+        return check_launch("bn_eval_backward(fold)");
+    }
     if (plane_ok(HW, vec_ok)) {
         static const int per_sm = resident_ctas(bn_plane_bwdx_kernel<true, true>, kBThreads);
         const int split = pick_split(C, N, reduce ? kMaxBnSplit : (1 << 20), kNumSM * per_sm);

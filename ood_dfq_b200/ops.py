@@ -177,14 +177,17 @@ def weight_fq_multi(weights: Sequence[torch.Tensor], ks: Sequence[int], symmetri
         device = device or w.device
         if w.device != device:
             raise RuntimeError("ood_dfq_b200: all weights of one launch must live on the same device")
-        wc = w.detach().contiguous()
+        wc = w.detach()
+        if not (wc.is_contiguous() or (wc.dim() == 4 and wc.is_contiguous(memory_format=torch.channels_last))):
+            wc = wc.contiguous()
+        # dim 0 is the slowest axis in both dense formats, so an output row is one contiguous run either way
         keep.append(wc)
         rows = wc.shape[0]
         row_len = wc.numel() // rows if rows else 0
         wq = outs[i] if outs is not None else torch.empty_like(wc)
         lo = torch.empty(rows, dtype=torch.float32, device=device) if want_range else None
         hi = torch.empty(rows, dtype=torch.float32, device=device) if want_range else None
-        cd = torch.empty(wc.shape, dtype=torch.int8, device=device) if want_codes else None
+        cd = torch.empty_like(wc, dtype=torch.int8) if want_codes else None
         d = descs[i]
         d.w, d.wq, d.lo, d.hi, d.codes = wc.data_ptr(), wq.data_ptr(), _ptr(lo), _ptr(hi), _ptr(cd)
         d.rows, d.row_len, d.k = rows, row_len, int(ks[i])
@@ -290,14 +293,27 @@ def _bn_ptrs(weight, bias, running_mean, running_var, c):
     return _ptr(weight), _ptr(bias), running_mean.data_ptr(), running_var.data_ptr()
 
 
+def _nchw_or_nhwc(x: torch.Tensor):
+    """(dense tensor, N, C, HW, nhwc?) -- channels_last tensors are used as they are (C % 4 == 0)."""
+    if x.dim() != 4:
+        raise RuntimeError(f"ood_dfq_b200: expected an NCHW / channels_last 4-D tensor, got {x.dim()}-D")
+    n, c, h, w = x.shape
+    if (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last) and c % 4 == 0:
+        return x, n, c, h * w, True
+    return x.contiguous(), n, c, h * w, False
+
+
 def bn_eval_forward(x, weight, bias, running_mean, running_var, eps, relu=False, fq=None, want_z=False):
-    """``[fakequant]([relu](BN_eval(x)))`` in one pass.  ``fq = (k, lo, hi)`` with a scalar range."""
+    """``[fakequant]([relu](BN_eval(x)))`` in one pass.  ``fq = (k, lo, hi)`` with a scalar range.
+
+    NCHW-contiguous and channels_last inputs both run natively; the output keeps the input's memory format.
+    """
     _need(x, "input")
-    xc, n, c, hw = _nchw(x)
+    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
     y = torch.empty_like(xc)
     z = torch.empty_like(xc) if want_z else None
-    flags, k, lo, hi = (N.BN_RELU if relu else 0), 0, None, None
+    flags, k, lo, hi = (N.BN_RELU if relu else 0) | (N.BN_NHWC if nhwc else 0), 0, None, None
     if fq is not None:
         k, lo, hi = fq
         _need(lo, "fq range min")
@@ -320,14 +336,15 @@ def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, re
     """Backward of ``bn_eval_forward`` (identity STE through the quantiser): (grad_x, dweight, dbias)."""
     _need(x, "input")
     _need(grad_y, "grad_output")
-    xc, n, c, hw = _nchw(x)
-    gy = grad_y.contiguous()
+    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
+    gy = grad_y.contiguous(memory_format=torch.channels_last) if nhwc else grad_y.contiguous()
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
     gx = torch.empty_like(xc)
     dwdb = torch.empty(2 * c, dtype=torch.float64, device=x.device) if want_param_grads else None
     ws = workspace(x.device).data_ptr() if want_param_grads else None
     rc = N.load().oodfq_bn_eval_backward(xc.data_ptr(), gy.data_ptr(), gx.data_ptr(), n, c, hw, pw, pb, prm, prv,
-                                         float(eps), N.BN_RELU if relu else 0, _ptr(dwdb), ws, _stream(x.device))
+                                         float(eps), (N.BN_RELU if relu else 0) | (N.BN_NHWC if nhwc else 0),
+                                         _ptr(dwdb), ws, _stream(x.device))
     N.check(rc, "bn_eval_backward")
     if not want_param_grads:
         return gx, None, None

@@ -128,3 +128,44 @@ def test_fusion_pass_matches_unfused_model(net_name, classes, k, shape):
     for a, b in zip([m for m in plain.modules() if type(m) is qm.QuantAct],
                     [m for m in fused.modules() if type(m) is qm.QuantAct]):
         assert torch.equal(a.x_max, b.x_max) and torch.equal(a.beta_t, b.beta_t)
+
+
+NHWC_SHAPES = [(8, 64, 56, 56), (16, 128, 28, 28), (32, 512, 7, 7), (4, 24, 9, 11), (3, 960, 5, 5), (2, 1280, 3, 3),
+               (5, 8, 1, 7)]
+
+
+@pytest.mark.parametrize("shape", NHWC_SHAPES)
+@pytest.mark.parametrize("relu,k", [(True, 4), (False, 0), (True, 0)])
+def test_fused_channels_last_matches_nchw(shape, relu, k):
+    """The NHWC kernels compute exactly what the NCHW kernels compute (same arithmetic per element)."""
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + k)
+    x = (torch.randn(shape, generator=g) * 1.4).to(DEV)
+    gy = torch.randn(shape, generator=g).to(DEV)
+    w, b, rm, rv = (cu(t) for t in make_bn(shape[1], g))
+    lo, hi = torch.zeros(1, device=DEV), torch.full((1,), 1.9, device=DEV)
+    fq = (k, lo, hi) if k else None
+    y = ops.bn_eval_forward(x, w, b, rm, rv, 1e-5, relu=relu, fq=fq)
+    xl, gl = x.contiguous(memory_format=torch.channels_last), gy.contiguous(memory_format=torch.channels_last)
+    yl = ops.bn_eval_forward(xl, w, b, rm, rv, 1e-5, relu=relu, fq=fq)
+    assert yl.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(yl, y)
+    gx, dw, db = ops.bn_eval_backward(x, gy, w, b, rm, rv, 1e-5, relu=relu)
+    gxl, dwl, dbl = ops.bn_eval_backward(xl, gl, w, b, rm, rv, 1e-5, relu=relu)
+    assert torch.equal(gxl, gx)
+    n_red = x.numel() / shape[1]
+    np.testing.assert_allclose(dwl.cpu().numpy(), dw.cpu().numpy(), rtol=1e-4, atol=1e-5 * n_red ** 0.5)
+    np.testing.assert_allclose(dbl.cpu().numpy(), db.cpu().numpy(), rtol=1e-4, atol=1e-5 * n_red ** 0.5)
+
+
+def test_channels_last_weights_and_activations():
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    w = (torch.randn(32, 16, 3, 3, generator=g) * 0.05).to(DEV)
+    wl = w.contiguous(memory_format=torch.channels_last)
+    (r,) = ops.weight_fq_multi([w], [4], [False], want_range=True, want_codes=True)
+    (rl,) = ops.weight_fq_multi([wl], [4], [False], want_range=True, want_codes=True)
+    assert rl["wq"].is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(rl["wq"], r["wq"]) and torch.equal(rl["codes"], r["codes"]) and torch.equal(rl["lo"], r["lo"])
+    ref = fq_torch.fake_quant(w.cpu(), 4, *fq_torch.row_minmax(w.cpu()))
+    assert np.array_equal(bits(rl["wq"].cpu().contiguous().numpy()), bits(ref.numpy()))

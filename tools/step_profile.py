@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--out", default="")
     ap.add_argument("--no-fuse", action="store_true")
+    ap.add_argument("--channels-last", action="store_true")
     args = ap.parse_args()
     from ood_dfq_b200.quantization_utils import quant_modules as qm
     dev = torch.device("cuda:0")
@@ -43,6 +44,10 @@ def main():
         from ood_dfq_b200 import fusion
         fusion.fuse_eval_bn(student, xs[0][:2])
         fusion.fuse_eval_bn(teacher, None)
+    if args.channels_last:
+        student.to(memory_format=torch.channels_last)
+        teacher.to(memory_format=torch.channels_last)
+        xs = [x.contiguous(memory_format=torch.channels_last) for x in xs]
     for i in range(3):
         qat(xs[i % 2])
     torch.cuda.synchronize()
