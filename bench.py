@@ -192,12 +192,18 @@ def main_ours(args):
     _, _, shape, bits, default_batch, cfg = WORKLOADS[args.workload]
     batch = args.batch or default_batch
     teacher, student = build_pair(args.workload, qm, dev)
-    qat = make_step(args.workload, teacher, student, qm)
+    channels_last = not args.nchw
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    if channels_last:
+        # cuDNN's tensor-core convolutions are NHWC inside; channels_last tensors spare it the layout transposes
+        # (28 % of the NCHW step).  Every kernel of the quantisation path takes both layouts.
+        student.to(memory_format=fmt)
+        teacher.to(memory_format=fmt)
 
     # synthetic inputs: seed = rank; a small pool of distinct batches
     g = torch.Generator().manual_seed(rank)
     pool = 3
-    host = [torch.randn((batch,) + shape, generator=g).pin_memory() for _ in range(pool)]
+    host = [torch.randn((batch,) + shape, generator=g).contiguous(memory_format=fmt).pin_memory() for _ in range(pool)]
     resident = [h.to(dev) for h in host]
     calibrate(student, resident, qm)
     if not args.no_fuse:
@@ -205,13 +211,7 @@ def main_ours(args):
         from ood_dfq_b200 import fusion
         fusion.fuse_eval_bn(student, resident[0][:2])
         fusion.fuse_eval_bn(teacher, None)
-    if args.channels_last:
-        # cuDNN's tensor-core convolutions are NHWC inside; channels_last tensors spare it the layout transposes.
-        # Every kernel of the quantisation path takes both layouts (flat walk / NHWC column mapping).
-        student.to(memory_format=torch.channels_last)
-        teacher.to(memory_format=torch.channels_last)
-        host = [h.contiguous(memory_format=torch.channels_last).pin_memory() for h in host]
-        resident = [h.to(dev) for h in host]
+    qat = make_step(args.workload, teacher, student, qm)      # after .to(): gradients alias one flat buffer
     if world > 1:
         ddist.reduce_minmax(student)
         for m in student.modules():               # ranges stay frozen from here on
@@ -260,11 +260,15 @@ def main_ours(args):
         done.record(copy_stream)
         return buf, done
 
-    for i in range(min(2, args.warmup)):
-        qat(host[i % pool].to(dev, non_blocking=True)).item()
+    for i in range(args.warmup):                  # same fetch path as the timed loop (copy stream, allocator)
+        buf, done = fetch(i)
+        torch.cuda.current_stream().wait_event(done)
+        buf.record_stream(torch.cuda.current_stream())
+        qat(buf).item()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_wall = time.perf_counter()
     nxt = fetch(0)
     for i in range(args.steps):
         buf, done = nxt
@@ -274,6 +278,8 @@ def main_ours(args):
             nxt = fetch(i + 1)                    # next batch crosses PCIe while this step computes
         loss = qat(buf)
         _ = loss.item()                           # device -> host read of the step's result
+        if args.verbose and rank == 0:
+            print(f"[e2e] step {i}: {1e3 * (time.perf_counter() - t_wall):.1f} ms since start", file=sys.stderr)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -295,7 +301,7 @@ def main_ours(args):
                        "l2": "inputs larger than L2: every step streams a 154 MB batch and GBs of activations",
                        "convolutions": "cuDNN (TF32 default, as the reference)",
                        "bn_relu_quant_fusion": not args.no_fuse,
-                       "memory_format": "channels_last" if args.channels_last else "NCHW (as the reference)"},
+                       "memory_format": "channels_last" if channels_last else "NCHW (as the reference)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
@@ -325,7 +331,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="keep BatchNorm / ReLU / QuantAct as separate modules")
-    ap.add_argument("--channels-last", action="store_true", help="run the networks in NHWC memory format")
+    ap.add_argument("--nchw", action="store_true", help="keep NCHW tensors (default: channels_last memory format)")
+    ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

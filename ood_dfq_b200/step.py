@@ -74,8 +74,17 @@ class FlatGrads:
         self.flat = torch.zeros(n, dtype=ref.dtype, device=ref.device)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            # same strides as the parameter (NCHW or channels_last), so the optimiser's element-wise
+            # updates stay on the vectorised same-layout path
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            p.grad = (torch.as_strided(self.flat, p.shape, p.stride(), off) if dense
+                      else self.flat[off: off + p.numel()].view_as(p))
             off += p.numel()
+
+    def attached(self):
+        """True while every parameter's .grad still aliases the flat buffer (Module.to() would break that)."""
+        lo, hi = self.flat.data_ptr(), self.flat.data_ptr() + self.flat.numel() * self.flat.element_size()
+        return all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in self.params)
 
     def zero(self):
         self.flat.zero_()
@@ -134,6 +143,9 @@ class QATStep:
                 t_out_p = self.teacher(images_p.detach())
             _, kl_p, fa_p = self._losses(images_p.detach(), t_out_p.detach())
             total = loss + (kl_p + fa_p)
+        if not self.grads.attached():
+            raise RuntimeError("QATStep: parameter gradients no longer alias the flat buffer (the model was moved or "
+                               "re-formatted after the step was built); create the step after model.to(...)")
         self.grads.zero()
         total.backward()
         self.grads.all_reduce_mean(self.group)

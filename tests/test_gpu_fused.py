@@ -169,3 +169,42 @@ def test_channels_last_weights_and_activations():
     assert torch.equal(rl["wq"], r["wq"]) and torch.equal(rl["codes"], r["codes"]) and torch.equal(rl["lo"], r["lo"])
     ref = fq_torch.fake_quant(w.cpu(), 4, *fq_torch.row_minmax(w.cpu()))
     assert np.array_equal(bits(rl["wq"].cpu().contiguous().numpy()), bits(ref.numpy()))
+
+
+def test_channels_last_student_matches_nchw_student():
+    """Whole fused student in channels_last vs NCHW: same logits / gradients up to convolution rounding."""
+    from ood_dfq_b200 import fusion, nets, step, surgery
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(1)
+    base = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(base)
+    a = surgery.quantize_model(base, 4, 4).to(DEV).eval()
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(16, 3, 32, 32, generator=g).to(DEV) for _ in range(3)]
+    with torch.no_grad():
+        for x in xs:
+            a(x)
+    surgery.freeze_model(a)
+    b = copy.deepcopy(a).to(memory_format=torch.channels_last)
+    fusion.fuse_eval_bn(a, xs[0][:2])
+    fusion.fuse_eval_bn(b, xs[0][:2].contiguous(memory_format=torch.channels_last))
+    xa = xs[2].clone().requires_grad_(True)
+    xb = xs[2].clone().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ya, yb = a(xa), b(xb)
+    assert (ya - yb).abs().max().item() < 0.2 * ya.std().item()
+    ya.square().mean().backward()
+    yb.square().mean().backward()
+    for (n1, p1), (n2, p2) in zip(a.named_parameters(), b.named_parameters()):
+        n_a, n_b = p1.grad.norm().item(), p2.grad.norm().item()
+        if n_a == 0.0 and n_b == 0.0:
+            continue
+        c = torch.nn.functional.cosine_similarity(p1.grad.flatten(), p2.grad.flatten(), dim=0).item()
+        assert c > 0.95 and 0.8 < n_b / n_a < 1.25, (n1, c, n_a, n_b)
+    # flat gradients keep the parameters' layout and notice a later .to()
+    teacher = copy.deepcopy(base).to(DEV).to(memory_format=torch.channels_last)
+    qat = step.QATStep(b, teacher, unit_types=(nets.ResUnit,))
+    assert all(p.grad.stride() == p.stride() for p in qat.grads.params)
+    qat(xs[0].contiguous(memory_format=torch.channels_last))
+    b.to(memory_format=torch.contiguous_format)
+    with pytest.raises(RuntimeError, match="flat buffer"):
+        qat(xs[0])

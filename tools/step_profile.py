@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--out", default="")
     ap.add_argument("--no-fuse", action="store_true")
-    ap.add_argument("--channels-last", action="store_true")
+    ap.add_argument("--nchw", action="store_true")
     args = ap.parse_args()
     from ood_dfq_b200.quantization_utils import quant_modules as qm
     dev = torch.device("cuda:0")
@@ -36,18 +36,17 @@ def main():
     _, _, shape, bits, default_batch, cfg = bench.WORKLOADS[args.workload]
     batch = args.batch or default_batch
     teacher, student = bench.build_pair(args.workload, qm, dev)
-    qat = bench.make_step(args.workload, teacher, student, qm)
+    fmt = torch.contiguous_format if args.nchw else torch.channels_last
+    student.to(memory_format=fmt)
+    teacher.to(memory_format=fmt)
     g = torch.Generator().manual_seed(0)
-    xs = [torch.randn((batch,) + shape, generator=g).to(dev) for _ in range(2)]
+    xs = [torch.randn((batch,) + shape, generator=g).to(dev).contiguous(memory_format=fmt) for _ in range(2)]
     bench.calibrate(student, xs + xs[:1], qm)
     if not args.no_fuse:
         from ood_dfq_b200 import fusion
         fusion.fuse_eval_bn(student, xs[0][:2])
         fusion.fuse_eval_bn(teacher, None)
-    if args.channels_last:
-        student.to(memory_format=torch.channels_last)
-        teacher.to(memory_format=torch.channels_last)
-        xs = [x.contiguous(memory_format=torch.channels_last) for x in xs]
+    qat = bench.make_step(args.workload, teacher, student, qm)
     for i in range(3):
         qat(xs[i % 2])
     torch.cuda.synchronize()
