@@ -242,8 +242,12 @@ def main_ours(args):
     launches = _native.launch_count()
     ms = ev0.elapsed_time(ev1)
     prof, ops.PROFILE = ops.PROFILE, None
-    fq_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    fq_bytes = sum(n for _, _, n in prof)
+    families = {}
+    for name, a, b, nbytes in prof:
+        f = families.setdefault(name, [0, 0.0, 0])
+        f[0] += 1
+        f[1] += a.elapsed_time(b)
+        f[2] += nbytes
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -291,7 +295,10 @@ def main_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
-        achieved = fq_bytes / (fq_ms * 1e-3) / 1e9 if fq_ms > 0 else None
+        table = {name: {"launches": n, "ms_per_step": t / args.steps, "gbs": nb / (t * 1e-3) / 1e9,
+                        "frac": nb / (t * 1e-3) / 1e9 / peak} for name, (n, t, nb) in families.items() if t > 0}
+        dominant = max(table, key=lambda k: table[k]["ms_per_step"]) if table else None
+        achieved = table[dominant]["gbs"] if dominant else None
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -306,10 +313,17 @@ def main_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "frozen QuantAct forward (fq_flat_kernel + fused bn_*_fwd_kernel<relu,quant>), 8 B/elem",
+            "roofline": {"bound": "hbm", "kernel": dominant,
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "launches_timed": len(prof), "peak_source": peak_src},
+                         "frac": (achieved / peak) if achieved else None,
+                         # ncu --set full, largest launch ([256,64,112,112]): dram read+write per launch vs
+                         # 1 644 167 168 algorithmic bytes (profiles/r1_fq_flat_after_lut.txt)
+                         "traffic": 1588173312,
+                         "launches_timed": len(prof), "peak_source": peak_src,
+                         "kernels": table,
+                         "note": "achieved = algorithmic bytes / CUDA-event time of every launch of the family inside the "
+                                 "timed steps (producer-warm L2, back-to-back launches); traffic = ncu dram bytes of the "
+                                 "largest fq_flat launch"},
         }
         if world == 1 and not args.no_cpu_baseline:
             res = run_cpu(args.workload, args.cpu_steps, 1, args.cpu_batch)

@@ -15,9 +15,30 @@ from . import _native as N
 
 _workspaces: dict = {}
 
-# bench.py sets this to a list to time every frozen fake-quant launch with CUDA events on the
-# launching stream: entries are (start_event, end_event, algorithmic_bytes).
+# bench.py sets this to a list to time the streaming launches with CUDA events on the launching
+# stream: entries are (kernel family, start_event, end_event, algorithmic_bytes).
 PROFILE = None
+
+
+class _Timed:
+    """``with _Timed(name, nbytes):`` brackets one launch with events when PROFILE is armed."""
+
+    __slots__ = ("name", "nbytes", "ev0")
+
+    def __init__(self, name, nbytes):
+        self.name, self.nbytes, self.ev0 = name, nbytes, None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.ev0 = torch.cuda.Event(enable_timing=True)
+            self.ev0.record()
+
+    def __exit__(self, *exc):
+        if self.ev0 is not None and exc[0] is None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            PROFILE.append((self.name, self.ev0, ev1, self.nbytes))
+        return False
 
 
 def _need(t: torch.Tensor, name: str, dtype=torch.float32):
@@ -104,17 +125,11 @@ def elementwise(x, p0, p1, k, mode, symmetric=False, params_given=False, out=Non
     if cd is not None and xd.stride() != cd.stride():
         cd = torch.empty_like(xd, dtype=torch.int8)
     flags = (N.SYMMETRIC if symmetric else 0) | (N.PARAMS_GIVEN if params_given else 0)
-    timed = PROFILE is not None and mode == N.MODE_FAKEQUANT and rows == 1
-    if timed:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-    rc = N.load().oodfq_fq_forward(xd.data_ptr(), y.data_ptr(), _ptr(cd), xd.numel(),
-                                   p0.contiguous().data_ptr(), p1.contiguous().data_ptr(), rows,
-                                   int(k), mode, flags, _stream(x.device))
-    N.check(rc, "fq_forward")
-    if timed:
-        ev1.record()
-        PROFILE.append((ev0, ev1, 8 * xd.numel()))
+    with _Timed("fq_flat_kernel (QuantAct forward, 8 B/elem)", 8 * xd.numel()):
+        rc = N.load().oodfq_fq_forward(xd.data_ptr(), y.data_ptr(), _ptr(cd), xd.numel(),
+                                       p0.contiguous().data_ptr(), p1.contiguous().data_ptr(), rows,
+                                       int(k), mode, flags, _stream(x.device))
+        N.check(rc, "fq_forward")
     return (y, cd) if codes else y
 
 
@@ -319,16 +334,12 @@ def bn_eval_forward(x, weight, bias, running_mean, running_var, eps, relu=False,
         _need(lo, "fq range min")
         _need(hi, "fq range max")
         flags |= N.BN_QUANT
-    timed = PROFILE is not None and fq is not None
-    if timed:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-    rc = N.load().oodfq_bn_eval_forward(xc.data_ptr(), y.data_ptr(), _ptr(z), n, c, hw, pw, pb, prm, prv, float(eps),
-                                        flags, _ptr(lo), _ptr(hi), int(k), _stream(x.device))
-    N.check(rc, "bn_eval_forward")
-    if timed:
-        ev1.record()
-        PROFILE.append((ev0, ev1, 8 * xc.numel()))
+    name = "bn_*_fwd_kernel<relu,quant> (BN+ReLU+QuantAct forward, 8 B/elem)" if fq is not None else \
+        "bn_*_fwd_kernel (eval BN forward, 8 B/elem)"
+    with _Timed(name, 8 * xc.numel()):
+        rc = N.load().oodfq_bn_eval_forward(xc.data_ptr(), y.data_ptr(), _ptr(z), n, c, hw, pw, pb, prm, prv,
+                                            float(eps), flags, _ptr(lo), _ptr(hi), int(k), _stream(x.device))
+        N.check(rc, "bn_eval_forward")
     return (y, z) if want_z else y
 
 
@@ -342,10 +353,13 @@ def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, re
     gx = torch.empty_like(xc)
     dwdb = torch.empty(2 * c, dtype=torch.float64, device=x.device) if want_param_grads else None
     ws = workspace(x.device).data_ptr() if want_param_grads else None
-    rc = N.load().oodfq_bn_eval_backward(xc.data_ptr(), gy.data_ptr(), gx.data_ptr(), n, c, hw, pw, pb, prm, prv,
-                                         float(eps), (N.BN_RELU if relu else 0) | (N.BN_NHWC if nhwc else 0),
-                                         _ptr(dwdb), ws, _stream(x.device))
-    N.check(rc, "bn_eval_backward")
+    reads_x = relu or want_param_grads          # otherwise grad_x = grad_y * a_c and x is never touched
+    with _Timed("bn_*_bwdx_kernel (fused BN backward, 12 B/elem; 8 without ReLU mask and parameter grads)",
+                (12 if reads_x else 8) * xc.numel()):
+        rc = N.load().oodfq_bn_eval_backward(xc.data_ptr(), gy.data_ptr(), gx.data_ptr(), n, c, hw, pw, pb, prm, prv,
+                                             float(eps), (N.BN_RELU if relu else 0) | (N.BN_NHWC if nhwc else 0),
+                                             _ptr(dwdb), ws, _stream(x.device))
+        N.check(rc, "bn_eval_backward")
     if not want_param_grads:
         return gx, None, None
     d = dwdb.float()

@@ -77,7 +77,7 @@ def main():
         gbs = nbytes / (med * 1e-3) / 1e9
         rows.append({"kernel": kernel, "shape": list(shape), "bytes": nbytes, "ms_median": med, "ms_best": best,
                      "gbs": gbs, "frac_of_peak": gbs / pk})
-        print(f"{kernel:10s} {str(tuple(shape)):24s} {nbytes / 1e6:9.1f} MB  {med * 1e3:9.1f} us  "
+        print(f"{kernel:11s} {str(tuple(shape)):24s} {nbytes / 1e6:9.1f} MB  {med * 1e3:9.1f} us  "
               f"{gbs:7.0f} GB/s  {100 * gbs / pk:5.1f}% of {pk:.0f}", flush=True)
 
     torch.manual_seed(0)
@@ -114,6 +114,20 @@ def main():
             m = float(n // c)
             report("bwd", shape, 12 * n, *timer(lambda: ops.bn_stats_backward(x, g, mean, gm, gv, m)))
             del g
+        if "bn_fwd" in only or "bn_bwd" in only:
+            w, b = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
+            rm, rv = torch.randn(c, device="cuda") * 0.1, torch.rand(c, device="cuda") + 0.5
+            for fmt, tag in ((torch.contiguous_format, "nchw"), (torch.channels_last, "nhwc")):
+                xf = torch.randn(shape, device="cuda").contiguous(memory_format=fmt)
+                if "bn_fwd" in only:
+                    report(f"bnq_{tag}", shape, 8 * n, *timer(lambda: ops.bn_eval_forward(xf, w, b, rm, rv, 1e-5, relu=True, fq=(4, lo, hi))))
+                    report(f"bn_{tag}", shape, 8 * n, *timer(lambda: ops.bn_eval_forward(xf, w, b, rm, rv, 1e-5)))
+                if "bn_bwd" in only:
+                    gf = torch.randn(shape, device="cuda").contiguous(memory_format=fmt)
+                    report(f"bnbw_{tag}", shape, 12 * n, *timer(lambda: ops.bn_eval_backward(xf, gf, w, b, rm, rv, 1e-5, relu=True)))
+                    report(f"bnbx_{tag}", shape, 8 * n, *timer(lambda: ops.bn_eval_backward(xf, gf, w, b, rm, rv, 1e-5, relu=False, want_param_grads=False)))
+                    del gf
+                del xf
         del x
         torch.cuda.empty_cache()
     if "weights" in only:
