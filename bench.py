@@ -42,6 +42,9 @@ WORKLOADS = {
     "pathmnist_resnet18_w2a2": ("resnet18_small", 9, (3, 28, 28), 2, 64,
                                 "pathmnist_resnet18_w2a2.hocon ResNet-18 W2A2 QAT step, 28x28, batch 64 per GPU"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of each kernel family (ncu --set full)
+NCU_TRAFFIC = {"bn_*_bwdx_kernel": 2431773184, "bn_*_fwd_kernel<relu,quant>": 1598203000, "bn_*_fwd_kernel": 1598398000,
+               "fq_flat_kernel": 1588173312}
 METRIC = "QAT images/sec ResNet-18 W4A4 224x224 (data-free QAT step, fake-quant path on sm_100a kernels)"
 
 
@@ -316,14 +319,15 @@ def main_ours(args):
             "roofline": {"bound": "hbm", "kernel": dominant,
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
-                         # ncu --set full, largest launch ([256,64,112,112]): dram read+write per launch vs
-                         # 1 644 167 168 algorithmic bytes (profiles/r1_fq_flat_after_lut.txt)
-                         "traffic": 1588173312,
+                         # ncu --set full dram read+write of the family's largest launch ([256,64,112,112]):
+                         # backward 2 431 773 184 B vs 2 466 250 752 algorithmic (profiles/r1_bn_nhwc_kernels.txt);
+                         # fq_flat 1 588 173 312 B vs 1 644 167 168 (profiles/r1_fq_flat_after_lut.txt)
+                         "traffic": NCU_TRAFFIC.get((dominant or "").split(" ")[0]),
                          "launches_timed": len(prof), "peak_source": peak_src,
                          "kernels": table,
                          "note": "achieved = algorithmic bytes / CUDA-event time of every launch of the family inside the "
                                  "timed steps (producer-warm L2, back-to-back launches); traffic = ncu dram bytes of the "
-                                 "largest fq_flat launch"},
+                                 "family's largest launch ([256,64,112,112]), see profiles/"},
         }
         if world == 1 and not args.no_cpu_baseline:
             res = run_cpu(args.workload, args.cpu_steps, 1, args.cpu_batch)

@@ -521,9 +521,13 @@ extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float
     if (flags & OODFQ_BN_NHWC) {
         if (!vec_ok || (C % 4) != 0) return fail(OODFQ_EINVAL, "bn_eval_backward: NHWC needs C %% 4 == 0 and 16-byte alignment");
         const NhwcGeom G = make_nhwc((long long)N * HW, C);
-        static const int per_sm = resident_ctas(bn_nhwc_bwdx_kernel<true, true>, kBThreads);
+        // resident CTAs differ a lot between the variants (97 vs 48 registers): size each grid by its own
+        static const int occ[4] = {resident_ctas(bn_nhwc_bwdx_kernel<false, false>, kBThreads),
+                                   resident_ctas(bn_nhwc_bwdx_kernel<false, true>, kBThreads),
+                                   resident_ctas(bn_nhwc_bwdx_kernel<true, false>, kBThreads),
+                                   resident_ctas(bn_nhwc_bwdx_kernel<true, true>, kBThreads)};
         long long want = (G.R + (long long)G.lanes_r * kDepth - 1) / ((long long)G.lanes_r * kDepth);
-        long long cap = (long long)kNumSM * per_sm;
+        long long cap = (long long)kNumSM * occ[(relu ? 2 : 0) + (reduce ? 1 : 0)];
         const long long table = (long long)kMaxBnSplit * kMaxBnChannels / C;     // partial slots that fit
         if (reduce && cap > table) cap = table;
         const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
@@ -539,8 +543,12 @@ extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float
         return check_launch("bn_eval_backward(fold)");
     }
     if (plane_ok(HW, vec_ok)) {
-        static const int per_sm = resident_ctas(bn_plane_bwdx_kernel<true, true>, kBThreads);
-        const int split = pick_split(C, N, reduce ? kMaxBnSplit : (1 << 20), kNumSM * per_sm);
+        static const int occ[4] = {resident_ctas(bn_plane_bwdx_kernel<false, false>, kBThreads),
+                                   resident_ctas(bn_plane_bwdx_kernel<false, true>, kBThreads),
+                                   resident_ctas(bn_plane_bwdx_kernel<true, false>, kBThreads),
+                                   resident_ctas(bn_plane_bwdx_kernel<true, true>, kBThreads)};
+        const int split = pick_split(C, N, reduce ? kMaxBnSplit : (1 << 20),
+                                     kNumSM * occ[(relu ? 2 : 0) + (reduce ? 1 : 0)]);
         const unsigned grid = (unsigned)C * split;
         if (relu && reduce) bn_plane_bwdx_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, N, C, HW, split, P, dwdb, ws);
         else if (relu) bn_plane_bwdx_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, N, C, HW, split, P, dwdb, ws);
