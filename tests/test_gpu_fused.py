@@ -208,3 +208,47 @@ def test_channels_last_student_matches_nchw_student():
     b.to(memory_format=torch.contiguous_format)
     with pytest.raises(RuntimeError, match="flat buffer"):
         qat(xs[0])
+
+
+def test_graphed_step_matches_eager_step():
+    """The whole QAT iteration replayed as a CUDA graph updates the student exactly like the eager step."""
+    from ood_dfq_b200 import fusion, nets, step, surgery
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+
+    def build():
+        torch.manual_seed(1)
+        teacher = nets.resnet20_cifar(num_classes=10)
+        nets.perturb_bn_stats(teacher)
+        student = surgery.quantize_model(copy.deepcopy(teacher), 4, 4).to(DEV)
+        teacher = teacher.to(DEV)
+        g = torch.Generator().manual_seed(2)
+        xs = [torch.randn(16, 3, 32, 32, generator=g).to(DEV) for _ in range(4)]
+        with torch.no_grad():
+            for x in xs[:2]:
+                student(x)
+        surgery.freeze_model(student)
+        fusion.fuse_eval_bn(student, xs[0][:2])
+        qat = step.QATStep(student, teacher, lr=1e-2, unit_types=(nets.ResUnit,))
+        return student, qat, xs
+
+    s_eager, q_eager, xs = build()
+    s_graph, q_graph, _ = build()
+    graphed = step.GraphedStep(q_graph, xs[0], warmup=2)          # 2 eager warm-up steps + capture = 3 updates on xs[0]
+    for _ in range(3):
+        q_eager(xs[0])
+    losses = []
+    for x in xs[1:]:
+        le, lg = q_eager(x), graphed(x)
+        losses.append((le.item(), lg.item()))
+    for le, lg in losses:
+        assert abs(le - lg) <= 1e-4 * abs(le) + 1e-6, losses
+    for (n1, p1), (n2, p2) in zip(s_eager.named_parameters(), s_graph.named_parameters()):
+        assert torch.allclose(p1, p2, rtol=1e-4, atol=1e-6), n1
+    # an eager forward after the replays sees the up-to-date quantised weights
+    with torch.no_grad():
+        ye, yg = s_eager(xs[0]), s_graph(xs[0])
+    assert torch.allclose(ye, yg, rtol=1e-3, atol=1e-4)
+    torch.backends.cudnn.deterministic = False
