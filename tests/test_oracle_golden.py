@@ -179,3 +179,56 @@ def test_bns_closed_form_gradient(golden):
     loss = torch.nn.functional.mse_loss(mean, rm) + torch.nn.functional.mse_loss(var, rv)
     loss.backward()
     np.testing.assert_allclose(bns_torch.bns_input_grad(x.detach(), rm, rv).numpy(), x.grad.numpy(), rtol=2e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------ the plain-C restatement (gcc)
+from oracle import fq_c  # noqa: E402
+
+
+@pytest.mark.parametrize("case", FROZEN_CASES)
+def test_c_oracle_frozen(golden, case):
+    g = golden("act_frozen")
+    k = int(case.rsplit("_k", 1)[1])
+    x, lo, hi = (g[f"{case}_{n}"] for n in ("x", "lo", "hi"))
+    s, z = fq_c.params(k, lo[0], hi[0])
+    assert bits(np.array([s, z])).tolist() == bits(np.array([g[f"{case}_scale"][0], g[f"{case}_zp"][0]])).tolist()
+    y, codes = fq_c.fake_quant(x, k, lo, hi)
+    assert np.array_equal(bits(y), bits(g[f"{case}_y"]))
+    assert np.array_equal(bits(codes), bits(g[f"{case}_codes"]))
+
+
+@pytest.mark.parametrize("tag", ["asym", "sym"])
+@pytest.mark.parametrize("k", [2, 4, 8])
+def test_c_oracle_calibrating_sequence(golden, tag, k):
+    g = golden("act_calib")
+    p = f"{tag}_k{k}_"
+    st = np.array([0, 0, 1], dtype=np.float32)
+    for step in range(6):
+        x = g[p + f"x{step}"]
+        if step != 4:
+            mn, mx = fq_c.minmax(x)
+            st = fq_c.range_update(st, g[p + "beta"][0], mn, mx, symmetric=(tag == "sym"))
+        assert np.array_equal(bits(st), g[p + f"state_bits{step}"]), step
+        y, _ = fq_c.fake_quant(x, k, st[0], st[1], symmetric=(tag == "sym"))
+        assert np.array_equal(bits(y), bits(g[p + f"y{step}"])), step
+
+
+@pytest.mark.parametrize("tag", ["c3x3", "c1x1", "c7x7", "wide"])
+@pytest.mark.parametrize("sym", [False, True])
+def test_c_oracle_weights(golden, tag, sym):
+    g = golden("weights")
+    for k in (2, 4, 8):
+        p = f"{tag}_k{k}_{'sym' if sym else 'asym'}_"
+        lo, hi = fq_c.row_ranges(g[p + "w"], symmetric=sym)
+        assert np.array_equal(bits(lo), bits(g[p + "lo"])) and np.array_equal(bits(hi), bits(g[p + "hi"]))
+        y, codes = fq_c.fake_quant(g[p + "w"], k, lo, hi, symmetric=sym)
+        assert np.array_equal(bits(y), bits(g[p + "wq"]))
+        assert np.array_equal(bits(codes), bits(g[p + "codes"]))
+
+
+def test_c_oracle_channel_stats(golden):
+    g = golden("bns")
+    for tag in ("off0", "off10", "off100"):
+        mean, var = fq_c.channel_stats(g[f"stat_{tag}_x"])
+        np.testing.assert_allclose(mean, g[f"stat_{tag}_mean"], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(var, g[f"stat_{tag}_var64"], rtol=1e-9)
