@@ -129,6 +129,17 @@ class QATStep:
             self.tap_t.clear()
 
     def __call__(self, images, labels=None):
+        total = self.compute(images)
+        self.apply()
+        return total
+
+    def apply(self):
+        """Gradient exchange over the data-parallel group, then the optimiser update."""
+        self.grads.all_reduce_mean(self.group)
+        self.opt.step()
+
+    def compute(self, images):
+        """Both forwards and the backward of one iteration; leaves the gradients in the flat buffer."""
         self._clear_taps()
         images = images.detach().requires_grad_(True)
         t_out = self.teacher(images)
@@ -148,8 +159,6 @@ class QATStep:
                                "re-formatted after the step was built); create the step after model.to(...)")
         self.grads.zero()
         total.backward()
-        self.grads.all_reduce_mean(self.group)
-        self.opt.step()
         return total.detach()
 
 
@@ -207,12 +216,21 @@ class GraphedStep:
     ``step``: a ``QATStep`` / ``DistillStep``-like callable taking one batch (or none) and returning a scalar tensor.
     """
 
-    def __init__(self, step, example=None, warmup=3):
+    def __init__(self, step, example=None, warmup=3, capture_update=None):
         from .quantization_utils.quant_modules import WeightBank
         self._bank = WeightBank
         self.step = step
         self.static_in = None if example is None else example.clone()
         args = () if self.static_in is None else (self.static_in,)
+        # With more than one rank the gradient all-reduce stays OUTSIDE the graph: forward and backward are
+        # replayed, the NCCL collective and the (few-launch, foreach) optimiser update run eagerly behind it.
+        split = hasattr(step, "compute") and hasattr(step, "apply")
+        if capture_update is None:
+            import torch.distributed as dist
+            capture_update = not (split and dist.is_available() and dist.is_initialized()
+                                  and dist.get_world_size(getattr(step, "group", None)) > 1)
+        self._eager_tail = step.apply if (split and not capture_update) else None
+        body = step.compute if self._eager_tail is not None else step
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):              # eager warm-up off the capture stream (cuDNN autotune, workspaces)
@@ -222,13 +240,15 @@ class GraphedStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.static_out = step(*args)
+            self.static_out = body(*args)
         self._bank.invalidate()
 
     def __call__(self, batch=None, non_blocking=True):
         if batch is not None:
             self.static_in.copy_(batch, non_blocking=non_blocking)
         self.graph.replay()
+        if self._eager_tail is not None:
+            self._eager_tail()
         # the graph re-quantised and then updated the weights behind Python's back: an eager forward after
         # this must not trust the modules' cached quantised weights
         self._bank.invalidate()
