@@ -116,7 +116,7 @@ def build_pair(workload, namespace, device, seed=1):
 
 def make_step(workload, teacher, student, namespace, group=None):
     from ood_dfq_b200 import nets, step
-    lr = 1e-6 if workload != "cifar100_resnet20_w4a4" else 1e-5      # config/*.hocon lr_S
+    lr = 1e-5 if WORKLOADS[workload][0] == "resnet20_cifar" else 1e-6      # config/*.hocon lr_S
     return step.QATStep(student, teacher, lr=lr, momentum=0.9, weight_decay=1e-4, temperature=20.0, alpha=20.0,
                         lam=1000.0, eps=0.01, unit_types=(nets.ResUnit,), group=group)
 
@@ -215,7 +215,7 @@ def main_ours(args):
         fusion.fuse_eval_bn(student, resident[0][:2])
         fusion.fuse_eval_bn(teacher, None)
     qat = make_step(args.workload, teacher, student, qm)      # after .to(): gradients alias one flat buffer
-    use_graph = args.graph == "on" or (args.graph == "auto" and args.workload != "imagenet_resnet18_w4a4")
+    use_graph = args.graph == "on" or (args.graph == "auto" and shape[1] <= 64)   # launch-bound small images
     if world > 1:
         ddist.reduce_minmax(student)
         for m in student.modules():               # ranges stay frozen from here on
@@ -370,13 +370,36 @@ def main_ours(args):
         dist.destroy_process_group()
 
 
+def workload_from_conf(path):
+    """Register a workload described by one of the reference's config/*.hocon files (verbatim settings:
+    the file's own qw/qa/batchSize, not the W4A4 / batch-256 overrides BASELINE.json quotes the metric on)."""
+    from ood_dfq_b200 import hocon
+    s = hocon.QuantSettings.from_file(path)
+    if s.img_size == 28:
+        net = "resnet18_small"
+    elif s.model_name.startswith("resnet20"):
+        net = "resnet20_cifar"
+    elif s.model_name == "resnet18":
+        net = "resnet18_imagenet"
+    else:
+        raise SystemExit(f"bench.py: no carrier network for model_name={s.model_name!r} (see ood_dfq_b200/nets.py)")
+    if s.qw != s.qa:
+        raise SystemExit("bench.py: the workload table assumes qw == qa")
+    name = "conf:" + os.path.basename(path)
+    WORKLOADS[name] = (net, s.nClasses, (s.channels, s.img_size, s.img_size), s.qw, s.batchSize,
+                       f"{os.path.basename(path)} {s.model_name} W{s.qw}A{s.qa} QAT step, {s.img_size}x{s.img_size}, "
+                       f"batch {s.batchSize} per GPU (file values)")
+    return name
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="imagenet_resnet18_w4a4")
+    ap.add_argument("--workload", default="imagenet_resnet18_w4a4", help="one of: " + ", ".join(sorted(WORKLOADS)))
+    ap.add_argument("--conf", default="", help="take the workload from a reference config/*.hocon file instead")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--cpu-batch", type=int, default=32, help="images per step of the CPU sample")
     ap.add_argument("--cpu-steps", type=int, default=6)
@@ -387,6 +410,10 @@ def main():
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
                     help="replay the whole iteration as a CUDA graph (auto: the launch-bound small-image workloads)")
     args = ap.parse_args()
+    if args.conf:
+        args.workload = workload_from_conf(args.conf)
+    if args.workload not in WORKLOADS:
+        raise SystemExit(f"bench.py: unknown workload {args.workload!r}")
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
