@@ -56,6 +56,12 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def metric_name(workload):
+    if workload == "imagenet_resnet18_w4a4":
+        return METRIC
+    return "QAT images/sec " + WORKLOADS[workload][5] + " (data-free QAT step, fake-quant path on sm_100a kernels)"
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
@@ -160,7 +166,7 @@ def main_reference(args):
         return
     res = run_cpu(args.workload, args.steps, args.warmup, args.cpu_batch)
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "images/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args.workload), "value": res["value"], "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOADS[args.workload][5], "name": args.workload,
@@ -335,7 +341,7 @@ def main_ours(args):
         dominant = max(table, key=lambda k: table[k]["ms_per_step"]) if table else None
         achieved = table[dominant]["gbs"] if dominant else None
         line = {
-            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args.workload), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg, "name": args.workload, "batch_per_gpu": batch, "global_batch": batch * world,

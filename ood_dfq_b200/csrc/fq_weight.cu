@@ -7,9 +7,9 @@
 // Here each output row is read from HBM once, reduced on chip, and its
 // fake-quantised twin written once: 8 B/elem, one launch for the whole model.
 //
-// Work split: rows of <= kWarpRowMax elements are handled one per warp, longer rows
-// get a whole CTA; either way the row is reduced, then re-read through L1 (a
-// 4608-element row is 18 KB) and quantised.
+// Work split: rows of <= kWarpRowMax elements are handled one per warp (8 rows per CTA, no
+// block barrier, one dequantisation table per warp), longer rows get a whole CTA; either way
+// the row is reduced, then re-read through L1 (a 4608-element row is 18 KB) and quantised.
 //
 // Roofline: HBM, 8 algorithmic bytes per weight element.
 #include "common.cuh"
@@ -18,7 +18,7 @@ namespace oodfq {
 
 constexpr int kWThreads = 256;
 constexpr int kWarpsPerCta = kWThreads / 32;
-constexpr int kWarpRowMax = 1024;   // 4 KB: stays in L1 between the two passes
+constexpr int kWarpRowMax = 8192;   // 32 KB: a row still sits in L1 between the two passes of its warp
 constexpr int kMaxJobs = 40;        // descriptors travel in kernel-parameter space (< 4 KB)
 
 struct WeightJob {
@@ -58,11 +58,25 @@ __device__ __forceinline__ void warp_row(const WeightJob& jb, long long row, int
     const int len = (int)jb.row_len;
     const float* src = jb.w + row * jb.row_len;
     float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-    for (int i = lane; i < len; i += 32) {
-        float t = __ldg(src + i);
-        if (SYM) t = fabsf(t);
-        mn = min_nan(mn, t);
-        mx = max_nan(mx, t);
+    const bool vec = ((len & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(jb.wq + row * jb.row_len) & 15u) == 0);
+    if (vec) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll 4
+        for (int i = lane; i < (len >> 2); i += 32) {
+            float4 t = __ldg(s4 + i);
+            if (SYM) { t.x = fabsf(t.x); t.y = fabsf(t.y); t.z = fabsf(t.z); t.w = fabsf(t.w); }
+            mn = min_nan(min_nan(mn, t.x), min_nan(t.y, min_nan(t.z, t.w)));
+            mx = max_nan(max_nan(mx, t.x), max_nan(t.y, max_nan(t.z, t.w)));
+        }
+    } else {
+#pragma unroll 4
+        for (int i = lane; i < len; i += 32) {
+            float t = __ldg(src + i);
+            if (SYM) t = fabsf(t);
+            mn = min_nan(mn, t);
+            mx = max_nan(mx, t);
+        }
     }
     mn = warp_min_nan(mn);
     mx = warp_max_nan(mx);
@@ -79,7 +93,19 @@ __device__ __forceinline__ void warp_row(const WeightJob& jb, long long row, int
         build_lut(lut, p, jb.k, lane, 32);
         __syncwarp();
         const int h = 1 << (jb.k - 1), mask = (1 << jb.k) - 1;
-        for (int i = lane; i < len; i += 32) dst[i] = fake_quant_lut(__ldg(src + i), p, lut, h, mask);
+        if (vec) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+            for (int i = lane; i < (len >> 2); i += 32) {
+                float4 t = __ldg(s4 + i);
+                d4[i] = make_float4(fake_quant_lut(t.x, p, lut, h, mask), fake_quant_lut(t.y, p, lut, h, mask),
+                                    fake_quant_lut(t.z, p, lut, h, mask), fake_quant_lut(t.w, p, lut, h, mask));
+            }
+        } else {
+#pragma unroll 4
+            for (int i = lane; i < len; i += 32) dst[i] = fake_quant_lut(__ldg(src + i), p, lut, h, mask);
+        }
         return;
     }
     for (int i = lane; i < len; i += 32) {
