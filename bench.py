@@ -41,10 +41,15 @@ WORKLOADS = {
                                "cifar100_resnet20.hocon ResNet-20 W4A4 QAT step, 32x32, batch 256 per GPU"),
     "pathmnist_resnet18_w2a2": ("resnet18_small", 9, (3, 28, 28), 2, 64,
                                 "pathmnist_resnet18_w2a2.hocon ResNet-18 W2A2 QAT step, 28x28, batch 64 per GPU"),
+    "distill_imagenet_resnet18_w4a4": ("resnet18_imagenet", 1000, (3, 224, 224), 4, 256,
+                                       "distill_data.py BN-statistics distillation iteration, quantised ResNet-18 W4A4 "
+                                       "teacher, 256x3x224x224 images per GPU (independent shard per rank)"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of each kernel family (ncu --set full)
 NCU_TRAFFIC = {"bn_*_bwdx_kernel": 2431773184, "bn_*_fwd_kernel<relu,quant>": 1598203000, "bn_*_fwd_kernel": 1598398000,
                "fq_flat_kernel": 1588173312}
+# BASELINE.json configs[4]: BN-statistics image distillation against a quantised teacher (distill_data.py:229-275)
+KINDS = {"distill_imagenet_resnet18_w4a4": "distill"}
 METRIC = "QAT images/sec ResNet-18 W4A4 224x224 (data-free QAT step, fake-quant path on sm_100a kernels)"
 
 
@@ -59,6 +64,8 @@ def peaks():
 def metric_name(workload):
     if workload == "imagenet_resnet18_w4a4":
         return METRIC
+    if KINDS.get(workload) == "distill":
+        return "distilled images x iterations / sec, " + WORKLOADS[workload][5]
     return "QAT images/sec " + WORKLOADS[workload][5] + " (data-free QAT step, fake-quant path on sm_100a kernels)"
 
 
@@ -147,7 +154,16 @@ def run_cpu(workload, steps, warmup, sample_batch):
     g = torch.Generator().manual_seed(0)
     batches = [torch.randn((sample_batch,) + shape, generator=g) for _ in range(2)]
     calibrate(student, batches[:1] * 3, fq_torch)
-    qat = make_step(workload, teacher, student, fq_torch)
+    if KINDS.get(workload) == "distill":
+        from ood_dfq_b200 import step as step_mod
+        from oracle import bns_torch
+        labels = torch.randint(0, WORKLOADS[workload][1], (sample_batch,), generator=g)
+        dstep = step_mod.DistillStep(student, bns_torch.StatTap(student), batches[0] / 5, labels)
+
+        def qat(_batch=None):
+            return dstep()
+    else:
+        qat = make_step(workload, teacher, student, fq_torch)
     for i in range(warmup):
         qat(batches[i % 2])
     t0 = time.perf_counter()
@@ -220,7 +236,18 @@ def main_ours(args):
         from ood_dfq_b200 import fusion
         fusion.fuse_eval_bn(student, resident[0][:2])
         fusion.fuse_eval_bn(teacher, None)
-    qat = make_step(args.workload, teacher, student, qm)      # after .to(): gradients alias one flat buffer
+    kind = KINDS.get(args.workload, "qat")
+    if kind == "distill":
+        # the "student" IS the quantised teacher here; the optimised variable is the image batch itself
+        from ood_dfq_b200 import bns, step as step_mod
+        del teacher
+        labels = torch.randint(0, WORKLOADS[args.workload][1], (batch,), generator=g).to(dev)
+        dstep = step_mod.DistillStep(student, bns.BNStatLoss(student), resident[0] / 5, labels)   # distill_data.py:181
+
+        def qat(_batch=None):
+            return dstep()
+    else:
+        qat = make_step(args.workload, teacher, student, qm)      # after .to(): gradients alias one flat buffer
     use_graph = args.graph == "on" or (args.graph == "auto" and shape[1] <= 64)   # launch-bound small images
     if world > 1:
         ddist.reduce_minmax(student)
@@ -250,7 +277,7 @@ def main_ours(args):
         _native.reset_launch_count()
         qat(resident[0])
         launches_per_step = _native.launch_count()
-        qat = step_mod.GraphedStep(qat, resident[0])
+        qat = step_mod.GraphedStep(dstep, None) if kind == "distill" else step_mod.GraphedStep(qat, resident[0])
     else:
         ops.PROFILE = []                            # event pairs around every streaming launch
     _native.reset_launch_count()
@@ -286,7 +313,18 @@ def main_ours(args):
 
     # ---- end-to-end arm: pinned host batches in, loss out, every step --------------------------
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if use_graph:
+    if kind == "distill":
+        # an iteration has no host input (the images live on the device for the 1000 iterations of a batch,
+        # distill_data.py:195); the reference reads the three loss terms back every iteration (:266-268)
+        for i in range(args.warmup):
+            qat().item()
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            _ = qat().item()
+        e1.record()
+        barrier()
+    elif use_graph:
         # the graph reads its static input buffer: H2D straight into it, then replay (batches are a few MB here)
         for i in range(args.warmup):
             qat(host[i % pool]).item()
@@ -332,7 +370,7 @@ def main_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
     e2e_value = world * batch * args.steps / (e2e_ms / 1e3)
-    h2d = batch * shape[0] * shape[1] * shape[2] * 4
+    h2d = 0 if kind == "distill" else batch * shape[0] * shape[1] * shape[2] * 4
 
     if rank == 0:
         peak, peak_src = peaks()

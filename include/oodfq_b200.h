@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OODFQ_ABI_VERSION 1
+#define OODFQ_ABI_VERSION 2
 
 #define OODFQ_OK 0
 #define OODFQ_EINVAL (-1)  /* bad argument (null pointer, k out of range, misaligned ...) */
@@ -45,6 +45,11 @@ extern "C" {
 /* flags */
 #define OODFQ_SYMMETRIC 1      /* the *_DSG family: zero-point ignored               */
 #define OODFQ_PARAMS_GIVEN 2   /* p0/p1 are (scale, zero_point) instead of (min,max) */
+
+/* flags of the per-channel (BatchNorm) entry points */
+#define OODFQ_BN_RELU 1
+#define OODFQ_BN_QUANT 2
+#define OODFQ_BN_NHWC 4        /* x, y, grads are channels_last: [N*H*W rows][C]; needs C % 4 == 0 */
 
 typedef void* oodfq_stream_t;  /* cudaStream_t */
 
@@ -119,10 +124,11 @@ int oodfq_weight_fq_multi(const oodfq_weight_desc* descs_host, int n_tensors,
  * S2_c = sum((x - shift_c)^2) over N and HW (accumulated around a local pivot and
  * re-based in fp64, so no cancellation).  shift: [C] or NULL (zero).
  * Optional fused fake-quant of the same read (north_star (b)): when y != NULL,
- * y = fakequant(x) with the scalar range (fq_lo, fq_hi), k = fq_k. */
+ * y = fakequant(x) with the scalar range (fq_lo, fq_hi), k = fq_k <= 8.
+ * flags: 0, or OODFQ_BN_NHWC when x (and y) are channels_last [N*H*W rows][C] (C % 4 == 0). */
 int oodfq_bn_stats_forward(const float* x, int N, int C, long long HW, const float* shift,
                            double* sums, float* y, const float* fq_lo, const float* fq_hi,
-                           int fq_k, void* workspace, oodfq_stream_t stream);
+                           int fq_k, int flags, void* workspace, oodfq_stream_t stream);
 
 /* mean_c = shift_c + S1_c/count, var_c = S2_c/count - (S1_c/count)^2 (biased).
  * `sums` may have been all-reduced over ranks; count is the global N*HW. */
@@ -149,7 +155,7 @@ int oodfq_bns_loss(const double* sums, const float* shift, const float* run_mean
 int oodfq_bn_stats_backward(const float* x, const float* grad_in, float* grad_x,
                             int N, int C, long long HW, const float* mean,
                             const float* gmean, const float* gvar, double count,
-                            const float* gscale, oodfq_stream_t stream);
+                            const float* gscale, int flags, oodfq_stream_t stream);
 
 /* ---- eval-mode BatchNorm fused with the ReLU + QuantAct behind it ----------
  * replaces: nn.BatchNorm2d in eval() (student and teacher always are: trainer_direct.py:411-412)
@@ -160,9 +166,6 @@ int oodfq_bn_stats_backward(const float* x, const float* grad_in, float* grad_x,
  * flags: OODFQ_BN_RELU | OODFQ_BN_QUANT (QUANT: scalar range fq_lo/fq_hi, k = fq_k <= 8; its
  * backward is the identity STE).  z_debug (nullable): the fp32 value handed to the quantiser.
  * weight / bias may be NULL (1 / 0). */
-#define OODFQ_BN_RELU 1
-#define OODFQ_BN_QUANT 2
-#define OODFQ_BN_NHWC 4   /* x, y, grads are channels_last: [N*H*W rows][C]; needs C % 4 == 0 */
 int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, int N, int C, long long HW,
                           const float* weight, const float* bias, const float* running_mean,
                           const float* running_var, float eps, int flags, const float* fq_lo,

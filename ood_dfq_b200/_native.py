@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboodfq_b200.so")
 MODE_FAKEQUANT, MODE_QUANTIZE, MODE_DEQUANTIZE = 0, 1, 2
 SYMMETRIC, PARAMS_GIVEN = 1, 2
 BN_RELU, BN_QUANT, BN_NHWC = 1, 2, 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _vp, _ll, _i, _d = C.c_void_p, C.c_longlong, C.c_int, C.c_double
 
@@ -37,10 +37,10 @@ SIGNATURES = {
     "oodfq_act_calib_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "oodfq_minmax": (_i, [_vp, _ll, _vp, _vp, _vp]),
     "oodfq_weight_fq_multi": (_i, [C.POINTER(WeightDesc), _i, _vp]),
-    "oodfq_bn_stats_forward": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "oodfq_bn_stats_forward": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "oodfq_bn_stats_finalize": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp]),
     "oodfq_bns_loss": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(_d), _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "oodfq_bn_stats_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _d, _vp, _vp]),
+    "oodfq_bn_stats_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _d, _vp, _i, _vp]),
     "oodfq_bn_eval_forward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
     "oodfq_bn_eval_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
 }

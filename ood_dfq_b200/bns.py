@@ -39,7 +39,7 @@ class _ChannelStats(torch.autograd.Function):
     def forward(ctx, x, shift):
         n, c, h, w = x.shape
         count = float(n * h * w)
-        xc = x.contiguous()
+        xc = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous()
         if shift is None:
             # any sample of the channel is a good pivot for the one-pass variance
             shift = xc[0, :, 0, 0].contiguous()
@@ -93,7 +93,7 @@ class _Tap(torch.autograd.Function):
         lay = mgr._layers[idx]
         if c != lay.channels:
             raise RuntimeError(f"BNStatLoss: layer {idx} saw {c} channels, expected {lay.channels}")
-        xc = x.contiguous()
+        xc = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous()
         ops.bn_stats_forward(xc, lay.module.running_mean, sums=run.sums[2 * lay.offset: 2 * (lay.offset + c)])
         run.counts[idx] = float(n * h * w)
         run.fired[idx] += 1

@@ -302,21 +302,6 @@ bn_group_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
 // of the fused NCHW step (profiles/r1_step_share_fused.txt).  Mapping: a thread owns one 128-bit column
 // (4 consecutive channels, fixed for its lifetime -> coefficients in registers) and walks down the rows;
 // the CTA's 256 threads cover `lanes_r = 256 / (C/4)` rows at a time as ONE contiguous run of memory.
-struct NhwcGeom {
-    long long R;        // rows
-    int C, cols;        // channels, 128-bit columns per row (C/4)
-    int lanes_r;        // rows covered by one pass of the CTA (>= 1); threads >= lanes_r*min(cols,256) idle
-    int col_blocks;     // ceil(cols / 256) when a row is wider than the CTA
-};
-
-__host__ __device__ inline NhwcGeom make_nhwc(long long R, int C) {
-    NhwcGeom G;
-    G.R = R; G.C = C; G.cols = C / 4;
-    G.lanes_r = G.cols <= kBThreads ? kBThreads / G.cols : 1;
-    G.col_blocks = (G.cols + kBThreads - 1) / kBThreads;
-    return G;
-}
-
 template <bool RELU, bool QUANT>
 __global__ void __launch_bounds__(kBThreads)
 bn_nhwc_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ zdbg, const NhwcGeom G,
@@ -436,13 +421,6 @@ bn_nhwc_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, f
             }
         }
     }
-}
-
-__global__ void __launch_bounds__(kBThreads)
-bn_nhwc_fold_kernel(const double* __restrict__ partial, int C, int nparts, double* __restrict__ dwdb) {
-    const int lane = threadIdx.x & 31;
-    const int c = blockIdx.x * (kBThreads / 32) + (threadIdx.x >> 5);
-    if (c < C) fold_partials(partial, C, c, nparts, lane, dwdb);
 }
 
 }  // namespace oodfq

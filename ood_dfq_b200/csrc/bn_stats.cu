@@ -325,6 +325,127 @@ bn_group_bwd_kernel(const float* __restrict__ x, const float* grad_in, float* gr
     }
 }
 
+// =============================================================================== NHWC kernels
+template <bool QUANT>
+__global__ void __launch_bounds__(kBThreads)
+bn_nhwc_stats_kernel(const float* __restrict__ x, const NhwcGeom G, const float* __restrict__ shift,
+                     float* __restrict__ y, const float* __restrict__ fq_lo, const float* __restrict__ fq_hi,
+                     int fq_k, Workspace* ws) {
+    __shared__ double dred[2 * kBThreads];
+    __shared__ float lut[QUANT ? kLutMax : 1];
+    QParams qp;
+    const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
+    if (QUANT) {
+        qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
+    }
+    const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
+    const bool active = (int)threadIdx.x < G.lanes_r * wcols;
+    const int rsub = threadIdx.x / wcols;
+    const long long rstep = (long long)G.lanes_r * gridDim.x;
+    const long long r0 = (long long)blockIdx.x * G.lanes_r + rsub;
+    for (int cb = 0; cb < G.col_blocks; ++cb) {
+        __syncthreads();                       // LUT ready / `dred` free again
+        const int col = cb * kBThreads + threadIdx.x % wcols;
+        const bool on = active && col < G.cols && r0 < G.R;
+        float pv[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+        long long cnt = 0;
+        if (on) {
+            // pivot = this thread's first row: a sample of each of its 4 channels
+            const float4 p4 = __ldg(reinterpret_cast<const float4*>(x) + r0 * G.cols + col);
+            pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w;
+            for (long long r = r0; r < G.R; r += kDepth * rstep) {
+                float4 v[kDepth];
+#pragma unroll
+                for (int d = 0; d < kDepth; ++d) {
+                    const long long rr = r + d * rstep;
+                    if (rr < G.R) v[d] = ld_stream(reinterpret_cast<const float4*>(x) + rr * G.cols + col);
+                }
+#pragma unroll
+                for (int d = 0; d < kDepth; ++d) {
+                    const long long rr = r + d * rstep;
+                    if (rr < G.R) {
+                        ++cnt;
+                        const float xs[4] = {v[d].x, v[d].y, v[d].z, v[d].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float dl = xs[j] - pv[j];
+                            a1[j] += dl;
+                            a2[j] = fmaf(dl, dl, a2[j]);
+                        }
+                        if (QUANT)
+                            st_out(reinterpret_cast<float4*>(y) + rr * G.cols + col,
+                                   make_float4(fake_quant_lut(xs[0], qp, lut, qh, qmask), fake_quant_lut(xs[1], qp, lut, qh, qmask),
+                                               fake_quant_lut(xs[2], qp, lut, qh, qmask), fake_quant_lut(xs[3], qp, lut, qh, qmask)));
+                    }
+                }
+            }
+        }
+        // every thread re-bases its own (count, S1, S2) onto the shift in fp64; the CTA's row-lanes are then
+        // folded in lane order through shared memory, one channel of the column at a time
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double d1 = 0.0, d2 = 0.0;
+            if (on) rebase((double)cnt, a1[j], a2[j], pv[j], shift ? __ldg(shift + 4 * col + j) : 0.f, d1, d2);
+            __syncthreads();
+            dred[threadIdx.x] = d1;
+            dred[kBThreads + threadIdx.x] = d2;
+            __syncthreads();
+            if (active && col < G.cols && rsub == 0) {
+                const int lc = threadIdx.x % wcols;
+                double t1 = 0.0, t2 = 0.0;
+                for (int l = 0; l < G.lanes_r; ++l) { t1 += dred[l * wcols + lc]; t2 += dred[kBThreads + l * wcols + lc]; }
+                double* p = ws->bn_partial + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
+                p[0] = t1;
+                p[1] = t2;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBThreads)
+bn_nhwc_bwd_kernel(const float* __restrict__ x, const float* grad_in, float* grad_x, const NhwcGeom G,
+                   const float* __restrict__ mean, const float* __restrict__ gmean, const float* __restrict__ gvar,
+                   float inv_count, const float* __restrict__ gscale) {
+    const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
+    if ((int)threadIdx.x >= G.lanes_r * wcols) return;
+    const int rsub = threadIdx.x / wcols;
+    const float gs = gscale ? __ldg(gscale) : 1.0f;
+    const long long rstep = (long long)G.lanes_r * gridDim.x;
+    for (int cb = 0; cb < G.col_blocks; ++cb) {
+        const int col = cb * kBThreads + threadIdx.x % wcols;
+        if (col >= G.cols) continue;
+        float ca[4], cbv[4], mu[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ca[j] = gs * 2.0f * __ldg(gvar + 4 * col + j) * inv_count;
+            cbv[j] = gs * __ldg(gmean + 4 * col + j) * inv_count;
+            mu[j] = __ldg(mean + 4 * col + j);
+        }
+        for (long long r = (long long)blockIdx.x * G.lanes_r + rsub; r < G.R; r += kDepth * rstep) {
+            float4 v[kDepth], g[kDepth];
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const long long rr = r + d * rstep;
+                if (rr < G.R) {
+                    v[d] = ld_stream(reinterpret_cast<const float4*>(x) + rr * G.cols + col);
+                    if (grad_in) g[d] = reinterpret_cast<const float4*>(grad_in)[rr * G.cols + col];
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const long long rr = r + d * rstep;
+                if (rr < G.R) {
+                    float4 o = make_float4(fmaf(ca[0], v[d].x - mu[0], cbv[0]), fmaf(ca[1], v[d].y - mu[1], cbv[1]),
+                                           fmaf(ca[2], v[d].z - mu[2], cbv[2]), fmaf(ca[3], v[d].w - mu[3], cbv[3]));
+                    if (grad_in) { o.x += g[d].x; o.y += g[d].y; o.z += g[d].z; o.w += g[d].w; }
+                    st_out(reinterpret_cast<float4*>(grad_x) + rr * G.cols + col, o);
+                }
+            }
+        }
+    }
+}
+
 // =============================================================================== small kernels
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ shift, int C,
                                    double inv_count, float* mean, float* var) {
@@ -397,7 +518,7 @@ using namespace oodfq;
 
 extern "C" int oodfq_bn_stats_forward(const float* x, int N, int C, long long HW, const float* shift,
                                       double* sums, float* y, const float* fq_lo, const float* fq_hi,
-                                      int fq_k, void* workspace, oodfq_stream_t stream) {
+                                      int fq_k, int flags, void* workspace, oodfq_stream_t stream) {
     if (!x || !sums || !workspace) return fail(OODFQ_EINVAL, "bn_stats_forward: null pointer");
     if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "bn_stats_forward: empty tensor (N=%d C=%d HW=%lld)", N, C, HW);
     if (C > kMaxBnChannels) return fail(OODFQ_EINVAL, "bn_stats_forward: C=%d exceeds %d", C, kMaxBnChannels);
@@ -405,6 +526,25 @@ extern "C" int oodfq_bn_stats_forward(const float* x, int N, int C, long long HW
     cudaStream_t st = (cudaStream_t)stream;
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
     const bool vec_ok = aligned16(x) && (!y || aligned16(y));
+    if (flags & OODFQ_BN_NHWC) {
+        if (!vec_ok || (C % 4) != 0) return fail(OODFQ_EINVAL, "bn_stats_forward: NHWC needs C %% 4 == 0 and 16-byte alignment");
+        const NhwcGeom G = make_nhwc((long long)N * HW, C);
+        static const int occ[2] = {resident_ctas(bn_nhwc_stats_kernel<false>, kBThreads),
+                                   resident_ctas(bn_nhwc_stats_kernel<true>, kBThreads)};
+        long long want = (G.R + (long long)G.lanes_r * kDepth - 1) / ((long long)G.lanes_r * kDepth);
+        long long cap = (long long)kNumSM * occ[y ? 1 : 0];
+        const long long table = (long long)kMaxBnSplit * kMaxBnChannels / C;
+        if (cap > table) cap = table;
+        const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+        if (y) bn_nhwc_stats_kernel<true><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws);
+        else bn_nhwc_stats_kernel<false><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws);
+        count_launch();
+        int rc = check_launch("bn_stats_forward");
+        if (rc != OODFQ_OK) return rc;
+        bn_nhwc_fold_kernel<<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, sums);
+        count_launch();
+        return check_launch("bn_stats_forward(fold)");
+    }
     if (plane_ok(HW, vec_ok)) {
         static const int per_sm_q = resident_ctas(bn_plane_stats_kernel<true>, kBThreads);
         static const int per_sm = resident_ctas(bn_plane_stats_kernel<false>, kBThreads);
@@ -462,13 +602,24 @@ extern "C" int oodfq_bns_loss(const double* sums, const float* shift, const floa
 
 extern "C" int oodfq_bn_stats_backward(const float* x, const float* grad_in, float* grad_x, int N, int C,
                                        long long HW, const float* mean, const float* gmean,
-                                       const float* gvar, double count, const float* gscale,
+                                       const float* gvar, double count, const float* gscale, int flags,
                                        oodfq_stream_t stream) {
     if (!x || !grad_x || !mean || !gmean || !gvar) return fail(OODFQ_EINVAL, "bn_stats_backward: null pointer");
     if (N <= 0 || C <= 0 || HW <= 0 || !(count > 0)) return fail(OODFQ_EINVAL, "bn_stats_backward: empty tensor");
     cudaStream_t st = (cudaStream_t)stream;
     const float ic = (float)(1.0 / count);
     const bool vec_ok = aligned16(x) && aligned16(grad_x) && (!grad_in || aligned16(grad_in));
+    if (flags & OODFQ_BN_NHWC) {
+        if (!vec_ok || (C % 4) != 0) return fail(OODFQ_EINVAL, "bn_stats_backward: NHWC needs C %% 4 == 0 and 16-byte alignment");
+        const NhwcGeom G = make_nhwc((long long)N * HW, C);
+        static const int per_sm = resident_ctas(bn_nhwc_bwd_kernel, kBThreads);
+        long long want = (G.R + (long long)G.lanes_r * kDepth - 1) / ((long long)G.lanes_r * kDepth);
+        long long cap = (long long)kNumSM * per_sm;
+        const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+        bn_nhwc_bwd_kernel<<<grid, kBThreads, 0, st>>>(x, grad_in, grad_x, G, mean, gmean, gvar, ic, gscale);
+        count_launch();
+        return check_launch("bn_stats_backward");
+    }
     if (plane_ok(HW, vec_ok)) {
         static const int per_sm = resident_ctas(bn_plane_bwd_kernel, kBThreads);
         const int split = pick_split(C, N, 1 << 20, kNumSM * per_sm);

@@ -215,12 +215,14 @@ def weight_fq_multi(weights: Sequence[torch.Tensor], ks: Sequence[int], symmetri
 
 
 # ----------------------------------------------------------------------------- a11 / a12
-def _nchw(x: torch.Tensor):
+def _nchw_or_nhwc(x: torch.Tensor):
+    """(dense tensor, N, C, HW, nhwc?) -- channels_last tensors are used as they are (C % 4 == 0)."""
     if x.dim() != 4:
-        raise RuntimeError(f"ood_dfq_b200: BN statistics need an NCHW tensor, got {x.dim()}-D")
-    xc = x.contiguous()
-    n, c, h, w = xc.shape
-    return xc, n, c, h * w
+        raise RuntimeError(f"ood_dfq_b200: expected an NCHW / channels_last 4-D tensor, got {x.dim()}-D")
+    n, c, h, w = x.shape
+    if (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last) and c % 4 == 0:
+        return x, n, c, h * w, True
+    return x.contiguous(), n, c, h * w, False
 
 
 def bn_stats_forward(x, shift=None, sums=None, fq=None):
@@ -230,7 +232,7 @@ def bn_stats_forward(x, shift=None, sums=None, fq=None):
     fake-quantised output of the same read.
     """
     _need(x, "input")
-    xc, n, c, hw = _nchw(x)
+    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
     if shift is not None:
         _need(shift, "shift")
         if shift.numel() != c or not shift.is_contiguous():
@@ -247,8 +249,8 @@ def bn_stats_forward(x, shift=None, sums=None, fq=None):
         _need(hi, "fq range max")
         y = torch.empty_like(xc)
     rc = N.load().oodfq_bn_stats_forward(xc.data_ptr(), n, c, hw, _ptr(shift), sums.data_ptr(), _ptr(y),
-                                         _ptr(lo), _ptr(hi), int(k), workspace(x.device).data_ptr(),
-                                         _stream(x.device))
+                                         _ptr(lo), _ptr(hi), int(k), N.BN_NHWC if nhwc else 0,
+                                         workspace(x.device).data_ptr(), _stream(x.device))
     N.check(rc, "bn_stats_forward")
     return (sums, y) if fq is not None else sums
 
@@ -285,15 +287,15 @@ def bns_loss(sums, shift, run_mean, run_var, ch_off: Sequence[int], counts: Sequ
 def bn_stats_backward(x, grad_in, mean, gmean, gvar, count: float, gscale=None, out=None):
     """grad_x = grad_in + g*(gmean_c/M + gvar_c*2(x-mean_c)/M); one fused pass."""
     _need(x, "input")
-    xc, n, c, hw = _nchw(x)
+    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
     gi = None
     if grad_in is not None:
         _need(grad_in, "grad_in")
-        gi = grad_in.contiguous()
+        gi = grad_in.contiguous(memory_format=torch.channels_last) if nhwc else grad_in.contiguous()
     gx = out if out is not None else torch.empty_like(xc)
     rc = N.load().oodfq_bn_stats_backward(xc.data_ptr(), _ptr(gi), gx.data_ptr(), n, c, hw, mean.data_ptr(),
                                           gmean.data_ptr(), gvar.data_ptr(), float(count), _ptr(gscale),
-                                          _stream(x.device))
+                                          N.BN_NHWC if nhwc else 0, _stream(x.device))
     N.check(rc, "bn_stats_backward")
     return gx
 
@@ -306,16 +308,6 @@ def _bn_ptrs(weight, bias, running_mean, running_var, c):
         if t is not None and (t.numel() != c or not t.is_contiguous() or t.dtype != torch.float32):
             raise RuntimeError(f"ood_dfq_b200: BN {nme} must be a contiguous fp32 [C] tensor")
     return _ptr(weight), _ptr(bias), running_mean.data_ptr(), running_var.data_ptr()
-
-
-def _nchw_or_nhwc(x: torch.Tensor):
-    """(dense tensor, N, C, HW, nhwc?) -- channels_last tensors are used as they are (C % 4 == 0)."""
-    if x.dim() != 4:
-        raise RuntimeError(f"ood_dfq_b200: expected an NCHW / channels_last 4-D tensor, got {x.dim()}-D")
-    n, c, h, w = x.shape
-    if (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last) and c % 4 == 0:
-        return x, n, c, h * w, True
-    return x.contiguous(), n, c, h * w, False
 
 
 def bn_eval_forward(x, weight, bias, running_mean, running_var, eps, relu=False, fq=None, want_z=False):

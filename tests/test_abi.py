@@ -49,7 +49,7 @@ def test_bad_arguments_return_error_codes_without_a_gpu(lib_path):
     assert b"k=99" in lib.oodfq_last_error()
     assert lib.oodfq_fq_forward(1, 1, None, 0, 1, 1, 1, 4, 0, 0, None) == 0      # empty tensor: no launch
     assert lib.oodfq_minmax(1, 0, 1, 1, None) == -1
-    assert lib.oodfq_bn_stats_forward(1, 0, 4, 4, None, 1, None, None, None, 0, 1, None) == -1
+    assert lib.oodfq_bn_stats_forward(1, 0, 4, 4, None, 1, None, None, None, 0, 0, 1, None) == -1
     with pytest.raises(RuntimeError, match="null pointer"):
         _native.check(lib.oodfq_quant_params(None, None, None, None, 1, 4, None), "quant_params")
 

@@ -252,3 +252,37 @@ def test_graphed_step_matches_eager_step():
         ye, yg = s_eager(xs[0]), s_graph(xs[0])
     assert torch.allclose(ye, yg, rtol=1e-3, atol=1e-4)
     torch.backends.cudnn.deterministic = False
+
+
+@pytest.mark.parametrize("shape", NHWC_SHAPES)
+def test_bn_statistics_channels_last_matches_nchw(shape):
+    from ood_dfq_b200 import bns, ops
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(shape, generator=g) * 1.3 + 0.4).to(DEV)
+    gy = torch.randn(shape, generator=g).to(DEV)
+    c = shape[1]
+    rm = (torch.randn(c, generator=g) * 0.2).to(DEV)
+    xl, gl = x.contiguous(memory_format=torch.channels_last), gy.contiguous(memory_format=torch.channels_last)
+    lo, hi = torch.zeros(1, device=DEV), torch.full((1,), 1.7, device=DEV)
+    s_a, y_a = ops.bn_stats_forward(x, rm, fq=(4, lo, hi))
+    s_b, y_b = ops.bn_stats_forward(xl, rm, fq=(4, lo, hi))
+    assert y_b.is_contiguous(memory_format=torch.channels_last) and torch.equal(y_a, y_b)
+    np.testing.assert_allclose(s_b.cpu().numpy(), s_a.cpu().numpy(), rtol=1e-6, atol=1e-6 * x.numel() / c)
+    np.testing.assert_allclose(ops.bn_stats_forward(xl, rm).cpu().numpy(), s_b.cpu().numpy(), rtol=1e-12)
+    cnt = float(x.numel() // c)
+    mean, var = ops.bn_stats_finalize(s_b, rm, cnt)
+    np.testing.assert_allclose(mean.cpu().numpy(), x.mean([0, 2, 3]).cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(var.cpu().numpy(), x.var([0, 2, 3], unbiased=False).cpu().numpy(), rtol=2e-5)
+    gm, gv = torch.randn(c, generator=g).to(DEV), torch.randn(c, generator=g).to(DEV)
+    for gin_a, gin_b in ((gy, gl), (None, None)):
+        ga = ops.bn_stats_backward(x, gin_a, mean, gm, gv, cnt)
+        gb = ops.bn_stats_backward(xl, gin_b, mean, gm, gv, cnt)
+        assert gb.is_contiguous(memory_format=torch.channels_last) and torch.equal(ga, gb)
+    # the differentiable front end on a channels_last tensor
+    xr = xl.clone().requires_grad_(True)
+    m2, v2 = bns.bn_channel_stats(xr, rm)
+    (m2.square().sum() + v2.square().sum()).backward()
+    xn = x.clone().requires_grad_(True)
+    m1, v1 = bns.bn_channel_stats(xn, rm)
+    (m1.square().sum() + v1.square().sum()).backward()
+    np.testing.assert_allclose(xr.grad.cpu().numpy(), xn.grad.cpu().numpy(), rtol=1e-4, atol=1e-7)
