@@ -248,10 +248,13 @@ def bn_stats_forward(x, shift=None, sums=None, fq=None):
         _need(lo, "fq range min")
         _need(hi, "fq range max")
         y = torch.empty_like(xc)
-    rc = N.load().oodfq_bn_stats_forward(xc.data_ptr(), n, c, hw, _ptr(shift), sums.data_ptr(), _ptr(y),
-                                         _ptr(lo), _ptr(hi), int(k), N.BN_NHWC if nhwc else 0,
-                                         workspace(x.device).data_ptr(), _stream(x.device))
-    N.check(rc, "bn_stats_forward")
+    name = "bn_*_stats_kernel + fused fake-quant (8 B/elem)" if fq is not None else \
+        "bn_*_stats_kernel (BN-input statistics, 4 B/elem)"
+    with _Timed(name, (8 if fq is not None else 4) * xc.numel()):
+        rc = N.load().oodfq_bn_stats_forward(xc.data_ptr(), n, c, hw, _ptr(shift), sums.data_ptr(), _ptr(y),
+                                             _ptr(lo), _ptr(hi), int(k), N.BN_NHWC if nhwc else 0,
+                                             workspace(x.device).data_ptr(), _stream(x.device))
+        N.check(rc, "bn_stats_forward")
     return (sums, y) if fq is not None else sums
 
 
@@ -293,10 +296,12 @@ def bn_stats_backward(x, grad_in, mean, gmean, gvar, count: float, gscale=None, 
         _need(grad_in, "grad_in")
         gi = grad_in.contiguous(memory_format=torch.channels_last) if nhwc else grad_in.contiguous()
     gx = out if out is not None else torch.empty_like(xc)
-    rc = N.load().oodfq_bn_stats_backward(xc.data_ptr(), _ptr(gi), gx.data_ptr(), n, c, hw, mean.data_ptr(),
-                                          gmean.data_ptr(), gvar.data_ptr(), float(count), _ptr(gscale),
-                                          N.BN_NHWC if nhwc else 0, _stream(x.device))
-    N.check(rc, "bn_stats_backward")
+    with _Timed("bn_*_bwd_kernel (BNS-loss backward, 12 B/elem accumulating, 8 fresh)",
+                (12 if gi is not None else 8) * xc.numel()):
+        rc = N.load().oodfq_bn_stats_backward(xc.data_ptr(), _ptr(gi), gx.data_ptr(), n, c, hw, mean.data_ptr(),
+                                              gmean.data_ptr(), gvar.data_ptr(), float(count), _ptr(gscale),
+                                              N.BN_NHWC if nhwc else 0, _stream(x.device))
+        N.check(rc, "bn_stats_backward")
     return gx
 
 
