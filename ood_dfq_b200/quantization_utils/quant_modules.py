@@ -48,8 +48,28 @@ class _CalibratingSTE(torch.autograd.Function):
         return grad_output, None
 
 
+class _StatsSTE(torch.autograd.Function):
+    """Frozen fake-quant that also leaves the per-channel sums of its input on the module (one read)."""
+
+    @staticmethod
+    def forward(ctx, x, owner):
+        sums, y = _ops.bn_stats_forward(x, None, fq=(owner.activation_bit, owner.x_min, owner.x_max))
+        owner.channel_sums = sums
+        owner.channel_count = float(x.numel() // x.shape[1])
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None
+
+
 class _ActQuantBase(Module):
     _symmetric = False
+    # opt-in (BASELINE.json north_star (b)): when True and the input is 4-D, the same pass that emits the
+    # fake-quantised tensor also accumulates sum(x) and sum(x^2) per channel; read them with channel_mean_var()
+    collect_channel_stats = False
+    channel_sums = None
+    channel_count = 0.0
 
     def __init__(self, activation_bit, full_precision_flag=False, running_stat=True, beta=0.9):
         super().__init__()
@@ -81,8 +101,22 @@ class _ActQuantBase(Module):
             if t.numel() != 1 or not t.is_contiguous():
                 setattr(self, name, t.reshape(-1)[:1].contiguous())
 
+    def channel_mean_var(self):
+        """Per-channel mean and biased variance of the last input seen with ``collect_channel_stats``."""
+        if self.channel_sums is None:
+            raise RuntimeError("no statistics collected: set collect_channel_stats = True and run a forward")
+        return _ops.bn_stats_finalize(self.channel_sums, None, self.channel_count)
+
     def forward(self, x):
         quantise = not self.full_precision_flag
+        fused_stats = (self.collect_channel_stats and quantise and not self._symmetric and x.dim() == 4
+                       and self.activation_bit <= 8)
+        if fused_stats:
+            if self.running_stat:       # pass 1: range; pass 2: quantise + channel sums with the updated range
+                self._state_ready()
+                _ops.act_calib_forward(x.detach(), self.activation_bit, self.x_min, self.x_max, self.beta,
+                                       self.beta_t, quantize=False)
+            return _StatsSTE.apply(x, self)
         if self.running_stat:
             self._state_ready()
             if quantise:

@@ -383,3 +383,25 @@ def test_full_size_properties(ops, shape):
     # a slice against the CPU oracle
     sl = x[:2].cpu()
     assert same_bits(y[:2], fq_torch.fake_quant(sl, k, lo.cpu(), hi.cpu()))
+
+
+def test_quantact_collects_channel_statistics(qm):
+    """north_star (b): the QuantAct pass can also deliver per-channel sum / sum of squares of its input."""
+    g = torch.Generator().manual_seed(31)
+    ref, m = fq_torch.OracleQuantAct(4), qm.QuantAct(4).to(DEV)
+    m.collect_channel_stats = True
+    for step in range(4):
+        if step == 3:
+            ref.fix()
+            m.fix()
+        x = torch.relu(torch.randn(6, 12, 9, 9, generator=g) * (1 + step))
+        xg = x.to(DEV).requires_grad_(True)
+        y, y_ref = m(xg), ref(x)
+        assert same_bits(y, y_ref), step
+        assert same_bits(torch.cat([m.x_min, m.x_max, m.beta_t]), torch.cat([ref.x_min, ref.x_max, ref.beta_t]))
+        mean, var = m.channel_mean_var()
+        np.testing.assert_allclose(mean.cpu().numpy(), x.mean([0, 2, 3]).numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(var.cpu().numpy(), x.var([0, 2, 3], unbiased=False).numpy(), rtol=1e-5)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        assert torch.equal(xg.grad, gy)

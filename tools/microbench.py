@@ -114,6 +114,15 @@ def main():
             m = float(n // c)
             report("bwd", shape, 12 * n, *timer(lambda: ops.bn_stats_backward(x, g, mean, gm, gv, m)))
             del g
+        if "stats_nhwc" in only:
+            xl = x.contiguous(memory_format=torch.channels_last)
+            report("st_nhwc", shape, 4 * n, *timer(lambda: ops.bn_stats_forward(xl, shift)))
+            report("stq_nhwc", shape, 8 * n, *timer(lambda: ops.bn_stats_forward(xl, shift, fq=(4, lo, hi))))
+            gl = torch.randn_like(xl)
+            mean0 = torch.zeros(c, device="cuda")
+            gm0, gv0 = torch.randn(c, device="cuda"), torch.randn(c, device="cuda")
+            report("bwd_nhwc", shape, 12 * n, *timer(lambda: ops.bn_stats_backward(xl, gl, mean0, gm0, gv0, float(n // c))))
+            del xl, gl
         if "bn_fwd" in only or "bn_bwd" in only:
             w, b = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda")
             rm, rv = torch.randn(c, device="cuda") * 0.1, torch.rand(c, device="cuda") + 0.5
