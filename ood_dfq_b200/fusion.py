@@ -55,8 +55,8 @@ class AbsorbedTail(nn.Sequential):
         return nn.Sequential.forward(self, x)
 
 
-class FusedEvalBN(nn.BatchNorm2d):
-    """BatchNorm2d whose eval-mode forward/backward are single sm_100a kernels, optionally with ReLU + QuantAct."""
+class _FusedEvalMixin:
+    """Eval-mode forward/backward as single sm_100a kernels, optionally with the absorbed ReLU + QuantAct."""
 
     _tail = None          # AbsorbedTail or None (plain attribute: not a registered child)
 
@@ -84,7 +84,8 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
     BatchNorm feeds which ``Sequential(ReLU, QuantAct)``; without it only the BatchNorms themselves are fused."""
     was_training = model.training
     model.eval()
-    bns = [m for m in model.modules() if type(m) in (nn.BatchNorm2d, FusedEvalBN)]
+    fusable = (nn.BatchNorm2d, nn.SyncBatchNorm, FusedEvalBN, FusedEvalSyncBN)
+    bns = [m for m in model.modules() if type(m) in fusable]
     tails = [m for m in model.modules() if type(m) is nn.Sequential and len(m) == 2
              and type(m[0]) in (nn.ReLU, nn.ReLU6) and type(m[1]) is QuantAct]
     pairs = []
@@ -101,7 +102,7 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
             h.remove()
         produced.clear()
     for b in bns:
-        b.__class__ = FusedEvalBN
+        b.__class__ = _FUSED_CLASS.get(type(b), type(b))
     for b, t in pairs:
         if type(t[0]) is nn.ReLU6:
             continue                              # ReLU6 clamps from above as well: leave it unfused
@@ -116,3 +117,16 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
             raise RuntimeError(f"fuse_eval_bn: fused model deviates from the original ({err:.3e} vs scale {scale:.3e})")
     model.train(was_training)
     return model
+
+
+class FusedEvalBN(_FusedEvalMixin, nn.BatchNorm2d):
+    """``nn.BatchNorm2d`` with the fused eval path."""
+
+
+class FusedEvalSyncBN(_FusedEvalMixin, nn.SyncBatchNorm):
+    """``nn.SyncBatchNorm`` with the fused eval path: the reference converts the student with
+    ``SyncBatchNorm.convert_sync_batchnorm`` (main_direct.py:483) and then only ever runs it in eval(), where
+    SyncBatchNorm is the same per-channel affine (no collective)."""
+
+
+_FUSED_CLASS = {nn.BatchNorm2d: FusedEvalBN, nn.SyncBatchNorm: FusedEvalSyncBN}

@@ -286,3 +286,28 @@ def test_bn_statistics_channels_last_matches_nchw(shape):
     m1, v1 = bns.bn_channel_stats(xn, rm)
     (m1.square().sum() + v1.square().sum()).backward()
     np.testing.assert_allclose(xr.grad.cpu().numpy(), xn.grad.cpu().numpy(), rtol=1e-4, atol=1e-7)
+
+
+def test_fusion_handles_sync_batchnorm():
+    """main_direct.py:483 converts the student to SyncBatchNorm; in eval() that is the same affine."""
+    from ood_dfq_b200 import fusion, nets, surgery
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(1)
+    base = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(base)
+    plain = surgery.quantize_model(base, 4, 4)
+    plain = torch.nn.SyncBatchNorm.convert_sync_batchnorm(plain).to(DEV).eval()
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(8, 3, 32, 32, generator=g).to(DEV) for _ in range(3)]
+    with torch.no_grad():
+        for x in xs:
+            plain(x)
+    surgery.freeze_model(plain)
+    fused = copy.deepcopy(plain)
+    fusion.fuse_eval_bn(fused, xs[0][:2])
+    assert sum(type(m) is fusion.FusedEvalSyncBN for m in fused.modules()) == 21
+    assert sum(type(m) is fusion.AbsorbedTail for m in fused.modules()) == 10
+    assert all(isinstance(m, torch.nn.SyncBatchNorm) for m in fused.modules() if type(m) is fusion.FusedEvalSyncBN)
+    with torch.no_grad():
+        yp, yf = plain(xs[2]), fused(xs[2])
+    assert (yf - yp).abs().max().item() < 0.2 * yp.std().item()
