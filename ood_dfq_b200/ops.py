@@ -125,7 +125,9 @@ def elementwise(x, p0, p1, k, mode, symmetric=False, params_given=False, out=Non
     if cd is not None and xd.stride() != cd.stride():
         cd = torch.empty_like(xd, dtype=torch.int8)
     flags = (N.SYMMETRIC if symmetric else 0) | (N.PARAMS_GIVEN if params_given else 0)
-    with _Timed("fq_flat_kernel (QuantAct forward, 8 B/elem)", 8 * xd.numel()):
+    family = "fq_flat_kernel (QuantAct forward, 8 B/elem)" if (mode == N.MODE_FAKEQUANT and rows == 1) else \
+        "fq_* helper kernels (linear_quantize / dequantize / per-row ranges, 8 B/elem)"
+    with _Timed(family, 8 * xd.numel()):
         rc = N.load().oodfq_fq_forward(xd.data_ptr(), y.data_ptr(), _ptr(cd), xd.numel(),
                                        p0.contiguous().data_ptr(), p1.contiguous().data_ptr(), rows,
                                        int(k), mode, flags, _stream(x.device))
