@@ -335,32 +335,41 @@ def main_ours(args):
         e1.record()
         barrier()
     else:
+        # double-buffered prefetcher: two fixed device buffers, H2D on a copy stream while the previous step
+        # computes (no allocation inside the loop: allocator traffic made this number jitter by 20 %)
         copy_stream = torch.cuda.Stream(dev)
+        slots = [torch.empty_like(resident[0]) for _ in range(2)]
+        released = [None, None]                    # event: the step that last read the slot has finished
 
         def fetch(i):
+            k = i % 2
             with torch.cuda.stream(copy_stream):
-                buf = host[i % pool].to(dev, non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(copy_stream)
-            return buf, done
+                if released[k] is not None:
+                    copy_stream.wait_event(released[k])
+                slots[k].copy_(host[i % pool], non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            return k, done
 
-        def take(pending):
-            buf, done = pending
+        def run(pending, nxt_index):
+            k, done = pending
             torch.cuda.current_stream().wait_event(done)
-            buf.record_stream(torch.cuda.current_stream())
-            return buf
+            nxt = fetch(nxt_index) if nxt_index is not None else None   # crosses PCIe while this step computes
+            loss = qat(slots[k])
+            released[k] = torch.cuda.Event()
+            released[k].record(torch.cuda.current_stream())
+            return loss.item(), nxt                # device -> host read of the step's result
 
-        for i in range(args.warmup):              # same fetch path as the timed loop (copy stream, allocator)
-            qat(take(fetch(i))).item()
+        pending = fetch(0)
+        for i in range(args.warmup):
+            _, pending = run(pending, i + 1 if i + 1 < args.warmup else None)
         barrier()
         e0.record()
         t_wall = time.perf_counter()
-        nxt = fetch(0)
+        pending = fetch(args.warmup)               # all K host->device copies happen inside the timed region
         for i in range(args.steps):
-            buf = take(nxt)
-            if i + 1 < args.steps:
-                nxt = fetch(i + 1)                # next batch crosses PCIe while this step computes
-            _ = qat(buf).item()                   # device -> host read of the step's result
+            j = args.warmup + i
+            _, pending = run(pending, j + 1 if i + 1 < args.steps else None)
             if args.verbose and rank == 0:
                 print(f"[e2e] step {i}: {1e3 * (time.perf_counter() - t_wall):.1f} ms since start", file=sys.stderr)
         e1.record()
