@@ -235,7 +235,7 @@ def main_ours(args):
         # eval-mode BN (+ ReLU + frozen QuantAct) as one kernel forward / one backward
         from ood_dfq_b200 import fusion
         fusion.fuse_eval_bn(student, resident[0][:2])
-        fusion.fuse_eval_bn(teacher, None)
+        fusion.fuse_eval_bn(teacher, resident[0][:2])
     kind = KINDS.get(args.workload, "qat")
     if kind == "distill":
         # the "student" IS the quantised teacher here; the optimised variable is the image batch itself

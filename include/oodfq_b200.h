@@ -45,6 +45,8 @@ extern "C" {
 /* flags */
 #define OODFQ_SYMMETRIC 1      /* the *_DSG family: zero-point ignored               */
 #define OODFQ_PARAMS_GIVEN 2   /* p0/p1 are (scale, zero_point) instead of (min,max) */
+#define OODFQ_RELU_FIRST 4     /* x <- max(x, 0) before quantising: the nn.Sequential(ReLU, QuantAct) of
+                                  main_direct.py:464-465 in one pass (scalar range, FAKEQUANT mode) */
 
 /* flags of the per-channel (BatchNorm) entry points */
 #define OODFQ_BN_RELU 1

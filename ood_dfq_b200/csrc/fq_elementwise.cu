@@ -20,7 +20,7 @@ template <int MODE, bool SYM, bool CODES, bool LUT>
 __global__ void __launch_bounds__(kThreads)
 fq_flat_kernel(const float* x, float* y, int8_t* __restrict__ codes,
                long long numel, const float* __restrict__ p0, const float* __restrict__ p1,
-               int k, int given, int aliased, int reverse) {
+               int k, int given, int aliased, int reverse, int relu) {
     __shared__ float lut[LUT ? kLutMax : 1];
     const QParams p = given ? given_qparams(__ldg(p0), __ldg(p1), k)
                             : make_qparams(__ldg(p0), __ldg(p1), k);
@@ -47,6 +47,10 @@ fq_flat_kernel(const float* x, float* y, int8_t* __restrict__ codes,
             long long i = base + u * kThreads + threadIdx.x;
             if (i < n8) {
                 f8 r;
+                if (relu) {                      // the ReLU in front of the QuantAct, NaN-preserving like clamp_min
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u].v[j] = max_nan(v[u].v[j], 0.0f);
+                }
                 if (CODES) {
                     union { signed char c[8]; int2 w; } pk;
 #pragma unroll
@@ -71,7 +75,7 @@ fq_flat_kernel(const float* x, float* y, int8_t* __restrict__ codes,
     if (blockIdx.x == 0) {
         long long i = (n8 << 3) + threadIdx.x;
         if (i < numel) {
-            float xv = x[i];
+            float xv = relu ? max_nan(x[i], 0.0f) : x[i];
             if (CODES) {
                 float q = code_of<SYM>(xv, p);
                 codes[i] = (int8_t)q;
@@ -87,12 +91,12 @@ fq_flat_kernel(const float* x, float* y, int8_t* __restrict__ codes,
 template <int MODE, bool SYM, bool CODES>
 __global__ void __launch_bounds__(kThreads)
 fq_flat_scalar_kernel(const float* x, float* y, int8_t* codes, long long numel,
-                      const float* __restrict__ p0, const float* __restrict__ p1, int k, int given) {
+                      const float* __restrict__ p0, const float* __restrict__ p1, int k, int given, int relu) {
     const QParams p = given ? given_qparams(__ldg(p0), __ldg(p1), k)
                             : make_qparams(__ldg(p0), __ldg(p1), k);
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < numel;
          i += (long long)gridDim.x * kThreads) {
-        float xv = x[i];
+        float xv = relu ? max_nan(x[i], 0.0f) : x[i];
         if (CODES) {
             float q = code_of<SYM>(xv, p);
             codes[i] = (int8_t)q;
@@ -140,7 +144,8 @@ __global__ void quant_params_kernel(const float* __restrict__ lo, const float* _
 
 template <int MODE, bool SYM, bool CODES>
 static int launch_fq(const float* x, float* y, int8_t* codes, long long numel, const float* p0,
-                     const float* p1, long long rows, int k, int given, cudaStream_t st, int reverse = 0) {
+                     const float* p1, long long rows, int k, int given, cudaStream_t st, int reverse = 0,
+                     int relu = 0) {
     if (rows == 1) {
         const bool vec = aligned32(x) && aligned32(y) && (!CODES || (reinterpret_cast<uintptr_t>(codes) & 7u) == 0);
         if (vec) {
@@ -153,19 +158,19 @@ static int launch_fq(const float* x, float* y, int8_t* codes, long long numel, c
                 long long cap = (long long)kNumSM * per_sm;
                 int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
                 fq_flat_kernel<MODE, SYM, CODES, kCanLut><<<grid, kThreads, 0, st>>>(x, y, codes, numel, p0, p1, k,
-                                                                                    given, aliased, reverse);
+                                                                                    given, aliased, reverse, relu);
             } else {
                 static const int per_sm = resident_ctas(fq_flat_kernel<MODE, SYM, CODES, false>, kThreads);
                 long long cap = (long long)kNumSM * per_sm;
                 int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
                 fq_flat_kernel<MODE, SYM, CODES, false><<<grid, kThreads, 0, st>>>(x, y, codes, numel, p0, p1, k,
-                                                                                  given, aliased, reverse);
+                                                                                  given, aliased, reverse, relu);
             }
         } else {
             long long blocks = (numel + kThreads - 1) / kThreads;
             long long cap = (long long)kNumSM * 8;
             int grid = (int)(blocks < cap ? blocks : cap);
-            fq_flat_scalar_kernel<MODE, SYM, CODES><<<grid, kThreads, 0, st>>>(x, y, codes, numel, p0, p1, k, given);
+            fq_flat_scalar_kernel<MODE, SYM, CODES><<<grid, kThreads, 0, st>>>(x, y, codes, numel, p0, p1, k, given, relu);
         }
     } else {
         long long row_len = numel / rows;
@@ -217,7 +222,10 @@ extern "C" int oodfq_fq_forward(const float* x, float* y, int8_t* codes, long lo
     const bool sym = (flags & OODFQ_SYMMETRIC) != 0;
     const int given = (flags & OODFQ_PARAMS_GIVEN) ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
-#define OODFQ_GO(MODE, SYM, CODES) return launch_fq<MODE, SYM, CODES>(x, y, codes, numel, p0, p1, rows, k, given, st)
+    const int relu = (flags & OODFQ_RELU_FIRST) ? 1 : 0;
+    if (relu && (rows != 1 || mode != OODFQ_MODE_FAKEQUANT))
+        return fail(OODFQ_EINVAL, "fq_forward: RELU_FIRST needs a scalar range and FAKEQUANT mode");
+#define OODFQ_GO(MODE, SYM, CODES) return launch_fq<MODE, SYM, CODES>(x, y, codes, numel, p0, p1, rows, k, given, st, 0, relu)
     switch (mode) {
         case OODFQ_MODE_FAKEQUANT:
             if (codes) { if (sym) OODFQ_GO(OODFQ_MODE_FAKEQUANT, true, true); else OODFQ_GO(OODFQ_MODE_FAKEQUANT, false, true); }

@@ -45,6 +45,42 @@ class _FusedBN(torch.autograd.Function):
                 None, None, None)
 
 
+class _ReLUQuantSTE(torch.autograd.Function):
+    """``QuantAct(ReLU(x))`` with a frozen range in one pass; backward = ReLU mask (the quantiser is an identity STE)."""
+
+    @staticmethod
+    def forward(ctx, x, qact):
+        ctx.save_for_backward(x)
+        return ops.fake_quant(x, qact.activation_bit, qact.x_min, qact.x_max, relu_first=True)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        (x,) = ctx.saved_tensors
+        return torch.ops.aten.threshold_backward(grad_y, x, 0), None
+
+
+class FusedReLUQuant(nn.Sequential):
+    """A ``Sequential(ReLU, QuantAct)`` that no BatchNorm could absorb (it follows a residual add): still one
+    kernel instead of two once the range is frozen."""
+
+    def forward(self, x):
+        qact = self[1]
+        if (x.is_cuda and x.dtype == torch.float32 and type(qact) is QuantAct and not qact.running_stat
+                and not qact.full_precision_flag and qact.activation_bit <= 16):
+            return _ReLUQuantSTE.apply(x, qact)
+        return nn.Sequential.forward(self, x)
+
+
+class AbsorbedReLU(nn.ReLU):
+    """A plain ReLU whose work the preceding FusedEvalBN has taken over (full-precision teacher)."""
+
+    def forward(self, x):
+        return x
+
+    def run(self, x):
+        return nn.ReLU.forward(self, x)
+
+
 class AbsorbedTail(nn.Sequential):
     """The ``Sequential(ReLU, QuantAct)`` whose work the preceding FusedEvalBN has taken over."""
 
@@ -63,19 +99,20 @@ class _FusedEvalMixin:
     def _tail_parts(self):
         if self._tail is None:
             return False, None
-        qact = self._tail[1]
-        return True, qact
+        if isinstance(self._tail, AbsorbedReLU):
+            return True, None                     # ReLU only (no quantiser behind it)
+        return True, self._tail[1]
 
     def forward(self, x):
         has_tail, qact = self._tail_parts()
         fusable = (not self.training) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 \
             and self.track_running_stats and self.running_mean is not None
-        if has_tail and (qact.running_stat or type(qact) is not QuantAct):
+        if has_tail and qact is not None and (qact.running_stat or type(qact) is not QuantAct):
             fusable = False                       # still calibrating (or not the asymmetric QuantAct): exact old path
         if not fusable:
             y = super().forward(x)
             return self._tail.run(y) if has_tail else y
-        q = qact if (has_tail and not qact.full_precision_flag) else None
+        q = qact if (qact is not None and not qact.full_precision_flag) else None
         return _FusedBN.apply(x, self.weight, self.bias, self, has_tail, q)
 
 
@@ -88,14 +125,16 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
     bns = [m for m in model.modules() if type(m) in fusable]
     tails = [m for m in model.modules() if type(m) is nn.Sequential and len(m) == 2
              and type(m[0]) in (nn.ReLU, nn.ReLU6) and type(m[1]) is QuantAct]
+    in_tail = {id(t[0]) for t in tails}
+    relus = [m for m in model.modules() if type(m) is nn.ReLU and id(m) not in in_tail]
     pairs = []
     ref_out = None
-    if example is not None and absorb_tails and tails:
+    if example is not None and absorb_tails and (tails or relus):
         produced = {}     # id(tensor) -> (module, tensor): the tensor is kept alive so ids cannot be recycled
         handles = [b.register_forward_hook(lambda mod, i, o: produced.__setitem__(id(o), (mod, o))) for b in bns]
         handles += [t.register_forward_pre_hook(
             lambda mod, i: pairs.append((produced[id(i[0])][0], mod)) if id(i[0]) in produced else None)
-            for t in tails]
+            for t in tails + relus]
         with torch.no_grad():
             ref_out = model(example)
         for h in handles:
@@ -103,11 +142,22 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
         produced.clear()
     for b in bns:
         b.__class__ = _FUSED_CLASS.get(type(b), type(b))
+    taken = set()
     for b, t in pairs:
-        if type(t[0]) is nn.ReLU6:
+        if id(b) in taken or getattr(b, "_tail", None) is not None:
+            continue                              # one tail per BatchNorm
+        if type(t) is nn.ReLU:
+            t.__class__ = AbsorbedReLU
+        elif type(t[0]) is nn.ReLU6:
             continue                              # ReLU6 clamps from above as well: leave it unfused
-        t.__class__ = AbsorbedTail
+        else:
+            t.__class__ = AbsorbedTail
         object.__setattr__(b, "_tail", t)
+        taken.add(id(b))
+    if absorb_tails:
+        for t in tails:                           # ReLU + QuantAct behind a residual add: fuse the pair itself
+            if type(t) is nn.Sequential and type(t[0]) is nn.ReLU:
+                t.__class__ = FusedReLUQuant
     if verify and ref_out is not None:
         with torch.no_grad():
             new_out = model(example)

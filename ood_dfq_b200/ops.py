@@ -106,7 +106,7 @@ def _rows_for(x: torch.Tensor, p: torch.Tensor, what: str) -> int:
     return n
 
 
-def elementwise(x, p0, p1, k, mode, symmetric=False, params_given=False, out=None, codes=False):
+def elementwise(x, p0, p1, k, mode, symmetric=False, params_given=False, out=None, codes=False, relu_first=False):
     """One launch of oodfq_fq_forward.  p0/p1 = (min, max) or, with params_given, (scale, zero_point)."""
     _need(x, "input")
     _need(p0, "range/scale")
@@ -124,7 +124,8 @@ def elementwise(x, p0, p1, k, mode, symmetric=False, params_given=False, out=Non
     cd = torch.empty(xd.shape, dtype=torch.int8, device=x.device) if codes else None
     if cd is not None and xd.stride() != cd.stride():
         cd = torch.empty_like(xd, dtype=torch.int8)
-    flags = (N.SYMMETRIC if symmetric else 0) | (N.PARAMS_GIVEN if params_given else 0)
+    flags = (N.SYMMETRIC if symmetric else 0) | (N.PARAMS_GIVEN if params_given else 0) | \
+        (N.RELU_FIRST if relu_first else 0)
     family = "fq_flat_kernel (QuantAct forward, 8 B/elem)" if (mode == N.MODE_FAKEQUANT and rows == 1) else \
         "fq_* helper kernels (linear_quantize / dequantize / per-row ranges, 8 B/elem)"
     with _Timed(family, 8 * xd.numel()):
@@ -135,9 +136,12 @@ def elementwise(x, p0, p1, k, mode, symmetric=False, params_given=False, out=Non
     return (y, cd) if codes else y
 
 
-def fake_quant(x, k, lo, hi, symmetric=False, codes=False):
-    """quantise -> clamp -> dequantise with the reference's rounding sequence (quant_utils.py:138-157)."""
-    return elementwise(x, lo, hi, k, N.MODE_FAKEQUANT, symmetric=symmetric, codes=codes)
+def fake_quant(x, k, lo, hi, symmetric=False, codes=False, relu_first=False):
+    """quantise -> clamp -> dequantise with the reference's rounding sequence (quant_utils.py:138-157).
+
+    ``relu_first``: apply ``max(x, 0)`` in the same pass (the ``Sequential(ReLU, QuantAct)`` of main_direct.py:464-465).
+    """
+    return elementwise(x, lo, hi, k, N.MODE_FAKEQUANT, symmetric=symmetric, codes=codes, relu_first=relu_first)
 
 
 # ----------------------------------------------------------------------------- a6

@@ -311,3 +311,50 @@ def test_fusion_handles_sync_batchnorm():
     with torch.no_grad():
         yp, yf = plain(xs[2]), fused(xs[2])
     assert (yf - yp).abs().max().item() < 0.2 * yp.std().item()
+
+
+def test_relu_first_flat_kernel_and_fused_tail():
+    from ood_dfq_b200 import fusion, ops
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 7, 9, 11, generator=g) * 2
+    x[0, 0, 0, 0] = float("nan")
+    lo, hi = torch.zeros(1), torch.full((1,), 2.2)
+    for k in (2, 4, 8):
+        y = ops.fake_quant(x.to(DEV), k, lo.to(DEV), hi.to(DEV), relu_first=True).cpu()
+        ref = fq_torch.fake_quant(torch.relu(x), k, lo, hi)
+        assert np.array_equal(bits(y.numpy()), bits(ref.numpy()))
+    tail = torch.nn.Sequential(torch.nn.ReLU(inplace=True), qm.QuantAct(4)).to(DEV)
+    tail(torch.relu(x[1:]).to(DEV))                      # one calibrating pass
+    tail[1].fix()
+    plain_out_in = x[1:].clone().to(DEV).requires_grad_(True)
+    yp = tail(plain_out_in * 1.0)
+    tail.__class__ = fusion.FusedReLUQuant
+    fused_in = x[1:].clone().to(DEV).requires_grad_(True)
+    yf = tail(fused_in * 1.0)
+    assert torch.equal(yp, yf)
+    gy = torch.randn_like(yp)
+    yp.backward(gy)
+    yf.backward(gy)
+    assert torch.equal(plain_out_in.grad, fused_in.grad)
+
+
+def test_fused_full_precision_teacher_matches_plain():
+    from ood_dfq_b200 import fusion, nets
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(4)
+    plain = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(plain)
+    plain = plain.to(DEV).eval()
+    fused = copy.deepcopy(plain)
+    x = torch.randn(8, 3, 32, 32, device=DEV)
+    fusion.fuse_eval_bn(fused, x[:2])
+    assert sum(type(m) is fusion.AbsorbedReLU for m in fused.modules()) == 10
+    a, b = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = plain(a), fused(b)
+    assert torch.allclose(ya, yb, rtol=1e-4, atol=1e-4)
+    ya.square().mean().backward()
+    yb.square().mean().backward()
+    assert torch.allclose(a.grad, b.grad, rtol=1e-3, atol=1e-6)
+    for (n1, p1), (n2, p2) in zip(plain.named_parameters(), fused.named_parameters()):
+        assert torch.allclose(p1.grad, p2.grad, rtol=2e-3, atol=1e-5), n1

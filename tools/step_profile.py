@@ -45,7 +45,7 @@ def main():
     if not args.no_fuse:
         from ood_dfq_b200 import fusion
         fusion.fuse_eval_bn(student, xs[0][:2])
-        fusion.fuse_eval_bn(teacher, None)
+        fusion.fuse_eval_bn(teacher, xs[0][:2])
     qat = bench.make_step(args.workload, teacher, student, qm)
     for i in range(3):
         qat(xs[i % 2])
