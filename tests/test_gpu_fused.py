@@ -323,7 +323,8 @@ def test_relu_first_flat_kernel_and_fused_tail():
     for k in (2, 4, 8):
         y = ops.fake_quant(x.to(DEV), k, lo.to(DEV), hi.to(DEV), relu_first=True).cpu()
         ref = fq_torch.fake_quant(torch.relu(x), k, lo, hi)
-        assert np.array_equal(bits(y.numpy()), bits(ref.numpy()))
+        assert torch.isnan(y[0, 0, 0, 0]) and torch.isnan(ref[0, 0, 0, 0])       # NaN payloads may differ
+        assert np.array_equal(bits(torch.nan_to_num(y, 9.0).numpy()), bits(torch.nan_to_num(ref, 9.0).numpy()))
     tail = torch.nn.Sequential(torch.nn.ReLU(inplace=True), qm.QuantAct(4)).to(DEV)
     tail(torch.relu(x[1:]).to(DEV))                      # one calibrating pass
     tail[1].fix()
