@@ -177,6 +177,18 @@ int oodfq_bn_eval_backward(const float* x, const float* grad_y, float* grad_x, i
                            const float* running_mean, const float* running_var, float eps,
                            int flags, double* dwdb, void* workspace, oodfq_stream_t stream);
 
+/* ---- the reduction inside the feature-alignment loss ----------------------
+ * replaces: x.pow(2).mean([2,3]) of Trainer.channel_attention, trainer_direct.py:382-383 (hooks :432-440,
+ *           loss :325-330) and its autograd tape
+ * forward : e[n,c] = mean_{hw} x[n,c,hw]^2          e: [N, C]
+ * backward: grad_x[n,c,hw] = grad_e[n,c] * 2/HW * x[n,c,hw]
+ * flags: 0 or OODFQ_BN_NHWC.  scratch (NHWC forward only): oodfq_channel_energy_scratch_floats(N, C) floats. */
+size_t oodfq_channel_energy_scratch_floats(int N, int C);
+int oodfq_channel_energy_forward(const float* x, float* e, int N, int C, long long HW, int flags,
+                                 float* scratch, oodfq_stream_t stream);
+int oodfq_channel_energy_backward(const float* x, const float* grad_e, float* grad_x, int N, int C,
+                                  long long HW, int flags, oodfq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -367,3 +367,34 @@ def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, re
         return gx, None, None
     d = dwdb.float()
     return gx, d[:c], d[c:]
+
+
+# ----------------------------------------------------------------------------- 8(f)-2: feature-alignment reduction
+def channel_energy_forward(x):
+    """``x.pow(2).mean([2, 3])`` of an NCHW / channels_last tensor in one read (trainer_direct.py:382-383)."""
+    _need(x, "input")
+    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
+    e = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    scratch = None
+    if nhwc:
+        scratch = torch.empty(int(N.load().oodfq_channel_energy_scratch_floats(n, c)), dtype=torch.float32,
+                              device=x.device)
+    with _Timed("energy_*_kernel (feature-alignment mean of squares, 4 B/elem)", 4 * xc.numel()):
+        rc = N.load().oodfq_channel_energy_forward(xc.data_ptr(), e.data_ptr(), n, c, hw, N.BN_NHWC if nhwc else 0,
+                                                   _ptr(scratch), _stream(x.device))
+        N.check(rc, "channel_energy_forward")
+    return e
+
+
+def channel_energy_backward(x, grad_e):
+    """``grad_x = grad_e[n,c] * 2/HW * x``; keeps x's memory format."""
+    _need(x, "input")
+    _need(grad_e, "grad_e")
+    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
+    ge = grad_e.contiguous()
+    gx = torch.empty_like(xc)
+    with _Timed("energy_*_bwd (feature-alignment backward, 8 B/elem)", 8 * xc.numel()):
+        rc = N.load().oodfq_channel_energy_backward(xc.data_ptr(), ge.data_ptr(), gx.data_ptr(), n, c, hw,
+                                                    N.BN_NHWC if nhwc else 0, _stream(x.device))
+        N.check(rc, "channel_energy_backward")
+    return gx

@@ -31,20 +31,43 @@ def kd_loss(student_logits, teacher_logits, temperature: float, alpha: float):
 
 
 def channel_attention(x):
-    """trainer_direct.py:382-383."""
+    """``F.normalize(x.pow(2).mean([2,3]))`` exactly as the reference writes it (trainer_direct.py:382-383)."""
     return F.normalize(x.pow(2).mean([2, 3]).view(x.size(0), -1))
 
 
-class FeatureTap:
-    """Forward hooks collecting channel attention of the residual bodies (trainer_direct.py:432-440)."""
+class _ChannelEnergy(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        from . import ops
+        ctx.save_for_backward(x)
+        return ops.channel_energy_forward(x)
 
-    def __init__(self, model: nn.Module, unit_types: tuple):
-        self.maps = []
+    @staticmethod
+    def backward(ctx, grad_e):
+        from . import ops
+        (x,) = ctx.saved_tensors
+        return ops.channel_energy_backward(x, grad_e)
+
+
+def channel_attention_fused(x):
+    """Same quantity with the per-(image, channel) mean of squares as one sm_100a kernel forward and one
+    backward (the clone / pow / mean chain and its tape are 20 + 24 B/elem in eager PyTorch, 4 + 8 here)."""
+    return F.normalize(_ChannelEnergy.apply(x))
+
+
+class FeatureTap:
+    """Forward hooks collecting channel attention of the residual bodies (trainer_direct.py:432-440).
+
+    ``fused``: use the kernel (CUDA tensors); otherwise the reference's expression on a clone of the output.
+    """
+
+    def __init__(self, model: nn.Module, unit_types: tuple, fused=False):
+        self.maps, self.fused = [], fused
         self.handles = [m.body.register_forward_hook(self._hook) for m in model.modules()
                         if isinstance(m, unit_types) and hasattr(m, "body")]
 
     def _hook(self, module, inputs, output):
-        self.maps.append(channel_attention(output.clone()))
+        self.maps.append(channel_attention_fused(output) if self.fused else channel_attention(output.clone()))
 
     def clear(self):
         self.maps.clear()
@@ -100,7 +123,8 @@ class QATStep:
     """One data-free QAT iteration (see module docstring).  ``__call__`` returns the detached losses."""
 
     def __init__(self, student, teacher, lr=1e-6, momentum=0.9, weight_decay=1e-4, temperature=20.0,
-                 alpha=20.0, lam=1000.0, eps=0.01, unit_types: tuple = (), group=None, perturb=True):
+                 alpha=20.0, lam=1000.0, eps=0.01, unit_types: tuple = (), group=None, perturb=True,
+                 fused_attention=None):
         self.student, self.teacher = student, teacher
         self.T, self.alpha, self.lam, self.eps = temperature, alpha, lam, eps
         self.group, self.perturb = group, perturb
@@ -109,8 +133,10 @@ class QATStep:
         self.grads = FlatGrads(student.parameters())
         self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, weight_decay=weight_decay,
                                    nesterov=True)
-        self.tap_s = FeatureTap(student, unit_types) if unit_types else None
-        self.tap_t = FeatureTap(teacher, unit_types) if unit_types else None
+        if fused_attention is None:             # the kernel where the model lives on a GPU; the CPU arm keeps torch
+            fused_attention = next(student.parameters()).is_cuda
+        self.tap_s = FeatureTap(student, unit_types, fused_attention) if unit_types else None
+        self.tap_t = FeatureTap(teacher, unit_types, fused_attention) if unit_types else None
         student.eval()       # trainer_direct.py:411-412: both nets use BN running statistics
         teacher.eval()
 

@@ -359,3 +359,23 @@ def test_fused_full_precision_teacher_matches_plain():
     assert torch.allclose(a.grad, b.grad, rtol=1e-3, atol=1e-6)
     for (n1, p1), (n2, p2) in zip(plain.named_parameters(), fused.named_parameters()):
         assert torch.allclose(p1.grad, p2.grad, rtol=2e-3, atol=1e-5), n1
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 56, 56), (16, 128, 28, 28), (32, 512, 7, 7), (3, 5, 7, 9), (4, 24, 9, 11),
+                                   (2, 1280, 3, 3), (5, 8, 1, 7), (2, 16, 40, 40)])
+def test_channel_energy_matches_reference_expression(shape):
+    """The feature-alignment reduction (trainer_direct.py:382-383), NCHW and channels_last, forward and backward."""
+    from ood_dfq_b200 import step
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(shape, generator=g) * 1.3).to(DEV)
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        a = x.clone().contiguous(memory_format=fmt).requires_grad_(True)
+        b = x.clone().contiguous(memory_format=fmt).requires_grad_(True)
+        ref, out = step.channel_attention(a.clone()), step.channel_attention_fused(b)
+        np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), rtol=2e-5, atol=1e-7)
+        w = torch.randn_like(ref)
+        (ref * w).sum().backward()
+        (out * w).sum().backward()
+        scale = a.grad.abs().max().item()
+        np.testing.assert_allclose(b.grad.cpu().numpy(), a.grad.cpu().numpy(), rtol=1e-4, atol=1e-5 * scale)
+        assert b.grad.stride() == b.stride()
