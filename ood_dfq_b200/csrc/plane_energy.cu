@@ -142,13 +142,13 @@ __global__ void energy_fold_kernel(const float* __restrict__ partial, float* __r
     e[i] = t;
 }
 
-static EnergyNhwc make_energy_nhwc(int N, int C, int HW) {
+static EnergyNhwc make_energy_nhwc(int N, int C, int HW, int slots) {
     EnergyNhwc G;
     G.N = N; G.C = C; G.HW = HW; G.cols = C / 4;
     G.lanes_r = G.cols <= kBThreads ? kBThreads / G.cols : 1;
     G.col_blocks = (G.cols + kBThreads - 1) / kBThreads;
     int passes = (HW + G.lanes_r * kDepth - 1) / (G.lanes_r * kDepth);     // pipeline rounds per image
-    int want = (kNumSM * 4 + N - 1) / N;                                    // CTAs per image to fill the machine
+    int want = slots / N;                          // CTAs per image: fill the resident slots once, never 1.x waves
     if (want > passes) want = passes;
     if (want > 16) want = 16;
     if (want < 1) want = 1;
@@ -172,7 +172,8 @@ extern "C" int oodfq_channel_energy_forward(const float* x, float* e, int N, int
     if (flags & OODFQ_BN_NHWC) {
         if ((C % 4) != 0 || !aligned16(x)) return fail(OODFQ_EINVAL, "channel_energy_forward: NHWC needs C %% 4 == 0 and 16-byte alignment");
         if (!scratch) return fail(OODFQ_EINVAL, "channel_energy_forward: NHWC needs the scratch buffer");
-        const EnergyNhwc G = make_energy_nhwc(N, C, (int)HW);
+        static const int per_sm = resident_ctas(energy_nhwc_kernel<false>, kBThreads);
+        const EnergyNhwc G = make_energy_nhwc(N, C, (int)HW, kNumSM * per_sm);
         energy_nhwc_kernel<false><<<(unsigned)N * G.chunks, kBThreads, 0, st>>>(x, nullptr, G.chunks == 1 ? e : scratch, G, inv);
         count_launch();
         int rc = check_launch("channel_energy_forward");
@@ -198,7 +199,8 @@ extern "C" int oodfq_channel_energy_backward(const float* x, const float* grad_e
     if (flags & OODFQ_BN_NHWC) {
         if ((C % 4) != 0 || !aligned16(x) || !aligned16(grad_x))
             return fail(OODFQ_EINVAL, "channel_energy_backward: NHWC needs C %% 4 == 0 and 16-byte alignment");
-        const EnergyNhwc G = make_energy_nhwc(N, C, (int)HW);
+        static const int per_sm = resident_ctas(energy_nhwc_kernel<true>, kBThreads);
+        const EnergyNhwc G = make_energy_nhwc(N, C, (int)HW, kNumSM * per_sm);
         energy_nhwc_kernel<true><<<(unsigned)N * G.chunks, kBThreads, 0, st>>>(x, grad_e, grad_x, G, two_inv);
         count_launch();
         return check_launch("channel_energy_backward");
