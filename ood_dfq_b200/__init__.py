@@ -5,8 +5,11 @@ Layout
     _native.py, ops.py     ctypes binding and tensor-level launch wrappers
     quantization_utils/    drop-in mirror of the reference's operator API
     bns.py                 BN-statistics matching loss (fused forward / loss / backward)
+    fusion.py              eval-mode BatchNorm (+ ReLU + QuantAct) fusion pass
     dist.py                data-parallel glue: packed range and BN-sum all-reduces
-    surgery.py, nets.py    host-side consumers used by the benchmark (model surgery, shapes)
+    step.py                host code of the QAT / distillation iteration, flat gradients, CUDA-graph replay
+    surgery.py, nets.py    host-side consumers used by the benchmark (model surgery, carrier networks)
+    hocon.py               reader for the reference's config/*.hocon files
 
 ``install()`` makes ``from quantization_utils.quant_modules import *`` (main_direct.py:21,
 trainer_direct.py:19) resolve to this implementation.
