@@ -189,6 +189,21 @@ int oodfq_channel_energy_forward(const float* x, float* e, int N, int C, long lo
 int oodfq_channel_energy_backward(const float* x, const float* grad_e, float* grad_x, int N, int C,
                                   long long HW, int flags, oodfq_stream_t stream);
 
+/* ---- stem fusion: eval BatchNorm -> ReLU -> [QuantAct] -> MaxPool2d(3, stride 2, padding 1) -----------
+ * replaces: the first QuantAct site of the ImageNet ResNets together with the max-pool that consumes it
+ *           (pytorchcv ResInitBlock behind ptcv_get_model, main_direct.py:380-397; quantize_model :464-465)
+ * channels_last only: x [N,H,W,C], out / idx / xhat [N,Ho,Wo,C], Ho = (H-1)/2+1.  flags must contain
+ * OODFQ_BN_NHWC | OODFQ_BN_RELU, optionally OODFQ_BN_QUANT.  idx: one byte per output (window-local argmax
+ * 0..8, bit 7 = ReLU active).  xhat (nullable): normalised input at the argmax, needed only for dwdb. */
+int oodfq_bn_pool_forward(const float* x, float* out, uint8_t* idx, float* xhat, int N, int C, int H, int W,
+                          const float* weight, const float* bias, const float* running_mean,
+                          const float* running_var, float eps, int flags, const float* fq_lo,
+                          const float* fq_hi, int fq_k, oodfq_stream_t stream);
+int oodfq_bn_pool_backward(const float* grad_out, const uint8_t* idx, const float* xhat, float* grad_x,
+                           int N, int C, int H, int W, const float* weight, const float* bias,
+                           const float* running_mean, const float* running_var, float eps,
+                           double* dwdb, void* workspace, oodfq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

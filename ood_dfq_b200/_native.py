@@ -42,6 +42,8 @@ SIGNATURES = {
     "oodfq_bns_loss": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(_d), _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "oodfq_bn_stats_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _d, _vp, _i, _vp]),
     "oodfq_bn_eval_forward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
+    "oodfq_bn_pool_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
+    "oodfq_bn_pool_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp]),
     "oodfq_channel_energy_scratch_floats": (C.c_size_t, [_i, _i]),
     "oodfq_channel_energy_forward": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp, _vp]),
     "oodfq_channel_energy_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _vp]),

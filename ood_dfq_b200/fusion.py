@@ -81,6 +81,44 @@ class AbsorbedReLU(nn.ReLU):
         return nn.ReLU.forward(self, x)
 
 
+class _FusedStem(torch.autograd.Function):
+    """BN -> ReLU -> [QuantAct] -> MaxPool(3,2,1) in one kernel each way; the input itself is not saved."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, bn, qact):
+        fq = (qact.activation_bit, qact.x_min, qact.x_max) if qact is not None else None
+        need_p = (weight is not None and ctx.needs_input_grad[1]) or (bias is not None and ctx.needs_input_grad[2])
+        out, idx, xhat = ops.bn_pool_forward(x, weight, bias, bn.running_mean, bn.running_var, bn.eps, fq=fq,
+                                             want_xhat=need_p)
+        ctx.save_for_backward(idx, xhat, weight, bias)
+        ctx.bn, ctx.in_shape = bn, tuple(x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, xhat, weight, bias = ctx.saved_tensors
+        need_p = xhat is not None and ((weight is not None and ctx.needs_input_grad[1]) or
+                                       (bias is not None and ctx.needs_input_grad[2]))
+        gx, dw, db = ops.bn_pool_backward(grad_out, idx, xhat, ctx.in_shape, weight, bias, ctx.bn.running_mean,
+                                          ctx.bn.running_var, ctx.bn.eps, want_param_grads=need_p)
+        return (gx,
+                dw if (weight is not None and ctx.needs_input_grad[1]) else None,
+                db if (bias is not None and ctx.needs_input_grad[2]) else None,
+                None, None)
+
+
+class AbsorbedPool(nn.MaxPool2d):
+    """The stem ``MaxPool2d(3, 2, 1)`` whose work the FusedEvalBN two modules upstream has taken over."""
+
+    _bypass = False                              # set by the owning BatchNorm for the call that follows it
+
+    def forward(self, x):
+        if self._bypass:
+            self._bypass = False
+            return x
+        return nn.MaxPool2d.forward(self, x)
+
+
 class AbsorbedTail(nn.Sequential):
     """The ``Sequential(ReLU, QuantAct)`` whose work the preceding FusedEvalBN has taken over."""
 
@@ -94,7 +132,8 @@ class AbsorbedTail(nn.Sequential):
 class _FusedEvalMixin:
     """Eval-mode forward/backward as single sm_100a kernels, optionally with the absorbed ReLU + QuantAct."""
 
-    _tail = None          # AbsorbedTail or None (plain attribute: not a registered child)
+    _tail = None          # AbsorbedTail / AbsorbedReLU or None (plain attribute: not a registered child)
+    _pool = None          # AbsorbedPool or None: the stem max-pool behind the tail
 
     def _tail_parts(self):
         if self._tail is None:
@@ -113,7 +152,17 @@ class _FusedEvalMixin:
             y = super().forward(x)
             return self._tail.run(y) if has_tail else y
         q = qact if (qact is not None and not qact.full_precision_flag) else None
+        if self._pool is not None and has_tail and ops.bn_pool_supported(x) and (q is None or q.activation_bit <= 8):
+            self._pool._bypass = True             # the pool module two steps downstream just hands this through
+            return _FusedStem.apply(x, self.weight, self.bias, self, q)
         return _FusedBN.apply(x, self.weight, self.bias, self, has_tail, q)
+
+
+def _is_stem_pool(m):
+    def two(v):
+        return (v, v) if isinstance(v, int) else tuple(v)
+    return (two(m.kernel_size) == (3, 3) and two(m.stride) == (2, 2) and two(m.padding) == (1, 1)
+            and two(m.dilation) == (1, 1) and not m.ceil_mode and not m.return_indices)
 
 
 def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=True, verify=True):
@@ -140,6 +189,21 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
         for h in handles:
             h.remove()
         produced.clear()
+    # stem: a MaxPool2d(3, 2, 1) fed directly by a tail (found with a second traced forward)
+    stems = []
+    pools = [m for m in model.modules() if type(m) is nn.MaxPool2d and _is_stem_pool(m)]
+    if example is not None and absorb_tails and pools and pairs:
+        tail_of = {id(t): b for b, t in pairs}
+        made = {}
+        handles = [t.register_forward_hook(lambda mod, i, o: made.__setitem__(id(o), (mod, o))) for _, t in pairs]
+        handles += [p.register_forward_pre_hook(
+            lambda mod, i: stems.append((tail_of[id(made[id(i[0])][0])], mod)) if id(i[0]) in made else None)
+            for p in pools]
+        with torch.no_grad():
+            model(example)
+        for h in handles:
+            h.remove()
+        made.clear()
     for b in bns:
         b.__class__ = _FUSED_CLASS.get(type(b), type(b))
     taken = set()
@@ -154,6 +218,10 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
             t.__class__ = AbsorbedTail
         object.__setattr__(b, "_tail", t)
         taken.add(id(b))
+    for b, p in stems:
+        if getattr(b, "_tail", None) is not None and getattr(b, "_pool", None) is None:
+            p.__class__ = AbsorbedPool
+            object.__setattr__(b, "_pool", p)
     if absorb_tails:
         for t in tails:                           # ReLU + QuantAct behind a residual add: fuse the pair itself
             if type(t) is nn.Sequential and type(t[0]) is nn.ReLU:

@@ -398,3 +398,60 @@ def channel_energy_backward(x, grad_e):
                                                     N.BN_NHWC if nhwc else 0, _stream(x.device))
         N.check(rc, "channel_energy_backward")
     return gx
+
+
+# ----------------------------------------------------------------------------- stem: BN -> ReLU -> [QuantAct] -> MaxPool(3,2,1)
+def bn_pool_supported(x) -> bool:
+    return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] <= 1024
+            and (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def bn_pool_forward(x, weight, bias, running_mean, running_var, eps, fq=None, want_xhat=True):
+    """``max_pool2d(fakequant(relu(BN_eval(x))), 3, 2, 1)`` without ever writing the full-resolution tensor.
+
+    channels_last input only.  Returns (out, idx, xhat): idx is the one-byte argmax code the backward needs,
+    xhat the normalised input at the argmax (None unless ``want_xhat``; only BN parameter gradients use it).
+    """
+    _need(x, "input")
+    if not bn_pool_supported(x):
+        raise RuntimeError("ood_dfq_b200: the fused stem needs a channels_last fp32 tensor with C % 4 == 0")
+    n, c, h, w = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
+    out = torch.empty((n, c, ho, wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    idx = torch.empty((n, c, ho, wo), dtype=torch.uint8, device=x.device, memory_format=torch.channels_last)
+    xhat = torch.empty_like(out) if want_xhat else None
+    flags, k, lo, hi = N.BN_RELU | N.BN_NHWC, 0, None, None
+    if fq is not None:
+        k, lo, hi = fq
+        flags |= N.BN_QUANT
+    with _Timed("bn_pool_fwd_kernel (BN+ReLU+QuantAct+MaxPool stem forward, 4 B/elem in + 1/4 size outputs)",
+                4 * x.numel() + (9 if want_xhat else 5) * out.numel()):
+        rc = N.load().oodfq_bn_pool_forward(x.data_ptr(), out.data_ptr(), idx.data_ptr(), _ptr(xhat), n, c, h, w,
+                                            pw, pb, prm, prv, float(eps), flags, _ptr(lo), _ptr(hi), int(k),
+                                            _stream(x.device))
+        N.check(rc, "bn_pool_forward")
+    return out, idx, xhat
+
+
+def bn_pool_backward(grad_out, idx, xhat, in_shape, weight, bias, running_mean, running_var, eps,
+                     want_param_grads=True):
+    """Backward of ``bn_pool_forward``: (grad_x channels_last, dweight, dbias).  The forward input is not needed."""
+    _need(grad_out, "grad_output")
+    n, c, h, w = in_shape
+    go = grad_out.contiguous(memory_format=torch.channels_last)
+    pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
+    gx = torch.empty((n, c, h, w), dtype=torch.float32, device=grad_out.device, memory_format=torch.channels_last)
+    need = want_param_grads and xhat is not None
+    dwdb = torch.empty(2 * c, dtype=torch.float64, device=grad_out.device) if need else None
+    ws = workspace(grad_out.device).data_ptr() if need else None
+    with _Timed("bn_pool_bwd_kernel (stem backward, 4 B/elem out + 1/4 size inputs)",
+                4 * gx.numel() + (9 if need else 5) * go.numel()):
+        rc = N.load().oodfq_bn_pool_backward(go.data_ptr(), idx.data_ptr(), _ptr(xhat) if need else None, gx.data_ptr(),
+                                             n, c, h, w, pw, pb, prm, prv, float(eps), _ptr(dwdb), ws,
+                                             _stream(grad_out.device))
+        N.check(rc, "bn_pool_backward")
+    if not need:
+        return gx, None, None
+    d = dwdb.float()
+    return gx, d[:c], d[c:]

@@ -379,3 +379,62 @@ def test_channel_energy_matches_reference_expression(shape):
         scale = a.grad.abs().max().item()
         np.testing.assert_allclose(b.grad.cpu().numpy(), a.grad.cpu().numpy(), rtol=1e-4, atol=1e-5 * scale)
         assert b.grad.stride() == b.stride()
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 112, 112), (3, 16, 9, 11), (2, 8, 7, 7), (2, 128, 5, 6), (1, 4, 1, 1)])
+@pytest.mark.parametrize("k", [4, 2, 0])
+def test_fused_stem_matches_unfused_chain(shape, k):
+    """BN -> ReLU -> [QuantAct] -> MaxPool2d(3,2,1) as one kernel vs the fused BN kernel followed by ATen's
+    max_pool2d: same values, same argmax tie-breaking (first maximum), hence the same gradient field."""
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + k)
+    x = (torch.randn(shape, generator=g) * 1.4).to(DEV).contiguous(memory_format=torch.channels_last)
+    w, b, rm, rv = (cu(t) for t in make_bn(shape[1], g))
+    lo, hi = torch.zeros(1, device=DEV), torch.full((1,), 1.9, device=DEV)
+    fq = (k, lo, hi) if k else None
+    y = ops.bn_eval_forward(x, w, b, rm, rv, 1e-5, relu=True, fq=fq).requires_grad_(True)
+    ref = torch.nn.functional.max_pool2d(y, 3, 2, 1)
+    out, idx, xhat = ops.bn_pool_forward(x, w, b, rm, rv, 1e-5, fq=fq)
+    assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(out, ref)
+    go = torch.randn(ref.shape, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    ref.backward(go)
+    gx_ref, dw_ref, db_ref = ops.bn_eval_backward(x, y.grad, w, b, rm, rv, 1e-5, relu=True)
+    gx, dw, db = ops.bn_pool_backward(go, idx, xhat, x.shape, w, b, rm, rv, 1e-5)
+    assert torch.equal(gx, gx_ref)
+    n_red = x.numel() / shape[1]
+    np.testing.assert_allclose(dw.cpu().numpy(), dw_ref.cpu().numpy(), rtol=2e-4, atol=2e-5 * n_red ** 0.5)
+    np.testing.assert_allclose(db.cpu().numpy(), db_ref.cpu().numpy(), rtol=2e-4, atol=2e-5 * n_red ** 0.5)
+    gx2, dw2, _ = ops.bn_pool_backward(go, idx, None, x.shape, w, b, rm, rv, 1e-5, want_param_grads=False)
+    assert dw2 is None and torch.equal(gx2, gx)
+
+
+def test_fused_stem_in_the_imagenet_student():
+    from ood_dfq_b200 import fusion, nets, surgery
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(1)
+    base = nets.resnet18_imagenet(num_classes=10)
+    nets.perturb_bn_stats(base)
+    plain = surgery.quantize_model(base, 4, 4).to(DEV).to(memory_format=torch.channels_last).eval()
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(4, 3, 224, 224, generator=g).to(DEV).contiguous(memory_format=torch.channels_last) for _ in range(3)]
+    with torch.no_grad():
+        for x in xs:
+            plain(x)
+    surgery.freeze_model(plain)
+    fused = copy.deepcopy(plain)
+    fusion.fuse_eval_bn(fused, xs[0][:2])
+    assert sum(type(m) is fusion.AbsorbedPool for m in fused.modules()) == 1
+    a, b = xs[2].clone().requires_grad_(True), xs[2].clone().requires_grad_(True)
+    ya, yb = plain(a), fused(b)
+    assert (ya - yb).abs().max().item() < 0.2 * ya.std().item()
+    ya.square().mean().backward()
+    yb.square().mean().backward()
+    assert torch.nn.functional.cosine_similarity(a.grad.flatten(), b.grad.flatten(), dim=0).item() > 0.98
+    stem_p = dict(plain.named_parameters())["features.0.conv.bn.weight"].grad
+    stem_f = dict(fused.named_parameters())["features.0.conv.bn.weight"].grad
+    assert stem_f is not None and torch.nn.functional.cosine_similarity(stem_p, stem_f, dim=0).item() > 0.98
+    # NCHW input falls back to fused-BN + ordinary pooling
+    with torch.no_grad():
+        yc = fused(xs[2].contiguous())
+    assert torch.allclose(yc, yb.detach(), rtol=1e-3, atol=1e-3)
