@@ -324,19 +324,10 @@ def main_ours(args):
             _ = qat().item()
         e1.record()
         barrier()
-    elif use_graph:
-        # the graph reads its static input buffer: H2D straight into it, then replay (batches are a few MB here)
-        for i in range(args.warmup):
-            qat(host[i % pool]).item()
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            _ = qat(host[i % pool]).item()         # device -> host read of the step's result
-        e1.record()
-        barrier()
     else:
         # double-buffered prefetcher: two fixed device buffers, H2D on a copy stream while the previous step
-        # computes (no allocation inside the loop: allocator traffic made this number jitter by 20 %)
+        # computes (no allocation inside the loop: allocator traffic made this number jitter by 20 %).  Under
+        # CUDA-graph replay the step copies the slot into the graph's static input (device to device) first.
         copy_stream = torch.cuda.Stream(dev)
         slots = [torch.empty_like(resident[0]) for _ in range(2)]
         released = [None, None]                    # event: the step that last read the slot has finished

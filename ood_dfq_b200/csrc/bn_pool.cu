@@ -38,7 +38,126 @@ __device__ __forceinline__ void affine2(const BnParams2& P, int c, float& a, flo
 
 struct PoolGeom {
     int N, C, H, W, Ho, Wo, cols, lanes_r;
+    int seg, nseg;          // forward: output rows per work item, work items per column of windows
 };
+
+// One candidate of the running "first maximum in window scan order" search, per channel.
+//   key   what max_pool2d compares: the fake-quantised value's integer code when the dequantisation table is
+//         strictly increasing (the code orders exactly like the value, and skips the table), else the value
+//   meta  column of the candidate inside its window row (0..2) | 128 if the ReLU was active there
+//   x     the raw input at the candidate (only kept when the normalised input is wanted)
+struct Cand {
+    float key[4];
+    int meta[4];
+    float x[4];
+};
+
+// ATen's max_pool2d rule: a later element replaces the running maximum when it is greater or NaN
+__device__ __forceinline__ bool takes_over(float v, float best) { return v > best || v != v; }
+
+template <bool QUANT, bool STRICT, bool XHAT>
+__device__ __forceinline__ void scan_pixel(Cand& r, const float4 v, const int j, const float (&a)[4], const float (&b)[4],
+                                           const QParams& qp, const float* lut, const int qh, const int qmask) {
+    const float xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float z = max_nan(fmaf(xs[c], a[c], b[c]), 0.0f);       // BN affine, ReLU (NaN stays NaN)
+        float key = z;
+        if (QUANT) {
+            key = code_of<false>(z, qp);
+            if (!STRICT) { const float y = lut[lut_index(key, qh, qmask)]; key = (key != key) ? key : y; }
+        }
+        if (takes_over(key, r.key[c])) {
+            r.key[c] = key;
+            r.meta[c] = j | (z > 0.0f ? 128 : 0);
+            if (XHAT) r.x[c] = xs[c];
+        }
+    }
+}
+
+__device__ __forceinline__ void reset(Cand& r) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { r.key[c] = -INFINITY; r.meta[c] = 0; r.x[c] = 0.0f; }
+}
+
+// best candidate of input row h inside the window columns 2*wo-1 .. 2*wo+1 (three independent loads first)
+template <bool QUANT, bool STRICT, bool XHAT>
+__device__ __forceinline__ void scan_row(Cand& r, const float4* __restrict__ x4, const PoolGeom& G, const long long n,
+                                         const int h, const int wo, const int col, const float (&a)[4],
+                                         const float (&b)[4], const QParams& qp, const float* lut, const int qh,
+                                         const int qmask) {
+    reset(r);
+    const float4* row = x4 + ((n * G.H + h) * G.W) * G.cols + col;
+    const int w0 = 2 * wo - 1;
+    float4 v[3];
+    bool ok[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        ok[j] = (w0 + j >= 0) && (w0 + j < G.W);
+        if (ok[j]) v[j] = __ldg(row + (long long)(w0 + j) * G.cols);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        if (ok[j]) scan_pixel<QUANT, STRICT, XHAT>(r, v[j], j, a, b, qp, lut, qh, qmask);
+}
+
+// A lane owns one column of windows (n, wo) and walks down a segment of output rows: window ho covers input
+// rows 2ho-1, 2ho, 2ho+1, and the candidate of row 2ho+1 is carried over as row 2(ho+1)-1 of the next window,
+// so every step evaluates 6 new pixels instead of 9.
+template <bool QUANT, bool STRICT, bool XHAT>
+__device__ __forceinline__ void pool_fwd_body(const float* __restrict__ x, float* __restrict__ out,
+                                              uint8_t* __restrict__ idx, float* __restrict__ xhat, const PoolGeom& G,
+                                              const BnParams2& P, const QParams& qp, const float* lut, const int qh,
+                                              const int qmask) {
+    if ((int)threadIdx.x >= G.lanes_r * G.cols) return;
+    const int col = threadIdx.x % G.cols, rsub = threadIdx.x / G.cols;
+    float a[4], b[4], rm[4], inv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { affine2(P, 4 * col + j, a[j], b[j], inv[j]); rm[j] = __ldg(P.rm + 4 * col + j); }
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const long long columns = (long long)G.N * G.Wo;
+    const long long groups = (columns + G.lanes_r - 1) / G.lanes_r;
+    const long long items = groups * G.nseg;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long u = (item / G.nseg) * G.lanes_r + rsub;
+        if (u >= columns) continue;
+        const int sidx = (int)(item % G.nseg);
+        const int wo = (int)(u % G.Wo);
+        const long long n = u / G.Wo;
+        const int ho_begin = sidx * G.seg, ho_end = min(G.Ho, ho_begin + G.seg);
+        Cand carried, r1, r2;
+        if (ho_begin > 0) scan_row<QUANT, STRICT, XHAT>(carried, x4, G, n, 2 * ho_begin - 1, wo, col, a, b, qp, lut, qh, qmask);
+        else reset(carried);
+        for (int ho = ho_begin; ho < ho_end; ++ho) {
+            scan_row<QUANT, STRICT, XHAT>(r1, x4, G, n, 2 * ho, wo, col, a, b, qp, lut, qh, qmask);
+            if (2 * ho + 1 < G.H) scan_row<QUANT, STRICT, XHAT>(r2, x4, G, n, 2 * ho + 1, wo, col, a, b, qp, lut, qh, qmask);
+            else reset(r2);
+            float y[4], xh[4];
+            unsigned char code[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                // rows in scan order; the window-local index is 3*row + column
+                float key = carried.key[c], bx = carried.x[c];
+                int meta = carried.meta[c];
+                if (takes_over(r1.key[c], key)) { key = r1.key[c]; meta = r1.meta[c] + 3; bx = r1.x[c]; }
+                if (takes_over(r2.key[c], key)) { key = r2.key[c]; meta = r2.meta[c] + 6; bx = r2.x[c]; }
+                if (QUANT && STRICT) {
+                    const float v = lut[lut_index(key, qh, qmask)];
+                    y[c] = (key != key) ? key : v;
+                } else {
+                    y[c] = key;
+                }
+                code[c] = (unsigned char)meta;
+                xh[c] = (bx - rm[c]) * inv[c];
+            }
+            const long long o = ((n * G.Ho + ho) * G.Wo + wo) * G.cols + col;
+            st_out(reinterpret_cast<float4*>(out) + o, make_float4(y[0], y[1], y[2], y[3]));
+            reinterpret_cast<uchar4*>(idx)[o] = make_uchar4(code[0], code[1], code[2], code[3]);
+            if (XHAT) st_out(reinterpret_cast<float4*>(xhat) + o, make_float4(xh[0], xh[1], xh[2], xh[3]));
+            carried = r2;
+        }
+    }
+}
 
 template <bool QUANT, bool XHAT>
 __global__ void __launch_bounds__(kBThreads)
@@ -46,64 +165,26 @@ bn_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, uint8_t
                    float* __restrict__ xhat, const PoolGeom G, const BnParams2 P,
                    const float* __restrict__ fq_lo, const float* __restrict__ fq_hi, int fq_k) {
     __shared__ float lut[QUANT ? kLutMax : 1];
-    QParams qp;
+    QParams qp = given_qparams(1.0f, 0.0f, 1);
     const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
     if (QUANT) {
         qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
         build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
         __syncthreads();
-    }
-    if ((int)threadIdx.x >= G.lanes_r * G.cols) return;
-    const int col = threadIdx.x % G.cols, rsub = threadIdx.x / G.cols;
-    float a[4], b[4], rm[4], inv[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { affine2(P, 4 * col + j, a[j], b[j], inv[j]); rm[j] = __ldg(P.rm + 4 * col + j); }
-    const long long outs = (long long)G.N * G.Ho * G.Wo;
-    const float4* x4 = reinterpret_cast<const float4*>(x);
-    for (long long o = (long long)blockIdx.x * G.lanes_r + rsub; o < outs; o += (long long)gridDim.x * G.lanes_r) {
-        const int wo = (int)(o % G.Wo);
-        const int ho = (int)((o / G.Wo) % G.Ho);
-        const long long n = o / ((long long)G.Wo * G.Ho);
-        float4 v[9];
-        bool ok[9];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int h = 2 * ho - 1 + i, w = 2 * wo - 1 + j;
-                ok[i * 3 + j] = (h >= 0) && (h < G.H) && (w >= 0) && (w < G.W);
-                if (ok[i * 3 + j]) v[i * 3 + j] = __ldg(x4 + ((n * G.H + h) * G.W + w) * G.cols + col);
-            }
-        }
-        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, bx[4] = {0.f, 0.f, 0.f, 0.f};
-        int code[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int li = 0; li < 9; ++li) {
-            if (ok[li]) {
-                const float xs[4] = {v[li].x, v[li].y, v[li].z, v[li].w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float z = fmaf(xs[j], a[j], b[j]);
-                    z = (z != z) ? z : fmaxf(z, 0.0f);
-                    const float y = QUANT ? fake_quant_lut(z, qp, lut, qh, qmask) : z;
-                    if (y > best[j] || y != y) {          // first maximum in scan order; NaN wins (as max_pool2d)
-                        best[j] = y;
-                        bx[j] = xs[j];
-                        code[j] = li | (z > 0.0f ? 128 : 0);
-                    }
-                }
-            }
-        }
-        st_out(reinterpret_cast<float4*>(out) + o * G.cols + col, make_float4(best[0], best[1], best[2], best[3]));
-        reinterpret_cast<uchar4*>(idx)[o * G.cols + col] =
-            make_uchar4((unsigned char)code[0], (unsigned char)code[1], (unsigned char)code[2], (unsigned char)code[3]);
-        if (XHAT)
-            st_out(reinterpret_cast<float4*>(xhat) + o * G.cols + col,
-                   make_float4((bx[0] - rm[0]) * inv[0], (bx[1] - rm[1]) * inv[1], (bx[2] - rm[2]) * inv[2],
-                               (bx[3] - rm[3]) * inv[3]));
+        // the integer code orders like the dequantised value iff the table is strictly increasing (it is
+        // whenever zp is small, i.e. always for post-ReLU ranges; a huge |lo|/range ratio can merge entries)
+        bool inc = true;
+        for (int j = threadIdx.x; j + 1 < (1 << fq_k); j += kBThreads) inc = inc && (lut[j] < lut[j + 1]);
+        if (__syncthreads_and(inc)) pool_fwd_body<QUANT, true, XHAT>(x, out, idx, xhat, G, P, qp, lut, qh, qmask);
+        else pool_fwd_body<QUANT, false, XHAT>(x, out, idx, xhat, G, P, qp, lut, qh, qmask);
+    } else {
+        pool_fwd_body<false, false, XHAT>(x, out, idx, xhat, G, P, qp, lut, qh, qmask);
     }
 }
 
+// A thread owns one 2x2 block of input pixels (rows 2m, 2m+1; columns 2n, 2n+1).  The only windows that cover it
+// are (m,n), (m,n+1), (m+1,n), (m+1,n+1): four loads of (grad, argmax code) serve four stores, and the window
+// whose centre the block holds -- (m,n), centre (2m,2n) -- is this thread's share of dW / dB.
 template <bool REDUCE>
 __global__ void __launch_bounds__(kBThreads)
 bn_pool_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ idx, const float* __restrict__ xhat,
@@ -116,46 +197,69 @@ bn_pool_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ i
 #pragma unroll
         for (int j = 0; j < 4; ++j) { float b, inv; affine2(P, 4 * col + j, a[j], b, inv); }
     }
-    const long long pixels = (long long)G.N * G.H * G.W;
+    const long long blocks = (long long)G.N * G.Ho * G.Wo;
     const float4* g4 = reinterpret_cast<const float4*>(gout);
     const uchar4* i4 = reinterpret_cast<const uchar4*>(idx);
+    float4* gx4 = reinterpret_cast<float4*>(gx);
     if (active) {
-        for (long long p = (long long)blockIdx.x * G.lanes_r + rsub; p < pixels; p += (long long)gridDim.x * G.lanes_r) {
-            const int w = (int)(p % G.W);
-            const int h = (int)((p / G.W) % G.H);
-            const long long n = p / ((long long)G.W * G.H);
-            // windows covering row h: ho in [ceil((h-1)/2), floor((h+1)/2)], same for columns
-            const int ho0 = h >> 1, ho1 = (h + 1) >> 1, wo0 = w >> 1, wo1 = (w + 1) >> 1;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (long long o = (long long)blockIdx.x * G.lanes_r + rsub; o < blocks; o += (long long)gridDim.x * G.lanes_r) {
+            const int n2 = (int)(o % G.Wo);
+            const int m = (int)((o / G.Wo) % G.Ho);
+            const long long n = o / ((long long)G.Wo * G.Ho);
+            const bool right = n2 + 1 < G.Wo, below = m + 1 < G.Ho;
+            // windows in the order a pixel's contributions are summed: (m,n) (m,n+1) (m+1,n) (m+1,n+1)
+            const long long base = o * G.cols + col;
+            const long long off[4] = {0, (long long)G.cols, (long long)G.Wo * G.cols, ((long long)G.Wo + 1) * G.cols};
+            const bool have[4] = {true, right, below, right && below};
+            float gs[4][4];
+            unsigned char cs[4][4];
 #pragma unroll
-            for (int ih = 0; ih < 2; ++ih) {
-                const int ho = ih ? ho1 : ho0;
-                if ((ih && ho1 == ho0) || ho >= G.Ho) continue;
-#pragma unroll
-                for (int iw = 0; iw < 2; ++iw) {
-                    const int wo = iw ? wo1 : wo0;
-                    if ((iw && wo1 == wo0) || wo >= G.Wo) continue;
-                    const int li = (h - 2 * ho + 1) * 3 + (w - 2 * wo + 1);
-                    const long long o = ((n * G.Ho + ho) * G.Wo + wo) * G.cols + col;
-                    const uchar4 c = __ldg(i4 + o);
-                    const float4 g = __ldg(g4 + o);
-                    const unsigned char cs[4] = {c.x, c.y, c.z, c.w};
-                    const float gs[4] = {g.x, g.y, g.z, g.w};
-                    float xh[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (REDUCE && li == 4) {                      // this thread sits on the window's centre
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(xhat) + o);
-                        xh[0] = t.x; xh[1] = t.y; xh[2] = t.z; xh[3] = t.w;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const bool on = (cs[j] & 128) != 0;
-                        if (on && (cs[j] & 15) == li) acc[j] += gs[j];
-                        if (REDUCE && li == 4 && on) { sb[j] += gs[j]; sw[j] = fmaf(gs[j], xh[j], sw[j]); }
-                    }
-                }
+            for (int k = 0; k < 4; ++k) {
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                uchar4 c = make_uchar4(0, 0, 0, 0);
+                if (have[k]) { g = __ldg(g4 + base + off[k]); c = __ldg(i4 + base + off[k]); }
+                gs[k][0] = g.x; gs[k][1] = g.y; gs[k][2] = g.z; gs[k][3] = g.w;
+                cs[k][0] = c.x; cs[k][1] = c.y; cs[k][2] = c.z; cs[k][3] = c.w;
             }
-            st_out(reinterpret_cast<float4*>(gx) + p * G.cols + col,
-                   make_float4(acc[0] * a[0], acc[1] * a[1], acc[2] * a[2], acc[3] * a[3]));
+            float xh[4] = {0.f, 0.f, 0.f, 0.f};
+            if (REDUCE) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(xhat) + base);
+                xh[0] = t.x; xh[1] = t.y; xh[2] = t.z; xh[3] = t.w;
+            }
+            float p00[4], p01[4], p10[4], p11[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // a code with the ReLU bit clear (< 128) never matches: the gradient stops at an inactive ReLU
+                // window-local index of each pixel of the block inside each window:
+                //   (2m,2n): centre 4 of W0      (2m,2n+1): 5 of W0, 3 of W1
+                //   (2m+1,2n): 7 of W0, 1 of W2  (2m+1,2n+1): 8 of W0, 6 of W1, 2 of W2, 0 of W3
+                const int c0 = cs[0][j], c1 = cs[1][j], c2 = cs[2][j], c3 = cs[3][j];
+                p00[j] = (c0 == (128 | 4)) ? gs[0][j] : 0.f;
+                float t = 0.f;
+                if (c0 == (128 | 5)) t += gs[0][j];
+                if (c1 == (128 | 3)) t += gs[1][j];
+                p01[j] = t;
+                t = 0.f;
+                if (c0 == (128 | 7)) t += gs[0][j];
+                if (c2 == (128 | 1)) t += gs[2][j];
+                p10[j] = t;
+                t = 0.f;
+                if (c0 == (128 | 8)) t += gs[0][j];
+                if (c1 == (128 | 6)) t += gs[1][j];
+                if (c2 == (128 | 2)) t += gs[2][j];
+                if (c3 == (128 | 0)) t += gs[3][j];
+                p11[j] = t;
+                if (REDUCE && (c0 & 128)) { sb[j] += gs[0][j]; sw[j] = fmaf(gs[0][j], xh[j], sw[j]); }
+            }
+            const int h = 2 * m, w = 2 * n2;
+            float4* dst = gx4 + ((n * G.H + h) * G.W + w) * G.cols + col;
+            st_out(dst, make_float4(p00[0] * a[0], p00[1] * a[1], p00[2] * a[2], p00[3] * a[3]));
+            if (w + 1 < G.W) st_out(dst + G.cols, make_float4(p01[0] * a[0], p01[1] * a[1], p01[2] * a[2], p01[3] * a[3]));
+            if (h + 1 < G.H) {
+                dst += (long long)G.W * G.cols;
+                st_out(dst, make_float4(p10[0] * a[0], p10[1] * a[1], p10[2] * a[2], p10[3] * a[3]));
+                if (w + 1 < G.W) st_out(dst + G.cols, make_float4(p11[0] * a[0], p11[1] * a[1], p11[2] * a[2], p11[3] * a[3]));
+            }
         }
     }
     if (REDUCE) {

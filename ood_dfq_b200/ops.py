@@ -403,7 +403,7 @@ def channel_energy_backward(x, grad_e):
 # ----------------------------------------------------------------------------- stem: BN -> ReLU -> [QuantAct] -> MaxPool(3,2,1)
 def bn_pool_supported(x) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] <= 1024
-            and (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last))
+            and x.is_contiguous(memory_format=torch.channels_last))
 
 
 def bn_pool_forward(x, weight, bias, running_mean, running_var, eps, fq=None, want_xhat=True):

@@ -124,10 +124,16 @@ class QATStep:
 
     def __init__(self, student, teacher, lr=1e-6, momentum=0.9, weight_decay=1e-4, temperature=20.0,
                  alpha=20.0, lam=1000.0, eps=0.01, unit_types: tuple = (), group=None, perturb=True,
-                 fused_attention=None):
+                 fused_attention=None, prune_backward=True):
         self.student, self.teacher = student, teacher
         self.T, self.alpha, self.lam, self.eps = temperature, alpha, lam, eps
         self.group, self.perturb = group, perturb
+        # The final backward only has to deliver the student's parameter gradients.  ``loss.backward()`` as the
+        # reference writes it (trainer_direct.py:350-356) also walks the teacher's graph and the student's stem
+        # dgrad down to ``images.grad``, which nothing reads after the sign perturbation; with
+        # ``backward(inputs=params)`` autograd prunes those branches.  The update is bit-identical
+        # (tests/test_dist_gloo.py, tests/test_gpu_fused.py); ``prune_backward=False`` restores the full sweep.
+        self.prune_backward = prune_backward
         for p in teacher.parameters():
             p.requires_grad_(False)
         self.grads = FlatGrads(student.parameters())
@@ -184,7 +190,10 @@ class QATStep:
             raise RuntimeError("QATStep: parameter gradients no longer alias the flat buffer (the model was moved or "
                                "re-formatted after the step was built); create the step after model.to(...)")
         self.grads.zero()
-        total.backward()
+        if self.prune_backward:
+            total.backward(inputs=self.grads.params)
+        else:
+            total.backward()
         return total.detach()
 
 
