@@ -248,7 +248,9 @@ def main_ours(args):
             return dstep()
     else:
         qat = make_step(args.workload, teacher, student, qm)      # after .to(): gradients alias one flat buffer
-    use_graph = args.graph == "on" or (args.graph == "auto" and shape[1] <= 64)   # launch-bound small images
+    # Every workload is replayed as one CUDA graph: the small-image configs are launch-bound outright, and even
+    # the 224x224 step loses ~9 % to host gaps in its 7x7 / 14x14 stages (profiles/r1_bench_n1_graph.json)
+    use_graph = args.graph in ("on", "auto")
     if world > 1:
         ddist.reduce_minmax(student)
         for m in student.modules():               # ranges stay frozen from here on
@@ -452,7 +454,7 @@ def main():
     ap.add_argument("--nchw", action="store_true", help="keep NCHW tensors (default: channels_last memory format)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
-                    help="replay the whole iteration as a CUDA graph (auto: the launch-bound small-image workloads)")
+                    help="replay the whole iteration as a CUDA graph (auto = on; off: eager launches)")
     args = ap.parse_args()
     if args.conf:
         args.workload = workload_from_conf(args.conf)

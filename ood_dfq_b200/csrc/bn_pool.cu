@@ -67,11 +67,10 @@ __device__ __forceinline__ void scan_pixel(Cand& r, const float4 v, const int j,
             key = code_of<false>(z, qp);
             if (!STRICT) { const float y = lut[lut_index(key, qh, qmask)]; key = (key != key) ? key : y; }
         }
-        if (takes_over(key, r.key[c])) {
-            r.key[c] = key;
-            r.meta[c] = j | (z > 0.0f ? 128 : 0);
-            if (XHAT) r.x[c] = xs[c];
-        }
+        const bool t = takes_over(key, r.key[c]);
+        r.key[c] = t ? key : r.key[c];
+        r.meta[c] = t ? (z > 0.0f ? (j | 128) : j) : r.meta[c];
+        if (XHAT) r.x[c] = t ? xs[c] : r.x[c];
     }
 }
 
@@ -80,30 +79,33 @@ __device__ __forceinline__ void reset(Cand& r) {
     for (int c = 0; c < 4; ++c) { r.key[c] = -INFINITY; r.meta[c] = 0; r.x[c] = 0.0f; }
 }
 
-// best candidate of input row h inside the window columns 2*wo-1 .. 2*wo+1 (three independent loads first)
-template <bool QUANT, bool STRICT, bool XHAT>
-__device__ __forceinline__ void scan_row(Cand& r, const float4* __restrict__ x4, const PoolGeom& G, const long long n,
-                                         const int h, const int wo, const int col, const float (&a)[4],
-                                         const float (&b)[4], const QParams& qp, const float* lut, const int qh,
-                                         const int qmask) {
-    reset(r);
-    const float4* row = x4 + ((n * G.H + h) * G.W) * G.cols + col;
-    const int w0 = 2 * wo - 1;
-    float4 v[3];
-    bool ok[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        ok[j] = (w0 + j >= 0) && (w0 + j < G.W);
-        if (ok[j]) v[j] = __ldg(row + (long long)(w0 + j) * G.cols);
-    }
+// the three pixels of one input row inside the window columns 2*wo-1 .. 2*wo+1; `row` points at column 2*wo-1
+// (this thread's four channels), `ok` says which of the three columns exist
+struct RowPixels { float4 v[3]; };
+
+__device__ __forceinline__ void load_row(RowPixels& p, const float4* __restrict__ row, const int cols, const bool (&ok)[3],
+                                         const bool row_ok) {
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-        if (ok[j]) scan_pixel<QUANT, STRICT, XHAT>(r, v[j], j, a, b, qp, lut, qh, qmask);
+        if (row_ok && ok[j]) p.v[j] = __ldg(row + j * cols);
+}
+
+// best candidate of a loaded row
+template <bool QUANT, bool STRICT, bool XHAT>
+__device__ __forceinline__ void scan_row(Cand& r, const RowPixels& p, const bool (&ok)[3], const bool row_ok,
+                                         const float (&a)[4], const float (&b)[4], const QParams& qp, const float* lut,
+                                         const int qh, const int qmask) {
+    reset(r);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        if (row_ok && ok[j]) scan_pixel<QUANT, STRICT, XHAT>(r, p.v[j], j, a, b, qp, lut, qh, qmask);
 }
 
 // A lane owns one column of windows (n, wo) and walks down a segment of output rows: window ho covers input
 // rows 2ho-1, 2ho, 2ho+1, and the candidate of row 2ho+1 is carried over as row 2(ho+1)-1 of the next window,
-// so every step evaluates 6 new pixels instead of 9.
+// so every step evaluates 6 new pixels instead of 9.  The six loads of step ho+1 are issued before step ho is
+// evaluated (register double buffer): at 2-3 resident CTAs per SM the kernel is otherwise latency-bound
+// (ncu: 24 % warps active, long-scoreboard stalls; profiles/r1_bn_pool_kernels.txt).
 template <bool QUANT, bool STRICT, bool XHAT>
 __device__ __forceinline__ void pool_fwd_body(const float* __restrict__ x, float* __restrict__ out,
                                               uint8_t* __restrict__ idx, float* __restrict__ xhat, const PoolGeom& G,
@@ -118,6 +120,8 @@ __device__ __forceinline__ void pool_fwd_body(const float* __restrict__ x, float
     const long long columns = (long long)G.N * G.Wo;
     const long long groups = (columns + G.lanes_r - 1) / G.lanes_r;
     const long long items = groups * G.nseg;
+    const long long row_stride = (long long)G.W * G.cols;            // float4 units
+    const int ostride = G.Wo * G.cols;
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         const long long u = (item / G.nseg) * G.lanes_r + rsub;
         if (u >= columns) continue;
@@ -125,13 +129,23 @@ __device__ __forceinline__ void pool_fwd_body(const float* __restrict__ x, float
         const int wo = (int)(u % G.Wo);
         const long long n = u / G.Wo;
         const int ho_begin = sidx * G.seg, ho_end = min(G.Ho, ho_begin + G.seg);
+        const bool ok[3] = {wo > 0, true, 2 * wo + 1 < G.W};
+        // input row 2*ho_begin - 1, column 2*wo - 1 (either may lie outside the image: never dereferenced then)
+        const float4* row = x4 + (n * G.H + (2 * ho_begin - 1)) * row_stride + (long long)(2 * wo - 1) * G.cols + col;
+        long long o = ((n * G.Ho + ho_begin) * G.Wo + wo) * G.cols + col;
         Cand carried, r1, r2;
-        if (ho_begin > 0) scan_row<QUANT, STRICT, XHAT>(carried, x4, G, n, 2 * ho_begin - 1, wo, col, a, b, qp, lut, qh, qmask);
-        else reset(carried);
-        for (int ho = ho_begin; ho < ho_end; ++ho) {
-            scan_row<QUANT, STRICT, XHAT>(r1, x4, G, n, 2 * ho, wo, col, a, b, qp, lut, qh, qmask);
-            if (2 * ho + 1 < G.H) scan_row<QUANT, STRICT, XHAT>(r2, x4, G, n, 2 * ho + 1, wo, col, a, b, qp, lut, qh, qmask);
-            else reset(r2);
+        RowPixels p0, p1, p2, q1, q2;
+        load_row(p0, row, G.cols, ok, ho_begin > 0);
+        load_row(p1, row + row_stride, G.cols, ok, true);
+        load_row(p2, row + 2 * row_stride, G.cols, ok, 2 * ho_begin + 1 < G.H);
+        scan_row<QUANT, STRICT, XHAT>(carried, p0, ok, ho_begin > 0, a, b, qp, lut, qh, qmask);
+        for (int ho = ho_begin; ho < ho_end; ++ho, o += ostride) {
+            row += 2 * row_stride;                       // now at input row 2*ho + 1
+            const bool more = ho + 1 < ho_end;           // rows 2ho+2 (always inside the image then) and 2ho+3
+            load_row(q1, row + row_stride, G.cols, ok, more);
+            load_row(q2, row + 2 * row_stride, G.cols, ok, more && 2 * ho + 3 < G.H);
+            scan_row<QUANT, STRICT, XHAT>(r1, p1, ok, true, a, b, qp, lut, qh, qmask);
+            scan_row<QUANT, STRICT, XHAT>(r2, p2, ok, 2 * ho + 1 < G.H, a, b, qp, lut, qh, qmask);
             float y[4], xh[4];
             unsigned char code[4];
 #pragma unroll
@@ -139,8 +153,10 @@ __device__ __forceinline__ void pool_fwd_body(const float* __restrict__ x, float
                 // rows in scan order; the window-local index is 3*row + column
                 float key = carried.key[c], bx = carried.x[c];
                 int meta = carried.meta[c];
-                if (takes_over(r1.key[c], key)) { key = r1.key[c]; meta = r1.meta[c] + 3; bx = r1.x[c]; }
-                if (takes_over(r2.key[c], key)) { key = r2.key[c]; meta = r2.meta[c] + 6; bx = r2.x[c]; }
+                const bool t1 = takes_over(r1.key[c], key);
+                key = t1 ? r1.key[c] : key; meta = t1 ? r1.meta[c] + 3 : meta; bx = t1 ? r1.x[c] : bx;
+                const bool t2 = takes_over(r2.key[c], key);
+                key = t2 ? r2.key[c] : key; meta = t2 ? r2.meta[c] + 6 : meta; bx = t2 ? r2.x[c] : bx;
                 if (QUANT && STRICT) {
                     const float v = lut[lut_index(key, qh, qmask)];
                     y[c] = (key != key) ? key : v;
@@ -150,17 +166,18 @@ __device__ __forceinline__ void pool_fwd_body(const float* __restrict__ x, float
                 code[c] = (unsigned char)meta;
                 xh[c] = (bx - rm[c]) * inv[c];
             }
-            const long long o = ((n * G.Ho + ho) * G.Wo + wo) * G.cols + col;
             st_out(reinterpret_cast<float4*>(out) + o, make_float4(y[0], y[1], y[2], y[3]));
             reinterpret_cast<uchar4*>(idx)[o] = make_uchar4(code[0], code[1], code[2], code[3]);
             if (XHAT) st_out(reinterpret_cast<float4*>(xhat) + o, make_float4(xh[0], xh[1], xh[2], xh[3]));
             carried = r2;
+            p1 = q1;
+            p2 = q2;
         }
     }
 }
 
 template <bool QUANT, bool XHAT>
-__global__ void __launch_bounds__(kBThreads)
+__global__ void __launch_bounds__(kBThreads, 2)
 bn_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, uint8_t* __restrict__ idx,
                    float* __restrict__ xhat, const PoolGeom G, const BnParams2 P,
                    const float* __restrict__ fq_lo, const float* __restrict__ fq_hi, int fq_k) {
@@ -292,6 +309,8 @@ static int make_pool_geom(int N, int C, int H, int W, PoolGeom& G) {
     G.Wo = (W - 1) / 2 + 1;
     G.cols = C / 4;
     G.lanes_r = kBThreads / G.cols;
+    G.seg = G.Ho;
+    G.nseg = 1;
     return OODFQ_OK;
 }
 
@@ -315,9 +334,20 @@ extern "C" int oodfq_bn_pool_forward(const float* x, float* out, uint8_t* idx, f
         return fail(OODFQ_EINVAL, "bn_pool_forward: needs C %% 4 == 0, C <= 1024 and aligned buffers");
     cudaStream_t st = (cudaStream_t)stream;
     const BnParams2 P{weight, bias, running_mean, running_var, eps};
-    static const int per_sm = resident_ctas(bn_pool_fwd_kernel<true, true>, kBThreads);
-    const long long outs = (long long)N * G.Ho * G.Wo;
-    long long want = (outs + G.lanes_r - 1) / G.lanes_r, cap = (long long)kNumSM * per_sm;
+    static const int occ[4] = {resident_ctas(bn_pool_fwd_kernel<false, false>, kBThreads), resident_ctas(bn_pool_fwd_kernel<false, true>, kBThreads),
+                               resident_ctas(bn_pool_fwd_kernel<true, false>, kBThreads), resident_ctas(bn_pool_fwd_kernel<true, true>, kBThreads)};
+    const int per_sm = occ[(quant ? 2 : 0) + (xhat ? 1 : 0)];
+    // work item = lanes_r window columns x one segment of output rows.  Each segment re-reads one input row, so
+    // segments stay >= 8 rows; within that, aim for ~6 items per resident CTA so the last wave is short.
+    const long long cap = (long long)kNumSM * per_sm;
+    const long long groups = ((long long)N * G.Wo + G.lanes_r - 1) / G.lanes_r;
+    long long nseg = (6 * cap + groups - 1) / groups;
+    const long long max_seg = (G.Ho + 7) / 8;
+    if (nseg > max_seg) nseg = max_seg;
+    if (nseg < 1) nseg = 1;
+    G.seg = (int)((G.Ho + nseg - 1) / nseg);
+    G.nseg = (G.Ho + G.seg - 1) / G.seg;
+    const long long want = groups * G.nseg;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     if (quant && xhat) bn_pool_fwd_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, out, idx, xhat, G, P, fq_lo, fq_hi, fq_k);
     else if (quant) bn_pool_fwd_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, out, idx, xhat, G, P, fq_lo, fq_hi, fq_k);

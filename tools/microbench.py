@@ -137,6 +137,19 @@ def main():
                     report(f"bnbx_{tag}", shape, 8 * n, *timer(lambda: ops.bn_eval_backward(xf, gf, w, b, rm, rv, 1e-5, relu=False, want_param_grads=False)))
                     del gf
                 del xf
+        if "pool" in only and shape[2] >= 56:
+            w, b = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.3
+            rm, rv = torch.randn(c, device="cuda") * 0.1, torch.rand(c, device="cuda") + 0.5
+            xf = torch.randn(shape, device="cuda").contiguous(memory_format=torch.channels_last)
+            out, idx, xhat = ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, fq=(4, lo, hi))
+            no = out.numel()
+            report("pool_fqx", shape, 4 * n + 9 * no, *timer(lambda: ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, fq=(4, lo, hi))))
+            report("pool_fq", shape, 4 * n + 5 * no, *timer(lambda: ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, fq=(4, lo, hi), want_xhat=False)))
+            report("pool_plain", shape, 4 * n + 5 * no, *timer(lambda: ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, want_xhat=False)))
+            go = torch.randn_like(out)
+            report("poolbw_p", shape, 4 * n + 9 * no, *timer(lambda: ops.bn_pool_backward(go, idx, xhat, xf.shape, w, b, rm, rv, 1e-5)))
+            report("poolbw_x", shape, 4 * n + 5 * no, *timer(lambda: ops.bn_pool_backward(go, idx, None, xf.shape, w, b, rm, rv, 1e-5, want_param_grads=False)))
+            del xf, out, idx, xhat, go
         del x
         torch.cuda.empty_cache()
     if "weights" in only:
