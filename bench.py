@@ -236,6 +236,10 @@ def main_ours(args):
         from ood_dfq_b200 import fusion
         fusion.fuse_eval_bn(student, resident[0][:2])
         fusion.fuse_eval_bn(teacher, resident[0][:2])
+        if not args.no_tail_fuse:
+            # ... and the tail of every residual unit (BN + add + ReLU + QuantAct + feature tap) as one kernel
+            fusion.fuse_residual_tails(student, resident[0][:2])
+            fusion.fuse_residual_tails(teacher, resident[0][:2])
     kind = KINDS.get(args.workload, "qat")
     if kind == "distill":
         # the "student" IS the quantised teacher here; the optimised variable is the image batch itself
@@ -389,6 +393,7 @@ def main_ours(args):
                        "l2": "inputs larger than L2: every step streams a 154 MB batch and GBs of activations",
                        "convolutions": "cuDNN (TF32 default, as the reference)",
                        "bn_relu_quant_fusion": not args.no_fuse,
+                       "residual_tail_fusion": not (args.no_fuse or args.no_tail_fuse),
                        "memory_format": "channels_last" if channels_last else "NCHW (as the reference)",
                        "cuda_graph": use_graph},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
@@ -451,6 +456,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="keep BatchNorm / ReLU / QuantAct as separate modules")
+    ap.add_argument("--no-tail-fuse", action="store_true", help="keep the residual add and the ReLU + QuantAct behind it separate")
     ap.add_argument("--nchw", action="store_true", help="keep NCHW tensors (default: channels_last memory format)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",

@@ -204,6 +204,29 @@ int oodfq_bn_pool_backward(const float* grad_out, const uint8_t* idx, const floa
                            const float* running_mean, const float* running_var, float eps,
                            double* dwdb, void* workspace, oodfq_stream_t stream);
 
+/* ---- residual-unit tail: BN1(x1) + identity -> ReLU -> [QuantAct], with the feature-alignment energy -------
+ * replaces: the last BatchNorm of a residual body, the residual add of the unit's forward (pytorchcv ResUnit /
+ *           reference models.py:40-47 `out += self.shortcut(x); out = self.relu2(out)`), the
+ *           Sequential(ReLU, QuantAct) quantize_model puts behind it (main_direct.py:464-465) and the
+ *           channel-attention reduction the trainer hooks onto the body output (trainer_direct.py:432-440,
+ *           :382-383)
+ * channels_last only (flags must contain OODFQ_BN_NHWC, optionally OODFQ_BN_QUANT): x1, r, y, grads [N,H,W,C].
+ * rv2 == NULL: the identity is r itself; otherwise identity = BN2(r) with (w2, b2, rm2, rv2, eps2).
+ * energy (nullable) [N, C] = mean_hw BN1(x1)^2; scratch: oodfq_res_tail_scratch_floats(N, C) floats.
+ * backward: grad_energy nullable; dwdb nullable, else [2*Ct] doubles with Ct = C (or 2C with BN2):
+ *           dW of BN1 (then BN2), followed by dB of BN1 (then BN2). */
+size_t oodfq_res_tail_scratch_floats(int N, int C);
+int oodfq_res_tail_forward(const float* x1, const float* r, float* y, float* energy, float* scratch, int N, int C,
+                           long long HW, const float* w1, const float* b1, const float* rm1, const float* rv1,
+                           float eps1, const float* w2, const float* b2, const float* rm2, const float* rv2,
+                           float eps2, int flags, const float* fq_lo, const float* fq_hi, int fq_k,
+                           oodfq_stream_t stream);
+int oodfq_res_tail_backward(const float* grad_y, const float* grad_energy, const float* x1, const float* r,
+                            float* grad_x1, float* grad_r, int N, int C, long long HW, const float* w1,
+                            const float* b1, const float* rm1, const float* rv1, float eps1, const float* w2,
+                            const float* b2, const float* rm2, const float* rv2, float eps2, int flags,
+                            double* dwdb, void* workspace, oodfq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

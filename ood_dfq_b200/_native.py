@@ -47,6 +47,11 @@ SIGNATURES = {
     "oodfq_channel_energy_scratch_floats": (C.c_size_t, [_i, _i]),
     "oodfq_channel_energy_forward": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp, _vp]),
     "oodfq_channel_energy_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _vp]),
+    "oodfq_res_tail_scratch_floats": (C.c_size_t, [_i, _i]),
+    "oodfq_res_tail_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float,
+                                    _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
+    "oodfq_res_tail_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float,
+                                     _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
     "oodfq_bn_eval_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
 }
 

@@ -1,0 +1,365 @@
+// Tail of a residual unit as ONE kernel each way, channels_last:
+//
+//     y = QuantAct(ReLU( BN1(x1) + id ))        id = r   or   BN2(r)        (+ E[n,c] = mean_hw BN1(x1)^2)
+//
+// After quantize_model (main_direct.py:444-479) every residual unit of the student ends in
+//   body.conv2.bn (eval-mode affine)  ->  + identity (plain, or identity_conv.bn)  ->  Sequential(ReLU, QuantAct)
+// and the trainer's feature-alignment hook (trainer_direct.py:432-440, :382-383) reads the body output z1 once
+// more for its per-(image, channel) mean of squares.  With the BatchNorm fusion of bn_fused.cu that is still
+// four or five kernels forward (BN 8 B/elem, [BN 8], add 12, ReLU+QuantAct 8, energy 4) and, backward, the ReLU
+// mask (12), the energy gradient (8), autograd's accumulation add (12) and the BN backward(s) (12 each):
+// the adds and masks were 6 ms of the 47 ms ImageNet step (profiles/r1_step_share_pruned_stem2.txt).  Here:
+//
+//   forward   read x1, r; write y                       12 B/elem   (E comes out of the same read)
+//   backward  read gy, x1, r; write gx1, gr             20 B/elem
+//             s = z1 + id;  g = gy * [s > 0]  (ReLU; the quantiser is the identity STE, quant_utils.py:159-161)
+//             dz1 = g + gE[n,c] * 2/HW * z1;  gx1 = a1 * dz1;  gr = g  or  a2 * g
+//             dW1 = sum dz1 * xhat1, dB1 = sum dz1  (and dW2, dB2 over g) from the same pass
+//
+// Every intermediate is rounded exactly where the unfused chain rounds it (affine by FFMA as bn_fused.cu, the add
+// and the gradient sum as separate fp32 roundings), so y and the gradients are bit-identical to the chain of
+// bn_fused.cu + ATen add + fq_elementwise.cu; only the fp32 summation order of E, dW, dB differs.
+//
+// Mapping: a CTA owns (image, chunk of rows) work items -- the energy and its gradient coefficient are per
+// image -- and a thread one 128-bit column (4 channels) of those rows, as plane_energy.cu.  Parameter-gradient
+// partials stay in registers across the items of a CTA and are folded in CTA order (deterministic, no atomics).
+// Roofline: HBM.
+#include "bn_geom.cuh"
+
+namespace oodfq {
+
+struct TailBn {
+    const float* w;
+    const float* b;
+    const float* rm;
+    const float* rv;     // NULL: this BatchNorm is absent (plain identity)
+    float eps;
+};
+
+__device__ __forceinline__ void tail_affine(const TailBn& P, int c, float& a, float& b, float& invstd) {
+    invstd = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(P.rv + c), P.eps)));
+    a = __fmul_rn(P.w ? __ldg(P.w + c) : 1.0f, invstd);
+    b = __fsub_rn(P.b ? __ldg(P.b + c) : 0.0f, __fmul_rn(__ldg(P.rm + c), a));
+}
+
+struct TailGeom {
+    int N, C, HW, cols, lanes_r, chunks, rows_per_chunk;
+};
+
+constexpr int kTailFwdDepth = 4;    // rows in flight per thread: 8 loads forward,
+constexpr int kTailBwdDepth = 2;    // 6 loads backward (more state in registers)
+
+template <bool QUANT, bool IDBN, bool ENERGY>
+__global__ void __launch_bounds__(kBThreads)
+res_tail_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ r, float* __restrict__ y,
+                    float* __restrict__ epart, const TailGeom G, const TailBn P1, const TailBn P2, float inv_hw,
+                    const float* __restrict__ fq_lo, const float* __restrict__ fq_hi, int fq_k) {
+    __shared__ float lut[QUANT ? kLutMax : 1];
+    __shared__ float red[ENERGY ? kBThreads * 4 : 1];
+    QParams qp = given_qparams(1.0f, 0.0f, 1);
+    const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
+    if (QUANT) {
+        qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
+        __syncthreads();
+    }
+    const bool active = (int)threadIdx.x < G.lanes_r * G.cols;
+    const int col = threadIdx.x % G.cols, rsub = threadIdx.x / G.cols;
+    float a1[4], b1[4], a2[4], b2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a1[j] = b1[j] = b2[j] = 0.f; a2[j] = 1.f;
+        if (active) {
+            float inv;
+            tail_affine(P1, 4 * col + j, a1[j], b1[j], inv);
+            if (IDBN) tail_affine(P2, 4 * col + j, a2[j], b2[j], inv);
+        }
+    }
+    const int items = G.N * G.chunks;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int n = item / G.chunks, ck = item % G.chunks;
+        const int r_begin = ck * G.rows_per_chunk, r_end = min(G.HW, r_begin + G.rows_per_chunk);
+        const long long base = (long long)n * G.HW * G.cols + col;
+        const float4* p1 = reinterpret_cast<const float4*>(x1) + base;
+        const float4* p2 = reinterpret_cast<const float4*>(r) + base;
+        float4* py = reinterpret_cast<float4*>(y) + base;
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        if (active) {
+            for (int row = r_begin + rsub; row < r_end; row += kTailFwdDepth * G.lanes_r) {
+                float4 u[kTailFwdDepth], v[kTailFwdDepth];
+#pragma unroll
+                for (int d = 0; d < kTailFwdDepth; ++d) {
+                    const int rr = row + d * G.lanes_r;
+                    if (rr < r_end) {
+                        u[d] = ld_stream(p1 + (long long)rr * G.cols);
+                        v[d] = ld_stream(p2 + (long long)rr * G.cols);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < kTailFwdDepth; ++d) {
+                    const int rr = row + d * G.lanes_r;
+                    if (rr < r_end) {
+                        const float xs[4] = {u[d].x, u[d].y, u[d].z, u[d].w};
+                        const float rs[4] = {v[d].x, v[d].y, v[d].z, v[d].w};
+                        float o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float z1 = fmaf(xs[j], a1[j], b1[j]);
+                            if (ENERGY) s[j] = fmaf(z1, z1, s[j]);
+                            const float id = IDBN ? fmaf(rs[j], a2[j], b2[j]) : rs[j];
+                            float t = __fadd_rn(z1, id);
+                            t = (t != t) ? t : fmaxf(t, 0.0f);
+                            o[j] = QUANT ? fake_quant_lut(t, qp, lut, qh, qmask) : t;
+                        }
+                        st_out(py + (long long)rr * G.cols, make_float4(o[0], o[1], o[2], o[3]));
+                    }
+                }
+            }
+        }
+        if (ENERGY) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[threadIdx.x * 4 + j] = active ? s[j] : 0.f;
+            __syncthreads();
+            if (active && rsub == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float t = 0.f;
+                    for (int l = 0; l < G.lanes_r; ++l) t += red[(l * G.cols + col) * 4 + j];
+                    epart[((long long)ck * G.N + n) * G.C + 4 * col + j] = t * inv_hw;     // partial[chunk][n][c]
+                }
+            }
+        }
+    }
+}
+
+__global__ void res_tail_fold_energy_kernel(const float* __restrict__ partial, float* __restrict__ e, long long nc,
+                                            int chunks) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    float t = 0.f;
+    for (int k = 0; k < chunks; ++k) t += partial[(long long)k * nc + i];
+    e[i] = t;
+}
+
+template <bool IDBN, bool ENERGY, bool REDUCE>
+__global__ void __launch_bounds__(kBThreads)
+res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ ge, const float* __restrict__ x1,
+                    const float* __restrict__ r, float* __restrict__ gx1, float* __restrict__ gr, const TailGeom G,
+                    const TailBn P1, const TailBn P2, float two_inv_hw, Workspace* ws) {
+    __shared__ float red[REDUCE ? (IDBN ? 4 : 2) * kBThreads * 4 : 1];
+    const bool active = (int)threadIdx.x < G.lanes_r * G.cols;
+    const int col = threadIdx.x % G.cols, rsub = threadIdx.x / G.cols;
+    float a1[4], b1[4], rm1[4], a2[4], b2[4], rm2[4];
+    float sb1[4], sw1[4], sb2[4], sw2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        a1[j] = b1[j] = rm1[j] = b2[j] = rm2[j] = 0.f; a2[j] = 1.f;
+        sb1[j] = sw1[j] = sb2[j] = sw2[j] = 0.f;
+        if (active) {
+            float inv;
+            tail_affine(P1, 4 * col + j, a1[j], b1[j], inv);
+            rm1[j] = __ldg(P1.rm + 4 * col + j);
+            if (IDBN) { tail_affine(P2, 4 * col + j, a2[j], b2[j], inv); rm2[j] = __ldg(P2.rm + 4 * col + j); }
+        }
+    }
+    const int items = G.N * G.chunks;
+    if (active) {
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int n = item / G.chunks, ck = item % G.chunks;
+            const int r_begin = ck * G.rows_per_chunk, r_end = min(G.HW, r_begin + G.rows_per_chunk);
+            const long long base = (long long)n * G.HW * G.cols + col;
+            const float4* pg = reinterpret_cast<const float4*>(gy) + base;
+            const float4* p1 = reinterpret_cast<const float4*>(x1) + base;
+            const float4* p2 = reinterpret_cast<const float4*>(r) + base;
+            float4* o1 = reinterpret_cast<float4*>(gx1) + base;
+            float4* o2 = reinterpret_cast<float4*>(gr) + base;
+            float ce[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ENERGY) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ce[j] = __fmul_rn(__ldg(ge + (long long)n * G.C + 4 * col + j), two_inv_hw);
+            }
+            for (int row = r_begin + rsub; row < r_end; row += kTailBwdDepth * G.lanes_r) {
+                float4 g[kTailBwdDepth], u[kTailBwdDepth], v[kTailBwdDepth];
+#pragma unroll
+                for (int d = 0; d < kTailBwdDepth; ++d) {
+                    const int rr = row + d * G.lanes_r;
+                    if (rr < r_end) {
+                        g[d] = ld_stream(pg + (long long)rr * G.cols);
+                        u[d] = ld_stream(p1 + (long long)rr * G.cols);
+                        v[d] = ld_stream(p2 + (long long)rr * G.cols);
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < kTailBwdDepth; ++d) {
+                    const int rr = row + d * G.lanes_r;
+                    if (rr < r_end) {
+                        const float gs[4] = {g[d].x, g[d].y, g[d].z, g[d].w};
+                        const float xs[4] = {u[d].x, u[d].y, u[d].z, u[d].w};
+                        const float rs[4] = {v[d].x, v[d].y, v[d].z, v[d].w};
+                        float d1[4], d2[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float z1 = fmaf(xs[j], a1[j], b1[j]);
+                            const float id = IDBN ? fmaf(rs[j], a2[j], b2[j]) : rs[j];
+                            const float s = __fadd_rn(z1, id);
+                            const float gm = (s <= 0.0f) ? 0.0f : gs[j];          // aten::threshold_backward
+                            const float dz = ENERGY ? __fadd_rn(gm, __fmul_rn(ce[j], z1)) : gm;
+                            if (REDUCE) {
+                                sb1[j] += dz; sw1[j] = fmaf(dz, xs[j] - rm1[j], sw1[j]);
+                                if (IDBN) { sb2[j] += gm; sw2[j] = fmaf(gm, rs[j] - rm2[j], sw2[j]); }
+                            }
+                            d1[j] = dz * a1[j];
+                            d2[j] = IDBN ? gm * a2[j] : gm;
+                        }
+                        st_out(o1 + (long long)rr * G.cols, make_float4(d1[0], d1[1], d1[2], d1[3]));
+                        st_out(o2 + (long long)rr * G.cols, make_float4(d2[0], d2[1], d2[2], d2[3]));
+                    }
+                }
+            }
+        }
+    }
+    if (REDUCE) {
+        constexpr int kSets = IDBN ? 2 : 1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            red[threadIdx.x * 4 + j] = active ? sb1[j] : 0.f;
+            red[kBThreads * 4 + threadIdx.x * 4 + j] = active ? sw1[j] : 0.f;
+            if (IDBN) {
+                red[2 * kBThreads * 4 + threadIdx.x * 4 + j] = active ? sb2[j] : 0.f;
+                red[3 * kBThreads * 4 + threadIdx.x * 4 + j] = active ? sw2[j] : 0.f;
+            }
+        }
+        __syncthreads();
+        if (active && rsub == 0) {
+            const int Ct = kSets * G.C;          // partial[cta][Ct][2]: BN1 channels first, then BN2
+#pragma unroll
+            for (int set = 0; set < kSets; ++set) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float tb = 0.f, tw = 0.f;
+                    for (int l = 0; l < G.lanes_r; ++l) {
+                        tb += red[(2 * set) * kBThreads * 4 + (l * G.cols + col) * 4 + j];
+                        tw += red[(2 * set + 1) * kBThreads * 4 + (l * G.cols + col) * 4 + j];
+                    }
+                    const TailBn& P = set ? P2 : P1;
+                    const float inv = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(P.rv + 4 * col + j), P.eps)));
+                    double* p = ws->bn_partial + ((size_t)blockIdx.x * Ct + (size_t)set * G.C + 4 * col + j) * 2;
+                    p[0] = (double)tw * (double)inv;     // dW
+                    p[1] = (double)tb;                   // dB
+                }
+            }
+        }
+    }
+}
+
+static int make_tail_geom(int N, int C, long long HW, int slots, int depth, TailGeom& G) {
+    if (C % 4 != 0 || C / 4 > kBThreads || HW > 0x7fffffffLL || (long long)N * 16 > 0x7fffffffLL) return OODFQ_EINVAL;
+    G.N = N; G.C = C; G.HW = (int)HW; G.cols = C / 4;
+    G.lanes_r = kBThreads / G.cols;
+    const int passes = (int)((HW + (long long)G.lanes_r * depth - 1) / ((long long)G.lanes_r * depth));
+    int want = slots / N;                  // work items per image: fill the resident slots, never 1.x waves
+    if (want > passes) want = passes;
+    if (want > 16) want = 16;
+    if (want < 1) want = 1;
+    G.chunks = want;
+    G.rows_per_chunk = (int)((HW + want - 1) / want);
+    return OODFQ_OK;
+}
+
+template <bool QUANT, bool IDBN>
+static void launch_tail_fwd(bool energy, unsigned grid, cudaStream_t st, const float* x1, const float* r, float* y,
+                            float* epart, const TailGeom& G, const TailBn& P1, const TailBn& P2, float inv_hw,
+                            const float* lo, const float* hi, int k) {
+    if (energy) res_tail_fwd_kernel<QUANT, IDBN, true><<<grid, kBThreads, 0, st>>>(x1, r, y, epart, G, P1, P2, inv_hw, lo, hi, k);
+    else res_tail_fwd_kernel<QUANT, IDBN, false><<<grid, kBThreads, 0, st>>>(x1, r, y, epart, G, P1, P2, inv_hw, lo, hi, k);
+}
+
+template <bool IDBN, bool ENERGY>
+static void launch_tail_bwd(bool reduce, unsigned grid, cudaStream_t st, const float* gy, const float* ge,
+                            const float* x1, const float* r, float* gx1, float* gr, const TailGeom& G,
+                            const TailBn& P1, const TailBn& P2, float two_inv_hw, Workspace* ws) {
+    if (reduce) res_tail_bwd_kernel<IDBN, ENERGY, true><<<grid, kBThreads, 0, st>>>(gy, ge, x1, r, gx1, gr, G, P1, P2, two_inv_hw, ws);
+    else res_tail_bwd_kernel<IDBN, ENERGY, false><<<grid, kBThreads, 0, st>>>(gy, ge, x1, r, gx1, gr, G, P1, P2, two_inv_hw, ws);
+}
+
+}  // namespace oodfq
+
+using namespace oodfq;
+
+extern "C" size_t oodfq_res_tail_scratch_floats(int N, int C) { return (size_t)16 * (size_t)N * (size_t)C; }
+
+extern "C" int oodfq_res_tail_forward(const float* x1, const float* r, float* y, float* energy, float* scratch, int N,
+                                      int C, long long HW, const float* w1, const float* b1, const float* rm1,
+                                      const float* rv1, float eps1, const float* w2, const float* b2,
+                                      const float* rm2, const float* rv2, float eps2, int flags, const float* fq_lo,
+                                      const float* fq_hi, int fq_k, oodfq_stream_t stream) {
+    if (!x1 || !r || !y || !rm1 || !rv1) return fail(OODFQ_EINVAL, "res_tail_forward: null pointer");
+    if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "res_tail_forward: empty tensor");
+    if (!(flags & OODFQ_BN_NHWC)) return fail(OODFQ_EINVAL, "res_tail_forward: channels_last only");
+    const bool quant = flags & OODFQ_BN_QUANT, idbn = rv2 != nullptr;
+    if (idbn && !rm2) return fail(OODFQ_EINVAL, "res_tail_forward: identity BatchNorm needs both running statistics");
+    if (quant && (!fq_lo || !fq_hi || fq_k < 1 || fq_k > 8))
+        return fail(OODFQ_EINVAL, "res_tail_forward: fake-quant needs a range and k in [1,8]");
+    if (energy && !scratch) return fail(OODFQ_EINVAL, "res_tail_forward: the energy output needs the scratch buffer");
+    static const int per_sm = resident_ctas(res_tail_fwd_kernel<true, true, true>, kBThreads);
+    TailGeom G;
+    if (make_tail_geom(N, C, HW, kNumSM * per_sm, kTailFwdDepth, G) != OODFQ_OK || !aligned16(x1) || !aligned16(r) || !aligned16(y))
+        return fail(OODFQ_EINVAL, "res_tail_forward: needs C %% 4 == 0, C <= 1024 and 16-byte aligned buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    const TailBn P1{w1, b1, rm1, rv1, eps1}, P2{w2, b2, rm2, rv2, eps2};
+    const long long items = (long long)N * G.chunks, cap = (long long)kNumSM * per_sm;
+    const unsigned grid = (unsigned)(items < cap ? items : cap);
+    const float inv_hw = (float)(1.0 / (double)HW);
+    float* epart = energy ? (G.chunks == 1 ? energy : scratch) : nullptr;
+    if (quant && idbn) launch_tail_fwd<true, true>(energy, grid, st, x1, r, y, epart, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
+    else if (quant) launch_tail_fwd<true, false>(energy, grid, st, x1, r, y, epart, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
+    else if (idbn) launch_tail_fwd<false, true>(energy, grid, st, x1, r, y, epart, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
+    else launch_tail_fwd<false, false>(energy, grid, st, x1, r, y, epart, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
+    count_launch();
+    int rc = check_launch("res_tail_forward");
+    if (rc != OODFQ_OK || !energy || G.chunks == 1) return rc;
+    const long long nc = (long long)N * C;
+    res_tail_fold_energy_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(scratch, energy, nc, G.chunks);
+    count_launch();
+    return check_launch("res_tail_forward(fold)");
+}
+
+extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_energy, const float* x1, const float* r,
+                                       float* grad_x1, float* grad_r, int N, int C, long long HW, const float* w1,
+                                       const float* b1, const float* rm1, const float* rv1, float eps1,
+                                       const float* w2, const float* b2, const float* rm2, const float* rv2,
+                                       float eps2, int flags, double* dwdb, void* workspace, oodfq_stream_t stream) {
+    if (!grad_y || !x1 || !r || !grad_x1 || !grad_r || !rm1 || !rv1) return fail(OODFQ_EINVAL, "res_tail_backward: null pointer");
+    if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "res_tail_backward: empty tensor");
+    if (!(flags & OODFQ_BN_NHWC)) return fail(OODFQ_EINVAL, "res_tail_backward: channels_last only");
+    const bool idbn = rv2 != nullptr, energy = grad_energy != nullptr, reduce = dwdb != nullptr;
+    if (idbn && !rm2) return fail(OODFQ_EINVAL, "res_tail_backward: identity BatchNorm needs both running statistics");
+    if (reduce && !workspace) return fail(OODFQ_EINVAL, "res_tail_backward: parameter gradients need the workspace");
+    static const int per_sm = resident_ctas(res_tail_bwd_kernel<true, true, true>, kBThreads);
+    TailGeom G;
+    if (make_tail_geom(N, C, HW, kNumSM * per_sm, kTailBwdDepth, G) != OODFQ_OK || !aligned16(grad_y) || !aligned16(x1) ||
+        !aligned16(r) || !aligned16(grad_x1) || !aligned16(grad_r))
+        return fail(OODFQ_EINVAL, "res_tail_backward: needs C %% 4 == 0, C <= 1024 and 16-byte aligned buffers");
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace* ws = reinterpret_cast<Workspace*>(workspace);
+    const TailBn P1{w1, b1, rm1, rv1, eps1}, P2{w2, b2, rm2, rv2, eps2};
+    const int Ct = (idbn ? 2 : 1) * C;
+    long long cap = (long long)kNumSM * per_sm;
+    const long long table = (long long)kMaxBnSplit * kMaxBnChannels / Ct;     // rows of ws->bn_partial
+    if (reduce && cap > table) cap = table;
+    const long long items = (long long)N * G.chunks;
+    const unsigned grid = (unsigned)(items < cap ? items : cap);
+    const float two_inv_hw = (float)(2.0 / (double)HW);
+    if (idbn && energy) launch_tail_bwd<true, true>(reduce, grid, st, grad_y, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
+    else if (idbn) launch_tail_bwd<true, false>(reduce, grid, st, grad_y, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
+    else if (energy) launch_tail_bwd<false, true>(reduce, grid, st, grad_y, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
+    else launch_tail_bwd<false, false>(reduce, grid, st, grad_y, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
+    count_launch();
+    int rc = check_launch("res_tail_backward");
+    if (rc != OODFQ_OK || !reduce) return rc;
+    // dwdb[0 .. Ct) = dW (BN1 channels, then BN2), dwdb[Ct .. 2 Ct) = dB
+    bn_nhwc_fold_kernel<<<(Ct + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, Ct, (int)grid, dwdb);
+    count_launch();
+    return check_launch("res_tail_backward(fold)");
+}

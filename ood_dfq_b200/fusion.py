@@ -237,6 +237,207 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
     return model
 
 
+# ------------------------------------------------------------------------------ residual-unit tail
+class _FusedTail(torch.autograd.Function):
+    """``QuantAct(ReLU(BN1(x1) + id))`` (+ the feature-alignment energy of ``BN1(x1)``) as one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, x1, r, w1, b1, w2, b2, bn1, bn2, qact, want_energy):
+        fq = (qact.activation_bit, qact.x_min, qact.x_max) if qact is not None else None
+        t1 = (w1, b1, bn1.running_mean, bn1.running_var, bn1.eps)
+        t2 = None if bn2 is None else (w2, b2, bn2.running_mean, bn2.running_var, bn2.eps)
+        y, e = ops.res_tail_forward(x1, r, t1, t2, fq=fq, want_energy=want_energy)
+        ctx.save_for_backward(x1, r, w1, b1, w2, b2)
+        ctx.bn1, ctx.bn2, ctx.want_energy = bn1, bn2, want_energy
+        if e is None:
+            e = x1.new_empty(0)
+            ctx.mark_non_differentiable(e)
+        return y, e
+
+    @staticmethod
+    def backward(ctx, grad_y, grad_e):
+        x1, r, w1, b1, w2, b2 = ctx.saved_tensors
+        bn1, bn2 = ctx.bn1, ctx.bn2
+        t1 = (w1, b1, bn1.running_mean, bn1.running_var, bn1.eps)
+        t2 = None if bn2 is None else (w2, b2, bn2.running_mean, bn2.running_var, bn2.eps)
+        if grad_y is None:
+            grad_y = torch.zeros_like(x1)
+        need = ctx.needs_input_grad
+        need_p = any(need[i] and t is not None for i, t in ((2, w1), (3, b1), (4, w2), (5, b2)))
+        gx1, gr, dw1, db1, dw2, db2 = ops.res_tail_backward(grad_y, grad_e if ctx.want_energy else None, x1, r, t1, t2,
+                                                            want_param_grads=need_p)
+        return (gx1 if need[0] else None, gr if need[1] else None,
+                dw1 if (w1 is not None and need[2]) else None, db1 if (b1 is not None and need[3]) else None,
+                dw2 if (w2 is not None and need[4]) else None, db2 if (b2 is not None and need[5]) else None,
+                None, None, None, None)
+
+
+class _TailPlan:
+    """Where the pieces of a residual unit's tail live (module references only, so ``copy.deepcopy`` of the model
+    stays consistent): ``front`` are the modules of the body before its last convolution, applied in order,
+    ``conv`` / ``bn1`` are that convolution and its BatchNorm, ``idconv`` / ``bn2`` the projection
+    shortcut (None for a plain identity), ``act`` the ``Sequential(ReLU, QuantAct)`` or ReLU behind the add,
+    ``hooked`` the module the trainer's feature hook sits on, ``watch`` modules the fused forward does not call."""
+
+    def __init__(self, front, conv, bn1, idconv, bn2, act, hooked, watch):
+        self.front, self.conv, self.bn1, self.idconv, self.bn2 = front, conv, bn1, idconv, bn2
+        self.act, self.hooked, self.watch = act, hooked, watch
+
+    def head(self, x):
+        for m in self.front:
+            x = m(x)
+        return x
+
+
+def _is_block(m):
+    return isinstance(getattr(m, "conv", None), nn.Module) and isinstance(getattr(m, "bn", None), nn.Module) \
+        and not getattr(m, "activate", False) and getattr(m, "activ", None) is None
+
+
+def _plan_of(u):
+    """Recognise the two residual-unit layouts of the reference's model zoo; None if ``u`` is neither."""
+    body, act = getattr(u, "body", None), getattr(u, "activ", None)
+    if isinstance(body, nn.Module) and isinstance(act, nn.Module) and hasattr(u, "resize_identity"):
+        # pytorchcv ResUnit (ptcv_get_model, main_direct.py:380-397): body = ResBlock / ResBottleneck of ConvBlocks
+        blocks = list(body.children())
+        if not blocks or not _is_block(blocks[-1]):
+            return None
+        last, ident = blocks[-1], None
+        if u.resize_identity:
+            ident = getattr(u, "identity_conv", None)
+            if ident is None or not _is_block(ident):
+                return None
+        return _TailPlan(blocks[:-1], last.conv, last.bn, ident.conv if ident is not None else None,
+                         ident.bn if ident is not None else None, act, body,
+                         [body, last] + ([ident] if ident is not None else []))
+    names = ("conv1", "bn1", "relu1", "conv2", "bn2", "shortcut", "relu2")
+    if all(isinstance(getattr(u, n, None), nn.Module) for n in names) and not hasattr(u, "conv3"):
+        # reference models.py:9-47 BasicBlock
+        sc = u.shortcut
+        if not isinstance(sc, nn.Sequential) or len(sc) not in (0, 2):
+            return None
+        return _TailPlan([u.conv1, u.bn1, u.relu1], u.conv2, u.bn2, sc[0] if len(sc) else None, sc[1] if len(sc) else None, u.relu2,
+                         None, [sc])
+    return None
+
+
+def _no_hooks(m, allow_forward=()):
+    if m._forward_pre_hooks or m._backward_hooks or getattr(m, "_backward_pre_hooks", None):
+        return False
+    return all(h in allow_forward for h in m._forward_hooks.values())
+
+
+class _FusedUnitMixin:
+    """Residual unit whose tail -- last BatchNorm, residual add, ReLU, QuantAct and the feature-alignment tap of
+    the body output -- runs as one kernel forward and one backward (csrc/res_tail.cu).  Falls back to the
+    class's own forward whenever the fused path does not apply (training mode, calibrating QuantAct, CPU or NCHW
+    tensors, foreign hooks on the modules it would bypass)."""
+
+    _tail_plan = None
+
+    def _fused_setup(self, x):
+        p = self._tail_plan
+        if p is None or self.training or not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4):
+            return None
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            return None
+        for bn in (p.bn1, p.bn2):
+            if bn is None:
+                continue
+            if not isinstance(bn, _FusedEvalMixin) or bn._tail is not None or bn.training \
+                    or not bn.track_running_stats or bn.running_mean is None or bn.num_features % 4 \
+                    or bn.num_features > 1024 or not _no_hooks(bn):
+                return None
+        act, qact = p.act, None
+        if isinstance(act, nn.Sequential):
+            if len(act) != 2 or type(act[0]) is not nn.ReLU or type(act[1]) is not QuantAct:
+                return None
+            qact = act[1]
+            if qact.running_stat or (not qact.full_precision_flag and qact.activation_bit > 8) \
+                    or not (_no_hooks(act[0]) and _no_hooks(qact)):
+                return None
+            if qact.full_precision_flag:
+                qact = None
+        elif type(act) is not nn.ReLU:
+            return None
+        if not _no_hooks(act):
+            return None
+        taps = []
+        from .step import FeatureTap
+        for m in p.watch:
+            allowed = ()
+            if m is p.hooked:
+                allowed = tuple(h for h in m._forward_hooks.values()
+                                if isinstance(getattr(h, "__self__", None), FeatureTap) and h.__self__.fused)
+                taps = [h.__self__ for h in allowed]
+            if not _no_hooks(m, allowed):
+                return None
+        return p, qact, taps
+
+    def forward(self, x):
+        setup = self._fused_setup(x)
+        if setup is None:
+            return super().forward(x)
+        p, qact, taps = setup
+        x1 = p.conv(p.head(x))
+        r = p.idconv(x) if p.idconv is not None else x
+        bn1, bn2 = p.bn1, p.bn2
+        if not ops.res_tail_supported(x1, r):
+            # (a convolution handed back another layout) finish with the ordinary modules
+            z = bn1(x1)
+            for t in taps:
+                t._hook(p.hooked, (x,), z)
+            return p.act(z + (bn2(r) if bn2 is not None else r))
+        y, e = _FusedTail.apply(x1, r, bn1.weight, bn1.bias, bn2.weight if bn2 is not None else None,
+                                bn2.bias if bn2 is not None else None, bn1, bn2, qact, bool(taps))
+        for t in taps:
+            t.maps.append(F.normalize(e))
+        return y
+
+
+_FUSED_UNIT_CLASSES = {}
+
+
+def fuse_residual_tails(model: nn.Module, example: torch.Tensor = None, verify=True):
+    """Class-swap every residual unit whose layout ``_plan_of`` recognises to a subclass with the fused tail
+    (parameters, buffers, state_dict keys and ``isinstance`` checks untouched).  Call after ``fuse_eval_bn`` (the
+    tail needs the BatchNorms already in their fused form) and before hooks such as ``step.FeatureTap`` are
+    attached.  With ``example`` the fused model is checked against the unfused one and the swap is undone if they
+    disagree (an unknown unit class whose forward is not the layout its attributes suggest)."""
+    was_training = model.training
+    model.eval()
+    ref = None
+    if verify and example is not None:
+        with torch.no_grad():
+            ref = model(example)
+    swapped = []
+    for u in list(model.modules()):
+        if isinstance(u, _FusedUnitMixin):
+            continue
+        plan = _plan_of(u)
+        if plan is None:
+            continue
+        cls = type(u)
+        fused_cls = _FUSED_UNIT_CLASSES.get(cls)
+        if fused_cls is None:
+            fused_cls = type("Fused" + cls.__name__, (_FusedUnitMixin, cls), {"__module__": __name__})
+            _FUSED_UNIT_CLASSES[cls] = fused_cls
+        u.__class__ = fused_cls
+        object.__setattr__(u, "_tail_plan", plan)
+        swapped.append((u, cls))
+    if ref is not None and swapped:
+        with torch.no_grad():
+            out = model(example)
+        err, scale = (out - ref).abs().max().item(), ref.abs().max().item() + 1e-12
+        if not err <= 0.05 * scale:
+            for u, cls in swapped:
+                u.__class__ = cls
+                object.__delattr__(u, "_tail_plan")
+            swapped = []
+    model.train(was_training)
+    return len(swapped)
+
+
 class FusedEvalBN(_FusedEvalMixin, nn.BatchNorm2d):
     """``nn.BatchNorm2d`` with the fused eval path."""
 

@@ -455,3 +455,80 @@ def bn_pool_backward(grad_out, idx, xhat, in_shape, weight, bias, running_mean, 
         return gx, None, None
     d = dwdb.float()
     return gx, d[:c], d[c:]
+
+
+# ----------------------------------------------------------------------------- residual-unit tail
+def res_tail_supported(x1, r) -> bool:
+    """channels_last fp32 CUDA tensors of one shape with C % 4 == 0 and C <= 1024."""
+    return (isinstance(x1, torch.Tensor) and isinstance(r, torch.Tensor) and x1.is_cuda and r.is_cuda
+            and x1.dtype == torch.float32 and r.dtype == torch.float32 and x1.dim() == 4 and x1.shape == r.shape
+            and x1.shape[1] % 4 == 0 and x1.shape[1] <= 1024 and x1.numel() > 0
+            and x1.is_contiguous(memory_format=torch.channels_last)
+            and r.is_contiguous(memory_format=torch.channels_last))
+
+
+def _tail_bn(bn, c):
+    """(w, b, rm, rv, eps) pointers of an eval-mode BatchNorm given as a tuple, or NULLs for 'no BatchNorm'."""
+    if bn is None:
+        return None, None, None, None, 0.0
+    weight, bias, running_mean, running_var, eps = bn
+    return _bn_ptrs(weight, bias, running_mean, running_var, c) + (float(eps),)
+
+
+def res_tail_forward(x1, r, bn1, bn2=None, fq=None, want_energy=False):
+    """``y = [fakequant](relu(BN1(x1) + id))`` with ``id = r`` or ``BN2(r)``, and optionally the per-(image,
+    channel) mean of squares of ``BN1(x1)`` (the feature-alignment tap of the body output) from the same read.
+
+    ``bn1`` / ``bn2``: ``(weight, bias, running_mean, running_var, eps)``; ``fq = (k, lo, hi)``.
+    Returns ``(y, energy or None)``.
+    """
+    _need(x1, "body output")
+    _need(r, "identity")
+    if not res_tail_supported(x1, r):
+        raise RuntimeError("ood_dfq_b200: the fused residual tail needs two channels_last fp32 tensors of one shape "
+                           "with C % 4 == 0 and C <= 1024")
+    n, c, h, w = x1.shape
+    p1, p2 = _tail_bn(bn1, c), _tail_bn(bn2, c)
+    y = torch.empty_like(x1)
+    energy = scratch = None
+    if want_energy:
+        energy = torch.empty((n, c), dtype=torch.float32, device=x1.device)
+        scratch = torch.empty(int(N.load().oodfq_res_tail_scratch_floats(n, c)), dtype=torch.float32, device=x1.device)
+    flags, k, lo, hi = N.BN_NHWC, 0, None, None
+    if fq is not None:
+        k, lo, hi = fq
+        flags |= N.BN_QUANT
+    with _Timed("res_tail_fwd_kernel (BN + residual add + ReLU + QuantAct [+ energy], 12 B/elem)", 12 * x1.numel()):
+        rc = N.load().oodfq_res_tail_forward(x1.data_ptr(), r.data_ptr(), y.data_ptr(), _ptr(energy), _ptr(scratch),
+                                             n, c, h * w, *p1, *p2, flags, _ptr(lo), _ptr(hi), int(k),
+                                             _stream(x1.device))
+        N.check(rc, "res_tail_forward")
+    return y, energy
+
+
+def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grads=True):
+    """Backward of ``res_tail_forward``: ``(grad_x1, grad_r, dW1, dB1, dW2, dB2)`` (parameter gradients None
+    unless wanted; dW2 / dB2 None without ``bn2``)."""
+    _need(grad_y, "grad_output")
+    n, c, h, w = x1.shape
+    gy = grad_y.contiguous(memory_format=torch.channels_last)
+    ge = None
+    if grad_energy is not None:
+        _need(grad_energy, "grad_energy")
+        ge = grad_energy.contiguous()
+    p1, p2 = _tail_bn(bn1, c), _tail_bn(bn2, c)
+    gx1, gr = torch.empty_like(x1), torch.empty_like(r)
+    ct = c * (2 if bn2 is not None else 1)
+    dwdb = torch.empty(2 * ct, dtype=torch.float64, device=x1.device) if want_param_grads else None
+    ws = workspace(x1.device).data_ptr() if want_param_grads else None
+    with _Timed("res_tail_bwd_kernel (ReLU mask + energy gradient + BN backward(s), 20 B/elem)", 20 * x1.numel()):
+        rc = N.load().oodfq_res_tail_backward(gy.data_ptr(), _ptr(ge), x1.data_ptr(), r.data_ptr(), gx1.data_ptr(),
+                                              gr.data_ptr(), n, c, h * w, *p1, *p2, N.BN_NHWC, _ptr(dwdb), ws,
+                                              _stream(x1.device))
+        N.check(rc, "res_tail_backward")
+    if not want_param_grads:
+        return gx1, gr, None, None, None, None
+    d = dwdb.float()
+    if bn2 is None:
+        return gx1, gr, d[:c], d[c:], None, None
+    return gx1, gr, d[:c], d[2 * c:3 * c], d[c:2 * c], d[3 * c:]

@@ -1,0 +1,52 @@
+"""Host logic of the fusion passes on CPU: the class swaps keep the module tree, the state_dict and the results
+(every fused module falls back to its class's own forward off the GPU)."""
+import copy
+
+import torch
+
+from ood_dfq_b200 import fusion, nets
+
+
+def _student(name):
+    torch.manual_seed(1)
+    base = nets.resnet18_small(3, 9) if name == "resnet18_small" else getattr(nets, name)(num_classes=10)
+    nets.perturb_bn_stats(base)
+    # the full-precision teacher: the quantised student's modules have no CPU path at all (by design), the
+    # passes treat both the same way
+    model = base.eval()
+    g = torch.Generator().manual_seed(2)
+    side = 28 if name == "resnet18_small" else 32
+    return model, torch.randn(2, 3, side, side, generator=g)
+
+
+def test_passes_keep_results_and_state_dict_on_cpu():
+    for name, units in (("resnet20_cifar", 9), ("resnet18_small", 8)):
+        model, x = _student(name)
+        with torch.no_grad():
+            ref = model(x)
+        keys = list(model.state_dict())
+        fusion.fuse_eval_bn(model, x)
+        assert fusion.fuse_residual_tails(model, x) == units
+        assert fusion.fuse_residual_tails(model, x) == 0                 # idempotent
+        with torch.no_grad():
+            out = model(x)
+        assert torch.equal(out, ref) and list(model.state_dict()) == keys
+        clone = copy.deepcopy(model)
+        unit = next(m for m in clone.modules() if isinstance(m, fusion._FusedUnitMixin))
+        own = {id(m) for m in clone.modules()}
+        plan = unit._tail_plan
+        assert all(id(m) in own for m in [plan.conv, plan.bn1, plan.act] + list(plan.front))
+
+
+def test_unknown_unit_layouts_are_left_alone():
+    class Odd(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 1))
+            self.activ = torch.nn.ReLU()
+            self.resize_identity = False
+
+        def forward(self, x):
+            return self.activ(self.body(x))
+    m = Odd().eval()
+    assert fusion.fuse_residual_tails(m, torch.randn(1, 3, 4, 4)) == 0 and type(m) is Odd

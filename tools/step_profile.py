@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--nchw", action="store_true")
+    ap.add_argument("--no-tail-fuse", action="store_true")
     args = ap.parse_args()
     from ood_dfq_b200.quantization_utils import quant_modules as qm
     dev = torch.device("cuda:0")
@@ -46,6 +47,9 @@ def main():
         from ood_dfq_b200 import fusion
         fusion.fuse_eval_bn(student, xs[0][:2])
         fusion.fuse_eval_bn(teacher, xs[0][:2])
+        if not args.no_tail_fuse:
+            fusion.fuse_residual_tails(student, xs[0][:2])
+            fusion.fuse_residual_tails(teacher, xs[0][:2])
     qat = bench.make_step(args.workload, teacher, student, qm)
     for i in range(3):
         qat(xs[i % 2])
