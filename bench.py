@@ -240,13 +240,19 @@ def main_ours(args):
             # ... and the tail of every residual unit (BN + add + ReLU + QuantAct + feature tap) as one kernel
             fusion.fuse_residual_tails(student, resident[0][:2])
             fusion.fuse_residual_tails(teacher, resident[0][:2])
+        if not args.no_s2d:
+            # ... and hand the 3-channel stride-2 stem convolution a space-to-depth image (cuDNN has no good
+            # kernel for the 3-channel form); no-op for the networks without such a stem
+            fusion.space_to_depth_stem(student, resident[0][:2])
+            fusion.space_to_depth_stem(teacher, resident[0][:2])
     kind = KINDS.get(args.workload, "qat")
     if kind == "distill":
         # the "student" IS the quantised teacher here; the optimised variable is the image batch itself
         from ood_dfq_b200 import bns, step as step_mod
         del teacher
         labels = torch.randint(0, WORKLOADS[args.workload][1], (batch,), generator=g).to(dev)
-        dstep = step_mod.DistillStep(student, bns.BNStatLoss(student), resident[0] / 5, labels)   # distill_data.py:181
+        dstep = step_mod.DistillStep(student, bns.BNStatLoss(student), resident[0] / 5, labels,   # distill_data.py:181
+                                     capturable=args.graph in ("on", "auto"))
 
         def qat(_batch=None):
             return dstep()
@@ -394,6 +400,7 @@ def main_ours(args):
                        "convolutions": "cuDNN (TF32 default, as the reference)",
                        "bn_relu_quant_fusion": not args.no_fuse,
                        "residual_tail_fusion": not (args.no_fuse or args.no_tail_fuse),
+                       "stem_space_to_depth": not (args.no_fuse or args.no_s2d),
                        "memory_format": "channels_last" if channels_last else "NCHW (as the reference)",
                        "cuda_graph": use_graph},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
@@ -457,6 +464,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="keep BatchNorm / ReLU / QuantAct as separate modules")
     ap.add_argument("--no-tail-fuse", action="store_true", help="keep the residual add and the ReLU + QuantAct behind it separate")
+    ap.add_argument("--no-s2d", action="store_true", help="keep the 3-channel stem convolution in its stride-2 form")
     ap.add_argument("--nchw", action="store_true", help="keep NCHW tensors (default: channels_last memory format)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",

@@ -227,6 +227,16 @@ int oodfq_res_tail_backward(const float* grad_y, const float* grad_energy, const
                             const float* b2, const float* rm2, const float* rv2, float eps2, int flags,
                             double* dwdb, void* workspace, oodfq_stream_t stream);
 
+/* ---- space-to-depth re-layout in front of the ImageNet stem convolution ---------------------------------
+ * replaces: nothing in the reference -- it is the data format on the input side of Quant_Conv2d's F.conv2d call
+ *           (quant_modules.py:279-281) for the 3-channel 7x7 stride-2 stem (main_direct.py:380-397), where a
+ *           stride-2 KxK convolution is run as the equal stride-1 convolution over the 2x2 space-to-depth image.
+ * x [N,H,W,C] channels_last -> xs [N,(H+2*pad)/2,(W+2*pad)/2,4C], xs[n,i,j,(s,t,c)] = x[n,2i+s-pad,2j+t-pad,c]
+ * (zero outside the image); backward is the inverse gather of the gradient. */
+int oodfq_s2d_stem_forward(const float* x, float* xs, int N, int H, int W, int C, int pad, oodfq_stream_t stream);
+int oodfq_s2d_stem_backward(const float* grad_xs, float* grad_x, int N, int H, int W, int C, int pad,
+                            oodfq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

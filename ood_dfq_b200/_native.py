@@ -52,6 +52,8 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
     "oodfq_res_tail_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float,
                                      _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
+    "oodfq_s2d_stem_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "oodfq_s2d_stem_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_bn_eval_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
 }
 

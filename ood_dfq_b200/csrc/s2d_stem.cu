@@ -1,0 +1,147 @@
+// Space-to-depth re-layout of the image batch in front of the ImageNet stem convolution, channels_last.
+//
+// The first convolution of the ImageNet ResNets (3 -> 64 channels, 7x7, stride 2, padding 3; pytorchcv
+// ResInitBlock behind ptcv_get_model, main_direct.py:380-397, wrapped by Quant_Conv2d :455-458) is the one
+// layer cuDNN has no good kernel for: with 3 input channels it falls back to `implicit_gemm_indexed_wo_smem`
+// at ~49 TFLOP/s and was 29 % of the fused step (profiles/r1_step_share_tail.txt: fprop 4.9 ms, wgrad 2.4 ms,
+// dgrad 1.9 ms, layout helpers 3 ms).  A stride-2 KxK convolution equals a stride-1 ceil(K/2) x ceil(K/2)
+// convolution over the 2x2 space-to-depth image:
+//
+//     xs[n, i, j, (s,t,c)] = x[n, 2i+s-p, 2j+t-p, c]   (zero outside the image),   i < (H+2p)/2, j < (W+2p)/2
+//     w2[o, (s,t,c), a, b] = w[o, c, 2a+s, 2b+t]       (zero for 2a+s = K or 2b+t = K)
+//     conv(x, w, stride 2, padding p)  ==  conv(xs, w2, stride 1, padding 0)          same products, same sums
+//
+// which cuDNN runs on its tensor-core implicit-GEMM path (12 channels, 4x4 taps): fprop 1.32 -> 0.72 ms,
+// dgrad 1.99 -> 0.94 ms, wgrad 1.78 -> 1.37 ms at 256x3x224x224 (profiles/r1_exp_stem_conv.txt).  The
+// convolution itself stays on cuDNN (BASELINE.json north_star); these two kernels are only the re-layout of
+// its input (and of the input gradient on the way back), which in eager PyTorch is three passes (pad, permute,
+// channels_last copy: 0.37 ms) and here one: 4 B read + 4 B written per element.  Roofline: HBM.
+#include "common.cuh"
+
+namespace oodfq {
+
+struct S2dGeom {
+    int N, H, W, C, pad, Hs, Ws;
+};
+
+// generic channel counts: one thread per element (gather), runtime divisors
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+s2d_stem_kernel(const float* __restrict__ src, float* __restrict__ dst, const S2dGeom G, long long total) {
+    const int c4 = 4 * G.C, c2 = 2 * G.C;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        if (!BWD) {
+            // e indexes xs[n][i][j][ch]
+            const int ch = (int)(e % c4);
+            long long q = e / c4;
+            const int j = (int)(q % G.Ws); q /= G.Ws;
+            const int i = (int)(q % G.Hs);
+            const long long n = q / G.Hs;
+            const int s = ch / c2, t = (ch / G.C) & 1, c = ch % G.C;
+            const int h = 2 * i + s - G.pad, w = 2 * j + t - G.pad;
+            float v = 0.0f;
+            if (h >= 0 && h < G.H && w >= 0 && w < G.W) v = __ldg(src + ((n * G.H + h) * G.W + w) * G.C + c);
+            dst[e] = v;
+        } else {
+            // e indexes gx[n][h][w][c]; every image pixel lives in exactly one xs element
+            const int c = (int)(e % G.C);
+            long long q = e / G.C;
+            const int w = (int)(q % G.W); q /= G.W;
+            const int h = (int)(q % G.H);
+            const long long n = q / G.H;
+            const int hp = h + G.pad, wp = w + G.pad;
+            const int ch = ((hp & 1) * 2 + (wp & 1)) * G.C + c;
+            dst[e] = __ldg(src + ((n * G.Hs + (hp >> 1)) * G.Ws + (wp >> 1)) * c4 + ch);
+        }
+    }
+}
+
+// Row form for the channel counts that matter (C = 3, and 1 / 4): for a fixed (image, xs row i, parity s) the
+// s-half of every xs pixel is the input row h = 2i+s-pad, shifted by pad pixels and cut into runs of 2C floats:
+//     xs_row[(q / 2C) * 4C + s*2C + q % 2C] = x_row[q - pad*C]        q in [0, 2C * Ws)
+// so one side of the copy is a fully contiguous row and all divisors are compile-time constants.
+template <int C, bool BWD>
+__global__ void __launch_bounds__(256)
+s2d_stem_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, const S2dGeom G) {
+    const long long rows = (long long)G.N * G.Hs * 2;
+    const int qn = 2 * C * G.Ws, shift = G.pad * C, wlen = G.W * C;
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int s = (int)(row & 1);
+        const long long ni = row >> 1;                 // n * Hs + i
+        const int i = (int)(ni % G.Hs);
+        const long long n = ni / G.Hs;
+        const int h = 2 * i + s - G.pad;
+        const bool inside = h >= 0 && h < G.H;
+        const long long xrow = (n * G.H + h) * (long long)wlen;         // image row (valid only if inside)
+        const long long srow = ni * (long long)(4 * C * G.Ws) + s * 2 * C;
+        if (!BWD) {
+            for (int q = threadIdx.x; q < qn; q += 256) {
+                const int m = q - shift;
+                float v = 0.0f;
+                if (inside && m >= 0 && m < wlen) v = __ldg(src + xrow + m);
+                dst[srow + (q / (2 * C)) * (4 * C) + q % (2 * C)] = v;
+            }
+        } else if (inside) {
+            for (int m = threadIdx.x; m < wlen; m += 256) {
+                const int q = m + shift;
+                dst[xrow + m] = __ldg(src + srow + (q / (2 * C)) * (4 * C) + q % (2 * C));
+            }
+        }
+    }
+}
+
+template <bool BWD>
+static bool launch_rows(const float* src, float* dst, const S2dGeom& G, cudaStream_t st) {
+    const long long rows = (long long)G.N * G.Hs * 2, cap = (long long)kNumSM * 32;
+    const unsigned grid = (unsigned)(rows < cap ? rows : cap);
+    switch (G.C) {
+        case 1: s2d_stem_rows_kernel<1, BWD><<<grid, 256, 0, st>>>(src, dst, G); return true;
+        case 3: s2d_stem_rows_kernel<3, BWD><<<grid, 256, 0, st>>>(src, dst, G); return true;
+        case 4: s2d_stem_rows_kernel<4, BWD><<<grid, 256, 0, st>>>(src, dst, G); return true;
+        default: return false;
+    }
+}
+
+static int s2d_geom(int N, int H, int W, int C, int pad, S2dGeom& G) {
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || pad < 0 || ((H + 2 * pad) & 1) || ((W + 2 * pad) & 1)) return OODFQ_EINVAL;
+    G.N = N; G.H = H; G.W = W; G.C = C; G.pad = pad;
+    G.Hs = (H + 2 * pad) / 2;
+    G.Ws = (W + 2 * pad) / 2;
+    return OODFQ_OK;
+}
+
+}  // namespace oodfq
+
+using namespace oodfq;
+
+extern "C" int oodfq_s2d_stem_forward(const float* x, float* xs, int N, int H, int W, int C, int pad,
+                                      oodfq_stream_t stream) {
+    if (!x || !xs) return fail(OODFQ_EINVAL, "s2d_stem_forward: null pointer");
+    S2dGeom G;
+    if (s2d_geom(N, H, W, C, pad, G) != OODFQ_OK)
+        return fail(OODFQ_EINVAL, "s2d_stem_forward: needs a non-empty tensor with even H + 2*pad and W + 2*pad");
+    const long long total = (long long)N * G.Hs * G.Ws * 4 * C;
+    if (!launch_rows<false>(x, xs, G, (cudaStream_t)stream)) {
+        static const int per_sm = resident_ctas(s2d_stem_kernel<false>, 256);
+        long long want = (total + 255) / 256, cap = (long long)kNumSM * per_sm * 4;
+        s2d_stem_kernel<false><<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(x, xs, G, total);
+    }
+    count_launch();
+    return check_launch("s2d_stem_forward");
+}
+
+extern "C" int oodfq_s2d_stem_backward(const float* grad_xs, float* grad_x, int N, int H, int W, int C, int pad,
+                                       oodfq_stream_t stream) {
+    if (!grad_xs || !grad_x) return fail(OODFQ_EINVAL, "s2d_stem_backward: null pointer");
+    S2dGeom G;
+    if (s2d_geom(N, H, W, C, pad, G) != OODFQ_OK)
+        return fail(OODFQ_EINVAL, "s2d_stem_backward: needs a non-empty tensor with even H + 2*pad and W + 2*pad");
+    const long long total = (long long)N * H * W * C;
+    if (!launch_rows<true>(grad_xs, grad_x, G, (cudaStream_t)stream)) {
+        static const int per_sm = resident_ctas(s2d_stem_kernel<true>, 256);
+        long long want = (total + 255) / 256, cap = (long long)kNumSM * per_sm * 4;
+        s2d_stem_kernel<true><<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(grad_xs, grad_x, G, total);
+    }
+    count_launch();
+    return check_launch("s2d_stem_backward");
+}

@@ -438,6 +438,117 @@ def fuse_residual_tails(model: nn.Module, example: torch.Tensor = None, verify=T
     return len(swapped)
 
 
+# ------------------------------------------------------------------------------ stem convolution: space-to-depth input
+class _S2D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        ctx.in_shape, ctx.pad = tuple(x.shape), pad
+        return ops.s2d_stem_forward(x, pad)
+
+    @staticmethod
+    def backward(ctx, grad_xs):
+        return ops.s2d_stem_backward(grad_xs, ctx.in_shape, ctx.pad), None
+
+
+class _S2DCache:
+    """The re-laid-out batch of the last call: teacher and student stems read the same images back to back
+    (trainer_direct.py:503-504, :513-514), so the second one reuses the first one's tensor (and, with autograd,
+    its graph node: one inverse re-layout on the way back).  The entry keeps the source tensor alive, so a
+    storage address cannot be recycled under it; an in-place write bumps the shared version counter."""
+
+    enabled = True
+    _key, _src, _out = None, None, None
+
+    @classmethod
+    def get(cls, x, pad):
+        want_graph = torch.is_grad_enabled() and x.requires_grad
+        key = (x.untyped_storage().data_ptr(), x.storage_offset(), tuple(x.shape), tuple(x.stride()), x._version, pad,
+               want_graph, x.device)
+        if cls.enabled and cls._key == key and cls._out is not None and cls._out.requires_grad == want_graph:
+            return cls._out
+        out = _S2D.apply(x, pad)
+        if cls.enabled:
+            cls._key, cls._src, cls._out = key, x, out
+        return out
+
+    @classmethod
+    def clear(cls):
+        cls._key, cls._src, cls._out = None, None, None
+
+
+def _s2d_weight(w):
+    """``[O,C,K,K] -> [O,4C,ceil(K/2),ceil(K/2)]`` with ``w2[o,(s,t,c),a,b] = w[o,c,2a+s,2b+t]`` (zero taps beyond K)."""
+    o, c, kh, kw = w.shape
+    w8 = F.pad(w, (0, kw % 2, 0, kh % 2))
+    a, b = w8.shape[2] // 2, w8.shape[3] // 2
+    w2 = w8.reshape(o, c, a, 2, b, 2).permute(0, 3, 5, 1, 2, 4).reshape(o, 4 * c, a, b)
+    return w2.contiguous(memory_format=torch.channels_last)
+
+
+class _S2DStemMixin:
+    """A stride-2 convolution over a few input channels run as the equal stride-1 convolution over the 2x2
+    space-to-depth image (csrc/s2d_stem.cu): same products and sums, but a shape cuDNN has tensor-core kernels
+    for.  The weights -- and for ``Quant_Conv2d`` their per-output-channel quantisation -- are untouched; only
+    the quantised tensor handed to ``F.conv2d`` is re-indexed."""
+
+    def forward(self, x):
+        pad = self.padding[0] if isinstance(self.padding, (tuple, list)) else self.padding
+        if not (isinstance(pad, int) and ops.s2d_stem_supported(x, pad) and x.shape[1] == self.in_channels):
+            return super().forward(x)
+        w = self.quantized_weight() if hasattr(self, "quantized_weight") else self.weight
+        return F.conv2d(_S2DCache.get(x, pad), _s2d_weight(w), self.bias, 1, 0, 1, 1)
+
+
+_S2D_CLASSES = {}
+
+
+def _is_stem_conv(m):
+    def two(v):
+        return (v, v) if isinstance(v, int) else tuple(v)
+    if not (type(m) is nn.Conv2d or hasattr(m, "quantized_weight")) or not hasattr(m, "in_channels"):
+        return False
+    if isinstance(m.padding, str) or getattr(m, "padding_mode", "zeros") != "zeros":
+        return False
+    p = two(m.padding)
+    return (m.in_channels <= 4 and two(m.stride) == (2, 2) and two(m.dilation) == (1, 1) and m.groups == 1
+            and p[0] == p[1] and m.weight.dim() == 4 and m.weight.shape[2] == m.weight.shape[3] >= 3)
+
+
+def space_to_depth_stem(model: nn.Module, example: torch.Tensor = None, verify=True):
+    """Class-swap the image-side stride-2 convolution(s) of ``model`` (``nn.Conv2d`` or this package's
+    ``Quant_Conv2d``) to the space-to-depth form.  Returns how many were swapped; with ``example`` the result is
+    checked against the original and undone if it deviates."""
+    was_training = model.training
+    model.eval()
+    ref = None
+    if verify and example is not None:
+        with torch.no_grad():
+            ref = model(example)
+    swapped = []
+    for m in model.modules():
+        if isinstance(m, _S2DStemMixin) or not _is_stem_conv(m):
+            continue
+        cls = type(m)
+        new_cls = _S2D_CLASSES.get(cls)
+        if new_cls is None:
+            new_cls = type("S2D" + cls.__name__, (_S2DStemMixin, cls), {"__module__": __name__})
+            _S2D_CLASSES[cls] = new_cls
+        m.__class__ = new_cls
+        swapped.append((m, cls))
+    if ref is not None and swapped:
+        _S2DCache.clear()
+        with torch.no_grad():
+            out = model(example)
+        err, scale = (out - ref).abs().max().item(), ref.abs().max().item() + 1e-12
+        if not err <= 0.02 * scale:
+            for m, cls in swapped:
+                m.__class__ = cls
+            swapped = []
+    _S2DCache.clear()
+    model.train(was_training)
+    return len(swapped)
+
+
 class FusedEvalBN(_FusedEvalMixin, nn.BatchNorm2d):
     """``nn.BatchNorm2d`` with the fused eval path."""
 

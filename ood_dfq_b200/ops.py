@@ -532,3 +532,37 @@ def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grad
     if bn2 is None:
         return gx1, gr, d[:c], d[c:], None, None
     return gx1, gr, d[:c], d[2 * c:3 * c], d[c:2 * c], d[3 * c:]
+
+
+# ----------------------------------------------------------------------------- stem convolution input re-layout
+def s2d_stem_supported(x, pad) -> bool:
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.numel() > 0
+            and (x.shape[2] + 2 * pad) % 2 == 0 and (x.shape[3] + 2 * pad) % 2 == 0
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def s2d_stem_forward(x, pad):
+    """channels_last ``[N,C,H,W]`` -> channels_last ``[N,4C,(H+2p)/2,(W+2p)/2]`` with channel order (s, t, c):
+    ``xs[n,(s,t,c),i,j] = x[n,c,2i+s-p,2j+t-p]``, zero outside the image."""
+    _need(x, "input")
+    if not s2d_stem_supported(x, pad):
+        raise RuntimeError("ood_dfq_b200: space-to-depth needs a channels_last fp32 CUDA tensor with even H+2p, W+2p")
+    n, c, h, w = x.shape
+    xs = torch.empty((n, 4 * c, (h + 2 * pad) // 2, (w + 2 * pad) // 2), dtype=torch.float32, device=x.device,
+                     memory_format=torch.channels_last)
+    with _Timed("s2d_stem_kernel (stem input re-layout, 8 B/elem)", 4 * (x.numel() + xs.numel())):
+        rc = N.load().oodfq_s2d_stem_forward(x.data_ptr(), xs.data_ptr(), n, h, w, c, int(pad), _stream(x.device))
+        N.check(rc, "s2d_stem_forward")
+    return xs
+
+
+def s2d_stem_backward(grad_xs, in_shape, pad):
+    """Gradient of ``s2d_stem_forward`` w.r.t. its input (channels_last ``in_shape``)."""
+    _need(grad_xs, "grad_output")
+    n, c, h, w = in_shape
+    g = grad_xs.contiguous(memory_format=torch.channels_last)
+    gx = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device, memory_format=torch.channels_last)
+    with _Timed("s2d_stem_kernel (stem input re-layout, 8 B/elem)", 4 * (gx.numel() + g.numel())):
+        rc = N.load().oodfq_s2d_stem_backward(g.data_ptr(), gx.data_ptr(), n, h, w, c, int(pad), _stream(g.device))
+        N.check(rc, "s2d_stem_backward")
+    return gx

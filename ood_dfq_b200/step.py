@@ -218,21 +218,25 @@ class DistillStep:
     gradient then reaches the images through cuDNN dgrad and the identity STE of every QuantAct.
     """
 
-    def __init__(self, teacher, stat, images, labels, lr=0.5, beta=0.1, gamma=0.5):
+    def __init__(self, teacher, stat, images, labels, lr=0.5, beta=0.1, gamma=0.5, capturable=False):
         self.teacher, self.stat, self.labels, self.beta, self.gamma = teacher, stat, labels, beta, gamma
         self.images = images.detach().clone().requires_grad_(True)
-        self.opt = torch.optim.Adam([self.images], lr=lr)           # distill_data.py:186-187
+        # ``capturable``: keep Adam's step counter on the device so the iteration can be replayed as a CUDA graph
+        self.opt = torch.optim.Adam([self.images], lr=lr, capturable=capturable)      # distill_data.py:186-187
         for p in teacher.parameters():
             p.requires_grad_(False)
         teacher.eval()
 
     def __call__(self):
         self.stat.clear()
-        out = self.teacher(self.images)
+        # a fresh autograd leaf over the optimised tensor every iteration: same gradient as zero_grad() +
+        # backward() on the parameter itself (:270-271), but no AccumulateGrad node tied to the stream the
+        # parameter was created on, so the iteration can be captured as a CUDA graph
+        x = self.images.detach().requires_grad_(True)
+        out = self.teacher(x)
         target = hard_sample_loss(out, self.labels, self.beta, self.gamma)
         total = self.stat.loss() + target                            # mean/L + var/L + target, :259-265
-        self.opt.zero_grad()
-        total.backward()
+        self.images.grad = torch.autograd.grad(total, [x])[0]
         torch.nn.utils.clip_grad_norm_([self.images], max_norm=1.0)  # :273
         self.opt.step()
         return total.detach()
@@ -279,7 +283,7 @@ class GraphedStep:
         self._bank.invalidate()
 
     def __call__(self, batch=None, non_blocking=True):
-        if batch is not None:
+        if batch is not None and self.static_in is not None:      # steps without an input (distillation) ignore it
             self.static_in.copy_(batch, non_blocking=non_blocking)
         self.graph.replay()
         if self._eager_tail is not None:

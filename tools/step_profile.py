@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--no-fuse", action="store_true")
     ap.add_argument("--nchw", action="store_true")
     ap.add_argument("--no-tail-fuse", action="store_true")
+    ap.add_argument("--no-s2d", action="store_true")
     args = ap.parse_args()
     from ood_dfq_b200.quantization_utils import quant_modules as qm
     dev = torch.device("cuda:0")
@@ -50,6 +51,9 @@ def main():
         if not args.no_tail_fuse:
             fusion.fuse_residual_tails(student, xs[0][:2])
             fusion.fuse_residual_tails(teacher, xs[0][:2])
+        if not args.no_s2d:
+            fusion.space_to_depth_stem(student, xs[0][:2])
+            fusion.space_to_depth_stem(teacher, xs[0][:2])
     qat = bench.make_step(args.workload, teacher, student, qm)
     for i in range(3):
         qat(xs[i % 2])
