@@ -46,8 +46,11 @@ WORKLOADS = {
                                        "teacher, 256x3x224x224 images per GPU (independent shard per rank)"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of the largest launch of each kernel family (ncu --set full)
+# (bn_* / fq_flat: the [256,64,112,112] launch; res_tail_*: [256,64,56,56]; bn_pool_fwd: [256,64,112,112] in);
+# sources: profiles/r1_bn_nhwc_kernels.txt, r1_fq_flat_after_lut.txt, r1_res_tail_kernels.txt, r1_bn_pool_kernels.txt
 NCU_TRAFFIC = {"bn_*_bwdx_kernel": 2431773184, "bn_*_fwd_kernel<relu,quant>": 1598203000, "bn_*_fwd_kernel": 1598398000,
-               "fq_flat_kernel": 1588173312}
+               "fq_flat_kernel": 1588173312, "res_tail_bwd_kernel": 985847296, "res_tail_fwd_kernel": 580081408,
+               "bn_pool_fwd_kernel": 1260052224}
 # BASELINE.json configs[4]: BN-statistics image distillation against a quantised teacher (distill_data.py:229-275)
 KINDS = {"distill_imagenet_resnet18_w4a4": "distill"}
 METRIC = "QAT images/sec ResNet-18 W4A4 224x224 (data-free QAT step, fake-quant path on sm_100a kernels)"
@@ -410,15 +413,15 @@ def main_ours(args):
             "roofline": {"bound": "hbm", "kernel": dominant,
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
-                         # ncu --set full dram read+write of the family's largest launch ([256,64,112,112]):
-                         # backward 2 431 773 184 B vs 2 466 250 752 algorithmic (profiles/r1_bn_nhwc_kernels.txt);
-                         # fq_flat 1 588 173 312 B vs 1 644 167 168 (profiles/r1_fq_flat_after_lut.txt)
+                         # ncu --set full dram read+write of the family's largest launch, e.g. res_tail backward
+                         # [256,64,56,56]: 985 847 296 B vs 1 027 604 480 algorithmic (profiles/r1_res_tail_kernels.txt)
                          "traffic": NCU_TRAFFIC.get((dominant or "").split(" ")[0]),
                          "launches_timed": len(prof), "peak_source": peak_src,
                          "kernels": table,
                          "note": "achieved = algorithmic bytes / CUDA-event time of every launch of the family inside the "
-                                 "timed steps (producer-warm L2, back-to-back launches); traffic = ncu dram bytes of the "
-                                 "family's largest launch ([256,64,112,112]), see profiles/"},
+                                 "timed steps (producer-warm L2, back-to-back launches; under CUDA-graph replay: of a few "
+                                 "eager steps taken just before the capture); traffic = ncu dram bytes of the family's "
+                                 "largest launch, see profiles/"},
         }
         if world == 1 and not args.no_cpu_baseline:
             res = run_cpu(args.workload, args.cpu_steps, 1, args.cpu_batch)

@@ -204,6 +204,19 @@ int oodfq_bn_pool_backward(const float* grad_out, const uint8_t* idx, const floa
                            const float* running_mean, const float* running_var, float eps,
                            double* dwdb, void* workspace, oodfq_stream_t stream);
 
+/* ---- QuantAct_MSE: clip-ratio range search --------------------------------------------------------------
+ * replaces: the 80-iteration loop of QuantAct_MSE.forward (quant_modules.py:160-178) with find_MSESmallest
+ *           (quant_utils.py:36-47) and lp_loss (quant_utils.py:26-33) inside it
+ * data_minmax: [2] device floats (oodfq_minmax of x).  Candidate i in [0, ncand) uses the range
+ * data_minmax * fp32(1 - i*step); score_i = mean |x - fakequant_i(x)|^p; the first strict minimum below 1e10 is
+ * kept and folded into (x_min, x_max) by the plain EMA x*beta + kept*(1-beta); beta_t *= beta.
+ * cur_min / cur_max (nullable) receive the data range; scores [ncand] and chosen (device int) are optional
+ * outputs for tests.  scratch: oodfq_act_mse_scratch_doubles(ncand) doubles.  ncand <= 96. */
+size_t oodfq_act_mse_scratch_doubles(int ncand);
+int oodfq_act_mse_search(const float* x, long long numel, const float* data_minmax, int k, int ncand, double step,
+                         float p, float* x_min, float* x_max, const float* beta, float* beta_t, float* cur_min,
+                         float* cur_max, double* scratch, float* scores, int* chosen, oodfq_stream_t stream);
+
 /* ---- residual-unit tail: BN1(x1) + identity -> ReLU -> [QuantAct], with the feature-alignment energy -------
  * replaces: the last BatchNorm of a residual body, the residual add of the unit's forward (pytorchcv ResUnit /
  *           reference models.py:40-47 `out += self.shortcut(x); out = self.relu2(out)`), the

@@ -52,6 +52,9 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
     "oodfq_res_tail_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float,
                                      _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
+    "oodfq_act_mse_scratch_doubles": (C.c_size_t, [_i]),
+    "oodfq_act_mse_search": (_i, [_vp, _ll, _vp, _i, _i, _d, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp]),
     "oodfq_s2d_stem_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_s2d_stem_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_bn_eval_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
@@ -65,6 +68,14 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if os.path.exists(LIB_PATH):
+        # a library older than its sources has the wrong ABI as often as not: rebuild it when nvcc is at hand
+        try:
+            from . import build as _build
+            if _build.stale():
+                _build.build()
+        except Exception:          # no nvcc / read-only tree: use what is there (the ABI version check still runs)
+            pass
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             f"ood_dfq_b200: native library not found at {LIB_PATH}. This package has no CPU or "

@@ -253,17 +253,26 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ ge, 
     }
 }
 
-static int make_tail_geom(int N, int C, long long HW, int slots, int depth, TailGeom& G) {
+// Work items per image.  The grid is min(items, slots) CTAs walking the items, so the kernel takes
+// ceil(items / slots) rounds: pick the split whose last round is fullest (256 images on 444 slots: one chunk
+// per image fills 58 % of one round, five chunks fill 2.88 of 3), preferring fewer chunks on near-ties -- but
+// only while a chunk keeps >= 8 passes of the row loop: below that the per-item epilogue (energy fold, barriers)
+// costs more than the fuller round gives (measured: 14x14 and 7x7 planes lose 10 % when split).
+static int make_tail_geom(int N, int C, long long HW, long long slots, int depth, TailGeom& G) {
     if (C % 4 != 0 || C / 4 > kBThreads || HW > 0x7fffffffLL || (long long)N * 16 > 0x7fffffffLL) return OODFQ_EINVAL;
     G.N = N; G.C = C; G.HW = (int)HW; G.cols = C / 4;
     G.lanes_r = kBThreads / G.cols;
     const int passes = (int)((HW + (long long)G.lanes_r * depth - 1) / ((long long)G.lanes_r * depth));
-    int want = slots / N;                  // work items per image: fill the resident slots, never 1.x waves
-    if (want > passes) want = passes;
-    if (want > 16) want = 16;
-    if (want < 1) want = 1;
-    G.chunks = want;
-    G.rows_per_chunk = (int)((HW + want - 1) / want);
+    const int cmax = passes / 8 < 1 ? 1 : (passes / 8 < 16 ? passes / 8 : 16);
+    int best = 1;
+    double best_eff = 0.0;
+    for (int c = 1; c <= cmax; ++c) {
+        const double rounds = (double)N * c / (double)slots;
+        const double eff = rounds / (double)(long long)(rounds + 0.999999);
+        if (eff > best_eff + 0.02) { best = c; best_eff = eff; }
+    }
+    G.chunks = best;
+    G.rows_per_chunk = (int)((HW + best - 1) / best);
     return OODFQ_OK;
 }
 
@@ -302,9 +311,14 @@ extern "C" int oodfq_res_tail_forward(const float* x1, const float* r, float* y,
     if (quant && (!fq_lo || !fq_hi || fq_k < 1 || fq_k > 8))
         return fail(OODFQ_EINVAL, "res_tail_forward: fake-quant needs a range and k in [1,8]");
     if (energy && !scratch) return fail(OODFQ_EINVAL, "res_tail_forward: the energy output needs the scratch buffer");
-    static const int per_sm = resident_ctas(res_tail_fwd_kernel<true, true, true>, kBThreads);
+    static const int occ[8] = {
+        resident_ctas(res_tail_fwd_kernel<false, false, false>, kBThreads), resident_ctas(res_tail_fwd_kernel<false, false, true>, kBThreads),
+        resident_ctas(res_tail_fwd_kernel<false, true, false>, kBThreads), resident_ctas(res_tail_fwd_kernel<false, true, true>, kBThreads),
+        resident_ctas(res_tail_fwd_kernel<true, false, false>, kBThreads), resident_ctas(res_tail_fwd_kernel<true, false, true>, kBThreads),
+        resident_ctas(res_tail_fwd_kernel<true, true, false>, kBThreads), resident_ctas(res_tail_fwd_kernel<true, true, true>, kBThreads)};
+    const int per_sm = occ[(quant ? 4 : 0) + (idbn ? 2 : 0) + (energy ? 1 : 0)];
     TailGeom G;
-    if (make_tail_geom(N, C, HW, kNumSM * per_sm, kTailFwdDepth, G) != OODFQ_OK || !aligned16(x1) || !aligned16(r) || !aligned16(y))
+    if (make_tail_geom(N, C, HW, (long long)kNumSM * per_sm, kTailFwdDepth, G) != OODFQ_OK || !aligned16(x1) || !aligned16(r) || !aligned16(y))
         return fail(OODFQ_EINVAL, "res_tail_forward: needs C %% 4 == 0, C <= 1024 and 16-byte aligned buffers");
     cudaStream_t st = (cudaStream_t)stream;
     const TailBn P1{w1, b1, rm1, rv1, eps1}, P2{w2, b2, rm2, rv2, eps2};
@@ -336,18 +350,23 @@ extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_en
     const bool idbn = rv2 != nullptr, energy = grad_energy != nullptr, reduce = dwdb != nullptr;
     if (idbn && !rm2) return fail(OODFQ_EINVAL, "res_tail_backward: identity BatchNorm needs both running statistics");
     if (reduce && !workspace) return fail(OODFQ_EINVAL, "res_tail_backward: parameter gradients need the workspace");
-    static const int per_sm = resident_ctas(res_tail_bwd_kernel<true, true, true>, kBThreads);
+    static const int occ[8] = {
+        resident_ctas(res_tail_bwd_kernel<false, false, false>, kBThreads), resident_ctas(res_tail_bwd_kernel<false, false, true>, kBThreads),
+        resident_ctas(res_tail_bwd_kernel<false, true, false>, kBThreads), resident_ctas(res_tail_bwd_kernel<false, true, true>, kBThreads),
+        resident_ctas(res_tail_bwd_kernel<true, false, false>, kBThreads), resident_ctas(res_tail_bwd_kernel<true, false, true>, kBThreads),
+        resident_ctas(res_tail_bwd_kernel<true, true, false>, kBThreads), resident_ctas(res_tail_bwd_kernel<true, true, true>, kBThreads)};
+    const int per_sm = occ[(idbn ? 4 : 0) + (energy ? 2 : 0) + (reduce ? 1 : 0)];
+    const int Ct = (idbn ? 2 : 1) * C;
+    long long cap = (long long)kNumSM * per_sm;
+    const long long table = (long long)kMaxBnSplit * kMaxBnChannels / Ct;     // rows of ws->bn_partial
+    if (reduce && cap > table) cap = table;
     TailGeom G;
-    if (make_tail_geom(N, C, HW, kNumSM * per_sm, kTailBwdDepth, G) != OODFQ_OK || !aligned16(grad_y) || !aligned16(x1) ||
+    if (make_tail_geom(N, C, HW, cap, kTailBwdDepth, G) != OODFQ_OK || !aligned16(grad_y) || !aligned16(x1) ||
         !aligned16(r) || !aligned16(grad_x1) || !aligned16(grad_r))
         return fail(OODFQ_EINVAL, "res_tail_backward: needs C %% 4 == 0, C <= 1024 and 16-byte aligned buffers");
     cudaStream_t st = (cudaStream_t)stream;
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
     const TailBn P1{w1, b1, rm1, rv1, eps1}, P2{w2, b2, rm2, rv2, eps2};
-    const int Ct = (idbn ? 2 : 1) * C;
-    long long cap = (long long)kNumSM * per_sm;
-    const long long table = (long long)kMaxBnSplit * kMaxBnChannels / Ct;     // rows of ws->bn_partial
-    if (reduce && cap > table) cap = table;
     const long long items = (long long)N * G.chunks;
     const unsigned grid = (unsigned)(items < cap ? items : cap);
     const float two_inv_hw = (float)(2.0 / (double)HW);

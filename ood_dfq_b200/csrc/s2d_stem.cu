@@ -59,32 +59,42 @@ s2d_stem_kernel(const float* __restrict__ src, float* __restrict__ dst, const S2
 // Row form for the channel counts that matter (C = 3, and 1 / 4): for a fixed (image, xs row i, parity s) the
 // s-half of every xs pixel is the input row h = 2i+s-pad, shifted by pad pixels and cut into runs of 2C floats:
 //     xs_row[(q / 2C) * 4C + s*2C + q % 2C] = x_row[q - pad*C]        q in [0, 2C * Ws)
-// so one side of the copy is a fully contiguous row and all divisors are compile-time constants.
+// A CTA step writes one whole destination row contiguously; all divisors are compile-time constants.
 template <int C, bool BWD>
 __global__ void __launch_bounds__(256)
 s2d_stem_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, const S2dGeom G) {
-    const long long rows = (long long)G.N * G.Hs * 2;
-    const int qn = 2 * C * G.Ws, shift = G.pad * C, wlen = G.W * C;
-    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-        const int s = (int)(row & 1);
-        const long long ni = row >> 1;                 // n * Hs + i
-        const int i = (int)(ni % G.Hs);
-        const long long n = ni / G.Hs;
-        const int h = 2 * i + s - G.pad;
-        const bool inside = h >= 0 && h < G.H;
-        const long long xrow = (n * G.H + h) * (long long)wlen;         // image row (valid only if inside)
-        const long long srow = ni * (long long)(4 * C * G.Ws) + s * 2 * C;
-        if (!BWD) {
+    const int shift = G.pad * C, wlen = G.W * C;
+    if (!BWD) {
+        // one xs row (n, i) per step: contiguous stores, loads from the two image rows 2i-pad and 2i+1-pad
+        const long long rows = (long long)G.N * G.Hs;
+        const int qn = 4 * C * G.Ws;
+        for (long long ni = blockIdx.x; ni < rows; ni += gridDim.x) {
+            const int i = (int)(ni % G.Hs);
+            const long long n = ni / G.Hs;
+            const int h0 = 2 * i - G.pad;
+            const long long xrow0 = (n * G.H + h0) * (long long)wlen;
+            float* out = dst + ni * (long long)qn;
             for (int q = threadIdx.x; q < qn; q += 256) {
-                const int m = q - shift;
+                const int r = q % (4 * C), s = r / (2 * C);
+                const int m = (q / (4 * C)) * (2 * C) + r % (2 * C) - shift;
+                const int h = h0 + s;
                 float v = 0.0f;
-                if (inside && m >= 0 && m < wlen) v = __ldg(src + xrow + m);
-                dst[srow + (q / (2 * C)) * (4 * C) + q % (2 * C)] = v;
+                if (h >= 0 && h < G.H && m >= 0 && m < wlen) v = __ldg(src + xrow0 + (long long)s * wlen + m);
+                out[q] = v;
             }
-        } else if (inside) {
+        }
+    } else {
+        // one image row (n, h) per step: contiguous stores, loads in runs of 2C floats from xs row (h+pad)/2
+        const long long rows = (long long)G.N * G.H;
+        for (long long nh = blockIdx.x; nh < rows; nh += gridDim.x) {
+            const int h = (int)(nh % G.H);
+            const long long n = nh / G.H;
+            const int hp = h + G.pad;
+            const float* in = src + (n * G.Hs + (hp >> 1)) * (long long)(4 * C * G.Ws) + (hp & 1) * 2 * C;
+            float* out = dst + nh * (long long)wlen;
             for (int m = threadIdx.x; m < wlen; m += 256) {
                 const int q = m + shift;
-                dst[xrow + m] = __ldg(src + srow + (q / (2 * C)) * (4 * C) + q % (2 * C));
+                out[m] = __ldg(in + (q / (2 * C)) * (4 * C) + q % (2 * C));
             }
         }
     }
@@ -92,7 +102,7 @@ s2d_stem_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, con
 
 template <bool BWD>
 static bool launch_rows(const float* src, float* dst, const S2dGeom& G, cudaStream_t st) {
-    const long long rows = (long long)G.N * G.Hs * 2, cap = (long long)kNumSM * 32;
+    const long long rows = BWD ? (long long)G.N * G.H : (long long)G.N * G.Hs, cap = (long long)kNumSM * 32;
     const unsigned grid = (unsigned)(rows < cap ? rows : cap);
     switch (G.C) {
         case 1: s2d_stem_rows_kernel<1, BWD><<<grid, 256, 0, st>>>(src, dst, G); return true;

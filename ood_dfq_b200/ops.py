@@ -566,3 +566,27 @@ def s2d_stem_backward(grad_xs, in_shape, pad):
         rc = N.load().oodfq_s2d_stem_backward(g.data_ptr(), gx.data_ptr(), n, h, w, c, int(pad), _stream(g.device))
         N.check(rc, "s2d_stem_backward")
     return gx
+
+
+# ----------------------------------------------------------------------------- QuantAct_MSE range search
+def act_mse_search(x, k, x_min, x_max, beta, beta_t, cur_min=None, cur_max=None, steps=80, step=0.01, p=2.4,
+                   debug=False):
+    """The clip-ratio search of ``QuantAct_MSE.forward`` (quant_modules.py:160-178) on the device: data min/max,
+    all ``steps`` candidates scored in one pass over ``x``, first strict minimum kept, plain EMA into
+    ``x_min / x_max / beta_t`` in place.  No host synchronisation.  ``debug``: also return (scores, chosen)."""
+    _need(x, "input")
+    for t, nme in ((x_min, "x_min"), (x_max, "x_max"), (beta, "beta"), (beta_t, "beta_t")):
+        _need(t, nme)
+        if t.numel() != 1 or not t.is_contiguous():
+            raise RuntimeError(f"ood_dfq_b200: {nme} must be a contiguous 1-element buffer")
+    xd = _dense(x)
+    mm = minmax(xd)
+    scratch = torch.empty(int(N.load().oodfq_act_mse_scratch_doubles(int(steps))), dtype=torch.float64, device=x.device)
+    scores = torch.empty(int(steps), dtype=torch.float32, device=x.device) if debug else None
+    chosen = torch.empty(1, dtype=torch.int32, device=x.device) if debug else None
+    rc = N.load().oodfq_act_mse_search(xd.data_ptr(), xd.numel(), mm.data_ptr(), int(k), int(steps), float(step),
+                                       float(p), x_min.data_ptr(), x_max.data_ptr(), beta.data_ptr(),
+                                       beta_t.data_ptr(), _ptr(cur_min), _ptr(cur_max), scratch.data_ptr(),
+                                       _ptr(scores), _ptr(chosen), _stream(x.device))
+    N.check(rc, "act_mse_search")
+    return (scores, chosen) if debug else None

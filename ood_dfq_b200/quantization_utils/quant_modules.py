@@ -150,10 +150,15 @@ class QuantAct_DSG(_ActQuantBase):
 class QuantAct_MSE(_ActQuantBase):
     """Range chosen by an 80-step L_2.4 clip search, plain EMA (reference quant_modules.py:98-186).
 
-    API-compatibility class (no entry point of the reference instantiates it): the data
-    min/max and every candidate fake-quant run on the sm_100a kernels, the score and the
-    scalar bookkeeping stay in torch as in the reference.
+    API-compatibility class (no entry point of the reference instantiates it).  The whole search
+    runs on the device: one pass over ``x`` scores all 80 candidates (csrc/fq_mse.cu), the first
+    strict minimum is kept and folded into the range by the plain EMA -- no host synchronisation,
+    where the reference syncs 80 times on ``score < best_score``.
     """
+
+    search_steps = 80          # quant_modules.py:163
+    search_step = 0.01         # :164-165
+    search_p = 2.4             # :170
 
     def __init__(self, activation_bit, full_precision_flag=False, running_stat=True, beta=0.9):
         super().__init__(activation_bit, full_precision_flag, running_stat, beta)
@@ -163,21 +168,11 @@ class QuantAct_MSE(_ActQuantBase):
 
     def forward(self, x):
         if self.running_stat:
-            xd = x.detach()
-            mm = _ops.minmax(xd)
-            lo, hi = mm[0], mm[1]
-            self.cur_x_min, self.cur_x_max = lo, hi
-            best, keep_lo, keep_hi = 1e+10, lo, hi
-            for i in range(80):
-                f = 1.0 - (i * 0.01)
-                cand_lo, cand_hi = lo * f, hi * f
-                score = lp_loss(xd, find_MSESmallest(xd, self.activation_bit, cand_lo.reshape(1), cand_hi.reshape(1)),
-                                p=2.4, reduction='all')
-                if score < best:
-                    best, keep_lo, keep_hi = score, cand_lo, cand_hi
-            self.beta_t = self.beta_t * self.beta
-            self.x_min = self.x_min * self.beta + keep_lo * (1 - self.beta)
-            self.x_max = self.x_max * self.beta + keep_hi * (1 - self.beta)
+            cur = torch.empty(2, dtype=torch.float32, device=x.device)
+            _ops.act_mse_search(x.detach(), self.activation_bit, self.x_min, self.x_max, self.beta, self.beta_t,
+                                cur_min=cur[0:1], cur_max=cur[1:2], steps=self.search_steps, step=self.search_step,
+                                p=self.search_p)
+            self.cur_x_min, self.cur_x_max = cur[0], cur[1]        # 0-dim, as the reference leaves them (:150-151)
         if not self.full_precision_flag:
             return self.act_function(x, self.activation_bit, self.x_min, self.x_max)
         return x

@@ -137,6 +137,22 @@ def main():
                     report(f"bnbx_{tag}", shape, 8 * n, *timer(lambda: ops.bn_eval_backward(xf, gf, w, b, rm, rv, 1e-5, relu=False, want_param_grads=False)))
                     del gf
                 del xf
+        if "tail" in only and shape[2] <= 56:
+            def bn():
+                return (torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.3,
+                        torch.randn(c, device="cuda") * 0.1, torch.rand(c, device="cuda") + 0.5, 1e-5)
+            bn1, bn2 = bn(), bn()
+            x1 = torch.randn(shape, device="cuda").contiguous(memory_format=torch.channels_last)
+            r = torch.relu(torch.randn(shape, device="cuda")).contiguous(memory_format=torch.channels_last)
+            gy = torch.randn(shape, device="cuda").contiguous(memory_format=torch.channels_last)
+            ge = torch.randn(shape[:2], device="cuda")
+            report("tail_fq_e", shape, 12 * n, *timer(lambda: ops.res_tail_forward(x1, r, bn1, None, fq=(4, lo, hi), want_energy=True)))
+            report("tail_fq_id", shape, 12 * n, *timer(lambda: ops.res_tail_forward(x1, r, bn1, bn2, fq=(4, lo, hi), want_energy=True)))
+            report("tail_plain", shape, 12 * n, *timer(lambda: ops.res_tail_forward(x1, r, bn1, None, want_energy=True)))
+            report("tailbw_ep", shape, 20 * n, *timer(lambda: ops.res_tail_backward(gy, ge, x1, r, bn1, None)))
+            report("tailbw_idp", shape, 20 * n, *timer(lambda: ops.res_tail_backward(gy, ge, x1, r, bn1, bn2)))
+            report("tailbw_e", shape, 20 * n, *timer(lambda: ops.res_tail_backward(gy, ge, x1, r, bn1, None, want_param_grads=False)))
+            del x1, r, gy
         if "pool" in only and shape[2] >= 56:
             w, b = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.3
             rm, rv = torch.randn(c, device="cuda") * 0.1, torch.rand(c, device="cuda") + 0.5
