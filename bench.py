@@ -196,7 +196,7 @@ def main_reference(args):
         "e2e": {"value": res["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -426,7 +426,7 @@ def main_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             res = run_cpu(args.workload, args.cpu_steps, 1, args.cpu_batch)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -453,7 +453,27 @@ def workload_from_conf(path):
     return name
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Point file descriptor 1 at stderr for the rest of the run: libraries write banners straight to it (NCCL
+    prints its version line on communicator creation) and the contract is ONE JSON line on stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)

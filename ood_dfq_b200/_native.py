@@ -70,10 +70,15 @@ def load():
         return _lib
     if os.path.exists(LIB_PATH):
         # a library older than its sources has the wrong ABI as often as not: rebuild it when nvcc is at hand
+        # (one process at a time: the ranks of a torchrun job all come through here)
         try:
+            import fcntl
             from . import build as _build
             if _build.stale():
-                _build.build()
+                with open(LIB_PATH + ".lock", "w") as lock:
+                    fcntl.flock(lock, fcntl.LOCK_EX)
+                    if _build.stale():
+                        _build.build()
         except Exception:          # no nvcc / read-only tree: use what is there (the ABI version check still runs)
             pass
     if not os.path.exists(LIB_PATH):

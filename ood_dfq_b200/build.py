@@ -42,11 +42,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
     nvcc = os.environ.get("NVCC") or os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    tmp = f"{LIB}.tmp.{os.getpid()}"          # build aside, then rename: a concurrent loader never sees half a file
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building liboodfq_b200.so")
+    os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(proc.stderr)
     return LIB
