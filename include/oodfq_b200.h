@@ -194,12 +194,13 @@ int oodfq_channel_energy_backward(const float* x, const float* grad_e, float* gr
  *           (pytorchcv ResInitBlock behind ptcv_get_model, main_direct.py:380-397; quantize_model :464-465)
  * channels_last only: x [N,H,W,C], out / idx / xhat [N,Ho,Wo,C], Ho = (H-1)/2+1.  flags must contain
  * OODFQ_BN_NHWC | OODFQ_BN_RELU, optionally OODFQ_BN_QUANT.  idx: one byte per output (window-local argmax
- * 0..8, bit 7 = ReLU active).  xhat (nullable): normalised input at the argmax, needed only for dwdb. */
+ * 0..8, bit 7 = ReLU active).  xhat (nullable): normalised input at the argmax, needed only for dwdb.
+ * grad_out2 (nullable): a second gradient w.r.t. out, added to grad_out in registers. */
 int oodfq_bn_pool_forward(const float* x, float* out, uint8_t* idx, float* xhat, int N, int C, int H, int W,
                           const float* weight, const float* bias, const float* running_mean,
                           const float* running_var, float eps, int flags, const float* fq_lo,
                           const float* fq_hi, int fq_k, oodfq_stream_t stream);
-int oodfq_bn_pool_backward(const float* grad_out, const uint8_t* idx, const float* xhat, float* grad_x,
+int oodfq_bn_pool_backward(const float* grad_out, const float* grad_out2, const uint8_t* idx, const float* xhat, float* grad_x,
                            int N, int C, int H, int W, const float* weight, const float* bias,
                            const float* running_mean, const float* running_var, float eps,
                            double* dwdb, void* workspace, oodfq_stream_t stream);
@@ -226,7 +227,8 @@ int oodfq_act_mse_search(const float* x, long long numel, const float* data_minm
  * channels_last only (flags must contain OODFQ_BN_NHWC, optionally OODFQ_BN_QUANT): x1, r, y, grads [N,H,W,C].
  * rv2 == NULL: the identity is r itself; otherwise identity = BN2(r) with (w2, b2, rm2, rv2, eps2).
  * energy (nullable) [N, C] = mean_hw BN1(x1)^2; scratch: oodfq_res_tail_scratch_floats(N, C) floats.
- * backward: grad_energy nullable; dwdb nullable, else [2*Ct] doubles with Ct = C (or 2C with BN2):
+ * backward: grad_y2 (nullable) is a second gradient w.r.t. y, added to grad_y in registers (the output fed two
+ *           consumers); grad_energy nullable; dwdb nullable, else [2*Ct] doubles with Ct = C (or 2C with BN2):
  *           dW of BN1 (then BN2), followed by dB of BN1 (then BN2). */
 size_t oodfq_res_tail_scratch_floats(int N, int C);
 int oodfq_res_tail_forward(const float* x1, const float* r, float* y, float* energy, float* scratch, int N, int C,
@@ -234,7 +236,7 @@ int oodfq_res_tail_forward(const float* x1, const float* r, float* y, float* ene
                            float eps1, const float* w2, const float* b2, const float* rm2, const float* rv2,
                            float eps2, int flags, const float* fq_lo, const float* fq_hi, int fq_k,
                            oodfq_stream_t stream);
-int oodfq_res_tail_backward(const float* grad_y, const float* grad_energy, const float* x1, const float* r,
+int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2, const float* grad_energy, const float* x1, const float* r,
                             float* grad_x1, float* grad_r, int N, int C, long long HW, const float* w1,
                             const float* b1, const float* rm1, const float* rv1, float eps1, const float* w2,
                             const float* b2, const float* rm2, const float* rv2, float eps2, int flags,

@@ -204,8 +204,9 @@ bn_pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, uint8_t
 // whose centre the block holds -- (m,n), centre (2m,2n) -- is this thread's share of dW / dB.
 template <bool REDUCE>
 __global__ void __launch_bounds__(kBThreads)
-bn_pool_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ idx, const float* __restrict__ xhat,
-                   float* __restrict__ gx, const PoolGeom G, const BnParams2 P, Workspace* ws) {
+bn_pool_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ gout2, const uint8_t* __restrict__ idx,
+                   const float* __restrict__ xhat, float* __restrict__ gx, const PoolGeom G, const BnParams2 P,
+                   Workspace* ws) {
     __shared__ float red[REDUCE ? 2 * kBThreads * 4 : 1];
     const bool active = (int)threadIdx.x < G.lanes_r * G.cols;
     const int col = threadIdx.x % G.cols, rsub = threadIdx.x / G.cols;
@@ -216,6 +217,7 @@ bn_pool_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ i
     }
     const long long blocks = (long long)G.N * G.Ho * G.Wo;
     const float4* g4 = reinterpret_cast<const float4*>(gout);
+    const float4* h4 = reinterpret_cast<const float4*>(gout2);      // nullable: second gradient w.r.t. the output
     const uchar4* i4 = reinterpret_cast<const uchar4*>(idx);
     float4* gx4 = reinterpret_cast<float4*>(gx);
     if (active) {
@@ -234,7 +236,14 @@ bn_pool_bwd_kernel(const float* __restrict__ gout, const uint8_t* __restrict__ i
             for (int k = 0; k < 4; ++k) {
                 float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
                 uchar4 c = make_uchar4(0, 0, 0, 0);
-                if (have[k]) { g = __ldg(g4 + base + off[k]); c = __ldg(i4 + base + off[k]); }
+                if (have[k]) {
+                    g = __ldg(g4 + base + off[k]);
+                    c = __ldg(i4 + base + off[k]);
+                    if (h4) {             // the pooled tensor fed two consumers: sum their gradients here
+                        const float4 t = __ldg(h4 + base + off[k]);
+                        g.x = __fadd_rn(g.x, t.x); g.y = __fadd_rn(g.y, t.y); g.z = __fadd_rn(g.z, t.z); g.w = __fadd_rn(g.w, t.w);
+                    }
+                }
                 gs[k][0] = g.x; gs[k][1] = g.y; gs[k][2] = g.z; gs[k][3] = g.w;
                 cs[k][0] = c.x; cs[k][1] = c.y; cs[k][2] = c.z; cs[k][3] = c.w;
             }
@@ -357,14 +366,15 @@ extern "C" int oodfq_bn_pool_forward(const float* x, float* out, uint8_t* idx, f
     return check_launch("bn_pool_forward");
 }
 
-extern "C" int oodfq_bn_pool_backward(const float* grad_out, const uint8_t* idx, const float* xhat, float* grad_x,
+extern "C" int oodfq_bn_pool_backward(const float* grad_out, const float* grad_out2, const uint8_t* idx, const float* xhat, float* grad_x,
                                       int N, int C, int H, int W, const float* weight, const float* bias,
                                       const float* running_mean, const float* running_var, float eps,
                                       double* dwdb, void* workspace, oodfq_stream_t stream) {
     if (!grad_out || !idx || !grad_x || !running_mean || !running_var) return fail(OODFQ_EINVAL, "bn_pool_backward: null pointer");
     if (dwdb && (!xhat || !workspace)) return fail(OODFQ_EINVAL, "bn_pool_backward: parameter gradients need xhat and the workspace");
     PoolGeom G;
-    if (make_pool_geom(N, C, H, W, G) != OODFQ_OK || !aligned16(grad_out) || !aligned16(grad_x) || (xhat && !aligned16(xhat)))
+    if (make_pool_geom(N, C, H, W, G) != OODFQ_OK || !aligned16(grad_out) || !aligned16(grad_x) || (xhat && !aligned16(xhat)) ||
+        (grad_out2 && !aligned16(grad_out2)))
         return fail(OODFQ_EINVAL, "bn_pool_backward: needs C %% 4 == 0, C <= 1024 and aligned buffers");
     cudaStream_t st = (cudaStream_t)stream;
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
@@ -375,8 +385,8 @@ extern "C" int oodfq_bn_pool_backward(const float* grad_out, const uint8_t* idx,
     const long long table = (long long)kMaxBnSplit * kMaxBnChannels / C;
     if (dwdb && cap > table) cap = table;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    if (dwdb) bn_pool_bwd_kernel<true><<<grid, kBThreads, 0, st>>>(grad_out, idx, xhat, grad_x, G, P, ws);
-    else bn_pool_bwd_kernel<false><<<grid, kBThreads, 0, st>>>(grad_out, idx, xhat, grad_x, G, P, ws);
+    if (dwdb) bn_pool_bwd_kernel<true><<<grid, kBThreads, 0, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, P, ws);
+    else bn_pool_bwd_kernel<false><<<grid, kBThreads, 0, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, P, ws);
     count_launch();
     int rc = check_launch("bn_pool_backward");
     if (rc != OODFQ_OK || !dwdb) return rc;

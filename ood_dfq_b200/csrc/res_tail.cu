@@ -11,10 +11,14 @@
 // the adds and masks were 6 ms of the 47 ms ImageNet step (profiles/r1_step_share_pruned_stem2.txt).  Here:
 //
 //   forward   read x1, r; write y                       12 B/elem   (E comes out of the same read)
-//   backward  read gy, x1, r; write gx1, gr             20 B/elem
+//   backward  read gy, x1, r; write gx1, gr             20 B/elem   (+4 with a second output gradient, see below)
 //             s = z1 + id;  g = gy * [s > 0]  (ReLU; the quantiser is the identity STE, quant_utils.py:159-161)
 //             dz1 = g + gE[n,c] * 2/HW * z1;  gx1 = a1 * dz1;  gr = g  or  a2 * g
 //             dW1 = sum dz1 * xhat1, dB1 = sum dz1  (and dW2, dB2 over g) from the same pass
+//
+// A unit's output feeds two consumers in the next unit (its body and its identity path).  Autograd would sum their
+// gradients with one more 12 B/elem kernel per unit and sweep (5.5 % of the step); instead the forward hands out
+// two handles of y and the backward takes both gradients (grad_y2, nullable) and adds them in registers.
 //
 // Every intermediate is rounded exactly where the unfused chain rounds it (affine by FFMA as bn_fused.cu, the add
 // and the gradient sum as separate fp32 roundings), so y and the gradients are bit-identical to the chain of
@@ -144,9 +148,10 @@ __global__ void res_tail_fold_energy_kernel(const float* __restrict__ partial, f
 
 template <bool IDBN, bool ENERGY, bool REDUCE>
 __global__ void __launch_bounds__(kBThreads)
-res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ ge, const float* __restrict__ x1,
-                    const float* __restrict__ r, float* __restrict__ gx1, float* __restrict__ gr, const TailGeom G,
-                    const TailBn P1, const TailBn P2, float two_inv_hw, Workspace* ws) {
+res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2, const float* __restrict__ ge,
+                    const float* __restrict__ x1, const float* __restrict__ r, float* __restrict__ gx1,
+                    float* __restrict__ gr, const TailGeom G, const TailBn P1, const TailBn P2, float two_inv_hw,
+                    Workspace* ws) {
     __shared__ float red[REDUCE ? (IDBN ? 4 : 2) * kBThreads * 4 : 1];
     const bool active = (int)threadIdx.x < G.lanes_r * G.cols;
     const int col = threadIdx.x % G.cols, rsub = threadIdx.x / G.cols;
@@ -170,6 +175,7 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ ge, 
             const int r_begin = ck * G.rows_per_chunk, r_end = min(G.HW, r_begin + G.rows_per_chunk);
             const long long base = (long long)n * G.HW * G.cols + col;
             const float4* pg = reinterpret_cast<const float4*>(gy) + base;
+            const float4* pg2 = gy2 ? reinterpret_cast<const float4*>(gy2) + base : nullptr;
             const float4* p1 = reinterpret_cast<const float4*>(x1) + base;
             const float4* p2 = reinterpret_cast<const float4*>(r) + base;
             float4* o1 = reinterpret_cast<float4*>(gx1) + base;
@@ -180,12 +186,13 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ ge, 
                 for (int j = 0; j < 4; ++j) ce[j] = __fmul_rn(__ldg(ge + (long long)n * G.C + 4 * col + j), two_inv_hw);
             }
             for (int row = r_begin + rsub; row < r_end; row += kTailBwdDepth * G.lanes_r) {
-                float4 g[kTailBwdDepth], u[kTailBwdDepth], v[kTailBwdDepth];
+                float4 g[kTailBwdDepth], g2[kTailBwdDepth], u[kTailBwdDepth], v[kTailBwdDepth];
 #pragma unroll
                 for (int d = 0; d < kTailBwdDepth; ++d) {
                     const int rr = row + d * G.lanes_r;
                     if (rr < r_end) {
                         g[d] = ld_stream(pg + (long long)rr * G.cols);
+                        if (pg2) g2[d] = ld_stream(pg2 + (long long)rr * G.cols);
                         u[d] = ld_stream(p1 + (long long)rr * G.cols);
                         v[d] = ld_stream(p2 + (long long)rr * G.cols);
                     }
@@ -194,7 +201,11 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ ge, 
                 for (int d = 0; d < kTailBwdDepth; ++d) {
                     const int rr = row + d * G.lanes_r;
                     if (rr < r_end) {
-                        const float gs[4] = {g[d].x, g[d].y, g[d].z, g[d].w};
+                        float gs[4] = {g[d].x, g[d].y, g[d].z, g[d].w};
+                        if (pg2) {        // the unit's output fed two consumers: their gradients are summed here
+                            gs[0] = __fadd_rn(gs[0], g2[d].x); gs[1] = __fadd_rn(gs[1], g2[d].y);
+                            gs[2] = __fadd_rn(gs[2], g2[d].z); gs[3] = __fadd_rn(gs[3], g2[d].w);
+                        }
                         const float xs[4] = {u[d].x, u[d].y, u[d].z, u[d].w};
                         const float rs[4] = {v[d].x, v[d].y, v[d].z, v[d].w};
                         float d1[4], d2[4];
@@ -285,11 +296,11 @@ static void launch_tail_fwd(bool energy, unsigned grid, cudaStream_t st, const f
 }
 
 template <bool IDBN, bool ENERGY>
-static void launch_tail_bwd(bool reduce, unsigned grid, cudaStream_t st, const float* gy, const float* ge,
-                            const float* x1, const float* r, float* gx1, float* gr, const TailGeom& G,
-                            const TailBn& P1, const TailBn& P2, float two_inv_hw, Workspace* ws) {
-    if (reduce) res_tail_bwd_kernel<IDBN, ENERGY, true><<<grid, kBThreads, 0, st>>>(gy, ge, x1, r, gx1, gr, G, P1, P2, two_inv_hw, ws);
-    else res_tail_bwd_kernel<IDBN, ENERGY, false><<<grid, kBThreads, 0, st>>>(gy, ge, x1, r, gx1, gr, G, P1, P2, two_inv_hw, ws);
+static void launch_tail_bwd(bool reduce, unsigned grid, cudaStream_t st, const float* gy, const float* gy2,
+                            const float* ge, const float* x1, const float* r, float* gx1, float* gr,
+                            const TailGeom& G, const TailBn& P1, const TailBn& P2, float two_inv_hw, Workspace* ws) {
+    if (reduce) res_tail_bwd_kernel<IDBN, ENERGY, true><<<grid, kBThreads, 0, st>>>(gy, gy2, ge, x1, r, gx1, gr, G, P1, P2, two_inv_hw, ws);
+    else res_tail_bwd_kernel<IDBN, ENERGY, false><<<grid, kBThreads, 0, st>>>(gy, gy2, ge, x1, r, gx1, gr, G, P1, P2, two_inv_hw, ws);
 }
 
 }  // namespace oodfq
@@ -339,7 +350,7 @@ extern "C" int oodfq_res_tail_forward(const float* x1, const float* r, float* y,
     return check_launch("res_tail_forward(fold)");
 }
 
-extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_energy, const float* x1, const float* r,
+extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2, const float* grad_energy, const float* x1, const float* r,
                                        float* grad_x1, float* grad_r, int N, int C, long long HW, const float* w1,
                                        const float* b1, const float* rm1, const float* rv1, float eps1,
                                        const float* w2, const float* b2, const float* rm2, const float* rv2,
@@ -362,7 +373,7 @@ extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_en
     if (reduce && cap > table) cap = table;
     TailGeom G;
     if (make_tail_geom(N, C, HW, cap, kTailBwdDepth, G) != OODFQ_OK || !aligned16(grad_y) || !aligned16(x1) ||
-        !aligned16(r) || !aligned16(grad_x1) || !aligned16(grad_r))
+        !aligned16(r) || !aligned16(grad_x1) || !aligned16(grad_r) || (grad_y2 && !aligned16(grad_y2)))
         return fail(OODFQ_EINVAL, "res_tail_backward: needs C %% 4 == 0, C <= 1024 and 16-byte aligned buffers");
     cudaStream_t st = (cudaStream_t)stream;
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
@@ -370,10 +381,10 @@ extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_en
     const long long items = (long long)N * G.chunks;
     const unsigned grid = (unsigned)(items < cap ? items : cap);
     const float two_inv_hw = (float)(2.0 / (double)HW);
-    if (idbn && energy) launch_tail_bwd<true, true>(reduce, grid, st, grad_y, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
-    else if (idbn) launch_tail_bwd<true, false>(reduce, grid, st, grad_y, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
-    else if (energy) launch_tail_bwd<false, true>(reduce, grid, st, grad_y, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
-    else launch_tail_bwd<false, false>(reduce, grid, st, grad_y, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
+    if (idbn && energy) launch_tail_bwd<true, true>(reduce, grid, st, grad_y, grad_y2, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
+    else if (idbn) launch_tail_bwd<true, false>(reduce, grid, st, grad_y, grad_y2, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
+    else if (energy) launch_tail_bwd<false, true>(reduce, grid, st, grad_y, grad_y2, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
+    else launch_tail_bwd<false, false>(reduce, grid, st, grad_y, grad_y2, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
     count_launch();
     int rc = check_launch("res_tail_backward");
     if (rc != OODFQ_OK || !reduce) return rc;

@@ -24,6 +24,33 @@ from . import ops
 from .quantization_utils.quant_modules import QuantAct
 
 
+_TWIN = "_oodfq_twin"
+
+
+def _twin_of(y):
+    """A second, independent handle of ``y``'s storage.  A fused producer returns it as an extra output and hangs
+    it on ``y`` (attribute ``_oodfq_twin``); a fused residual unit downstream feeds its body from ``y`` and its
+    identity path from the twin, so autograd hands the producer's backward the two gradients separately and the
+    kernel sums them in registers instead of autograd launching a 12 B/elem add per unit input and sweep.
+    A consumer that ignores the twin just leaves its gradient ``None``.  (Not an autograd view on purpose: the
+    two handles must be separate graph edges.  Nothing downstream writes to either in place.)"""
+    return torch.empty(0, dtype=y.dtype, device=y.device).set_(y.untyped_storage(), y.storage_offset(), y.size(),
+                                                              y.stride())
+
+
+def _pick_twin(x):
+    t = getattr(x, _TWIN, None)
+    if isinstance(t, torch.Tensor) and t.shape == x.shape and t.stride() == x.stride() and t.data_ptr() == x.data_ptr():
+        return t
+    return x
+
+
+def _two_grads(g, g2):
+    if g is None:
+        return g2, None
+    return g, g2
+
+
 class _FusedBN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, bn, relu, qact):
@@ -92,15 +119,20 @@ class _FusedStem(torch.autograd.Function):
                                              want_xhat=need_p)
         ctx.save_for_backward(idx, xhat, weight, bias)
         ctx.bn, ctx.in_shape = bn, tuple(x.shape)
-        return out
+        ctx.set_materialize_grads(False)
+        return out, _twin_of(out)
 
     @staticmethod
-    def backward(ctx, grad_out):
+    def backward(ctx, grad_out, grad_out2):
         idx, xhat, weight, bias = ctx.saved_tensors
         need_p = xhat is not None and ((weight is not None and ctx.needs_input_grad[1]) or
                                        (bias is not None and ctx.needs_input_grad[2]))
+        grad_out, grad_out2 = _two_grads(grad_out, grad_out2)
+        if grad_out is None:
+            return None, None, None, None, None
         gx, dw, db = ops.bn_pool_backward(grad_out, idx, xhat, ctx.in_shape, weight, bias, ctx.bn.running_mean,
-                                          ctx.bn.running_var, ctx.bn.eps, want_param_grads=need_p)
+                                          ctx.bn.running_var, ctx.bn.eps, want_param_grads=need_p,
+                                          grad_out2=grad_out2)
         return (gx,
                 dw if (weight is not None and ctx.needs_input_grad[1]) else None,
                 db if (bias is not None and ctx.needs_input_grad[2]) else None,
@@ -154,7 +186,9 @@ class _FusedEvalMixin:
         q = qact if (qact is not None and not qact.full_precision_flag) else None
         if self._pool is not None and has_tail and ops.bn_pool_supported(x) and (q is None or q.activation_bit <= 8):
             self._pool._bypass = True             # the pool module two steps downstream just hands this through
-            return _FusedStem.apply(x, self.weight, self.bias, self, q)
+            out, twin = _FusedStem.apply(x, self.weight, self.bias, self, q)
+            setattr(out, _TWIN, twin)
+            return out
         return _FusedBN.apply(x, self.weight, self.bias, self, has_tail, q)
 
 
@@ -249,23 +283,27 @@ class _FusedTail(torch.autograd.Function):
         y, e = ops.res_tail_forward(x1, r, t1, t2, fq=fq, want_energy=want_energy)
         ctx.save_for_backward(x1, r, w1, b1, w2, b2)
         ctx.bn1, ctx.bn2, ctx.want_energy = bn1, bn2, want_energy
+        ctx.set_materialize_grads(False)
         if e is None:
             e = x1.new_empty(0)
             ctx.mark_non_differentiable(e)
-        return y, e
+        return y, _twin_of(y), e
 
     @staticmethod
-    def backward(ctx, grad_y, grad_e):
+    def backward(ctx, grad_y, grad_y2, grad_e):
         x1, r, w1, b1, w2, b2 = ctx.saved_tensors
         bn1, bn2 = ctx.bn1, ctx.bn2
         t1 = (w1, b1, bn1.running_mean, bn1.running_var, bn1.eps)
         t2 = None if bn2 is None else (w2, b2, bn2.running_mean, bn2.running_var, bn2.eps)
+        grad_y, grad_y2 = _two_grads(grad_y, grad_y2)
         if grad_y is None:
+            if grad_e is None or not ctx.want_energy:
+                return (None,) * 10
             grad_y = torch.zeros_like(x1)
         need = ctx.needs_input_grad
         need_p = any(need[i] and t is not None for i, t in ((2, w1), (3, b1), (4, w2), (5, b2)))
         gx1, gr, dw1, db1, dw2, db2 = ops.res_tail_backward(grad_y, grad_e if ctx.want_energy else None, x1, r, t1, t2,
-                                                            want_param_grads=need_p)
+                                                            want_param_grads=need_p, grad_y2=grad_y2)
         return (gx1 if need[0] else None, gr if need[1] else None,
                 dw1 if (w1 is not None and need[2]) else None, db1 if (b1 is not None and need[3]) else None,
                 dw2 if (w2 is not None and need[4]) else None, db2 if (b2 is not None and need[5]) else None,
@@ -380,7 +418,8 @@ class _FusedUnitMixin:
             return super().forward(x)
         p, qact, taps = setup
         x1 = p.conv(p.head(x))
-        r = p.idconv(x) if p.idconv is not None else x
+        xr = _pick_twin(x)                        # the producer's second handle, if it left one (see _twin_of)
+        r = p.idconv(xr) if p.idconv is not None else xr
         bn1, bn2 = p.bn1, p.bn2
         if not ops.res_tail_supported(x1, r):
             # (a convolution handed back another layout) finish with the ordinary modules
@@ -388,8 +427,9 @@ class _FusedUnitMixin:
             for t in taps:
                 t._hook(p.hooked, (x,), z)
             return p.act(z + (bn2(r) if bn2 is not None else r))
-        y, e = _FusedTail.apply(x1, r, bn1.weight, bn1.bias, bn2.weight if bn2 is not None else None,
-                                bn2.bias if bn2 is not None else None, bn1, bn2, qact, bool(taps))
+        y, twin, e = _FusedTail.apply(x1, r, bn1.weight, bn1.bias, bn2.weight if bn2 is not None else None,
+                                      bn2.bias if bn2 is not None else None, bn1, bn2, qact, bool(taps))
+        setattr(y, _TWIN, twin)
         for t in taps:
             t.maps.append(F.normalize(e))
         return y

@@ -435,19 +435,24 @@ def bn_pool_forward(x, weight, bias, running_mean, running_var, eps, fq=None, wa
 
 
 def bn_pool_backward(grad_out, idx, xhat, in_shape, weight, bias, running_mean, running_var, eps,
-                     want_param_grads=True):
-    """Backward of ``bn_pool_forward``: (grad_x channels_last, dweight, dbias).  The forward input is not needed."""
+                     want_param_grads=True, grad_out2=None):
+    """Backward of ``bn_pool_forward``: (grad_x channels_last, dweight, dbias).  The forward input is not needed.
+    ``grad_out2``: a second gradient w.r.t. the output (it fed two consumers), summed inside the kernel."""
     _need(grad_out, "grad_output")
     n, c, h, w = in_shape
     go = grad_out.contiguous(memory_format=torch.channels_last)
+    go2 = None
+    if grad_out2 is not None:
+        _need(grad_out2, "grad_output (second)")
+        go2 = grad_out2.contiguous(memory_format=torch.channels_last)
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
     gx = torch.empty((n, c, h, w), dtype=torch.float32, device=grad_out.device, memory_format=torch.channels_last)
     need = want_param_grads and xhat is not None
     dwdb = torch.empty(2 * c, dtype=torch.float64, device=grad_out.device) if need else None
     ws = workspace(grad_out.device).data_ptr() if need else None
     with _Timed("bn_pool_bwd_kernel (stem backward, 4 B/elem out + 1/4 size inputs)",
-                4 * gx.numel() + (9 if need else 5) * go.numel()):
-        rc = N.load().oodfq_bn_pool_backward(go.data_ptr(), idx.data_ptr(), _ptr(xhat) if need else None, gx.data_ptr(),
+                4 * gx.numel() + ((9 if need else 5) + (4 if go2 is not None else 0)) * go.numel()):
+        rc = N.load().oodfq_bn_pool_backward(go.data_ptr(), _ptr(go2), idx.data_ptr(), _ptr(xhat) if need else None, gx.data_ptr(),
                                              n, c, h, w, pw, pb, prm, prv, float(eps), _ptr(dwdb), ws,
                                              _stream(grad_out.device))
         N.check(rc, "bn_pool_backward")
@@ -506,12 +511,17 @@ def res_tail_forward(x1, r, bn1, bn2=None, fq=None, want_energy=False):
     return y, energy
 
 
-def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grads=True):
+def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grads=True, grad_y2=None):
     """Backward of ``res_tail_forward``: ``(grad_x1, grad_r, dW1, dB1, dW2, dB2)`` (parameter gradients None
-    unless wanted; dW2 / dB2 None without ``bn2``)."""
+    unless wanted; dW2 / dB2 None without ``bn2``).  ``grad_y2``: a second gradient w.r.t. ``y`` (the output fed
+    two consumers), added to ``grad_y`` inside the kernel."""
     _need(grad_y, "grad_output")
     n, c, h, w = x1.shape
     gy = grad_y.contiguous(memory_format=torch.channels_last)
+    gy2 = None
+    if grad_y2 is not None:
+        _need(grad_y2, "grad_output (second)")
+        gy2 = grad_y2.contiguous(memory_format=torch.channels_last)
     ge = None
     if grad_energy is not None:
         _need(grad_energy, "grad_energy")
@@ -521,8 +531,9 @@ def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grad
     ct = c * (2 if bn2 is not None else 1)
     dwdb = torch.empty(2 * ct, dtype=torch.float64, device=x1.device) if want_param_grads else None
     ws = workspace(x1.device).data_ptr() if want_param_grads else None
-    with _Timed("res_tail_bwd_kernel (ReLU mask + energy gradient + BN backward(s), 20 B/elem)", 20 * x1.numel()):
-        rc = N.load().oodfq_res_tail_backward(gy.data_ptr(), _ptr(ge), x1.data_ptr(), r.data_ptr(), gx1.data_ptr(),
+    with _Timed("res_tail_bwd_kernel (ReLU mask + energy gradient + BN backward(s), 20 B/elem)",
+                (24 if gy2 is not None else 20) * x1.numel()):
+        rc = N.load().oodfq_res_tail_backward(gy.data_ptr(), _ptr(gy2), _ptr(ge), x1.data_ptr(), r.data_ptr(), gx1.data_ptr(),
                                               gr.data_ptr(), n, c, h * w, *p1, *p2, N.BN_NHWC, _ptr(dwdb), ws,
                                               _stream(x1.device))
         N.check(rc, "res_tail_backward")

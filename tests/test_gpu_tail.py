@@ -73,6 +73,54 @@ def test_tail_matches_the_kernel_chain(shape, idbn, k):
         assert dw1b is None and torch.equal(gx1b, gx1) and torch.equal(grb, gr)
 
 
+def test_second_output_gradient_is_summed_in_the_kernel():
+    """grad_y2 / grad_out2: the kernels add the two gradients exactly like autograd's accumulation would."""
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    shape = (6, 32, 14, 14)
+    x1 = torch.randn(shape, generator=g).to(DEV).contiguous(memory_format=CL)
+    r = torch.relu(torch.randn(shape, generator=g)).to(DEV).contiguous(memory_format=CL)
+    bn1, bn2 = make_bn(32, g), make_bn(32, g)
+    ga = torch.randn(shape, generator=g).to(DEV).contiguous(memory_format=CL)
+    gb = torch.randn(shape, generator=g).to(DEV).contiguous(memory_format=CL)
+    ge = torch.randn(shape[:2], generator=g).to(DEV)
+    for b2 in (None, bn2):
+        one = ops.res_tail_backward(ga + gb, ge, x1, r, bn1, b2)
+        two = ops.res_tail_backward(ga, ge, x1, r, bn1, b2, grad_y2=gb)
+        for a, b in zip(one, two):
+            assert (a is None and b is None) or torch.equal(a, b)
+    # stem
+    xs = (torch.randn(4, 16, 20, 18, generator=g) * 1.4).to(DEV).contiguous(memory_format=CL)
+    w, b, rm, rv, eps = make_bn(16, g)
+    fq = (4, torch.zeros(1, device=DEV), torch.full((1,), 1.9, device=DEV))
+    out, idx, xhat = ops.bn_pool_forward(xs, w, b, rm, rv, eps, fq=fq)
+    ga = torch.randn(out.shape, generator=g).to(DEV).contiguous(memory_format=CL)
+    gb = torch.randn(out.shape, generator=g).to(DEV).contiguous(memory_format=CL)
+    one = ops.bn_pool_backward(ga + gb, idx, xhat, xs.shape, w, b, rm, rv, eps)
+    two = ops.bn_pool_backward(ga, idx, xhat, xs.shape, w, b, rm, rv, eps, grad_out2=gb)
+    for a, b_ in zip(one, two):
+        assert torch.equal(a, b_)
+
+
+def test_fused_units_hand_each_other_a_second_handle():
+    """The producer hangs a twin of its output on the tensor; the next fused unit reads its identity through it,
+    so no autograd accumulation kernel runs at the unit input -- and the gradients do not change."""
+    from ood_dfq_b200 import fusion
+    plain, fused, xs, _ = _pair("resnet20_cifar", CL, 32)
+    units = [m for m in fused.modules() if isinstance(m, fusion._FusedUnitMixin)]
+    seen = []
+    hooks = [u.register_forward_hook(lambda m, i, o: seen.append((hasattr(i[0], fusion._TWIN), hasattr(o, fusion._TWIN))))
+             for u in units]
+    a, b = xs[1].clone().requires_grad_(True), xs[1].clone().requires_grad_(True)
+    ya, yb = plain(a), fused(b)
+    for h in hooks:
+        h.remove()
+    assert all(out for _, out in seen) and all(inp for inp, _ in seen[1:])
+    ya.square().mean().backward()
+    yb.square().mean().backward()
+    assert torch.allclose(a.grad, b.grad, rtol=1e-4, atol=1e-7 + 1e-5 * a.grad.abs().max().item())
+
+
 def test_tail_rejects_what_it_cannot_run():
     from ood_dfq_b200 import ops
     g = torch.Generator().manual_seed(0)
