@@ -210,8 +210,10 @@ def test_channels_last_student_matches_nchw_student():
         qat(xs[0])
 
 
-def test_graphed_step_matches_eager_step():
-    """The whole QAT iteration replayed as a CUDA graph updates the student exactly like the eager step."""
+@pytest.mark.parametrize("all_passes", [False, True])
+def test_graphed_step_matches_eager_step(all_passes):
+    """The whole QAT iteration replayed as a CUDA graph updates the student exactly like the eager step
+    (``all_passes``: channels_last with the residual-tail fusion and the twin handles as well)."""
     from ood_dfq_b200 import fusion, nets, step, surgery
     from ood_dfq_b200.quantization_utils import quant_modules as qm
     torch.backends.cudnn.allow_tf32 = False
@@ -222,15 +224,20 @@ def test_graphed_step_matches_eager_step():
         torch.manual_seed(1)
         teacher = nets.resnet20_cifar(num_classes=10)
         nets.perturb_bn_stats(teacher)
-        student = surgery.quantize_model(copy.deepcopy(teacher), 4, 4).to(DEV)
-        teacher = teacher.to(DEV)
+        fmt = torch.channels_last if all_passes else torch.contiguous_format
+        student = surgery.quantize_model(copy.deepcopy(teacher), 4, 4).to(DEV).to(memory_format=fmt)
+        teacher = teacher.to(DEV).to(memory_format=fmt)
         g = torch.Generator().manual_seed(2)
-        xs = [torch.randn(16, 3, 32, 32, generator=g).to(DEV) for _ in range(4)]
+        xs = [torch.randn(16, 3, 32, 32, generator=g).to(DEV).contiguous(memory_format=fmt) for _ in range(4)]
         with torch.no_grad():
             for x in xs[:2]:
                 student(x)
         surgery.freeze_model(student)
         fusion.fuse_eval_bn(student, xs[0][:2])
+        if all_passes:
+            fusion.fuse_eval_bn(teacher, xs[0][:2])
+            assert fusion.fuse_residual_tails(student, xs[0][:2]) == 9
+            assert fusion.fuse_residual_tails(teacher, xs[0][:2]) == 9
         qat = step.QATStep(student, teacher, lr=1e-5, unit_types=(nets.ResUnit,))
         return student, qat, xs
 
