@@ -1,0 +1,45 @@
+"""Host logic of the QAT step on CPU (oracle modules): the pruned final backward leaves the student's gradients
+and update bit-identical to the reference's full ``loss.backward()`` sweep (trainer_direct.py:350-356)."""
+import copy
+
+import torch
+
+from ood_dfq_b200 import nets, step, surgery
+from oracle import fq_torch
+
+
+def _pair():
+    torch.manual_seed(1)
+    teacher = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(teacher)
+    student = surgery.quantize_model(copy.deepcopy(teacher), 4, 4, namespace=fq_torch)
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(4, 3, 32, 32, generator=g) for _ in range(2)]
+    surgery.unfreeze_model(student, fq_torch)
+    with torch.no_grad():
+        student(xs[0])
+    surgery.freeze_model(student, fq_torch)
+    return teacher, student, xs
+
+
+def test_pruned_backward_gives_the_same_update():
+    results = []
+    for prune in (True, False):
+        teacher, student, xs = _pair()
+        qat = step.QATStep(student, teacher, lr=1e-3, unit_types=(nets.ResUnit,), prune_backward=prune)
+        losses = [qat(x).item() for x in xs]
+        results.append((losses, [p.detach().clone() for p in student.parameters()], qat.grads.flat.clone()))
+    (l0, p0, g0), (l1, p1, g1) = results
+    assert l0 == l1
+    assert torch.equal(g0, g1)
+    assert all(torch.equal(a, b) for a, b in zip(p0, p1))
+
+
+def test_teacher_stays_frozen_and_taps_line_up():
+    teacher, student, xs = _pair()
+    before = [p.detach().clone() for p in teacher.parameters()]
+    qat = step.QATStep(student, teacher, lr=1e-3, unit_types=(nets.ResUnit,))
+    qat(xs[0])
+    assert all(torch.equal(a, b) for a, b in zip(before, teacher.parameters()))
+    assert all(p.grad is None for p in teacher.parameters())
+    assert len(qat.tap_s.maps) == len(qat.tap_t.maps) == 9
