@@ -47,6 +47,7 @@ extern "C" {
 #define OODFQ_PARAMS_GIVEN 2   /* p0/p1 are (scale, zero_point) instead of (min,max) */
 #define OODFQ_RELU_FIRST 4     /* x <- max(x, 0) before quantising: the nn.Sequential(ReLU, QuantAct) of
                                   main_direct.py:464-465 in one pass (scalar range, FAKEQUANT mode) */
+#define OODFQ_NO_ONCHIP 8      /* act_calib_forward: always take the two-kernel path (tests, comparisons) */
 
 /* flags of the per-channel (BatchNorm) entry points */
 #define OODFQ_BN_RELU 1
@@ -90,6 +91,9 @@ int oodfq_fq_forward(const float* x, float* y, int8_t* codes, long long numel,
  * One call = data min/max of x, the bias-corrected running-range update of
  * (x_min, x_max, beta_t) IN PLACE on the device, then the fake-quantised y
  * with the UPDATED range.  y == NULL: range update only (full_precision_flag).
+ * Tensors of up to 96 MB (asymmetric, k <= 8, numel % 4 == 0) run as ONE cooperative kernel that keeps x in
+ * shared memory across the grid-wide range reduction, so x crosses HBM once; larger ones (or OODFQ_NO_ONCHIP)
+ * as a reducing kernel followed by the streaming fake-quant.  Results are bit-identical either way.
  * workspace: oodfq_workspace_bytes() of device memory, zeroed once by the
  * caller and then owned by this library between calls on one stream. */
 int oodfq_act_calib_forward(const float* x, float* y, int8_t* codes, long long numel,

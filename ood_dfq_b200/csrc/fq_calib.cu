@@ -10,7 +10,11 @@
 // Roofline: HBM.  12 algorithmic bytes per element when 4*numel exceeds L2 (the
 // quantised range depends on the min/max of the very tensor being quantised, so x
 // must be read twice), 8 B/elem when x stays L2-resident between the passes.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace oodfq {
 
@@ -127,6 +131,154 @@ static int launch_minmax(const float* x, long long numel, void* workspace, float
     return check_launch("minmax");
 }
 
+// ---- single-pass calibrating QuantAct for tensors the chip can hold ---------------------------------------
+// The quantised range depends on the min/max of the very tensor being quantised, so the two-kernel path reads x
+// twice.  148 SMs x 224 KB of shared memory hold 33 MB, though: a cooperative grid of one CTA per SM keeps its
+// slice of x on chip while the range is reduced across the grid, and quantises from shared memory after one
+// grid-wide barrier -- x crosses HBM exactly once (4 B read + 4 B written per element).  Every activation of
+// the 32x32 / 28x28 configurations and the 7x7 stage of the ImageNet one fit entirely; up to ~3x the on-chip
+// capacity the remainder of a slice is re-read through the 126 MB L2.  Larger tensors take the two-kernel
+// path (their second read has to come from HBM whatever the kernel does).
+//
+// Arithmetic is that of minmax_ema_kernel + fq_flat_kernel: NaN-propagating min/max (order-free), the EMA of
+// quant_modules.py:87-89 evaluated identically by every CTA from the state read BEFORE the barrier (CTA 0 writes
+// it back after), dequantisation by the exact 2^k-entry table.
+constexpr int kCThreads = 1024;
+constexpr int kCTileFloats = 56 * 1024;                    // 224 KB of the 227 KB a CTA may use
+constexpr long long kCoopMaxBytes = 96ll << 20;            // beyond this the two-kernel path is used
+
+__global__ void __launch_bounds__(kCThreads, 1)
+act_calib_onchip_kernel(const float* __restrict__ x, float* __restrict__ y, long long numel, Workspace* ws,
+                        float* x_min, float* x_max, const float* beta, float* beta_t, int k) {
+    extern __shared__ __align__(16) float tile[];
+    __shared__ float lut[kLutMax];
+    __shared__ float s_mn[kCThreads / 32], s_mx[kCThreads / 32];
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // contiguous slice of this CTA, a multiple of 4 elements (x and y are 16-byte aligned, numel % 4 == 0)
+    const long long n4 = numel >> 2;
+    const long long per = (n4 + gridDim.x - 1) / gridDim.x;
+    const long long b4 = (long long)blockIdx.x * per;
+    const long long e4 = b4 + per < n4 ? b4 + per : n4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    float4* t4 = reinterpret_cast<float4*>(tile);
+    const long long cap4 = kCTileFloats / 4;
+    // the state every CTA needs after the barrier, read before CTA 0 may overwrite it
+    const float old_min = *x_min, old_max = *x_max, b = *beta, old_bt = *beta_t;
+
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+    constexpr int kU = 4;                                        // 128-bit loads in flight per thread
+    for (long long base = b4; base < e4; base += (long long)kU * kCThreads) {
+        float4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long i = base + u * kCThreads + threadIdx.x;
+            if (i < e4) v[u] = ld_keep(x4 + i);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long i = base + u * kCThreads + threadIdx.x;
+            if (i < e4) {
+                if (i - b4 < cap4) t4[i - b4] = v[u];
+                mn = min_nan(min_nan(mn, v[u].x), min_nan(v[u].y, min_nan(v[u].z, v[u].w)));
+                mx = max_nan(max_nan(mx, v[u].x), max_nan(v[u].y, max_nan(v[u].z, v[u].w)));
+            }
+        }
+    }
+    mn = warp_min_nan(mn);
+    mx = warp_max_nan(mx);
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kCThreads / 32; ++w) { mn = min_nan(mn, s_mn[w]); mx = max_nan(mx, s_mx[w]); }
+        ws->mm_partial[2 * blockIdx.x] = mn;
+        ws->mm_partial[2 * blockIdx.x + 1] = mx;
+    }
+    grid.sync();
+
+    // every CTA folds the grid's partials and takes the same EMA step
+    mn = __int_as_float(0x7f800000);
+    mx = __int_as_float(0xff800000);
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += kCThreads) {
+        mn = min_nan(mn, __ldcg(&ws->mm_partial[2 * c]));
+        mx = max_nan(mx, __ldcg(&ws->mm_partial[2 * c + 1]));
+    }
+    mn = warp_min_nan(mn);
+    mx = warp_max_nan(mx);
+    __syncthreads();
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    mn = s_mn[0];
+    mx = s_mx[0];
+#pragma unroll
+    for (int w = 1; w < kCThreads / 32; ++w) { mn = min_nan(mn, s_mn[w]); mx = max_nan(mx, s_mx[w]); }
+    const float bt = __fmul_rn(old_bt, b);                       // quant_modules.py:87
+    const float new_min = ema_step(old_min, mn, b, bt);          // :88
+    const float new_max = ema_step(old_max, mx, b, bt);          // :89
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *x_min = new_min; *x_max = new_max; *beta_t = bt; }
+
+    const QParams qp = make_qparams(new_min, new_max, k);
+    const int qh = 1 << (k - 1), qmask = (1 << k) - 1;
+    build_lut(lut, qp, k, threadIdx.x, kCThreads);
+    __syncthreads();
+    for (long long base = b4; base < e4; base += (long long)kU * kCThreads) {
+        float4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long i = base + u * kCThreads + threadIdx.x;
+            if (i < e4) v[u] = (i - b4 < cap4) ? t4[i - b4] : ld_stream(x4 + i);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long i = base + u * kCThreads + threadIdx.x;
+            if (i < e4) {
+                float4 o;
+                o.x = fake_quant_lut(v[u].x, qp, lut, qh, qmask);
+                o.y = fake_quant_lut(v[u].y, qp, lut, qh, qmask);
+                o.z = fake_quant_lut(v[u].z, qp, lut, qh, qmask);
+                o.w = fake_quant_lut(v[u].w, qp, lut, qh, qmask);
+                st_out(y4 + i, o);
+            }
+        }
+    }
+}
+
+// true if the launch was made (the caller falls back to the two-kernel path otherwise)
+static bool try_onchip_calib(const float* x, float* y, long long numel, void* workspace, float* x_min, float* x_max,
+                             const float* beta, float* beta_t, int k, cudaStream_t st, int* rc) {
+    static int state = 0;            // 0 = not probed, 1 = usable, -1 = unavailable on this device / driver
+    static int grid = 0;
+    if (state < 0 || k > 8 || (numel & 3) || numel * 4 > kCoopMaxBytes || !aligned16(x) || !aligned16(y)) return false;
+    const size_t smem = (size_t)kCTileFloats * sizeof(float);
+    if (state == 0) {
+        int dev = 0, coop = 0, per_sm = 0, sms = 0;
+        bool ok = cudaGetDevice(&dev) == cudaSuccess &&
+                  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+                  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+                  cudaFuncSetAttribute(act_calib_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, act_calib_onchip_kernel, kCThreads, smem) == cudaSuccess &&
+                  per_sm >= 1;
+        (void)cudaGetLastError();
+        grid = ok ? (sms < kMaxReduceBlocks ? sms : kMaxReduceBlocks) : 0;
+        state = ok ? 1 : -1;
+        if (!ok) return false;
+    }
+    Workspace* ws = reinterpret_cast<Workspace*>(workspace);
+    void* args[] = {(void*)&x, (void*)&y, (void*)&numel, (void*)&ws, (void*)&x_min, (void*)&x_max, (void*)&beta,
+                    (void*)&beta_t, (void*)&k};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)act_calib_onchip_kernel, dim3(grid), dim3(kCThreads),
+                                                      args, smem, st);
+    if (e != cudaSuccess) {          // e.g. the grid cannot be co-resident right now: leave it to the other path
+        (void)cudaGetLastError();
+        return false;
+    }
+    count_launch();
+    *rc = check_launch("act_calib_forward(on-chip)");
+    return true;
+}
+
 }  // namespace oodfq
 
 using namespace oodfq;
@@ -148,7 +300,11 @@ extern "C" int oodfq_act_calib_forward(const float* x, float* y, int8_t* codes, 
     if (codes && k > 8) return fail(OODFQ_EINVAL, "act_calib_forward: int8 codes need k <= 8");
     const bool sym = (flags & OODFQ_SYMMETRIC) != 0;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_minmax(x, numel, workspace, nullptr, x_min, x_max, beta, beta_t, sym ? 1 : 0, st);
+    int rc = OODFQ_OK;
+    if (y && !codes && !sym && !(flags & OODFQ_NO_ONCHIP) &&
+        try_onchip_calib(x, y, numel, workspace, x_min, x_max, beta, beta_t, k, st, &rc))
+        return rc;
+    rc = launch_minmax(x, numel, workspace, nullptr, x_min, x_max, beta, beta_t, sym ? 1 : 0, st);
     if (rc != OODFQ_OK || !y) return rc;
     return launch_fakequant_scalar(x, y, codes, numel, x_min, x_max, k, sym, /*reverse=*/true, st);
 }

@@ -101,6 +101,11 @@ def main():
                 st[3].fill_(1.0)
                 ops.act_calib_forward(x, 4, st[0], st[1], st[2], st[3])
             report("calib", shape, 12 * n, *timer(calib))
+
+            def calib2():
+                st[3].fill_(1.0)
+                ops.act_calib_forward(x, 4, st[0], st[1], st[2], st[3], onchip=False)
+            report("calib_2k", shape, 12 * n, *timer(calib2))
         c = shape[1]
         shift = torch.zeros(c, device="cuda")
         if "stats" in only:
