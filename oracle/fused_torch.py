@@ -26,3 +26,23 @@ def bn_relu_quant(x, weight, bias, running_mean, running_var, eps, k, lo, hi, re
     if relu:
         z = F.relu(z)
     return fq_torch.fake_quant_ste(z, k, lo, hi) if k else z
+
+
+def residual_tail(x1, r, bn1, bn2=None, k=0, lo=None, hi=None):
+    """Tail of a residual unit exactly as the unfused modules run it on CPU (differentiable):
+    ``QuantAct(ReLU(BN1(x1) + id))`` with ``id = r`` or ``BN2(r)`` -- pytorchcv ResUnit.forward / reference
+    models.py:40-47 after quantize_model (main_direct.py:464-465) -- plus the trainer's channel attention input
+    ``BN1(x1).pow(2).mean([2, 3])`` (trainer_direct.py:382-383).  ``bn = (weight, bias, running_mean,
+    running_var, eps)``.  Returns ``(y, energy, pre_activation)``."""
+    w1, b1, rm1, rv1, eps1 = bn1
+    z1 = F.batch_norm(x1, rm1, rv1, w1, b1, False, 0.0, eps1)
+    if bn2 is not None:
+        w2, b2, rm2, rv2, eps2 = bn2
+        ident = F.batch_norm(r, rm2, rv2, w2, b2, False, 0.0, eps2)
+    else:
+        ident = r
+    s = z1 + ident
+    y = F.relu(s)
+    if k:
+        y = fq_torch.fake_quant_ste(y, k, lo, hi)
+    return y, z1.pow(2).mean([2, 3]), s

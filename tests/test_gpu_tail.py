@@ -73,6 +73,49 @@ def test_tail_matches_the_kernel_chain(shape, idbn, k):
         assert dw1b is None and torch.equal(gx1b, gx1) and torch.equal(grb, gr)
 
 
+@pytest.mark.parametrize("idbn", [False, True])
+@pytest.mark.parametrize("k", [4, 0])
+def test_tail_against_the_cpu_oracle(idbn, k):
+    """Directly against the unfused torch-CPU modules.  The kernel's affine rounds once (FFMA) where ATen's
+    batch_norm rounds more often, so the pre-activation may differ in the last ulp: outputs are then either equal
+    or -- where that ulp crosses a rounding boundary of the quantiser -- exactly one quantisation step apart, and
+    the ReLU mask of the gradient may differ only where the pre-activation is (numerically) zero."""
+    from ood_dfq_b200 import ops
+    from oracle import fused_torch
+    g = torch.Generator().manual_seed(21 + idbn + k)
+    shape = (6, 32, 14, 14)
+    x1 = (torch.randn(shape, generator=g) * 1.3).requires_grad_(True)
+    r = torch.randn(shape, generator=g)
+    r = (r if idbn else torch.relu(r)).requires_grad_(True)
+    bns = [tuple(t.cpu() if isinstance(t, torch.Tensor) else t for t in make_bn(32, g)) for _ in range(2)]
+    bn1, bn2 = bns[0], (bns[1] if idbn else None)
+    lo, hi = torch.zeros(1), torch.full((1,), 2.3)
+    y_ref, e_ref, s_ref = fused_torch.residual_tail(x1, r, bn1, bn2, k, lo, hi)
+    gy = torch.randn(shape, generator=g)
+    ge = torch.randn(shape[:2], generator=g)
+    (y_ref * gy).sum().backward(retain_graph=True)
+    gx1_y, gr_y = x1.grad.clone(), r.grad.clone()
+    x1.grad = None
+    (e_ref * ge).sum().backward()
+    gx1_ref = gx1_y + x1.grad
+
+    def dev(t):
+        return t.detach().to(DEV).contiguous(memory_format=CL) if t.dim() == 4 else t.to(DEV)
+    d1 = tuple(dev(t) if isinstance(t, torch.Tensor) else t for t in bn1)
+    d2 = None if bn2 is None else tuple(dev(t) if isinstance(t, torch.Tensor) else t for t in bn2)
+    fq = (k, lo.to(DEV), hi.to(DEV)) if k else None
+    y, e = ops.res_tail_forward(dev(x1), dev(r), d1, d2, fq=fq, want_energy=True)
+    diff = (y.cpu() - y_ref.detach()).abs()
+    step = (2.3 / (2 ** k - 1)) if k else 0.0
+    close = diff <= 1e-5 * (1 + y_ref.detach().abs())
+    assert (close | ((diff - step).abs() <= 1e-5)).all() and close.float().mean() > 0.999
+    np.testing.assert_allclose(e.cpu().numpy(), e_ref.detach().numpy(), rtol=1e-5, atol=1e-7)
+    gx1, gr, _, _, _, _ = ops.res_tail_backward(dev(gy), ge.to(DEV), dev(x1), dev(r), d1, d2)
+    sure = s_ref.detach().abs() > 1e-5                       # away from the ReLU kink both masks agree
+    np.testing.assert_allclose(gx1.cpu()[sure].numpy(), gx1_ref[sure].numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(gr.cpu()[sure].numpy(), gr_y[sure].numpy(), rtol=1e-4, atol=1e-6)
+
+
 def test_second_output_gradient_is_summed_in_the_kernel():
     """grad_y2 / grad_out2: the kernels add the two gradients exactly like autograd's accumulation would."""
     from ood_dfq_b200 import ops
