@@ -50,3 +50,34 @@ def test_unknown_unit_layouts_are_left_alone():
             return self.activ(self.body(x))
     m = Odd().eval()
     assert fusion.fuse_residual_tails(m, torch.randn(1, 3, 4, 4)) == 0 and type(m) is Odd
+
+
+def test_space_to_depth_pass_on_cpu_and_weight_reindexing():
+    """The pass only swaps the image-side stride-2 convolution; off the GPU the swapped layer runs its class's own
+    forward.  The weight re-indexing itself is checked against the stride-2 convolution with plain torch ops."""
+    import torch.nn.functional as F
+    model = nets.resnet18_imagenet(num_classes=10).eval()
+    x = torch.randn(1, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        ref = model(x)
+    convs_before = [type(m) for m in model.modules() if isinstance(m, torch.nn.Conv2d)]
+    assert fusion.space_to_depth_stem(model, x) == 1
+    assert fusion.space_to_depth_stem(model, x) == 0
+    swapped = [m for m in model.modules() if isinstance(m, fusion._S2DStemMixin)]
+    assert len(swapped) == 1 and swapped[0].in_channels == 3 and isinstance(swapped[0], torch.nn.Conv2d)
+    assert len([m for m in model.modules() if isinstance(m, torch.nn.Conv2d)]) == len(convs_before)
+    with torch.no_grad():
+        assert torch.equal(model(x), ref)
+    assert fusion.space_to_depth_stem(nets.resnet20_cifar().eval(), torch.randn(1, 3, 32, 32)) == 0   # stride-1 stem
+
+    g = torch.Generator().manual_seed(1)
+    for k, p, h in ((7, 3, 16), (3, 1, 10), (5, 2, 12), (4, 1, 8)):
+        xx = torch.randn(2, 3, h, h + 2, generator=g)
+        w = torch.randn(5, 3, k, k, generator=g)
+        n, c, hh, ww = xx.shape
+        xp = F.pad(xx, (p, p, p, p))
+        xs = xp.view(n, c, (hh + 2 * p) // 2, 2, (ww + 2 * p) // 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(
+            n, 4 * c, (hh + 2 * p) // 2, (ww + 2 * p) // 2)
+        out = F.conv2d(xs, fusion._s2d_weight(w), None, 1, 0)
+        want = F.conv2d(xx, w, None, 2, p)
+        assert out.shape == want.shape and torch.allclose(out, want, rtol=1e-4, atol=1e-4)
