@@ -20,6 +20,8 @@ def lib():
         _lib.fqc_row_ranges.argtypes = [_fp, C.c_size_t, C.c_size_t, C.c_int, _fp, _fp]
         _lib.fqc_range_update.argtypes = [_fp, C.c_float, C.c_float, C.c_float, C.c_int]
         _lib.fqc_channel_stats.argtypes = [_fp, C.c_size_t, C.c_size_t, C.c_size_t, _dp, _dp]
+        _lib.fqc_mse_search.argtypes = [_fp, C.c_size_t, C.c_int, C.c_int, C.c_double, C.c_float, _fp, _fp]
+        _lib.fqc_mse_search.restype = C.c_int
         for f in ("fqc_params", "fqc_fake_quant", "fqc_minmax", "fqc_row_ranges", "fqc_range_update", "fqc_channel_stats"):
             getattr(_lib, f).restype = None
     return _lib
@@ -75,3 +77,12 @@ def channel_stats(x):
     mean, var = np.empty(c, np.float64), np.empty(c, np.float64)
     lib().fqc_channel_stats(_p(x), n, c, h * w, mean.ctypes.data_as(_dp), var.ctypes.data_as(_dp))
     return mean, var
+
+
+def mse_search(x, k, state, beta=0.9, steps=80, p=2.4):
+    """QuantAct_MSE's clip search + plain EMA.  Returns (new state [x_min, x_max, beta_t], scores, kept index)."""
+    x = _f(x).reshape(-1)
+    st = _f(state).copy()
+    scores = np.empty(steps, np.float32)
+    keep = lib().fqc_mse_search(_p(x), x.size, int(k), int(steps), float(p), float(np.float32(beta)), _p(st), _p(scores))
+    return st, scores, int(keep)

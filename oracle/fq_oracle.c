@@ -116,3 +116,37 @@ void fqc_channel_stats(const float* x, size_t N, size_t C, size_t HW, double* me
         var[c] = ss / (double)(N * HW);
     }
 }
+
+/* QuantAct_MSE range search: quant_modules.py:160-178 with find_MSESmallest (quant_utils.py:36-47) and lp_loss
+ * (quant_utils.py:26-33, reduction='all').  Candidate i uses the range data_{min,max} * (float)(1.0 - i*0.01);
+ * score_i = mean |x - fakequant_i(x)|^p accumulated in fp64 (ATen's fp32 pairwise mean agrees to rounding);
+ * the first strict minimum below 1e10 is kept.  state = {x_min, x_max, beta_t}: plain EMA, no bias correction.
+ * scores (nullable) receives the `steps` scores; returns the kept candidate (-1: none). */
+int fqc_mse_search(const float* x, size_t n, int k, int steps, double p, float beta, float* state, float* scores) {
+    float mn, mx;
+    fqc_minmax(x, n, &mn, &mx);
+    float best = 1e+10f;
+    int keep = -1;
+    for (int i = 0; i < steps; ++i) {
+        const float f = (float)(1.0 - (double)i * 0.01);
+        const float lo = mn * f, hi = mx * f;
+        float scale, zp;
+        fqc_params(k, lo, hi, &scale, &zp);
+        double acc = 0.0;
+        for (size_t j = 0; j < n; ++j) {
+            const float y = value_of(code_of(x[j], scale, zp, k, 0), scale, zp, 0);
+            const float d = fabsf(x[j] - y);
+            acc += (double)powf(d, (float)p);
+        }
+        const float score = (float)(acc / (double)n);
+        if (scores) scores[i] = score;
+        if (score < best) { best = score; keep = i; }
+    }
+    const int c = keep < 0 ? 0 : keep;
+    const float f = (float)(1.0 - (double)c * 0.01);
+    const float omb = 1.0f - beta;
+    state[2] = state[2] * beta;
+    state[0] = state[0] * beta + (mn * f) * omb;
+    state[1] = state[1] * beta + (mx * f) * omb;
+    return keep;
+}

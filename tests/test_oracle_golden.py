@@ -232,3 +232,15 @@ def test_c_oracle_channel_stats(golden):
         mean, var = fq_c.channel_stats(g[f"stat_{tag}_x"])
         np.testing.assert_allclose(mean, g[f"stat_{tag}_mean"], rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(var, g[f"stat_{tag}_var64"], rtol=1e-9)
+
+
+def test_c_mse_search_matches_the_reference(golden):
+    """The plain-C restatement of QuantAct_MSE's search reproduces the reference-generated state and output."""
+    g = golden("act_mse")
+    st = np.array([0.0, 0.0, 1.0], np.float32)
+    for step in range(2):
+        st, scores, keep = fq_c.mse_search(g[f"x{step}"], 4, st)
+        assert 0 <= keep < 80 and np.all(np.isfinite(scores))
+        np.testing.assert_allclose(st, g[f"state{step}"], rtol=1e-6)
+        y, _ = fq_c.fake_quant(g[f"x{step}"], 4, st[0], st[1])
+        np.testing.assert_allclose(y, g[f"y{step}"], rtol=1e-5, atol=1e-6)
