@@ -1,0 +1,153 @@
+"""Randomised cross-check of the three oracle restatements against the LIVE reference.
+
+The committed golden vectors (tests/golden, tools/make_golden.py) pin the oracle at fixed seeds.  In the build
+container the reference tree itself is importable, so here hypothesis draws shapes, bit-widths, ranges and data
+(special values included) and every restatement must reproduce ``quantization_utils`` bit for bit.  The GPU box
+has no ``/root/reference``: the module skips there (nothing under ``-m gpu`` reads the reference).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+REF = os.environ.get("OODFQ_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REF, "quantization_utils")):
+    pytest.skip("reference tree not present (GPU box): golden vectors cover the pin there", allow_module_level=True)
+
+hyp = pytest.importorskip("hypothesis")
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+from conftest import bits  # noqa: E402
+from oracle import fq_c, fq_numpy, fq_torch  # noqa: E402
+
+
+def _reference():
+    """The reference package under a private name, so that the product's drop-in ``quantization_utils`` (which other
+    tests may have installed as a top-level module) is never what gets imported here."""
+    import importlib
+    import types
+    pkg = types.ModuleType("_live_reference_qu")
+    pkg.__path__ = [os.path.join(REF, "quantization_utils")]      # quant_modules.py:28 imports `.quant_utils`
+    sys.modules["_live_reference_qu"] = pkg
+    return (importlib.import_module("_live_reference_qu.quant_utils"),
+            importlib.import_module("_live_reference_qu.quant_modules"))
+
+
+RU, RM = _reference()
+torch.set_num_threads(1)
+
+COMMON = dict(deadline=None, max_examples=200, suppress_health_check=[HealthCheck.too_slow])
+SPECIALS = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-30, -1e-30, 3.4e38, -3.4e38, 0.5, 1.5, 2.5, -0.5, -1.5],
+                    dtype=np.float32)
+
+
+def draw_data(seed, shape, spread, shift, specials):
+    rng = np.random.default_rng(seed)
+    x = (rng.standard_normal(shape) * spread + shift).astype(np.float32)
+    if specials:
+        flat = x.reshape(-1)
+        idx = rng.integers(0, flat.size, size=min(flat.size, 6))
+        flat[idx] = rng.choice(SPECIALS, size=len(idx))
+    return x
+
+
+shapes4 = st.tuples(st.integers(1, 4), st.integers(1, 9), st.integers(1, 9), st.integers(1, 9))
+ranges = st.one_of(
+    st.tuples(st.floats(-8, 0, width=32), st.floats(0, 8, width=32)),
+    st.tuples(st.just(0.0), st.floats(2.0 ** -20, 50, width=32)),                 # post-ReLU: data-min = 0
+    st.tuples(st.floats(-3, 3, width=32), st.floats(-3, 3, width=32)),      # inverted / degenerate spans too
+    st.tuples(st.floats(-2.0 ** -30, 2.0 ** -30, width=32), st.floats(-2.0 ** -30, 2.0 ** -30, width=32)),
+)
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), shape=shapes4, k=st.sampled_from([1, 2, 3, 4, 5, 6, 8, 12, 16]), rng=ranges,
+       spread=st.sampled_from([1e-3, 1.0, 30.0]), specials=st.booleans())
+def test_frozen_fake_quant_matches_the_live_reference(seed, shape, k, rng, spread, specials):
+    """AsymmetricQuantFunction.forward (quant_utils.py:138-157) with a scalar range: codes and values, three oracles."""
+    lo, hi = np.float32(rng[0]), np.float32(rng[1])
+    x = draw_data(seed, shape, spread, 0.0, specials)
+    xt, lot, hit = torch.from_numpy(x), torch.tensor([lo]), torch.tensor([hi])
+    s, z = RU.asymmetric_linear_quantization_params(k, lot, hit)
+    h = 2 ** (k - 1)
+    q_ref = torch.clamp(RU.linear_quantize(xt, s, z, inplace=False), -h, h - 1).numpy()
+    y_ref = RU.AsymmetricQuantFunction.apply(xt, k, lot, hit).numpy()
+
+    s_o, z_o = fq_torch.quant_params(k, lot, hit)
+    assert np.array_equal(bits(s_o.numpy()), bits(s.numpy())) and np.array_equal(bits(z_o.numpy()), bits(z.numpy()))
+    assert np.array_equal(bits(fq_torch.codes(xt, k, lot, hit).numpy()), bits(q_ref))
+    assert np.array_equal(bits(fq_torch.fake_quant(xt, k, lot, hit).numpy()), bits(y_ref))
+
+    s_n, z_n = fq_numpy.quant_params(k, lo, hi)
+    assert np.array_equal(bits(s_n), bits(s.numpy().reshape(()))) and np.array_equal(bits(z_n), bits(z.numpy().reshape(())))
+    nan = np.isnan(y_ref)
+    with np.errstate(all="ignore"):
+        q_n, y_n = fq_numpy.codes(x, k, lo, hi), fq_numpy.fake_quant(x, k, lo, hi)
+        y_c, q_c = fq_c.fake_quant(x, k, lo, hi)
+    for q, y in ((q_n, y_n), (q_c, y_c)):           # NaN payloads are not part of the contract, NaN-ness is
+        assert np.array_equal(np.isnan(y), nan) and np.array_equal(np.isnan(q), np.isnan(q_ref))
+        assert np.array_equal(bits(y)[~nan], bits(y_ref)[~nan])
+        assert np.array_equal(bits(q)[~np.isnan(q_ref)], bits(q_ref)[~np.isnan(q_ref)])
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31), rows=st.integers(1, 12), cols=st.tuples(st.integers(1, 6), st.integers(1, 3), st.integers(1, 3)),
+       k=st.sampled_from([2, 3, 4, 8]), sym=st.booleans(), linear=st.booleans())
+def test_weight_modules_match_the_live_reference(seed, rows, cols, k, sym, linear):
+    """Quant_Conv2d / Quant_Linear and their DSG twins (quant_modules.py:188-281, :389-481): per-row ranges,
+    fake-quantised weight and the STE gradient reaching the Parameter."""
+    torch.manual_seed(seed % (2 ** 31))
+    if linear:
+        layer = torch.nn.Linear(cols[0] * cols[1], rows, bias=True)
+        ref = (RM.QuantLinear_DSG if sym else RM.Quant_Linear)(weight_bit=k)
+        ours = (fq_torch.OracleQuantLinearSym if sym else fq_torch.OracleQuantLinear)(k)
+        x = torch.randn(3, cols[0] * cols[1])
+    else:
+        layer = torch.nn.Conv2d(cols[0], rows, (cols[1], cols[2]), padding=1, bias=False)
+        ref = (RM.QuantConv2d_DSG if sym else RM.Quant_Conv2d)(weight_bit=k)
+        ours = (fq_torch.OracleQuantConv2dSym if sym else fq_torch.OracleQuantConv2d)(k)
+        x = torch.randn(2, cols[0], 5, 5)
+    ref.set_param(layer)
+    ours.set_param(layer)
+    out_ref, out = ref(x), ours(x)
+    assert np.array_equal(bits(out.detach().numpy()), bits(out_ref.detach().numpy()))
+    out_ref.square().sum().backward()
+    out.square().sum().backward()
+    assert np.array_equal(bits(ours.weight.grad.numpy()), bits(ref.weight.grad.numpy()))
+    # the C and numpy restatements on the same rows
+    w = layer.weight.detach().numpy().reshape(rows, -1)
+    lo, hi = fq_c.row_ranges(w, symmetric=sym)
+    wq_ref = ours.quantized_weight().detach().numpy().reshape(rows, -1)
+    y_c, _ = fq_c.fake_quant(w, k, lo, hi, symmetric=sym)
+    assert np.array_equal(bits(y_c), bits(wq_ref))
+    assert np.array_equal(bits(fq_numpy.fake_quant(w, k, lo, hi, symmetric=sym)), bits(wq_ref))
+
+
+@settings(**{**COMMON, "max_examples": 100})
+@given(seed=st.integers(0, 2 ** 31), shape=shapes4, k=st.sampled_from([2, 4, 8]), sym=st.booleans(),
+       steps=st.integers(1, 7), shift=st.sampled_from([0.0, 2.0, -5.0]), fix_at=st.integers(0, 7))
+def test_calibrating_sequences_match_the_live_reference(seed, shape, k, sym, steps, shift, fix_at):
+    """QuantAct / QuantAct_DSG over several forwards incl. fix(): state (x_min, x_max, beta_t) and output, bit-exact;
+    the numpy and C restatements follow the same state."""
+    ref = (RM.QuantAct_DSG if sym else RM.QuantAct)(activation_bit=k)
+    ours = (fq_torch.OracleQuantActSym if sym else fq_torch.OracleQuantAct)(k)
+    st_np = (np.float32(0), np.float32(0), np.float32(1))
+    st_c = np.array([0, 0, 1], dtype=np.float32)
+    for step in range(steps):
+        if step == fix_at:
+            ref.fix()
+            ours.fix()
+        x = draw_data(seed + step, shape, 1.0 + step, shift, False)
+        xt = torch.from_numpy(x)
+        y_ref, y = ref(xt), ours(xt)
+        assert np.array_equal(bits(y.numpy()), bits(y_ref.numpy()))
+        for name in ("x_min", "x_max", "beta_t"):
+            assert np.array_equal(bits(getattr(ours, name).numpy()), bits(getattr(ref, name).numpy())), (name, step)
+        if step < fix_at:
+            st_np = fq_numpy.range_update(*st_np[:2], np.float32(0.9), st_np[2], x.min(), x.max(), symmetric=sym)
+            st_c = fq_c.range_update(st_c, 0.9, x.min(), x.max(), symmetric=sym)
+            want = np.array([ref.x_min.item(), ref.x_max.item(), ref.beta_t.item()], dtype=np.float32)
+            assert np.array_equal(bits(np.array(st_np, dtype=np.float32)), bits(want))
+            assert np.array_equal(bits(st_c), bits(want))
