@@ -38,7 +38,7 @@ def _reference():
 RU, RM = _reference()
 torch.set_num_threads(1)
 
-COMMON = dict(deadline=None, max_examples=200, suppress_health_check=[HealthCheck.too_slow])
+COMMON = dict(deadline=None, max_examples=200, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 SPECIALS = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-30, -1e-30, 3.4e38, -3.4e38, 0.5, 1.5, 2.5, -0.5, -1.5],
                     dtype=np.float32)
 
@@ -89,7 +89,9 @@ def test_frozen_fake_quant_matches_the_live_reference(seed, shape, k, rng, sprea
     for q, y in ((q_n, y_n), (q_c, y_c)):           # NaN payloads are not part of the contract, NaN-ness is
         assert np.array_equal(np.isnan(y), nan) and np.array_equal(np.isnan(q), np.isnan(q_ref))
         assert np.array_equal(bits(y)[~nan], bits(y_ref)[~nan])
-        assert np.array_equal(bits(q)[~np.isnan(q_ref)], bits(q_ref)[~np.isnan(q_ref)])
+        # codes are integers: the sign of a zero code is unobservable (k = 1 clamps at an upper bound of 0, where
+        # torch.clamp, np.minimum and fminf each keep a different zero); the dequantised value above IS compared by bits
+        assert np.array_equal(q[~np.isnan(q_ref)], q_ref[~np.isnan(q_ref)])
 
 
 @settings(**COMMON)
