@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OODFQ_ABI_VERSION 2
+#define OODFQ_ABI_VERSION 3
 
 #define OODFQ_OK 0
 #define OODFQ_EINVAL (-1)  /* bad argument (null pointer, k out of range, misaligned ...) */
@@ -255,6 +255,22 @@ int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2, const flo
 int oodfq_s2d_stem_forward(const float* x, float* xs, int N, int H, int W, int C, int pad, oodfq_stream_t stream);
 int oodfq_s2d_stem_backward(const float* grad_xs, float* grad_x, int N, int H, int W, int C, int pad,
                             oodfq_stream_t stream);
+
+/* ---- batch assembly: gather -> RandomResizedCrop -> grey->RGB repeat -> RandomHorizontalFlip ----------------
+ * replaces: direct_dataset.__getitem__ (main_direct.py:200-204) and its torchvision pipeline
+ *           RandomResizedCrop(size, scale=(0.5, 1.0)) -> Lambda(repeat to 3 channels) -> RandomHorizontalFlip
+ *           (main_direct.py:158-169), run per sample on DataLoader workers, plus the collation and the per-step
+ *           host -> device copy of the batch (main_direct.py:525-533)
+ * images [M, C_in, H, W] NCHW fp32, the concatenated shards (main_direct.py:173-195) resident on the device;
+ * index [N] int64 sample -> image; boxes [N][4] int32 (top, left, height, width) as RandomResizedCrop.get_params
+ * returns them; flips [N] uint8 (non-zero = mirrored after the resize).  The draws themselves stay on the host.
+ * out [N, C_out, out_h, out_w] (flags & OODFQ_BN_NHWC: channels_last).  Channels: 1->1, 1->3 (repeat), 3->3.
+ * Resize = bilinear, align_corners=False, no antialiasing: identical to torchvision's antialiased filter
+ * whenever the crop is not larger than the output (always, in direct_dataset: size == image size).  Entries
+ * outside the image set are folded into it (never an out-of-bounds read). */
+int oodfq_crop_resize_flip(const float* images, long long n_images, int C_in, int H, int W, const long long* index,
+                           const int* boxes, const unsigned char* flips, float* out, int N, int C_out, int out_h,
+                           int out_w, int flags, oodfq_stream_t stream);
 
 #ifdef __cplusplus
 }

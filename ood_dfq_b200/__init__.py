@@ -10,6 +10,7 @@ Layout
     step.py                host code of the QAT / distillation iteration, flat gradients, CUDA-graph replay
     surgery.py, nets.py    host-side consumers used by the benchmark (model surgery, carrier networks)
     hocon.py               reader for the reference's config/*.hocon files
+    shards.py, augment.py  the step's input side: pickle-shard reader, device-side crop / resize / flip batches
 
 ``install()`` makes ``from quantization_utils.quant_modules import *`` (main_direct.py:21,
 trainer_direct.py:19) resolve to this implementation.

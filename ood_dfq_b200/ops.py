@@ -602,3 +602,45 @@ def act_mse_search(x, k, x_min, x_max, beta, beta_t, cur_min=None, cur_max=None,
                                        _ptr(scores), _ptr(chosen), _stream(x.device))
     N.check(rc, "act_mse_search")
     return (scores, chosen) if debug else None
+
+
+# ----------------------------------------------------------------------------- batch assembly (crop / resize / flip)
+def crop_resize_flip(images, index, boxes, flips, size, channels=None, channels_last=True, out=None):
+    """One per-rank batch straight from the device-resident image set: for sample ``n`` the crop ``boxes[n] = (top,
+    left, h, w)`` of ``images[index[n]]`` is resized (bilinear, ``align_corners=False``) to ``size``, a one-channel
+    image is repeated to ``channels`` (default 3) and the result mirrored when ``flips[n]`` -- the per-sample
+    torchvision pipeline of ``direct_dataset`` (main_direct.py:158-169, :200-204) as one kernel.
+
+    ``images`` ``[M,C,H,W]`` fp32 NCHW-contiguous, ``index`` int64 ``[N]``, ``boxes`` int32 ``[N,4]``, ``flips``
+    uint8 ``[N]``, all on the same CUDA device.  Returns ``[N, channels, *size]`` (channels_last by default).
+    """
+    _need(images, "image set")
+    _need(index, "index", torch.int64)
+    _need(boxes, "boxes", torch.int32)
+    _need(flips, "flips", torch.uint8)
+    if images.dim() != 4 or not images.is_contiguous():
+        raise RuntimeError("ood_dfq_b200: the image set must be an NCHW-contiguous [M,C,H,W] tensor")
+    n = index.numel()
+    if index.dim() != 1 or boxes.shape != (n, 4) or flips.shape != (n,):
+        raise RuntimeError(f"ood_dfq_b200: index [N], boxes [N,4], flips [N] expected, got {tuple(index.shape)}, "
+                           f"{tuple(boxes.shape)}, {tuple(flips.shape)}")
+    m, c_in, h, w = images.shape
+    c_out = int(channels) if channels is not None else (3 if c_in == 1 else c_in)
+    oh, ow = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
+    if out is None:
+        out = torch.empty((n, c_out, oh, ow), dtype=torch.float32, device=images.device, memory_format=fmt)
+    else:
+        _need(out, "out")
+        if out.shape != (n, c_out, oh, ow) or not out.is_contiguous(memory_format=fmt):
+            raise RuntimeError("ood_dfq_b200: `out` must be a dense [N, channels, *size] tensor in the requested memory format")
+    if n == 0:
+        return out
+    crop_bytes = 4 * c_in * h * w * n                         # upper bound of the read (the box is <= the image)
+    with _Timed("crop_resize_flip_kernel (batch assembly, <= 4 B/elem in + 4 B/elem out)", crop_bytes + 4 * out.numel()):
+        rc = N.load().oodfq_crop_resize_flip(images.data_ptr(), m, c_in, h, w, index.contiguous().data_ptr(),
+                                             boxes.contiguous().data_ptr(), flips.contiguous().data_ptr(),
+                                             out.data_ptr(), n, c_out, oh, ow, N.BN_NHWC if channels_last else 0,
+                                             _stream(images.device))
+        N.check(rc, "crop_resize_flip")
+    return out

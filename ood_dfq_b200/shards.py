@@ -11,7 +11,8 @@ restates that host-side logic without torchvision / the logger: ``load_shards`` 
 ``ShardBatches`` the per-rank batch stream -- whole batches gathered into reusable (pinned, when a GPU is present)
 host buffers in the memory format the kernels run in, which is what the double-buffered H2D prefetcher of
 ``bench.py`` consumes.  The per-sample ``RandomResizedCrop`` / flip of the reference (``main_direct.py:158-169``) is a
-caller-supplied ``transform`` here; a GPU-side version is a later-round item.
+caller-supplied ``transform`` here; the device-side version (image set resident in HBM, one kernel per batch) is
+``ood_dfq_b200/augment.py::DeviceShards``.
 
 The files are pickles: like the reference, only load shards you produced yourself.
 """

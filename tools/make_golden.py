@@ -268,9 +268,70 @@ def gen_bns():
     save("bns", **out)
 
 
+# ------------------------------------------------------------------ per-sample augmentation (torchvision)
+def gen_augment():
+    """The transform objects of direct_dataset (main_direct.py:158-169), built exactly as there, run per sample at
+    fixed seeds.  The pipeline hides its draws, so each sample is run twice from the same generator state: once
+    through the Compose itself (the expected output) and once through torchvision's own get_params / the flip's
+    ``torch.rand(1) < p`` (the recorded box and flip); the decomposition is asserted to reproduce the Compose
+    bit for bit before anything is saved.  ``*_out_exact`` comes from the same torchvision calls on the image in
+    double precision (coordinates and weights then carry no fp32 rounding), rounded to fp32 once at the end."""
+    import torchvision.transforms as T
+    import torchvision.transforms.functional as TF
+    out = {"torchvision_version": np.array(__import__("torchvision").__version__)}
+    sets = {"rgb32": (4, 3, 32, 32), "grey28": (5, 1, 28, 28), "tall224": (2, 3, 224, 24), "rect": (3, 3, 20, 36),
+            "big200": (1, 1, 200, 200)}   # small files
+    for tag, shape in sets.items():
+        g = torch.Generator().manual_seed(sum(shape))
+        images = torch.randn(shape, generator=g)
+        size = shape[2] if shape[2] == shape[3] else (shape[2], shape[3])
+        pipeline = T.Compose([
+            T.RandomResizedCrop(size=size, scale=(0.5, 1.0)),
+            T.Lambda(lambda x: x.repeat(3, 1, 1) if x.size(0) == 1 else x),
+            T.RandomHorizontalFlip(),
+        ])
+        crop = pipeline.transforms[0]
+        samples = 2 * shape[0] + 1 if tag != "big200" else 2
+        index = torch.randint(0, shape[0], (samples,), generator=g)
+        boxes, flips, ys, ys64 = [], [], [], []
+        torch.manual_seed(77 + shape[2])
+        for m in index.tolist():
+            state = torch.get_rng_state()
+            y = pipeline(images[m])
+            after = torch.get_rng_state()
+            torch.set_rng_state(state)
+            i, j, h, w = T.RandomResizedCrop.get_params(images[m], crop.scale, crop.ratio)
+            flip = bool(torch.rand(1) < 0.5)
+            assert torch.equal(torch.get_rng_state(), after)
+            z = TF.resized_crop(images[m], i, j, h, w, crop.size, crop.interpolation, antialias=crop.antialias)
+            z = z.repeat(3, 1, 1) if z.size(0) == 1 else z
+            z = TF.hflip(z) if flip else z
+            assert torch.equal(z, y), "decomposition differs from the Compose pipeline"
+            z64 = TF.resized_crop(images[m].double(), i, j, h, w, crop.size, crop.interpolation, antialias=crop.antialias)
+            z64 = z64.repeat(3, 1, 1) if z64.size(0) == 1 else z64
+            z64 = TF.hflip(z64) if flip else z64
+            # for an up-scaling the antialiased filter is the plain bilinear one
+            plain = TF.resized_crop(images[m].double(), i, j, h, w, crop.size, crop.interpolation, antialias=False)
+            plain = plain.repeat(3, 1, 1) if plain.size(0) == 1 else plain
+            assert (z64 - (TF.hflip(plain) if flip else plain)).abs().max() < 1e-12
+            boxes.append([i, j, h, w]); flips.append(flip); ys.append(y); ys64.append(z64)
+        out[f"{tag}_images"] = npy(images)
+        out[f"{tag}_index"] = index.numpy().astype(np.int64)
+        out[f"{tag}_boxes"] = np.array(boxes, dtype=np.int32)
+        out[f"{tag}_flips"] = np.array(flips, dtype=np.uint8)
+        out[f"{tag}_seed"] = np.array(77 + shape[2])
+        if tag == "big200":          # coordinates up to 200; the three repeated channels are identical: keep one
+            assert all(torch.equal(y[0], y[1]) and torch.equal(y[0], y[2]) for y in ys)
+            ys, ys64 = [y[:1] for y in ys], [y[:1] for y in ys64]
+        out[f"{tag}_out"] = npy(torch.stack(ys))
+        out[f"{tag}_out_exact"] = torch.stack(ys64).float().numpy().copy()     # double result, rounded once
+    save("augment", **out)
+
+
 if __name__ == "__main__":
     gen_act_frozen()
     gen_act_calib()
     gen_weights()
     gen_act_mse()
     gen_bns()
+    gen_augment()
