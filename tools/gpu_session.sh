@@ -1,0 +1,70 @@
+#!/usr/bin/env bash
+# One gpurun call that produces everything a round needs from the GPU, in the order that matters if the call is cut
+# short: parity tests, smoke, the bench line, the CPU arm, the ncu launch list of the bench command, one ncu --set full
+# capture of the headline kernel families, the microbenchmarks.  Everything lands under gpurun_out/ (merged back by
+# gpurun); copy what should be judged into profiles/ afterwards.
+#
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_session.sh'            # full session (~25 min)
+#   /usr/local/graft/bin/gpurun --timeout 900  -- 'bash tools/gpu_session.sh tests bench' # selected stages
+#
+# Stages: tests smoke bench ref launches ncu micro small   (default: all but "small")
+set -u
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+mkdir -p gpurun_out
+STAGES="${*:-tests smoke bench ref launches ncu micro}"
+has() { [[ " $STAGES " == *" $1 "* ]]; }
+log() { echo "[gpu_session $(date +%H:%M:%S)] $*" | tee -a gpurun_out/session.log; }
+
+if has tests; then
+  log "pytest -m gpu"
+  timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
+  log "pytest exit $? : $(tail -1 gpurun_out/pytest_gpu.log)"
+fi
+if has smoke; then
+  log "smoke"
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+  log "smoke exit $? : $(tail -1 gpurun_out/smoke.log)"
+fi
+if has bench; then
+  log "bench N=1"
+  timeout 900 python bench.py --gpus 1 --steps 8 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+  log "bench exit $? : $(head -c 300 gpurun_out/bench_n1.json)"
+fi
+if has ref; then
+  log "reference arm"
+  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+  log "reference exit $?"
+fi
+if has launches; then
+  # per-launch durations of the library's kernels over the same bench command (cold-cache, serialised: shares only)
+  log "ncu launch list"
+  timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'oodfq|fq_|bn_|res_tail|s2d|weight_fq|minmax|energy|crop_resize' \
+      -c 4000 --csv --log-file gpurun_out/launches.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --graph off > gpurun_out/launches_run.log 2>&1
+  log "launch list exit $?"
+  python tools/launch_list.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1 || true
+fi
+if has ncu; then
+  # one full capture per headline family, on the microbenchmark (a single tensor per launch, a few launches)
+  log "ncu --set full (tail, bn, stem, augment)"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'res_tail|bn_nhwc|bn_pool|crop_resize' -c 24 \
+      -o gpurun_out/full_kernels -f python tools/microbench.py --only tail,bn_fwd,bn_bwd,pool,augment --shapes 0,1 --iters 1 --flush none \
+      > gpurun_out/ncu_full.log 2>&1
+  log "ncu full exit $?"
+  ncu -i gpurun_out/full_kernels.ncu-rep --page raw --csv \
+      --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active \
+      > gpurun_out/full_kernels_raw.csv 2>/dev/null || true
+fi
+if has micro; then
+  log "microbench (read-flush)"
+  timeout 900 python tools/microbench.py --only copy,fq,calib,tail,pool,bn_fwd,bn_bwd,stats_nhwc,weights,augment --flush read \
+      --json gpurun_out/microbench.json > gpurun_out/microbench.txt 2>&1
+  log "microbench exit $?"
+fi
+if has small; then
+  for w in cifar100_resnet20_w4a4 pathmnist_resnet18_w2a2 distill_imagenet_resnet18_w4a4; do
+    log "bench $w"
+    timeout 600 python bench.py --workload $w --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
+  done
+fi
+log "done"

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-kernel bandwidth microbenchmark at the BASELINE tensor shapes.
 
-    python tools/microbench.py [--only fq,calib,minmax,stats,stats_fq,bwd,weights,copy] [--iters 10] [--json out.json]
+    python tools/microbench.py [--only fq,calib,minmax,stats,stats_fq,bwd,weights,copy,augment,...] [--iters 10] [--json out.json]
 
 Timing hygiene: 3 warm-up launches, L2 flushed between timed launches (a 512 MB memset-like
 write), CUDA events on the launching stream, median over --iters.  GB/s = algorithmic bytes /
@@ -173,6 +173,22 @@ def main():
             del xf, out, idx, xhat, go
         del x
         torch.cuda.empty_cache()
+    if "augment" in only:
+        from ood_dfq_b200 import augment
+        for (m, c, side, batch) in ((4096, 3, 224, 256), (20000, 3, 32, 256), (20000, 1, 28, 64)):
+            images = torch.randn((m, c, side, side), device="cuda")
+            gen = torch.Generator().manual_seed(0)
+            index = torch.randint(0, m, (batch,), generator=gen).cuda()
+            boxes, flips = augment.random_resized_crop_params_batched(batch, side, side, generator=gen)
+            read = int(4 * c * (boxes[:, 2].astype("int64") * boxes[:, 3]).sum())
+            boxes, flips = torch.from_numpy(boxes).cuda(), torch.from_numpy(flips).cuda()
+            for cl, tag in ((True, "aug_nhwc"), (False, "aug_nchw")):
+                out = torch.empty((batch, 3, side, side), device="cuda",
+                                  memory_format=torch.channels_last if cl else torch.contiguous_format)
+                report(tag, (batch, c, side, side), read + 4 * out.numel(),
+                       *timer(lambda: ops.crop_resize_flip(images, index, boxes, flips, side, channels_last=cl, out=out)))
+            del images
+            torch.cuda.empty_cache()
     if "weights" in only:
         ws = [torch.randn(s, device="cuda") * 0.02 for s in R18_WEIGHTS]
         outs = [torch.empty_like(w) for w in ws]
