@@ -161,6 +161,7 @@ class DeviceShards:
         self._stage = [(torch.empty(batch, dtype=torch.int64).pin_memory(),
                         torch.empty((batch, 4), dtype=torch.int32).pin_memory(),
                         torch.empty(batch, dtype=torch.uint8).pin_memory()) for _ in range(max(1, slots))]
+        self._copied = [None] * len(self._stage)        # event: the slot's staged draws have reached the device
         self._next = 0
 
     def set_epoch(self, epoch: int):
@@ -195,12 +196,18 @@ class DeviceShards:
             slot = self._next
             self._next = (self._next + 1) % len(self._out)
             h_idx, h_box, h_flip = self._stage[slot]
+            if self._copied[slot] is not None:
+                # the host may run far ahead of the GPU (graph replay): never overwrite staged draws whose
+                # asynchronous copy has not executed yet
+                self._copied[slot].synchronize()
             h_idx[:n].copy_(torch.from_numpy(np.ascontiguousarray(chunk, dtype=np.int64)))
             h_box[:n].copy_(torch.from_numpy(boxes))
             h_flip[:n].copy_(torch.from_numpy(flips))
             d_idx = h_idx[:n].to(self.device, non_blocking=True)
             d_box = h_box[:n].to(self.device, non_blocking=True)
             d_flip = h_flip[:n].to(self.device, non_blocking=True)
+            self._copied[slot] = torch.cuda.Event()
+            self._copied[slot].record()
             out = self._out[slot][:n]
             ops.crop_resize_flip(self.images, d_idx, d_box, d_flip, self.size, channels=3,
                                  channels_last=self.channels_last, out=out)
