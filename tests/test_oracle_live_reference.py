@@ -153,3 +153,76 @@ def test_calibrating_sequences_match_the_live_reference(seed, shape, k, sym, ste
             want = np.array([ref.x_min.item(), ref.x_max.item(), ref.beta_t.item()], dtype=np.float32)
             assert np.array_equal(bits(np.array(st_np, dtype=np.float32)), bits(want))
             assert np.array_equal(bits(st_c), bits(want))
+
+
+@settings(**{**COMMON, "max_examples": 12})
+@given(seed=st.integers(0, 2 ** 31), shape=shapes4, k=st.sampled_from([2, 4, 8]), steps=st.integers(1, 3),
+       relu=st.booleans())
+def test_mse_searched_ranges_match_the_live_reference(seed, shape, k, steps, relu):
+    """QuantAct_MSE (quant_modules.py:98-186): 80-candidate clip search + plain EMA, state and output bit-exact."""
+    ref, ours = RM.QuantAct_MSE(activation_bit=k), fq_torch.OracleQuantActMSE(k)
+    for step in range(steps):
+        x = draw_data(seed + step, shape, 1.0 + step, 0.3, False)
+        xt = torch.from_numpy(np.maximum(x, 0) if relu else x)
+        y_ref, y = ref(xt), ours(xt)
+        assert np.array_equal(bits(y.numpy()), bits(y_ref.numpy()))
+        for name in ("x_min", "x_max", "beta_t"):
+            assert np.array_equal(bits(getattr(ours, name).numpy()), bits(getattr(ref, name).numpy())), (name, step)
+
+
+@settings(**{**COMMON, "max_examples": 25})
+@given(seed=st.integers(0, 2 ** 31), shape=st.tuples(st.integers(2, 5), st.integers(1, 6), st.integers(1, 7), st.integers(1, 7)),
+       offset=st.sampled_from([0.0, 3.0, -40.0]), flavour=st.sampled_from(["trainer", "distill"]))
+def test_bn_statistics_hook_and_loss_match_the_live_reference(seed, shape, offset, flavour):
+    """The reference's BN hook (data_generate/distill_data.py:69-78, same body as trainer_direct.py:388-397) and
+    the loss lines around it (:252-265 / trainer_direct.py:473-486) against the oracle's StatTap: statistics, loss
+    and the gradient reaching the input, bit for bit (both are the same ATen calls in the same order)."""
+    sys.path.insert(0, REF)
+    try:
+        from data_generate.distill_data import DistillData
+    finally:
+        sys.path.remove(REF)
+    from oracle import bns_torch
+    torch.manual_seed(seed % (2 ** 31))
+    c = shape[1]
+    net = torch.nn.Sequential(torch.nn.BatchNorm2d(c), torch.nn.Conv2d(c, c + 1, 1), torch.nn.BatchNorm2d(c + 1)).eval()
+    for m in net:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features) * 0.3 + offset)
+            m.running_var.copy_(torch.rand(m.num_features) + 0.5)
+    x = torch.from_numpy(draw_data(seed, shape, 1.3, offset, False))
+    dd = DistillData()
+    handles = [m.register_forward_hook(dd.hook_fn_forward) for m in net if isinstance(m, torch.nn.BatchNorm2d)]
+    xr = x.clone().requires_grad_(True)
+    net(xr)
+    mse, n_l = torch.nn.MSELoss(), len(dd.mean_list)
+    if flavour == "trainer":             # the calls of trainer_direct.py:474-484 (the file itself has a TabError)
+        loss_ref = torch.zeros(1)
+        for i in range(n_l):
+            loss_ref += mse(dd.mean_list[i], dd.teacher_running_mean[i]) + mse(dd.var_list[i], dd.teacher_running_var[i])
+        loss_ref = loss_ref / n_l
+    else:                                # distill_data.py:252-265
+        ml, vl = torch.zeros(1), torch.zeros(1)
+        for i in range(n_l):
+            ml += mse(dd.mean_list[i], dd.teacher_running_mean[i].detach())
+            vl += mse(dd.var_list[i], dd.teacher_running_var[i].detach())
+        loss_ref = ml / n_l + vl / n_l
+    loss_ref.backward()
+    for h in handles:
+        h.remove()
+    xo = x.clone().requires_grad_(True)
+    tap = bns_torch.StatTap(net)
+    net(xo)
+    loss = tap.loss(flavour)
+    loss.backward()
+    tap.remove()
+    for i in range(n_l):
+        assert torch.equal(tap.means[i], dd.mean_list[i]) and torch.equal(tap.vars[i], dd.var_list[i])
+    assert torch.equal(loss, loss_ref) and torch.equal(xo.grad, xr.grad)
+    # the closed form the GPU backward implements (SURVEY 8 row a12), first layer only (its input IS x)
+    g = bns_torch.bns_input_grad(x.double(), net[0].running_mean.double(), net[0].running_var.double(), 1.0 / n_l)
+    x1 = x.clone().requires_grad_(True)
+    m1, v1 = bns_torch.channel_stats(x1)
+    ((mse(m1, net[0].running_mean) + mse(v1, net[0].running_var)) / n_l).backward()
+    scale = float(x1.grad.abs().max()) + 1e-30
+    assert float((x1.grad.double() - g).abs().max()) <= 2e-5 * scale
