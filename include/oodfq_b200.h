@@ -48,6 +48,7 @@ extern "C" {
 #define OODFQ_RELU_FIRST 4     /* x <- max(x, 0) before quantising: the nn.Sequential(ReLU, QuantAct) of
                                   main_direct.py:464-465 in one pass (scalar range, FAKEQUANT mode) */
 #define OODFQ_NO_ONCHIP 8      /* act_calib_forward: always take the two-kernel path (tests, comparisons) */
+#define OODFQ_ONCHIP_TMA 16    /* act_calib_forward: on-chip kernel variant fed by TMA bulk copies (opt-in, experimental) */
 
 /* flags of the per-channel (BatchNorm) entry points */
 #define OODFQ_BN_RELU 1

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "liboodfq_b200.so")
 
 MODE_FAKEQUANT, MODE_QUANTIZE, MODE_DEQUANTIZE = 0, 1, 2
-SYMMETRIC, PARAMS_GIVEN, RELU_FIRST, NO_ONCHIP = 1, 2, 4, 8
+SYMMETRIC, PARAMS_GIVEN, RELU_FIRST, NO_ONCHIP, ONCHIP_TMA = 1, 2, 4, 8, 16
 BN_RELU, BN_QUANT, BN_NHWC = 1, 2, 4
 ABI_VERSION = 3
 

@@ -245,37 +245,203 @@ act_calib_onchip_kernel(const float* __restrict__ x, float* __restrict__ y, long
     }
 }
 
+
+// ---- the same kernel with the on-chip part of the slice fetched by TMA bulk copies (north_star (b): "staged
+// through TMA / shared memory") -------------------------------------------------------------------------------
+// One thread arms one mbarrier per 16 KB chunk and issues all `cp.async.bulk` copies of the CTA's on-chip part up
+// front; the copy engine streams x into shared memory without passing through registers while the threads
+// (a) reduce the part of the slice that does not fit on chip straight from global memory and (b) follow the
+// chunks in arrival order, taking min / max from shared memory.  Everything after the grid barrier is the
+// register-staged kernel's.  OPT-IN (OODFQ_ONCHIP_TMA) until it has been measured against that kernel on a B200:
+// it was written in a session without GPU minutes.
+constexpr int kTChunkVec = 1024;                                   // 128-bit vectors per bulk copy (16 KB)
+constexpr int kTChunks = kCTileFloats / (4 * kTChunkVec);          // 14
+static_assert(kTChunkVec == kCThreads, "one vector per thread and chunk");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" :: "r"(count), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" :: "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// global -> shared bulk copy (size and both addresses multiples of 16 bytes), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a byte count that never completes must end in a trap (a CUDA error), not in a hung device
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    const uint32_t a = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(phase) : "memory");
+        if (ok) return;
+    }
+    asm volatile("trap;");
+}
+
+__global__ void __launch_bounds__(kCThreads, 1)
+act_calib_onchip_tma_kernel(const float* __restrict__ x, float* __restrict__ y, long long numel, Workspace* ws,
+                            float* x_min, float* x_max, const float* beta, float* beta_t, int k) {
+    extern __shared__ __align__(128) float tile_tma[];
+    __shared__ __align__(8) uint64_t bars[kTChunks];
+    __shared__ float lut[kLutMax];
+    __shared__ float s_mn[kCThreads / 32], s_mx[kCThreads / 32];
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long n4 = numel >> 2;
+    const long long per = (n4 + gridDim.x - 1) / gridDim.x;
+    const long long b4 = (long long)blockIdx.x * per;
+    const long long e4 = b4 + per < n4 ? b4 + per : n4;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    float4* t4 = reinterpret_cast<float4*>(tile_tma);
+    const long long cap4 = kCTileFloats / 4;
+    const long long len4 = e4 > b4 ? e4 - b4 : 0;
+    const int on4 = (int)(len4 < cap4 ? len4 : cap4);                // vectors of the slice held on chip
+    const int nch = (on4 + kTChunkVec - 1) / kTChunkVec;
+    const float old_min = *x_min, old_max = *x_max, b = *beta, old_bt = *beta_t;
+
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < nch; ++c) mbar_init(&bars[c], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < nch; ++c) {
+            const int vecs = on4 - c * kTChunkVec < kTChunkVec ? on4 - c * kTChunkVec : kTChunkVec;
+            const uint32_t bytes = (uint32_t)vecs * 16u;
+            mbar_arrive_expect_tx(&bars[c], bytes);
+            bulk_g2s(t4 + c * kTChunkVec, x4 + b4 + c * kTChunkVec, bytes, &bars[c]);
+        }
+    }
+
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+    constexpr int kU = 4;
+    // the part that does not fit on chip (tensors above 33 MB): through registers while the copies are in flight
+    for (long long base = b4 + on4; base < e4; base += (long long)kU * kCThreads) {
+        float4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long i = base + u * kCThreads + threadIdx.x;
+            if (i < e4) v[u] = ld_keep(x4 + i);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long i = base + u * kCThreads + threadIdx.x;
+            if (i < e4) {
+                mn = min_nan(min_nan(mn, v[u].x), min_nan(v[u].y, min_nan(v[u].z, v[u].w)));
+                mx = max_nan(max_nan(mx, v[u].x), max_nan(v[u].y, max_nan(v[u].z, v[u].w)));
+            }
+        }
+    }
+    // the on-chip part, chunk by chunk as the copies land (one vector per thread and chunk)
+    for (int c = 0; c < nch; ++c) {
+        mbar_wait(&bars[c], 0);
+        const int i = c * kTChunkVec + threadIdx.x;
+        if (i < on4) {
+            const float4 v = t4[i];
+            mn = min_nan(min_nan(mn, v.x), min_nan(v.y, min_nan(v.z, v.w)));
+            mx = max_nan(max_nan(mx, v.x), max_nan(v.y, max_nan(v.z, v.w)));
+        }
+    }
+    mn = warp_min_nan(mn);
+    mx = warp_max_nan(mx);
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kCThreads / 32; ++w) { mn = min_nan(mn, s_mn[w]); mx = max_nan(mx, s_mx[w]); }
+        ws->mm_partial[2 * blockIdx.x] = mn;
+        ws->mm_partial[2 * blockIdx.x + 1] = mx;
+    }
+    grid.sync();
+
+    mn = __int_as_float(0x7f800000);
+    mx = __int_as_float(0xff800000);
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += kCThreads) {
+        mn = min_nan(mn, __ldcg(&ws->mm_partial[2 * c]));
+        mx = max_nan(mx, __ldcg(&ws->mm_partial[2 * c + 1]));
+    }
+    mn = warp_min_nan(mn);
+    mx = warp_max_nan(mx);
+    __syncthreads();
+    if (lane == 0) { s_mn[warp] = mn; s_mx[warp] = mx; }
+    __syncthreads();
+    mn = s_mn[0];
+    mx = s_mx[0];
+#pragma unroll
+    for (int w = 1; w < kCThreads / 32; ++w) { mn = min_nan(mn, s_mn[w]); mx = max_nan(mx, s_mx[w]); }
+    const float bt = __fmul_rn(old_bt, b);                       // quant_modules.py:87
+    const float new_min = ema_step(old_min, mn, b, bt);          // :88
+    const float new_max = ema_step(old_max, mx, b, bt);          // :89
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *x_min = new_min; *x_max = new_max; *beta_t = bt; }
+
+    const QParams qp = make_qparams(new_min, new_max, k);
+    const int qh = 1 << (k - 1), qmask = (1 << k) - 1;
+    build_lut(lut, qp, k, threadIdx.x, kCThreads);
+    __syncthreads();
+    for (long long base = b4; base < e4; base += (long long)kU * kCThreads) {
+        float4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long i = base + u * kCThreads + threadIdx.x;
+            if (i < e4) v[u] = (i - b4 < on4) ? t4[i - b4] : ld_stream(x4 + i);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const long long i = base + u * kCThreads + threadIdx.x;
+            if (i < e4) {
+                float4 o;
+                o.x = fake_quant_lut(v[u].x, qp, lut, qh, qmask);
+                o.y = fake_quant_lut(v[u].y, qp, lut, qh, qmask);
+                o.z = fake_quant_lut(v[u].z, qp, lut, qh, qmask);
+                o.w = fake_quant_lut(v[u].w, qp, lut, qh, qmask);
+                st_out(y4 + i, o);
+            }
+        }
+    }
+}
+
 // true if the launch was made (the caller falls back to the two-kernel path otherwise)
+struct CoopProbe {
+    int state = 0;                   // 0 = not probed, 1 = usable, -1 = unavailable on this device / driver
+    int grid = 0;
+};
+
 static bool try_onchip_calib(const float* x, float* y, long long numel, void* workspace, float* x_min, float* x_max,
-                             const float* beta, float* beta_t, int k, cudaStream_t st, int* rc) {
-    static int state = 0;            // 0 = not probed, 1 = usable, -1 = unavailable on this device / driver
-    static int grid = 0;
-    if (state < 0 || k > 8 || (numel & 3) || numel * 4 > kCoopMaxBytes || !aligned16(x) || !aligned16(y)) return false;
+                             const float* beta, float* beta_t, int k, bool tma, cudaStream_t st, int* rc) {
+    static CoopProbe probes[2];
+    CoopProbe& pr = probes[tma ? 1 : 0];
+    const void* kernel = tma ? (const void*)act_calib_onchip_tma_kernel : (const void*)act_calib_onchip_kernel;
+    if (pr.state < 0 || k > 8 || (numel & 3) || numel * 4 > kCoopMaxBytes || !aligned16(x) || !aligned16(y)) return false;
     const size_t smem = (size_t)kCTileFloats * sizeof(float);
-    if (state == 0) {
+    if (pr.state == 0) {
         int dev = 0, coop = 0, per_sm = 0, sms = 0;
         bool ok = cudaGetDevice(&dev) == cudaSuccess &&
                   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
                   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
-                  cudaFuncSetAttribute(act_calib_onchip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
-                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, act_calib_onchip_kernel, kCThreads, smem) == cudaSuccess &&
+                  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+                  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kCThreads, smem) == cudaSuccess &&
                   per_sm >= 1;
         (void)cudaGetLastError();
-        grid = ok ? (sms < kMaxReduceBlocks ? sms : kMaxReduceBlocks) : 0;
-        state = ok ? 1 : -1;
+        pr.grid = ok ? (sms < kMaxReduceBlocks ? sms : kMaxReduceBlocks) : 0;
+        pr.state = ok ? 1 : -1;
         if (!ok) return false;
     }
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
     void* args[] = {(void*)&x, (void*)&y, (void*)&numel, (void*)&ws, (void*)&x_min, (void*)&x_max, (void*)&beta,
                     (void*)&beta_t, (void*)&k};
-    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)act_calib_onchip_kernel, dim3(grid), dim3(kCThreads),
-                                                      args, smem, st);
+    const cudaError_t e = cudaLaunchCooperativeKernel(kernel, dim3(pr.grid), dim3(kCThreads), args, smem, st);
     if (e != cudaSuccess) {          // e.g. the grid cannot be co-resident right now: leave it to the other path
         (void)cudaGetLastError();
         return false;
     }
     count_launch();
-    *rc = check_launch("act_calib_forward(on-chip)");
+    *rc = check_launch(tma ? "act_calib_forward(on-chip, TMA)" : "act_calib_forward(on-chip)");
     return true;
 }
 
@@ -302,7 +468,7 @@ extern "C" int oodfq_act_calib_forward(const float* x, float* y, int8_t* codes, 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = OODFQ_OK;
     if (y && !codes && !sym && !(flags & OODFQ_NO_ONCHIP) &&
-        try_onchip_calib(x, y, numel, workspace, x_min, x_max, beta, beta_t, k, st, &rc))
+        try_onchip_calib(x, y, numel, workspace, x_min, x_max, beta, beta_t, k, (flags & OODFQ_ONCHIP_TMA) != 0, st, &rc))
         return rc;
     rc = launch_minmax(x, numel, workspace, nullptr, x_min, x_max, beta, beta_t, sym ? 1 : 0, st);
     if (rc != OODFQ_OK || !y) return rc;

@@ -162,6 +162,8 @@ def act_calib_forward(x, k, x_min, x_max, beta, beta_t, symmetric=False, quantiz
     quant_modules.py:80-94 (DSG :365-386).  ``quantize=False`` only tracks the range
     (full_precision_flag) and returns None.  ``onchip=False`` forces the two-kernel path (tensors up to 96 MB
     otherwise run as one cooperative kernel that keeps x in shared memory; same bits either way).
+    ``onchip="tma"`` selects the experimental variant of that kernel whose shared-memory tile is filled by TMA bulk
+    copies (opt-in until measured on hardware).
     """
     _need(x, "input")
     for t, nme in ((x_min, "x_min"), (x_max, "x_max"), (beta, "beta"), (beta_t, "beta_t")):
@@ -173,7 +175,8 @@ def act_calib_forward(x, k, x_min, x_max, beta, beta_t, symmetric=False, quantiz
     cd = torch.empty_like(xd, dtype=torch.int8) if (codes and quantize) else None
     rc = N.load().oodfq_act_calib_forward(xd.data_ptr(), _ptr(y), _ptr(cd), xd.numel(), x_min.data_ptr(),
                                           x_max.data_ptr(), beta.data_ptr(), beta_t.data_ptr(), int(k),
-                                          (N.SYMMETRIC if symmetric else 0) | (0 if onchip else N.NO_ONCHIP),
+                                          (N.SYMMETRIC if symmetric else 0) | (0 if onchip else N.NO_ONCHIP) |
+                                          (N.ONCHIP_TMA if onchip == "tma" else 0),
                                           workspace(x.device).data_ptr(), _stream(x.device))
     N.check(rc, "act_calib_forward")
     return (y, cd) if codes else y

@@ -19,6 +19,9 @@ if has tests; then
   log "pytest -m gpu"
   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
   log "pytest exit $? : $(tail -1 gpurun_out/pytest_gpu.log)"
+  log "pytest experimental (opt-in kernels)"
+  OODFQ_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_experimental.py -q > gpurun_out/pytest_experimental.log 2>&1
+  log "pytest exit $? : $(tail -1 gpurun_out/pytest_gpu.log)"
 fi
 if has smoke; then
   log "smoke"
@@ -57,7 +60,7 @@ if has ncu; then
 fi
 if has micro; then
   log "microbench (read-flush)"
-  timeout 900 python tools/microbench.py --only copy,fq,calib,tail,pool,bn_fwd,bn_bwd,stats_nhwc,weights,augment --flush read \
+  OODFQ_EXPERIMENTAL=1 timeout 900 python tools/microbench.py --only copy,fq,calib,tail,pool,bn_fwd,bn_bwd,stats_nhwc,weights,augment --flush read \
       --json gpurun_out/microbench.json > gpurun_out/microbench.txt 2>&1
   log "microbench exit $?"
 fi

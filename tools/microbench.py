@@ -106,6 +106,11 @@ def main():
                 st[3].fill_(1.0)
                 ops.act_calib_forward(x, 4, st[0], st[1], st[2], st[3], onchip=False)
             report("calib_2k", shape, 12 * n, *timer(calib2))
+            if os.environ.get("OODFQ_EXPERIMENTAL"):
+                def calib3():
+                    st[3].fill_(1.0)
+                    ops.act_calib_forward(x, 4, st[0], st[1], st[2], st[3], onchip="tma")
+                report("calib_tma", shape, 12 * n, *timer(calib3))
         c = shape[1]
         shift = torch.zeros(c, device="cuda")
         if "stats" in only:
