@@ -21,7 +21,7 @@ if has tests; then
   log "pytest exit $? : $(tail -1 gpurun_out/pytest_gpu.log)"
   log "pytest experimental (opt-in kernels)"
   OODFQ_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_experimental.py -q > gpurun_out/pytest_experimental.log 2>&1
-  log "pytest exit $? : $(tail -1 gpurun_out/pytest_gpu.log)"
+  log "experimental exit $? : $(tail -1 gpurun_out/pytest_experimental.log)"
 fi
 if has smoke; then
   log "smoke"
