@@ -339,6 +339,33 @@ def main_ours(args):
             _ = qat().item()
         e1.record()
         barrier()
+    elif args.e2e_input == "device_shards":
+        # OPT-IN variant of the end-to-end arm: the synthetic image set lives in HBM and every step's
+        # batch is assembled on the device (gather + RandomResizedCrop + flip, csrc/augment.cu); what crosses PCIe
+        # per step is the sample indices, crop boxes and flip bits drawn on the host (25 B per image), and the loss
+        # on the way back.  The default arm below keeps the reference's data flow (host batches -> H2D).
+        import numpy as np
+        from ood_dfq_b200 import augment
+        rng = np.random.default_rng(rank)
+        m = max(4 * batch, 1024)
+        ds = augment.DeviceShards(rng.standard_normal((m,) + shape, dtype=np.float32), rng.integers(0, 1000, m), batch,
+                                  dev, rank=0, world=1, seed=rank, channels_last=channels_last, slots=2)
+
+        def batches():
+            epoch = 0
+            while True:
+                ds.set_epoch(epoch)
+                yield from ds
+                epoch += 1
+        stream = batches()
+        for i in range(args.warmup):
+            qat(next(stream)[0]).item()
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            _ = qat(next(stream)[0]).item()
+        e1.record()
+        barrier()
     else:
         # double-buffered prefetcher: two fixed device buffers, H2D on a copy stream while the previous step
         # computes (no allocation inside the loop: allocator traffic made this number jitter by 20 %).  Under
@@ -386,6 +413,8 @@ def main_ours(args):
     e2e_ms = float(t.item())
     e2e_value = world * batch * args.steps / (e2e_ms / 1e3)
     h2d = 0 if kind == "distill" else batch * shape[0] * shape[1] * shape[2] * 4
+    if kind != "distill" and args.e2e_input == "device_shards":
+        h2d = batch * (8 + 16 + 1)                 # index, box, flip per image
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -407,7 +436,7 @@ def main_ours(args):
                        "memory_format": "channels_last" if channels_last else "NCHW (as the reference)",
                        "cuda_graph": use_graph},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "input": args.e2e_input},
             "gpu_launches": int(launches),
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": dominant,
@@ -489,6 +518,9 @@ def main():
     ap.add_argument("--no-tail-fuse", action="store_true", help="keep the residual add and the ReLU + QuantAct behind it separate")
     ap.add_argument("--no-s2d", action="store_true", help="keep the 3-channel stem convolution in its stride-2 form")
     ap.add_argument("--nchw", action="store_true", help="keep NCHW tensors (default: channels_last memory format)")
+    ap.add_argument("--e2e-input", choices=["host", "device_shards"], default="host",
+                    help="end-to-end arm: pinned host batches copied every step (default, the reference's data flow) or "
+                         "batches assembled on the device from an HBM-resident image set (opt-in)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
                     help="replay the whole iteration as a CUDA graph (auto = on; off: eager launches)")

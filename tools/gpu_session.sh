@@ -32,6 +32,10 @@ if has bench; then
   log "bench N=1"
   timeout 900 python bench.py --gpus 1 --steps 8 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
   log "bench exit $? : $(head -c 300 gpurun_out/bench_n1.json)"
+  log "bench N=1, batches assembled on the device (opt-in e2e input)"
+  timeout 900 python bench.py --gpus 1 --steps 8 --warmup 3 --no-cpu-baseline --e2e-input device_shards \
+      > gpurun_out/bench_n1_device_shards.json 2> gpurun_out/bench_n1_device_shards.err
+  log "bench (device shards) exit $?"
 fi
 if has ref; then
   log "reference arm"
