@@ -1,0 +1,160 @@
+"""Drop-in proof on the consumer side: the reference's OWN host code, read from its tree at test time and executed
+unmodified against the mirror package.
+
+``main_direct.py`` and ``trainer_direct.py`` cannot be imported here (pyhocon / pytorchcv are absent and
+``trainer_direct.py`` has a TabError at :275), but the methods that consume the quantisation API are
+self-contained: ``ExperimentDesign.quantize_model`` / ``freeze_model`` / ``unfreeze_model``
+(main_direct.py:444-516) and ``Trainer.reduce_minmax`` (trainer_direct.py:368-374).  Their source text is cut out of
+the reference files, compiled, and run in a namespace set up the way the reference sets up its own
+(``from quantization_utils.quant_modules import *`` after ``ood_dfq_b200.install()``).  Nothing is copied into this
+repository; the module skips where ``/root/reference`` does not exist (the GPU box).
+
+Everything here is host logic on CPU tensors: surgery never runs a forward, and ``reduce_minmax`` only touches the
+``x_min`` / ``x_max`` buffers (all-reduce in place, then re-assignment), which must keep working on the mirror.
+"""
+import ast
+import copy
+import os
+import sys
+import textwrap
+import types
+
+import pytest
+import torch
+import torch.distributed as dist
+from torch import nn
+
+REF = os.environ.get("OODFQ_REFERENCE", "/root/reference")
+if not os.path.isfile(os.path.join(REF, "main_direct.py")):
+    pytest.skip("reference tree not present (GPU box)", allow_module_level=True)
+
+
+def reference_namespace():
+    """Globals as the reference's scripts see them after their imports (main_direct.py:1-30)."""
+    import ood_dfq_b200
+    ood_dfq_b200.install()
+    ns = {"nn": nn, "torch": torch, "copy": copy, "dist": dist}
+    exec("from quantization_utils.quant_modules import *", ns)           # main_direct.py:21, trainer_direct.py:19
+    return ns
+
+
+def methods_of(path, class_name, names):
+    """The named methods of one class, compiled from the reference file's own text (ast keeps it verbatim)."""
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name)
+    picked = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert sorted(n.name for n in picked) == sorted(names)
+    module = ast.Module(body=picked, type_ignores=[])
+    ns = reference_namespace()
+    exec(compile(module, path, "exec"), ns)
+    return ns
+
+
+def lines_of(path, first, last):
+    """Lines [first, last] of a file that cannot be parsed as a whole, dedented and compiled on their own."""
+    with open(path) as f:
+        text = "".join(f.readlines()[first - 1:last])
+    ns = reference_namespace()
+    exec(compile(textwrap.dedent(text.expandtabs(4)), f"{path}:{first}-{last}", "exec"), ns)
+    return ns
+
+
+@pytest.fixture(scope="module")
+def surgery_ns():
+    return methods_of(os.path.join(REF, "main_direct.py"), "ExperimentDesign",
+                      ["quantize_model", "freeze_model", "unfreeze_model"])
+
+
+def experiment(ns, qw, qa):
+    """A stand-in for ``ExperimentDesign``: only ``self.settings.qw / .qa`` and the three methods are touched."""
+    self = types.SimpleNamespace(settings=types.SimpleNamespace(qw=qw, qa=qa))
+    for name in ("quantize_model", "freeze_model", "unfreeze_model"):
+        setattr(self, name, types.MethodType(ns[name], self))
+    return self
+
+
+def reference_models():
+    """The importable model definition of the reference (models.py, 28x28 ResNet-18) plus this repo's carrier nets
+    for the pytorchcv-shaped ones."""
+    sys.path.insert(0, REF)
+    try:
+        import models as ref_models
+    finally:
+        sys.path.remove(REF)
+    from ood_dfq_b200 import nets
+    torch.manual_seed(0)
+    return {"reference models.ResNet18 (28x28)": ref_models.ResNet18(3, 9, img_size=28),
+            "resnet20_cifar": nets.resnet20_cifar(num_classes=100),
+            "resnet18_imagenet": nets.resnet18_imagenet(num_classes=1000)}
+
+
+@pytest.mark.parametrize("bits", [(4, 4), (2, 2)])
+def test_reference_quantize_model_runs_on_the_mirror(surgery_ns, bits):
+    from ood_dfq_b200 import surgery
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    exp = experiment(surgery_ns, *bits)
+    for name, net in reference_models().items():
+        theirs = exp.quantize_model(net)                                  # reference code, mirror classes
+        ours = surgery.quantize_model(copy.deepcopy(net), *bits)          # this repo's restatement of that code
+        sd_t, sd_o = theirs.state_dict(), ours.state_dict()
+        assert list(sd_t) == list(sd_o), name
+        assert all(torch.equal(sd_t[k], sd_o[k]) for k in sd_t), name
+        kinds_t = [(n, type(m).__name__) for n, m in theirs.named_modules()]
+        kinds_o = [(n, type(m).__name__) for n, m in ours.named_modules()]
+        assert kinds_t == kinds_o, name
+        convs = [m for m in theirs.modules() if type(m) is qm.Quant_Conv2d]
+        acts = [m for m in theirs.modules() if type(m) is qm.QuantAct]
+        lins = [m for m in theirs.modules() if type(m) is qm.Quant_Linear]
+        assert convs and acts and len(lins) == 1, name
+        assert not any(type(m) in (nn.Conv2d, nn.Linear) for m in theirs.modules()), name
+        assert all(m.weight_bit == bits[0] for m in convs + lins) and all(m.activation_bit == bits[1] for m in acts)
+        # the reference's key shape: "<relu name>.1.x_min" = the QuantAct inside Sequential(ReLU, QuantAct)
+        assert any(k.endswith(".1.x_min") for k in sd_t) and any(k.endswith(".1.beta_t") for k in sd_t), name
+        assert all(isinstance(p, nn.Parameter) for m in convs for p in [m.weight])
+
+
+def test_reference_freeze_and_unfreeze_walk_the_mirror(surgery_ns):
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    exp = experiment(surgery_ns, 4, 4)
+    for name, net in reference_models().items():
+        model = exp.quantize_model(net)
+        acts = [m for m in model.modules() if type(m) is qm.QuantAct]
+        assert all(m.running_stat for m in acts)
+        exp.freeze_model(model)                                           # main_direct.py:486-500, `type(m) == QuantAct`
+        assert not any(m.running_stat for m in acts), name
+        exp.unfreeze_model(model)
+        assert all(m.running_stat for m in acts), name
+        assert "Act_min" in repr(acts[0])                                 # quant_modules.py:57-61 (calls .item())
+
+
+def test_reference_reduce_minmax_runs_on_the_mirror(surgery_ns):
+    """trainer_direct.py:368-374 verbatim over a single-process gloo group: in-place all-reduce of the mirror's
+    buffers, then re-assignment -- the buffers must stay registered, 1-element, and hold sum / world."""
+    ns = lines_of(os.path.join(REF, "trainer_direct.py"), 368, 374)
+    exp = experiment(surgery_ns, 4, 4)
+    net = reference_models()["resnet20_cifar"]
+    model = exp.quantize_model(net)
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    acts = [m for m in model.modules() if isinstance(m, qm.QuantAct)]
+    for i, m in enumerate(acts):
+        m.x_min.fill_(-0.25 * i)
+        m.x_max.fill_(1.0 + i)
+    own_group = not dist.is_initialized()
+    if own_group:
+        import socket
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        trainer = types.SimpleNamespace(model=types.SimpleNamespace(module=model))      # self.model.module (DDP)
+        ns["reduce_minmax"](trainer)
+    finally:
+        if own_group:
+            dist.destroy_process_group()
+    for i, m in enumerate(acts):
+        assert m.x_min.shape == (1,) and m.x_max.shape == (1,)
+        assert m.x_min.item() == -0.25 * i and m.x_max.item() == 1.0 + i
+        assert "x_min" in dict(m.named_buffers()) and "x_max" in dict(m.named_buffers())
+    assert sum(k.endswith("x_max") for k in model.state_dict()) == len(acts)
