@@ -158,3 +158,94 @@ def test_reference_reduce_minmax_runs_on_the_mirror(surgery_ns):
         assert m.x_min.item() == -0.25 * i and m.x_max.item() == 1.0 + i
         assert "x_min" in dict(m.named_buffers()) and "x_max" in dict(m.named_buffers())
     assert sum(k.endswith("x_max") for k in model.state_dict()) == len(acts)
+
+
+def test_reference_dataset_reads_our_shards_and_our_reader_reads_the_same(tmp_path):
+    """``direct_dataset`` (main_direct.py:150-209), compiled from the reference file, opens shard files written by
+    ``shards.write_shards``; ``shards.load_shards`` returns exactly what it concatenated, and a ``ShardBatches`` fed the
+    reference's own ``train_transform`` reproduces its ``__getitem__`` samples under the same seed."""
+    pytest.importorskip("torchvision")
+    import pickle
+
+    import numpy as np
+    import torchvision.transforms as transforms
+    from torch.utils.data import Dataset
+
+    from ood_dfq_b200 import shards
+    path = os.path.join(REF, "main_direct.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "direct_dataset")
+    ns = {"Dataset": Dataset, "transforms": transforms, "pickle": pickle, "np": np, "torch": torch}
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), path, "exec"), ns)
+
+    rng = np.random.default_rng(0)
+    for channels in (3, 1):
+        images = rng.standard_normal((22, channels, 28, 28)).astype(np.float32)
+        labels = rng.integers(0, 9, 22).astype(np.int64)
+        data_prefix, label_prefix = str(tmp_path / f"data{channels}_group"), str(tmp_path / f"labels{channels}_group")
+        shards.write_shards(data_prefix, label_prefix, images, labels)
+        settings = types.SimpleNamespace(img_size=28, generateDataPath=data_prefix, generateLabelPath=label_prefix)
+        logger = types.SimpleNamespace(info=lambda *a, **k: None)
+        theirs = ns["direct_dataset"](settings, logger, "pathmnist")
+        got_images, got_labels = shards.load_shards(data_prefix, label_prefix)
+        assert len(theirs) == 22
+        assert np.array_equal(theirs.tmp_data, got_images) and np.array_equal(theirs.tmp_label, got_labels)
+        assert np.array_equal(got_images, images) and np.array_equal(got_labels, labels)
+
+        order = shards.rank_indices(22, 0, 1, epoch=0, shuffle=False)
+        torch.manual_seed(5)
+        want = [theirs[int(i)] for i in order[:8]]                       # the reference's __getitem__, in order
+        torch.manual_seed(5)
+        mine = shards.ShardBatches(got_images, got_labels, batch=8, shuffle=False, transform=theirs.train_transform,
+                                   channels_last=False)
+        x, y = next(iter(mine))
+        assert x.shape == (8, 3, 28, 28)
+        for j, (img, lab) in enumerate(want):
+            assert torch.equal(x[j], img) and int(y[j]) == int(lab)
+
+
+def test_step_losses_equal_the_reference_trainer_source():
+    """``Trainer.loss_fn_kd`` / ``loss_fa`` / ``channel_attention`` / ``hook_activation`` / ``hook_fn_forward``
+    (trainer_direct.py:308-330, :379-397), compiled from the reference file's text, against the step's host code
+    (ood_dfq_b200/step.py) and the oracle's BN hook on the same tensors: bit-identical."""
+    from ood_dfq_b200 import step
+    from oracle import bns_torch
+    path = os.path.join(REF, "trainer_direct.py")
+    ns = {}
+    for first, last in ((308, 330), (379, 397)):
+        ns.update(lines_of(path, first, last))        # `F`, `torch` come from the star import, as in the reference
+    g = torch.Generator().manual_seed(8)
+    trainer = types.SimpleNamespace(
+        settings=types.SimpleNamespace(alpha=20.0, temperature=20.0, lam=1000.0),
+        args=types.SimpleNamespace(local_rank="cpu"),
+        criterion=nn.CrossEntropyLoss(), KLloss=nn.KLDivLoss(reduction="batchmean"),       # trainer_direct.py:51, :54
+        activation=[], activation_teacher=[], mean_list=[], var_list=[], teacher_running_mean=[], teacher_running_var=[])
+    trainer.channel_attention = types.MethodType(ns["channel_attention"], trainer)
+    for name in ("loss_fn_kd", "loss_fa", "hook_activation", "hook_activation_teacher", "hook_fn_forward"):
+        setattr(trainer, name, types.MethodType(ns[name], trainer))
+
+    # KD loss
+    s_logits, t_logits = torch.randn(16, 100, generator=g) * 3, torch.randn(16, 100, generator=g) * 3
+    labels = torch.randint(0, 100, (16,), generator=g)
+    kd_ref, _ = trainer.loss_fn_kd(s_logits, labels, t_logits)
+    assert torch.equal(step.kd_loss(s_logits, t_logits, 20.0, 20.0), kd_ref)
+
+    # channel attention + feature-alignment loss over three "units"
+    feats_s = [torch.randn(4, c, 6, 6, generator=g) for c in (8, 16, 32)]
+    feats_t = [torch.randn(4, c, 6, 6, generator=g) for c in (8, 16, 32)]
+    for fs, ft in zip(feats_s, feats_t):
+        trainer.hook_activation(None, None, fs)
+        trainer.hook_activation_teacher(None, None, ft)
+    maps_s, maps_t = [step.channel_attention(f.clone()) for f in feats_s], [step.channel_attention(f.clone()) for f in feats_t]
+    assert all(torch.equal(a, b) for a, b in zip(maps_s, trainer.activation))
+    assert torch.equal(step.feature_alignment_loss(maps_s, maps_t, 1000.0, "cpu"), trainer.loss_fa())
+
+    # BN-statistics hook
+    bn = nn.BatchNorm2d(8).eval()
+    bn.running_mean.copy_(torch.randn(8, generator=g))
+    x = torch.randn(5, 8, 7, 7, generator=g)
+    trainer.hook_fn_forward(bn, (x,), None)
+    mean, var = bns_torch.channel_stats(x)
+    assert torch.equal(mean, trainer.mean_list[0]) and torch.equal(var, trainer.var_list[0])
+    assert trainer.teacher_running_mean[0] is bn.running_mean
