@@ -249,3 +249,69 @@ def test_step_losses_equal_the_reference_trainer_source():
     mean, var = bns_torch.channel_stats(x)
     assert torch.equal(mean, trainer.mean_list[0]) and torch.equal(var, trainer.var_list[0])
     assert trainer.teacher_running_mean[0] is bn.running_mean
+
+
+def test_qat_step_equals_the_reference_iteration_source():
+    """SURVEY row a16.  The student branch of ``Trainer.train`` (trainer_direct.py:500-518) with ``forward`` (:332-340),
+    ``loss_fn_kd`` / ``loss_fa`` (:308-330), the feature hooks (:379-386) and ``backward_S`` (:350-356), all compiled
+    from the reference file's own text, run one iteration on CPU oracle modules; ``step.QATStep`` runs the same
+    iteration on a copy.  Losses and the SGD-updated student weights must agree bit for bit, although the step
+    keeps the teacher frozen, prunes the final backward to the student's parameters and owns a flat gradient
+    buffer (the documented deviations: none of them may change the update)."""
+    from ood_dfq_b200 import nets, step, surgery
+    from oracle import fq_torch
+    path = os.path.join(REF, "trainer_direct.py")
+    ns = {}
+    for first, last in ((308, 340), (350, 356), (379, 386)):
+        ns.update(lines_of(path, first, last))
+    # the loop body itself, as a function of (self, images, labels)
+    with open(path) as f:
+        body = "".join(f.readlines()[499:518])
+    src = "def iteration(self, images, labels):\n" + textwrap.indent(textwrap.dedent(body.expandtabs(4)), "    ") + \
+          "    return loss_S, loss_S_perturbed, loss_total\n"
+    exec(compile(src, f"{path}:500-518", "exec"), ns)
+
+    torch.manual_seed(3)
+    teacher = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(teacher)
+    student = surgery.quantize_model(copy.deepcopy(teacher), 4, 4, namespace=fq_torch)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():                                            # epochs 0-3: calibrate, then freeze (:429, main_direct.py:538)
+        for _ in range(2):
+            student(torch.randn(4, 3, 32, 32, generator=g))
+    surgery.freeze_model(student, fq_torch)
+    teacher.eval()
+    student.eval()
+    images, labels = torch.randn(4, 3, 32, 32, generator=g), torch.randint(0, 10, (4,), generator=g)
+    hyper = dict(lr=1e-2, momentum=0.9, weight_decay=1e-4)            # a visible update; same rule as lr_S = 1e-5
+
+    # ---- the reference's iteration -------------------------------------------------------------------------------
+    ref_student, ref_teacher = copy.deepcopy(student), copy.deepcopy(teacher)
+    trainer = types.SimpleNamespace(
+        settings=types.SimpleNamespace(alpha=20.0, temperature=20.0, lam=1000.0, eps=0.01),
+        args=types.SimpleNamespace(local_rank="cpu"), model=ref_student, model_teacher=ref_teacher,
+        criterion=nn.CrossEntropyLoss(), KLloss=nn.KLDivLoss(reduction="batchmean"), activation=[], activation_teacher=[],
+        optimizer_S=torch.optim.SGD(params=ref_student.parameters(), nesterov=True, **hyper))      # :59-65
+    for name in ("loss_fn_kd", "loss_fa", "forward", "backward_S", "channel_attention", "hook_activation",
+                 "hook_activation_teacher", "iteration"):
+        setattr(trainer, name, types.MethodType(ns[name], trainer))
+    for m in ref_teacher.modules():                                   # :432-440 (ResUnit = the carrier nets' unit class)
+        if isinstance(m, nets.ResUnit):
+            m.body.register_forward_hook(trainer.hook_activation_teacher)
+    for m in ref_student.modules():
+        if isinstance(m, nets.ResUnit):
+            m.body.register_forward_hook(trainer.hook_activation)
+    loss_s, loss_p, loss_total = trainer.iteration(images.clone(), labels)
+
+    # ---- this repository's step -----------------------------------------------------------------------------------
+    my_student, my_teacher = copy.deepcopy(student), copy.deepcopy(teacher)
+    qat = step.QATStep(my_student, my_teacher, temperature=20.0, alpha=20.0, lam=1000.0, eps=0.01,
+                       unit_types=(nets.ResUnit,), **hyper)
+    total = qat(images.clone())
+    assert torch.equal(total.reshape(-1), loss_total.detach().reshape(-1))
+    moved = 0
+    for (name, a), (_, b) in zip(my_student.named_parameters(), ref_student.named_parameters()):
+        assert torch.equal(a, b), name
+        moved += int(not torch.equal(a, dict(student.named_parameters())[name]))
+    assert moved > 10                                                 # the update really happened
+    assert float(loss_s.detach()) > 0 and float(loss_p.detach()) > 0
