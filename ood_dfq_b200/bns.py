@@ -210,8 +210,15 @@ class BNStatLoss:
         counts = [c * run.world for c in run.counts]
         run.loss3, run.mean, run.var, run.gmean, run.gvar = ops.bns_loss(run.sums, rm, rm, rv, offs, counts)
 
-    def loss(self) -> torch.Tensor:
-        """``sum_l [MSE(mean_l, rm_l) + MSE(var_l, rv_l)] / L`` as a differentiable 0-dim tensor."""
+    def loss(self, flavour: str = "trainer") -> torch.Tensor:
+        """``sum_l [MSE(mean_l, rm_l) + MSE(var_l, rv_l)] / L`` as a differentiable 0-dim tensor.
+
+        ``flavour``: the reference writes this sum two ways -- ``(sum_l mean_l-term + var_l-term) / L``
+        (trainer_direct.py:473-486) and ``sum_l mean-term / L + sum_l var-term / L`` (distill_data.py:252-265).
+        The kernel accumulates all terms in fp64 and rounds once, so both are the same number here; the argument
+        only keeps the call interchangeable with the oracle's ``StatTap.loss(flavour)``."""
+        if flavour not in ("trainer", "distill"):
+            raise ValueError(f"BNStatLoss.loss: unknown flavour {flavour!r}")
         run = self._run
         if run is None:
             raise RuntimeError("BNStatLoss.loss(): no forward pass has been collected")

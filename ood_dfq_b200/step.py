@@ -210,19 +210,60 @@ def hard_sample_loss(logits, labels, beta: float, gamma: float):
     return beta * ((1 - p).pow(gamma) * ce).mean()
 
 
+class PlateauOnDevice:
+    """``ReduceLROnPlateau(optimizer, min_lr=1e-4, patience=50)`` of the distillation loop (distill_data.py:185-188,
+    stepped at :275 with ``total_loss.item()``) without the host round trip: best value, bad-iteration counter and
+    the learning rate live in device tensors and are updated by a handful of element-wise ops, so the iteration
+    stays free of host synchronisation and can be replayed as a CUDA graph.  Same rule as torch's scheduler
+    (mode "min", relative threshold 1e-4, factor 0.1, no cooldown, eps 1e-8), evaluated in float64 like there:
+    identical decisions for identical losses (tests/test_step_cpu.py)."""
+
+    def __init__(self, lr: torch.Tensor, factor=0.1, patience=50, threshold=1e-4, min_lr=1e-4, eps=1e-8):
+        self.lr = lr                                               # the optimiser's own lr tensor, updated in place
+        dev = lr.device
+        self.best = torch.full((), float("inf"), dtype=torch.float64, device=dev)
+        self.num_bad = torch.zeros((), dtype=torch.int64, device=dev)
+        self.factor, self.patience, self.threshold, self.min_lr, self.eps = factor, patience, threshold, min_lr, eps
+
+    def step(self, loss: torch.Tensor):
+        cur = loss.detach().double().reshape(())
+        better = cur < self.best * (1.0 - self.threshold)
+        self.best.copy_(torch.where(better, cur, self.best))
+        bad = torch.where(better, torch.zeros_like(self.num_bad), self.num_bad + 1)
+        reduce = bad > self.patience
+        old = self.lr.detach().double().reshape(())
+        new = torch.clamp(old * self.factor, min=self.min_lr)
+        apply = reduce & ((old - new) > self.eps)
+        self.lr.copy_(torch.where(apply, new, old).to(self.lr.dtype).reshape(self.lr.shape))
+        self.num_bad.copy_(torch.where(reduce, torch.zeros_like(bad), bad))
+
+
 class DistillStep:
     """One Adam iteration on a batch of synthetic images against BN statistics (distill_data.py:229-275).
 
     ``stat`` is either this package's ``bns.BNStatLoss`` (GPU) or the oracle's ``StatTap`` (CPU): both expose
-    ``clear()`` and ``loss()``.  The teacher may be wrapped by ``quantize_model`` first (BASELINE config 5); the
+    ``clear()`` and ``loss(flavour)``.  The teacher may be wrapped by ``quantize_model`` first (BASELINE config 5); the
     gradient then reaches the images through cuDNN dgrad and the identity STE of every QuantAct.
+
+    ``plateau``: the loop's ``ReduceLROnPlateau`` (:185-188, :275).  Eagerly it is torch's own scheduler fed
+    ``total.item()`` as in the reference; with ``capturable`` it is ``PlateauOnDevice`` (no host sync).  The per-image
+    RandomResizedCrop / flip that the loop applies to 224x224 batches on every other iteration (:197-227) is outside
+    the rows SURVEY.md section 8(d) scopes for this iteration (:229-275) and is not applied here.
     """
 
-    def __init__(self, teacher, stat, images, labels, lr=0.5, beta=0.1, gamma=0.5, capturable=False):
+    def __init__(self, teacher, stat, images, labels, lr=0.5, beta=0.1, gamma=0.5, capturable=False, plateau=True):
         self.teacher, self.stat, self.labels, self.beta, self.gamma = teacher, stat, labels, beta, gamma
         self.images = images.detach().clone().requires_grad_(True)
-        # ``capturable``: keep Adam's step counter on the device so the iteration can be replayed as a CUDA graph
-        self.opt = torch.optim.Adam([self.images], lr=lr, capturable=capturable)      # distill_data.py:186-187
+        # ``capturable``: keep Adam's step counter (and the learning rate) on the device so the iteration can be
+        # replayed as a CUDA graph
+        lr_arg = torch.tensor(float(lr), dtype=torch.float32, device=self.images.device) if capturable else lr
+        self.opt = torch.optim.Adam([self.images], lr=lr_arg, capturable=capturable)      # distill_data.py:183
+        self.scheduler = None
+        if plateau and capturable:
+            self.scheduler = PlateauOnDevice(self.opt.param_groups[0]["lr"])
+        elif plateau:
+            self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.opt, min_lr=1e-4, patience=50)   # :185-188
+        self._on_device = plateau and capturable
         for p in teacher.parameters():
             p.requires_grad_(False)
         teacher.eval()
@@ -235,10 +276,12 @@ class DistillStep:
         x = self.images.detach().requires_grad_(True)
         out = self.teacher(x)
         target = hard_sample_loss(out, self.labels, self.beta, self.gamma)
-        total = self.stat.loss() + target                            # mean/L + var/L + target, :259-265
+        total = self.stat.loss("distill") + target                   # mean/L + var/L + target, :259-265
         self.images.grad = torch.autograd.grad(total, [x])[0]
         torch.nn.utils.clip_grad_norm_([self.images], max_norm=1.0)  # :273
         self.opt.step()
+        if self.scheduler is not None:                               # :275
+            self.scheduler.step(total if self._on_device else total.item())
         return total.detach()
 
 

@@ -315,3 +315,63 @@ def test_qat_step_equals_the_reference_iteration_source():
         moved += int(not torch.equal(a, dict(student.named_parameters())[name]))
     assert moved > 10                                                 # the update really happened
     assert float(loss_s.detach()) > 0 and float(loss_p.detach()) > 0
+
+
+def test_distill_step_equals_the_reference_loop_source(monkeypatch):
+    """BASELINE config 5 / SURVEY 8(d).  The inner iteration of ``DistillData.getDistilData_hardsample``
+    (data_generate/distill_data.py:197-275: the image-size branch, BN hooks' lists, focal cross-entropy, BN-statistics
+    terms, Adam step with gradient clipping, ReduceLROnPlateau), compiled from the reference file's text, against
+    ``step.DistillStep`` for several iterations on CPU: images, loss and learning rate bit-identical.  The loop
+    hard-codes ``.cuda()``; here that call is made the identity (no source change)."""
+    import numpy as np
+    import torch.nn.functional as F
+    from torch import optim
+
+    from ood_dfq_b200 import nets, step
+    from oracle import bns_torch
+    sys.path.insert(0, REF)
+    try:
+        from data_generate.distill_data import DistillData
+    finally:
+        sys.path.remove(REF)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(nn.Module, "cuda", lambda self, *a, **k: self)
+    path = os.path.join(REF, "data_generate", "distill_data.py")
+    with open(path) as f:
+        body = "".join(f.readlines()[196:275])
+    src = ("def iteration(self, teacher_model, gaussian_data, labels, gt, beta, gamma, CE_loss, MSE_loss, optimizer, "
+           "scheduler, RRC, RHF, i, it):\n" + textwrap.indent(textwrap.dedent(body.expandtabs(4)), "    ") +
+           "    return total_loss\n")
+    ns = {"torch": torch, "np": np, "F": F, "random": __import__("random"), "print": lambda *a, **k: None}
+    exec(compile(src, f"{path}:197-275", "exec"), ns)
+
+    torch.manual_seed(2)
+    teacher = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(teacher)
+    teacher.img_size = 32                                            # the 28 / 32 branch: no augmentation (:198-204)
+    teacher.eval()
+    g = torch.Generator().manual_seed(6)
+    start = torch.randn(4, 3, 32, 32, generator=g) / 5.0             # :181
+    labels = torch.randint(0, 10, (4,), generator=g)
+
+    ref_teacher = copy.deepcopy(teacher)
+    dd = DistillData()
+    for m in ref_teacher.modules():                                  # :156-158
+        if isinstance(m, nn.BatchNorm2d):
+            m.register_forward_hook(dd.hook_fn_forward)
+    gaussian = start.clone()
+    gaussian.requires_grad = True                                    # :182
+    optimizer = optim.Adam([gaussian], lr=0.5)                       # :183
+    scheduler = optim.lr_scheduler.ReduceLROnPlateau(optimizer, min_lr=1e-4, patience=50)   # :185-188
+    ce, mse = nn.CrossEntropyLoss(reduction="none"), nn.MSELoss()    # :149-150
+
+    mine = step.DistillStep(copy.deepcopy(teacher), None, start, labels, lr=0.5, beta=0.1, gamma=0.5)
+    mine.stat = bns_torch.StatTap(mine.teacher)
+    for it in range(4):
+        want = ns["iteration"](dd, ref_teacher, gaussian, labels, labels.numpy(), 0.1, 0.5, ce, mse, optimizer, scheduler,
+                               None, None, 0, it)
+        got = mine()
+        assert torch.equal(got.reshape(-1), want.detach().reshape(-1)), it
+        assert torch.equal(mine.images.detach(), gaussian.detach()), it
+        assert mine.opt.param_groups[0]["lr"] == optimizer.param_groups[0]["lr"]
+    assert not torch.equal(gaussian.detach(), start)

@@ -43,3 +43,31 @@ def test_teacher_stays_frozen_and_taps_line_up():
     assert all(torch.equal(a, b) for a, b in zip(before, teacher.parameters()))
     assert all(p.grad is None for p in teacher.parameters())
     assert len(qat.tap_s.maps) == len(qat.tap_t.maps) == 9
+
+
+def test_device_side_plateau_scheduler_follows_torchs():
+    """``PlateauOnDevice`` (the sync-free twin of the distillation loop's ReduceLROnPlateau, distill_data.py:185-188,
+    :275) takes the same decisions as torch's scheduler on the same fp32 losses: improving, flat and worsening runs,
+    the relative threshold, the floor at min_lr."""
+    import random
+
+    from ood_dfq_b200.step import PlateauOnDevice
+    for seed in range(12):
+        random.seed(seed)
+        p = torch.zeros(1, requires_grad=True)
+        opt = torch.optim.Adam([p], lr=0.5)
+        sch = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, min_lr=1e-4, patience=4)
+        lr = torch.tensor(0.5)
+        dev = PlateauOnDevice(lr, patience=4)
+        loss, reductions = 10.0, 0
+        for it in range(300):
+            r = random.random()
+            loss *= 0.99 if r < 0.3 else (1.01 if r < 0.5 else (1 - 1e-4 if r < 0.55 else 1.0))
+            l32 = torch.tensor(loss, dtype=torch.float32)
+            before = opt.param_groups[0]["lr"]
+            sch.step(l32.item())
+            dev.step(l32)
+            after = opt.param_groups[0]["lr"]
+            reductions += int(after != before)
+            assert abs(after - float(lr)) <= 1e-7 * after, (seed, it, after, float(lr))
+        assert reductions >= 3 and float(lr) >= 1e-4 * (1 - 1e-6)
