@@ -254,7 +254,13 @@ def main_ours(args):
         from ood_dfq_b200 import bns, step as step_mod
         del teacher
         labels = torch.randint(0, WORKLOADS[args.workload][1], (batch,), generator=g).to(dev)
-        dstep = step_mod.DistillStep(student, bns.BNStatLoss(student), resident[0] / 5, labels,   # distill_data.py:181
+        # --distill-sync (second reading): ONE global batch of world x 256 images whose BN
+        # statistics are all-reduced every forward (packed fp64 partial sums over NCCL), instead of an independent
+        # 256-image problem per rank.  The collective sits inside the iteration, so that mode runs eagerly.
+        sync = bool(args.distill_sync and world > 1)
+        if sync:
+            args.graph = "off"
+        dstep = step_mod.DistillStep(student, bns.BNStatLoss(student, sync=sync), resident[0] / 5, labels,   # distill_data.py:181
                                      capturable=args.graph in ("on", "auto"))
 
         def qat(_batch=None):
@@ -434,7 +440,9 @@ def main_ours(args):
                        "residual_tail_fusion": not (args.no_fuse or args.no_tail_fuse),
                        "stem_space_to_depth": not (args.no_fuse or args.no_s2d),
                        "memory_format": "channels_last" if channels_last else "NCHW (as the reference)",
-                       "cuda_graph": use_graph},
+                       "cuda_graph": use_graph,
+                       **({"distill_batch": "global (BN statistics all-reduced)" if (args.distill_sync and world > 1)
+                           else "independent per rank"} if kind == "distill" else {})},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "input": args.e2e_input},
             "gpu_launches": int(launches),
@@ -521,6 +529,8 @@ def main():
     ap.add_argument("--e2e-input", choices=["host", "device_shards"], default="host",
                     help="end-to-end arm: pinned host batches copied every step (default, the reference's data flow) or "
                          "batches assembled on the device from an HBM-resident image set (opt-in)")
+    ap.add_argument("--distill-sync", action="store_true",
+                    help="distillation workload at N > 1: one global batch with all-reduced BN statistics (eager)")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--graph", choices=["auto", "on", "off"], default="auto",
                     help="replay the whole iteration as a CUDA graph (auto = on; off: eager launches)")
