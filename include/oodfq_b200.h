@@ -54,6 +54,7 @@ extern "C" {
 #define OODFQ_BN_RELU 1
 #define OODFQ_BN_QUANT 2
 #define OODFQ_BN_NHWC 4        /* x, y, grads are channels_last: [N*H*W rows][C]; needs C % 4 == 0 */
+#define OODFQ_AUG_SRC_NHWC 8   /* crop_resize_flip: the stored image set is channels_last too */
 
 typedef void* oodfq_stream_t;  /* cudaStream_t */
 
@@ -268,10 +269,18 @@ int oodfq_s2d_stem_backward(const float* grad_xs, float* grad_x, int N, int H, i
  * out [N, C_out, out_h, out_w] (flags & OODFQ_BN_NHWC: channels_last).  Channels: 1->1, 1->3 (repeat), 3->3.
  * Resize = bilinear, align_corners=False, no antialiasing: identical to torchvision's antialiased filter
  * whenever the crop is not larger than the output (always, in direct_dataset: size == image size).  Entries
- * outside the image set are folded into it (never an out-of-bounds read). */
+ * outside the image set are folded into it (never an out-of-bounds read).
+ * flags & OODFQ_AUG_SRC_NHWC: images is [M, H, W, C_in] (the optimised batch of the distillation loop, which the
+ * reference augments in place of a stored set: data_generate/distill_data.py:197-227).
+ * backward: grad_images (layout of images) += scatter of grad_out (layout of out) with the forward's tap weights --
+ * the caller zero-fills it (or passes an accumulating gradient); atomic adds, like ATen's upsample backward that
+ * autograd runs for the reference's RRC(gaussian_data[j]). */
 int oodfq_crop_resize_flip(const float* images, long long n_images, int C_in, int H, int W, const long long* index,
                            const int* boxes, const unsigned char* flips, float* out, int N, int C_out, int out_h,
                            int out_w, int flags, oodfq_stream_t stream);
+int oodfq_crop_resize_flip_backward(const float* grad_out, float* grad_images, long long n_images, int C_in, int H, int W,
+                                    const long long* index, const int* boxes, const unsigned char* flips, int N,
+                                    int C_out, int out_h, int out_w, int flags, oodfq_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboodfq_b200.so")
 MODE_FAKEQUANT, MODE_QUANTIZE, MODE_DEQUANTIZE = 0, 1, 2
 SYMMETRIC, PARAMS_GIVEN, RELU_FIRST, NO_ONCHIP, ONCHIP_TMA = 1, 2, 4, 8, 16
 BN_RELU, BN_QUANT, BN_NHWC = 1, 2, 4
+AUG_SRC_NHWC = 8
 ABI_VERSION = 3
 
 _vp, _ll, _i, _d = C.c_void_p, C.c_longlong, C.c_int, C.c_double
@@ -58,6 +59,7 @@ SIGNATURES = {
     "oodfq_s2d_stem_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_s2d_stem_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_crop_resize_flip": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "oodfq_crop_resize_flip_backward": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_bn_eval_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
 }
 

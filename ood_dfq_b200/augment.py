@@ -119,6 +119,29 @@ def check_boxes(boxes: np.ndarray, height: int, width: int, size: Tuple[int, int
                          "allow_downscale=True to accept the plain bilinear filter")
 
 
+class _CropResizeFlip(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, images, index, boxes, flips, size, channels, channels_last):
+        ctx.save_for_backward(index, boxes, flips)
+        ctx.like = images.detach()                   # shape / layout only; the backward never reads its values
+        return ops.crop_resize_flip(images.detach(), index, boxes, flips, size, channels=channels,
+                                    channels_last=channels_last)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        index, boxes, flips = ctx.saved_tensors
+        return ops.crop_resize_flip_backward(grad_out, ctx.like, index, boxes, flips), None, None, None, None, None, None
+
+
+def crop_resize_flip(images, index, boxes, flips, size=None, channels=None, channels_last=True):
+    """Differentiable ``ops.crop_resize_flip``: the gradient reaches ``images`` through one scatter kernel, as
+    autograd reaches ``gaussian_data`` through torchvision's ``RHF(RRC(gaussian_data[j]))`` in the distillation loop
+    (data_generate/distill_data.py:197-227).  ``size`` defaults to the image size."""
+    if size is None:
+        size = tuple(images.shape[2:])
+    return _CropResizeFlip.apply(images, index, boxes, flips, size, channels, channels_last)
+
+
 class DeviceShards:
     """The shard set resident on one GPU, iterated as augmented per-rank batches ``(images, labels)`` on the device.
 

@@ -19,14 +19,16 @@ struct AugGeom {
     int C_in, H, W;
     int N, OH, OW;           // batch of N outputs [N, C_out, OH, OW]
     int nhwc;                // output is channels_last ([N, OH, OW, C_out])
+    int src_nhwc;            // stored images are channels_last ([M, H, W, C_in]) instead of NCHW
 };
 
 struct AugArgs {
-    const float* images;           // device-resident image set
+    const float* images;           // device-resident image set (backward: unused)
     const long long* index;        // [N] sample -> image
     const int* boxes;              // [N][4] (top, left, height, width) of the crop, inside the image
     const unsigned char* flips;    // [N] non-zero: mirror the resized crop left-right
-    float* out;
+    float* out;                    // forward: the batch; backward: the gradient w.r.t. the image set (accumulated)
+    const float* grad_out;         // backward only: gradient w.r.t. the batch, in the batch's layout
     AugGeom g;
 };
 
@@ -77,37 +79,88 @@ OODFQ_HD AugTap aug_tap(int dst, int in, int out) {
 #define OODFQ_AUG_LOAD(p) (*(p))
 #endif
 
-// One output pixel, every stored channel: v[c] for c < C_IN.  `pix` counts (n, oy, ox) row-major (< 2^31 per launch).
-template <int C_IN>
-OODFQ_HD void aug_pixel(const AugArgs& a, int pix, float* v, int& n, int& oy, int& ox) {
+// Where one output pixel reads from: image, the two source rows / columns (offsets inside a plane) and weights.
+struct AugSite {
+    int n, oy, ox;
+    long long im;                  // image index inside the set
+    int y0, y1, x0, x1;            // absolute source rows / columns
+    float wy0, wy1, wx0, wx1;
+};
+
+// `pix` counts (n, oy, ox) row-major (< 2^31 per launch).
+OODFQ_HD AugSite aug_site(const AugArgs& a, int pix) {
     const AugGeom& g = a.g;
+    AugSite s;
     const int q = pix / g.OW;
-    ox = pix - q * g.OW;
-    n = q / g.OH;
-    oy = q - n * g.OH;
+    s.ox = pix - q * g.OW;
+    s.n = q / g.OH;
+    s.oy = q - s.n * g.OH;
     // boxes and indices come from device memory the host side cannot re-check at launch time: fold them into the
-    // image set so that a corrupt entry can never turn into an out-of-bounds read (valid entries are unchanged)
-    int bh = a.boxes[4 * n + 2], bw = a.boxes[4 * n + 3];
+    // image set so that a corrupt entry can never turn into an out-of-bounds access (valid entries are unchanged)
+    int bh = a.boxes[4 * s.n + 2], bw = a.boxes[4 * s.n + 3];
     bh = bh < 1 ? 1 : (bh > g.H ? g.H : bh);
     bw = bw < 1 ? 1 : (bw > g.W ? g.W : bw);
-    int top = a.boxes[4 * n], left = a.boxes[4 * n + 1];
+    int top = a.boxes[4 * s.n], left = a.boxes[4 * s.n + 1];
     top = top < 0 ? 0 : (top > g.H - bh ? g.H - bh : top);
     left = left < 0 ? 0 : (left > g.W - bw ? g.W - bw : left);
-    long long im = a.index[n];
-    im = im < 0 ? 0 : (im > g.M - 1 ? g.M - 1 : im);
+    long long im = a.index[s.n];
+    s.im = im < 0 ? 0 : (im > g.M - 1 ? g.M - 1 : im);
     // RandomHorizontalFlip runs AFTER the resize (main_direct.py:160-162): output column ox shows resized column
     // OW-1-ox
-    const int rx = a.flips[n] ? g.OW - 1 - ox : ox;
-    const AugTap ty = aug_tap(oy, bh, g.OH), tx = aug_tap(rx, bw, g.OW);
-    const long long plane = (long long)g.H * g.W;
-    const float* img = a.images + im * (long long)C_IN * plane;
-    const long long r0 = (long long)(top + ty.i0) * g.W + left, r1 = (long long)(top + ty.i1) * g.W + left;
+    const int rx = a.flips[s.n] ? g.OW - 1 - s.ox : s.ox;
+    const AugTap ty = aug_tap(s.oy, bh, g.OH), tx = aug_tap(rx, bw, g.OW);
+    s.y0 = top + ty.i0; s.y1 = top + ty.i1; s.x0 = left + tx.i0; s.x1 = left + tx.i1;
+    s.wy0 = ty.l0; s.wy1 = ty.l1; s.wx0 = tx.l0; s.wx1 = tx.l1;
+    return s;
+}
+
+// element offset of (image, channel, row, column) in the stored set, either layout
+template <int C_IN>
+OODFQ_HD long long aug_src_offset(const AugGeom& g, long long im, int c, int y, int x) {
+    return g.src_nhwc ? ((im * g.H + y) * g.W + x) * C_IN + c : ((im * C_IN + c) * g.H + y) * g.W + x;
+}
+
+// One output pixel, every stored channel: v[c] for c < C_IN.
+template <int C_IN>
+OODFQ_HD void aug_pixel(const AugArgs& a, int pix, float* v, int& n, int& oy, int& ox) {
+    const AugSite s = aug_site(a, pix);
+    n = s.n; oy = s.oy; ox = s.ox;
 #pragma unroll
     for (int c = 0; c < C_IN; ++c) {
-        const float* p = img + c * plane;
-        const float p00 = OODFQ_AUG_LOAD(p + r0 + tx.i0), p01 = OODFQ_AUG_LOAD(p + r0 + tx.i1);
-        const float p10 = OODFQ_AUG_LOAD(p + r1 + tx.i0), p11 = OODFQ_AUG_LOAD(p + r1 + tx.i1);
-        v[c] = ty.l0 * (tx.l0 * p00 + tx.l1 * p01) + ty.l1 * (tx.l0 * p10 + tx.l1 * p11);
+        const float p00 = OODFQ_AUG_LOAD(a.images + aug_src_offset<C_IN>(a.g, s.im, c, s.y0, s.x0));
+        const float p01 = OODFQ_AUG_LOAD(a.images + aug_src_offset<C_IN>(a.g, s.im, c, s.y0, s.x1));
+        const float p10 = OODFQ_AUG_LOAD(a.images + aug_src_offset<C_IN>(a.g, s.im, c, s.y1, s.x0));
+        const float p11 = OODFQ_AUG_LOAD(a.images + aug_src_offset<C_IN>(a.g, s.im, c, s.y1, s.x1));
+        v[c] = s.wy0 * (s.wx0 * p00 + s.wx1 * p01) + s.wy1 * (s.wx0 * p10 + s.wx1 * p11);
+    }
+}
+
+#if defined(__CUDA_ARCH__)
+#define OODFQ_AUG_ADD(p, v) atomicAdd((p), (v))
+#else
+#define OODFQ_AUG_ADD(p, v) (*(p) += (v))
+#endif
+
+// Backward of one output pixel: its gradient (summed over the repeated channels of a grey image) is scattered onto
+// the four taps with the forward's weights.  Taps are shared between neighbouring outputs, hence atomic adds on the
+// device (ATen's upsample backward does the same); zero-weight taps are skipped.
+template <int C_IN, int C_OUT>
+OODFQ_HD void aug_pixel_backward(const AugArgs& a, int pix) {
+    const AugGeom& g = a.g;
+    const AugSite s = aug_site(a, pix);
+    const long long oplane = (long long)g.OH * g.OW;
+#pragma unroll
+    for (int c = 0; c < C_IN; ++c) {
+        float go = 0.0f;
+#pragma unroll
+        for (int r = (C_IN == C_OUT ? c : 0); r < (C_IN == C_OUT ? c + 1 : C_OUT); ++r)
+            go += OODFQ_AUG_LOAD(a.grad_out + (g.nhwc ? (long long)pix * C_OUT + r
+                                                      : ((long long)s.n * C_OUT + r) * oplane + (long long)s.oy * g.OW + s.ox));
+        const float w00 = s.wy0 * s.wx0, w01 = s.wy0 * s.wx1, w10 = s.wy1 * s.wx0, w11 = s.wy1 * s.wx1;
+        if (w00 != 0.0f) OODFQ_AUG_ADD(a.out + aug_src_offset<C_IN>(g, s.im, c, s.y0, s.x0), w00 * go);
+        if (w01 != 0.0f) OODFQ_AUG_ADD(a.out + aug_src_offset<C_IN>(g, s.im, c, s.y0, s.x1), w01 * go);
+        if (w10 != 0.0f) OODFQ_AUG_ADD(a.out + aug_src_offset<C_IN>(g, s.im, c, s.y1, s.x0), w10 * go);
+        if (w11 != 0.0f) OODFQ_AUG_ADD(a.out + aug_src_offset<C_IN>(g, s.im, c, s.y1, s.x1), w11 * go);
     }
 }
 

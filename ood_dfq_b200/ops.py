@@ -608,26 +608,42 @@ def act_mse_search(x, k, x_min, x_max, beta, beta_t, cur_min=None, cur_max=None,
 
 
 # ----------------------------------------------------------------------------- batch assembly (crop / resize / flip)
+def _aug_source(images):
+    """(flags, m, c, h, w) of an image set that is NCHW- or channels_last-contiguous."""
+    if images.dim() != 4:
+        raise RuntimeError("ood_dfq_b200: the image set must be a 4-D [M,C,H,W] tensor")
+    m, c, h, w = images.shape
+    if images.is_contiguous():
+        return 0, m, c, h, w
+    if images.is_contiguous(memory_format=torch.channels_last):
+        return N.AUG_SRC_NHWC, m, c, h, w
+    raise RuntimeError("ood_dfq_b200: the image set must be NCHW- or channels_last-contiguous")
+
+
+def _aug_draws(index, boxes, flips):
+    _need(index, "index", torch.int64)
+    _need(boxes, "boxes", torch.int32)
+    _need(flips, "flips", torch.uint8)
+    n = index.numel()
+    if index.dim() != 1 or boxes.shape != (n, 4) or flips.shape != (n,):
+        raise RuntimeError(f"ood_dfq_b200: index [N], boxes [N,4], flips [N] expected, got {tuple(index.shape)}, "
+                           f"{tuple(boxes.shape)}, {tuple(flips.shape)}")
+    return n, index.contiguous(), boxes.contiguous(), flips.contiguous()
+
+
 def crop_resize_flip(images, index, boxes, flips, size, channels=None, channels_last=True, out=None):
     """One per-rank batch straight from the device-resident image set: for sample ``n`` the crop ``boxes[n] = (top,
     left, h, w)`` of ``images[index[n]]`` is resized (bilinear, ``align_corners=False``) to ``size``, a one-channel
     image is repeated to ``channels`` (default 3) and the result mirrored when ``flips[n]`` -- the per-sample
     torchvision pipeline of ``direct_dataset`` (main_direct.py:158-169, :200-204) as one kernel.
 
-    ``images`` ``[M,C,H,W]`` fp32 NCHW-contiguous, ``index`` int64 ``[N]``, ``boxes`` int32 ``[N,4]``, ``flips``
-    uint8 ``[N]``, all on the same CUDA device.  Returns ``[N, channels, *size]`` (channels_last by default).
+    ``images`` ``[M,C,H,W]`` fp32 (NCHW- or channels_last-contiguous), ``index`` int64 ``[N]``, ``boxes`` int32
+    ``[N,4]``, ``flips`` uint8 ``[N]``, all on the same CUDA device.  Returns ``[N, channels, *size]`` (channels_last
+    by default).
     """
     _need(images, "image set")
-    _need(index, "index", torch.int64)
-    _need(boxes, "boxes", torch.int32)
-    _need(flips, "flips", torch.uint8)
-    if images.dim() != 4 or not images.is_contiguous():
-        raise RuntimeError("ood_dfq_b200: the image set must be an NCHW-contiguous [M,C,H,W] tensor")
-    n = index.numel()
-    if index.dim() != 1 or boxes.shape != (n, 4) or flips.shape != (n,):
-        raise RuntimeError(f"ood_dfq_b200: index [N], boxes [N,4], flips [N] expected, got {tuple(index.shape)}, "
-                           f"{tuple(boxes.shape)}, {tuple(flips.shape)}")
-    m, c_in, h, w = images.shape
+    src_flag, m, c_in, h, w = _aug_source(images)
+    n, index, boxes, flips = _aug_draws(index, boxes, flips)
     c_out = int(channels) if channels is not None else (3 if c_in == 1 else c_in)
     oh, ow = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
     fmt = torch.channels_last if channels_last else torch.contiguous_format
@@ -641,9 +657,39 @@ def crop_resize_flip(images, index, boxes, flips, size, channels=None, channels_
         return out
     crop_bytes = 4 * c_in * h * w * n                         # upper bound of the read (the box is <= the image)
     with _Timed("crop_resize_flip_kernel (batch assembly, <= 4 B/elem in + 4 B/elem out)", crop_bytes + 4 * out.numel()):
-        rc = N.load().oodfq_crop_resize_flip(images.data_ptr(), m, c_in, h, w, index.contiguous().data_ptr(),
-                                             boxes.contiguous().data_ptr(), flips.contiguous().data_ptr(),
-                                             out.data_ptr(), n, c_out, oh, ow, N.BN_NHWC if channels_last else 0,
-                                             _stream(images.device))
+        rc = N.load().oodfq_crop_resize_flip(images.data_ptr(), m, c_in, h, w, index.data_ptr(), boxes.data_ptr(),
+                                             flips.data_ptr(), out.data_ptr(), n, c_out, oh, ow,
+                                             (N.BN_NHWC if channels_last else 0) | src_flag, _stream(images.device))
         N.check(rc, "crop_resize_flip")
     return out
+
+
+def crop_resize_flip_backward(grad_out, like, index, boxes, flips, accumulate_into=None):
+    """Gradient of ``crop_resize_flip`` w.r.t. the image set: ``grad_out`` ``[N, C_out, OH, OW]`` (NCHW- or
+    channels_last-contiguous) scattered onto a tensor shaped and laid out like ``like`` (the forward's ``images``)
+    with the forward's tap weights.  ``accumulate_into``: add into this existing gradient instead of a zero tensor."""
+    _need(grad_out, "grad_output")
+    _need(like, "image set")
+    src_flag, m, c_in, h, w = _aug_source(like)
+    n, index, boxes, flips = _aug_draws(index, boxes, flips)
+    if grad_out.dim() != 4 or grad_out.shape[0] != n:
+        raise RuntimeError("ood_dfq_b200: grad_output must be [N, C_out, OH, OW] with one sample per index entry")
+    if grad_out.is_contiguous(memory_format=torch.channels_last):
+        out_flag = N.BN_NHWC
+    else:
+        grad_out, out_flag = grad_out.contiguous(), 0
+    _, c_out, oh, ow = grad_out.shape
+    if accumulate_into is None:
+        grad_images = torch.zeros_like(like)                  # preserves the layout of `like`
+    else:
+        grad_images = accumulate_into
+        if grad_images.shape != like.shape or grad_images.stride() != like.stride():
+            raise RuntimeError("ood_dfq_b200: `accumulate_into` must have the shape and layout of the image set")
+    if n == 0:
+        return grad_images
+    with _Timed("crop_resize_flip_bwd_kernel (gradient scatter, 4 B/elem in + atomics)", 4 * grad_out.numel() + 8 * c_in * h * w * n):
+        rc = N.load().oodfq_crop_resize_flip_backward(grad_out.data_ptr(), grad_images.data_ptr(), m, c_in, h, w,
+                                                      index.data_ptr(), boxes.data_ptr(), flips.data_ptr(), n, c_out, oh,
+                                                      ow, out_flag | src_flag, _stream(like.device))
+        N.check(rc, "crop_resize_flip_backward")
+    return grad_images

@@ -76,7 +76,9 @@ def resized_crop_flip(img: torch.Tensor, box, flip: bool, size, antialias: bool 
 
 
 def batch(images: torch.Tensor, index, boxes, flips, size, channels: int = 3, dtype=None) -> torch.Tensor:
-    """A batch ``[N, channels, *size]`` from the image set ``[M,C,H,W]``; ``channels=1`` keeps grey images grey."""
+    """A batch ``[N, channels, *size]`` from the image set ``[M,C,H,W]``; ``channels=1`` keeps grey images grey.
+    Differentiable w.r.t. ``images`` (autograd runs ATen's interpolate backward, as it does for the reference's
+    ``RHF(RRC(gaussian_data[j]))``, data_generate/distill_data.py:197-227)."""
     outs = []
     for n, m in enumerate(index):
         img = images[int(m)]

@@ -18,7 +18,7 @@ import torch
 from oracle import augment_torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SETS = ["rgb32", "grey28", "tall224", "rect", "big200"]
+SETS = ["rgb32", "grey28", "tall160", "rect", "big200"]
 
 
 def case(golden, tag):
@@ -42,7 +42,7 @@ def test_oracle_reproduces_torchvision_outputs(golden, tag):
 @pytest.mark.parametrize("tag", SETS)
 def test_draws_reproduce_torchvision_streams(golden, tag):
     """From the recorded seed, the oracle's and the product's restatements of get_params + the flip coin yield the
-    recorded boxes and flips (tall224: every attempt is rejected, so this is the central-crop fallback)."""
+    recorded boxes and flips (tall160: every attempt is rejected, so this is the central-crop fallback)."""
     from ood_dfq_b200 import augment
     c = case(golden, tag)
     h, w = c["images"].shape[2:]
@@ -123,22 +123,41 @@ def host_kernel(tmp_path_factory):
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(out), src], check=True)
     lib = C.CDLL(str(out))
     vp = C.c_void_p
-    lib.augment_host.argtypes = [vp, C.c_longlong, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp] + [C.c_int] * 6
+    lib.augment_host.argtypes = [vp, C.c_longlong, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp] + [C.c_int] * 7
     lib.augment_host.restype = C.c_int
+    lib.augment_host_backward.argtypes = [vp, vp, C.c_longlong, C.c_int, C.c_int, C.c_int, vp, vp, vp] + [C.c_int] * 6
+    lib.augment_host_backward.restype = C.c_int
 
-    def run(images, index, boxes, flips, size, c_out, nhwc, px):
+    def draws(index, boxes, flips):
+        return (np.ascontiguousarray(index, np.int64), np.ascontiguousarray(boxes, np.int32),
+                np.ascontiguousarray(flips, np.uint8))
+
+    def run(images, index, boxes, flips, size, c_out, nhwc, px, src_nhwc=False):
         images = np.ascontiguousarray(images, np.float32)
-        index = np.ascontiguousarray(index, np.int64)
-        boxes = np.ascontiguousarray(boxes, np.int32)
-        flips = np.ascontiguousarray(flips, np.uint8)
+        index, boxes, flips = draws(index, boxes, flips)
         m, c_in, h, w = images.shape
+        stored = np.ascontiguousarray(images.transpose(0, 2, 3, 1)) if src_nhwc else images
         n = len(index)
         shape = (n, size[0], size[1], c_out) if nhwc else (n, c_out, size[0], size[1])
         out = np.full(shape, np.nan, np.float32)
-        rc = lib.augment_host(images.ctypes.data, m, c_in, h, w, index.ctypes.data, boxes.ctypes.data, flips.ctypes.data,
-                              out.ctypes.data, n, c_out, size[0], size[1], int(nhwc), px)
+        rc = lib.augment_host(stored.ctypes.data, m, c_in, h, w, index.ctypes.data, boxes.ctypes.data, flips.ctypes.data,
+                              out.ctypes.data, n, c_out, size[0], size[1], int(nhwc), px, int(src_nhwc))
         assert rc == 0
         return out.transpose(0, 3, 1, 2) if nhwc else out
+
+    def run_backward(grad_out, image_shape, index, boxes, flips, nhwc, src_nhwc=False):
+        """grad_out [N,C_out,OH,OW] (logical NCHW) -> gradient w.r.t. the image set, logical [M,C,H,W]."""
+        grad_out = np.asarray(grad_out, np.float32)
+        index, boxes, flips = draws(index, boxes, flips)
+        m, c_in, h, w = image_shape
+        n, c_out, oh, ow = grad_out.shape
+        go = np.ascontiguousarray(grad_out.transpose(0, 2, 3, 1)) if nhwc else np.ascontiguousarray(grad_out)
+        gi = np.zeros((m, h, w, c_in) if src_nhwc else (m, c_in, h, w), np.float32)
+        rc = lib.augment_host_backward(go.ctypes.data, gi.ctypes.data, m, c_in, h, w, index.ctypes.data, boxes.ctypes.data,
+                                       flips.ctypes.data, n, c_out, oh, ow, int(nhwc), int(src_nhwc))
+        assert rc == 0
+        return gi.transpose(0, 3, 1, 2) if src_nhwc else gi
+    run.backward = run_backward
     return run
 
 
@@ -207,3 +226,51 @@ def test_kernel_body_ragged_totals_and_corrupt_entries(host_kernel):
     np.testing.assert_allclose(y[2], plain[0], atol=2e-6)
     y5 = host_kernel(images, index[:1], boxes[1:2], flips[:1], (5, 5), 1, True, 4)   # 25 pixels: ragged last group
     assert np.isfinite(y5).all()
+
+
+@pytest.mark.parametrize("tag", SETS)
+def test_kernel_body_reads_channels_last_image_sets(golden, host_kernel, tag):
+    """The stored set may be channels_last (the distillation loop augments the optimised batch itself): same values."""
+    c = case(golden, tag)
+    size, c_out = c["out"].shape[2:], c["out"].shape[1]
+    a = host_kernel(c["images"], c["index"], c["boxes"], c["flips"], size, c_out, True, 4)
+    b = host_kernel(c["images"], c["index"], c["boxes"], c["flips"], size, c_out, True, 4, src_nhwc=True)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("tag", SETS)
+@pytest.mark.parametrize("nhwc,src_nhwc", [(True, False), (False, False), (True, True)])
+def test_kernel_body_backward_matches_torchvision_autograd(golden, host_kernel, tag, nhwc, src_nhwc):
+    """Gradient scatter against what autograd computes through torchvision's own pipeline in double precision
+    (tools/make_golden.py): taps shared by up to ~(out/in + 1)^2 outputs are summed in fp32 here."""
+    c = case(golden, tag)
+    # big200 stores ONE cotangent plane that the generator applied to each of the three (repeated) output channels
+    cot = np.repeat(c["cotangent"], 3, axis=1) if tag == "big200" else c["cotangent"]
+    g = host_kernel.backward(cot, c["images"].shape, c["index"], c["boxes"], c["flips"], nhwc, src_nhwc)
+    scale = float(np.abs(c["grad_exact"]).max())
+    assert np.abs(g - c["grad_exact"]).max() <= 2e-6 * scale
+
+
+def test_kernel_body_backward_is_the_adjoint_of_the_forward(host_kernel):
+    """<forward(x), g> == <x, backward(g)> for random x, g (all channel modes, flips, shared images)."""
+    rng = np.random.default_rng(12)
+    for c_in, c_out in ((3, 3), (1, 3), (1, 1)):
+        images = rng.standard_normal((3, c_in, 11, 13)).astype(np.float32)
+        index = np.array([2, 2, 0, 1, 2], np.int64)                 # image 2 feeds three samples: gradients add up
+        boxes = np.array([[0, 0, 11, 13], [2, 3, 6, 7], [1, 0, 9, 13], [4, 5, 5, 5], [0, 6, 11, 7]], np.int32)
+        flips = np.array([0, 1, 1, 0, 1], np.uint8)
+        y = host_kernel(images, index, boxes, flips, (11, 13), c_out, True, 4)
+        g = rng.standard_normal(y.shape).astype(np.float32)
+        gx = host_kernel.backward(g, images.shape, index, boxes, flips, True)
+        lhs, rhs = float((y.astype(np.float64) * g).sum()), float((images.astype(np.float64) * gx).sum())
+        assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)
+
+
+def test_oracle_gradient_reproduces_torchvision_autograd(golden):
+    """The oracle restatement is differentiable the same way (ATen's interpolate backward): its double-precision
+    gradient equals the recorded one."""
+    c = case(golden, "rect")
+    leaf = torch.from_numpy(c["images"]).double().requires_grad_(True)
+    y = augment_torch.batch(leaf, c["index"], c["boxes"], c["flips"], c["out"].shape[2:], channels=3)
+    (y * torch.from_numpy(c["cotangent"]).double()).sum().backward()
+    assert torch.equal(leaf.grad.float(), torch.from_numpy(c["grad_exact"]))

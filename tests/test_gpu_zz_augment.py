@@ -12,7 +12,7 @@ from oracle import augment_torch
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda:0"
-SETS = ["rgb32", "grey28", "tall224", "rect", "big200"]
+SETS = ["rgb32", "grey28", "tall160", "rect", "big200"]
 
 
 def case(golden, tag):
@@ -104,3 +104,53 @@ def test_device_shards_stream_batches():
     assert x.shape == (8, 3, 28, 28) and torch.isfinite(x).all()
     lo, hi = images[y.cpu().numpy()].min(), images[y.cpu().numpy()].max()
     assert x.min().item() >= lo - 1e-6 and x.max().item() <= hi + 1e-6       # bilinear blends stay inside the data range
+
+
+@pytest.mark.parametrize("tag", SETS)
+@pytest.mark.parametrize("grad_cl,src_cl", [(True, False), (False, False), (True, True)])
+def test_golden_augment_backward(golden, tag, grad_cl, src_cl):
+    """Gradient scatter against autograd through torchvision's own pipeline in double precision (fp32 atomics here,
+    any order: 2e-6 of the largest entry)."""
+    from ood_dfq_b200 import ops
+    c = case(golden, tag)
+    cot = np.repeat(c["cotangent"], 3, axis=1) if tag == "big200" else c["cotangent"]
+    go = torch.from_numpy(np.ascontiguousarray(cot)).to(DEV)
+    go = go.contiguous(memory_format=torch.channels_last) if grad_cl else go
+    like = torch.empty(c["images"].shape, device=DEV)
+    like = like.contiguous(memory_format=torch.channels_last) if src_cl else like
+    d = lambda a, t: torch.from_numpy(np.ascontiguousarray(a)).to(t).to(DEV)
+    g = ops.crop_resize_flip_backward(go, like, d(c["index"], torch.int64), d(c["boxes"], torch.int32),
+                                      d(c["flips"], torch.uint8))
+    assert g.shape == like.shape and g.stride() == like.stride()
+    scale = float(np.abs(c["grad_exact"]).max())
+    assert np.abs(g.cpu().numpy() - c["grad_exact"]).max() <= 2e-6 * scale
+    # accumulation into an existing gradient
+    base = torch.randn_like(like)
+    g2 = ops.crop_resize_flip_backward(go, like, d(c["index"], torch.int64), d(c["boxes"], torch.int32),
+                                       d(c["flips"], torch.uint8), accumulate_into=base.clone())
+    assert (g2 - base - g).abs().max().item() <= 4e-6 * scale + 1e-6
+
+
+@pytest.mark.parametrize("src_cl", [False, True])
+def test_differentiable_augmentation_matches_oracle_autograd(src_cl):
+    """augment.crop_resize_flip under autograd (the distillation loop's RHF(RRC(x[j])) on the optimised batch itself,
+    data_generate/distill_data.py:197-227): output and the gradient reaching the images against the oracle evaluated in
+    double precision."""
+    from ood_dfq_b200 import augment
+    g = torch.Generator().manual_seed(31)
+    b, h, w = 6, 40, 40
+    x = torch.randn(b, 3, h, w, generator=g) / 5
+    boxes, flips = augment.random_resized_crop_params(b, h, w, scale=(0.4, 1.0), generator=g)
+    index = torch.arange(b)
+    cot = torch.randn(b, 3, h, w, generator=g)
+    leaf = x.double().requires_grad_(True)
+    y_ref = augment_torch.batch(leaf, index.tolist(), boxes, flips, (h, w), channels=3)
+    (y_ref * cot.double()).sum().backward()
+    xd = x.to(DEV)
+    xd = (xd.contiguous(memory_format=torch.channels_last) if src_cl else xd).requires_grad_(True)
+    y = augment.crop_resize_flip(xd, index.to(DEV), torch.from_numpy(boxes).to(DEV), torch.from_numpy(flips).to(DEV))
+    (y * cot.to(DEV)).sum().backward()
+    assert (y.detach().cpu() - y_ref.detach().float()).abs().max().item() <= 4e-7 * x.abs().max().item()
+    assert xd.grad.shape == xd.shape and xd.grad.stride() == xd.stride()
+    scale = leaf.grad.abs().max().item()
+    assert (xd.grad.cpu() - leaf.grad.float()).abs().max().item() <= 2e-6 * scale

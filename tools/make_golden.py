@@ -279,7 +279,7 @@ def gen_augment():
     import torchvision.transforms as T
     import torchvision.transforms.functional as TF
     out = {"torchvision_version": np.array(__import__("torchvision").__version__)}
-    sets = {"rgb32": (4, 3, 32, 32), "grey28": (5, 1, 28, 28), "tall224": (2, 3, 224, 24), "rect": (3, 3, 20, 36),
+    sets = {"rgb32": (4, 3, 32, 32), "grey28": (5, 1, 28, 28), "tall160": (2, 3, 160, 16), "rect": (3, 3, 20, 36),
             "big200": (1, 1, 200, 200)}   # small files
     for tag, shape in sets.items():
         g = torch.Generator().manual_seed(sum(shape))
@@ -315,6 +315,23 @@ def gen_augment():
             plain = plain.repeat(3, 1, 1) if plain.size(0) == 1 else plain
             assert (z64 - (TF.hflip(plain) if flip else plain)).abs().max() < 1e-12
             boxes.append([i, j, h, w]); flips.append(flip); ys.append(y); ys64.append(z64)
+        # gradient reaching the image set through torchvision's own (differentiable) pipeline, as autograd computes it
+        # for the distillation loop's RHF(RRC(gaussian_data[j])) (data_generate/distill_data.py:197-227): a fixed
+        # cotangent per sample, float64 so that the result carries no accumulation-order noise
+        leaf = images.double().requires_grad_(True)
+        cot = torch.randn((samples,) + tuple(ys[0].shape), generator=g)
+        if tag == "big200":                                        # small file: one cotangent plane for all three channels
+            cot = cot[:, :1].repeat(1, 3, 1, 1)
+        total = 0.0
+        for s_i, m in enumerate(index.tolist()):
+            i, j, h, w = boxes[s_i]
+            z = TF.resized_crop(leaf[m], i, j, h, w, crop.size, crop.interpolation, antialias=crop.antialias)
+            z = z.repeat(3, 1, 1) if z.size(0) == 1 else z
+            z = TF.hflip(z) if flips[s_i] else z
+            total = total + (z * cot[s_i].double()).sum()
+        total.backward()
+        out[f"{tag}_cotangent"] = npy(cot if tag != "big200" else cot[:, :1])
+        out[f"{tag}_grad_exact"] = leaf.grad.float().numpy().copy()
         out[f"{tag}_images"] = npy(images)
         out[f"{tag}_index"] = index.numpy().astype(np.int64)
         out[f"{tag}_boxes"] = np.array(boxes, dtype=np.int32)
