@@ -148,7 +148,7 @@ def calibrate(student, batches, namespace):
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def run_cpu(workload, steps, warmup, sample_batch):
+def run_cpu(workload, steps, warmup, sample_batch, augment=False):
     """The reference algorithm (oracle port: same ATen op sequence as the reference) on host cores."""
     from oracle import fq_torch
     torch.set_num_threads(os.cpu_count() or 1)
@@ -161,7 +161,13 @@ def run_cpu(workload, steps, warmup, sample_batch):
         from ood_dfq_b200 import step as step_mod
         from oracle import bns_torch
         labels = torch.randint(0, WORKLOADS[workload][1], (sample_batch,), generator=g)
-        dstep = step_mod.DistillStep(student, bns_torch.StatTap(student), batches[0] / 5, labels)
+        aug = None
+        if augment:                                 # the loop's 224-pixel branch (distill_data.py:205-227), torch version
+            from oracle import augment_torch
+
+            def aug(t, boxes, flips):
+                return augment_torch.batch(t, range(t.shape[0]), boxes, flips, t.shape[2:], channels=3)
+        dstep = step_mod.DistillStep(student, bns_torch.StatTap(student), batches[0] / 5, labels, augment=aug)
 
         def qat(_batch=None):
             return dstep()
@@ -183,7 +189,7 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = run_cpu(args.workload, args.steps, args.warmup, args.cpu_batch)
+    res = run_cpu(args.workload, args.steps, args.warmup, args.cpu_batch, augment=args.distill_augment)
     line = {
         "impl": "reference", "metric": metric_name(args.workload), "value": res["value"], "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
@@ -260,8 +266,16 @@ def main_ours(args):
         sync = bool(args.distill_sync and world > 1)
         if sync:
             args.graph = "off"
+        aug = None
+        if args.distill_augment:
+            # --distill-augment: the loop's 224-pixel branch (distill_data.py:205-227) -- every other iteration each
+            # image passes RandomResizedCrop(scale=(0.4, 1)) + flip before the teacher, one kernel each way for the
+            # whole batch (csrc/augment.cu).  The draws happen on the host every iteration: eager launches.
+            from ood_dfq_b200 import augment as augment_mod
+            aug = augment_mod.batch_augmenter(channels_last)
+            args.graph = "off"
         dstep = step_mod.DistillStep(student, bns.BNStatLoss(student, sync=sync), resident[0] / 5, labels,   # distill_data.py:181
-                                     capturable=args.graph in ("on", "auto"))
+                                     capturable=args.graph in ("on", "auto"), augment=aug)
 
         def qat(_batch=None):
             return dstep()
@@ -442,7 +456,8 @@ def main_ours(args):
                        "memory_format": "channels_last" if channels_last else "NCHW (as the reference)",
                        "cuda_graph": use_graph,
                        **({"distill_batch": "global (BN statistics all-reduced)" if (args.distill_sync and world > 1)
-                           else "independent per rank"} if kind == "distill" else {})},
+                           else "independent per rank", "distill_augment": bool(args.distill_augment)}
+                          if kind == "distill" else {})},
             "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "input": args.e2e_input},
             "gpu_launches": int(launches),
@@ -461,7 +476,7 @@ def main_ours(args):
                                  "largest launch, see profiles/"},
         }
         if world == 1 and not args.no_cpu_baseline:
-            res = run_cpu(args.workload, args.cpu_steps, 1, args.cpu_batch)
+            res = run_cpu(args.workload, args.cpu_steps, 1, args.cpu_batch, augment=args.distill_augment)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)
     if world > 1:
@@ -529,6 +544,9 @@ def main():
     ap.add_argument("--e2e-input", choices=["host", "device_shards"], default="host",
                     help="end-to-end arm: pinned host batches copied every step (default, the reference's data flow) or "
                          "batches assembled on the device from an HBM-resident image set (opt-in)")
+    ap.add_argument("--distill-augment", action="store_true",
+                    help="distillation workload: apply the loop's per-image RandomResizedCrop / flip on every other "
+                         "iteration (distill_data.py:205-227; eager)")
     ap.add_argument("--distill-sync", action="store_true",
                     help="distillation workload at N > 1: one global batch with all-reduced BN statistics (eager)")
     ap.add_argument("--verbose", action="store_true")

@@ -142,6 +142,21 @@ def crop_resize_flip(images, index, boxes, flips, size=None, channels=None, chan
     return _CropResizeFlip.apply(images, index, boxes, flips, size, channels, channels_last)
 
 
+def batch_augmenter(channels_last: bool = True):
+    """``(x, boxes, flips) -> augmented x`` for ``step.DistillStep(augment=...)``: sample ``j`` is the crop
+    ``boxes[j]`` of ``x[j]`` resized back to the image size and mirrored when ``flips[j]``, differentiable, one kernel
+    each way for the whole batch (the reference loops over the images with torchvision,
+    data_generate/distill_data.py:205-210)."""
+    def run(x, boxes, flips):
+        dev = x.device
+        index = torch.arange(x.shape[0], device=dev)
+        b = torch.from_numpy(np.ascontiguousarray(boxes, dtype=np.int32)).to(dev, non_blocking=True)
+        f = torch.from_numpy(np.ascontiguousarray(flips, dtype=np.uint8)).to(dev, non_blocking=True)
+        check_boxes(boxes, x.shape[2], x.shape[3], tuple(x.shape[2:]))
+        return crop_resize_flip(x, index, b, f, channels=x.shape[1], channels_last=channels_last)
+    return run
+
+
 class DeviceShards:
     """The shard set resident on one GPU, iterated as augmented per-rank batches ``(images, labels)`` on the device.
 

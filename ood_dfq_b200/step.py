@@ -246,13 +246,24 @@ class DistillStep:
     gradient then reaches the images through cuDNN dgrad and the identity STE of every QuantAct.
 
     ``plateau``: the loop's ``ReduceLROnPlateau`` (:185-188, :275).  Eagerly it is torch's own scheduler fed
-    ``total.item()`` as in the reference; with ``capturable`` it is ``PlateauOnDevice`` (no host sync).  The per-image
-    RandomResizedCrop / flip that the loop applies to 224x224 batches on every other iteration (:197-227) is outside
-    the rows SURVEY.md section 8(d) scopes for this iteration (:229-275) and is not applied here.
+    ``total.item()`` as in the reference; with ``capturable`` it is ``PlateauOnDevice`` (no host sync).
+
+    ``augment``: the per-image ``RHF(RRC(gaussian_data[j]))`` the loop puts in front of the teacher on every other
+    iteration of a 224x224 batch (:197-227; RandomResizedCrop(size, scale=(augMargin, 1.0)) + RandomHorizontalFlip,
+    differentiable).  A callable ``(x, boxes, flips) -> tensor``: ``augment.batch_augmenter()`` runs the whole batch
+    as one kernel each way on the GPU, the CPU arm passes the oracle's torch version.  The coin (``random.random() <
+    augment_p``) and the per-image draws consume Python's and torch's generators exactly like the loop, so equal
+    seeds give equal crops.  Host-side randomness cannot be replayed from a CUDA graph: with ``augment`` the
+    iteration runs eagerly.  ``None`` (the 28 / 32-pixel branch of the loop, and the default) applies nothing.
     """
 
-    def __init__(self, teacher, stat, images, labels, lr=0.5, beta=0.1, gamma=0.5, capturable=False, plateau=True):
+    def __init__(self, teacher, stat, images, labels, lr=0.5, beta=0.1, gamma=0.5, capturable=False, plateau=True,
+                 augment=None, augment_p=0.5, aug_margin=0.4):
+        if augment is not None and capturable:
+            raise ValueError("DistillStep: the augmented iteration draws on the host every step and cannot be captured; "
+                             "use capturable=False")
         self.teacher, self.stat, self.labels, self.beta, self.gamma = teacher, stat, labels, beta, gamma
+        self.augment, self.augment_p, self.aug_margin = augment, augment_p, aug_margin
         self.images = images.detach().clone().requires_grad_(True)
         # ``capturable``: keep Adam's step counter (and the learning rate) on the device so the iteration can be
         # replayed as a CUDA graph
@@ -268,13 +279,24 @@ class DistillStep:
             p.requires_grad_(False)
         teacher.eval()
 
+    def _augmented(self, x):
+        """:197-227 -- every other iteration (on average) the teacher sees a random crop / mirror of each image."""
+        import random
+
+        from .augment import random_resized_crop_params
+        if random.random() < self.augment_p:
+            n, _, h, w = x.shape
+            boxes, flips = random_resized_crop_params(n, h, w, scale=(self.aug_margin, 1.0))
+            return self.augment(x, boxes, flips)
+        return x
+
     def __call__(self):
         self.stat.clear()
         # a fresh autograd leaf over the optimised tensor every iteration: same gradient as zero_grad() +
         # backward() on the parameter itself (:270-271), but no AccumulateGrad node tied to the stream the
         # parameter was created on, so the iteration can be captured as a CUDA graph
         x = self.images.detach().requires_grad_(True)
-        out = self.teacher(x)
+        out = self.teacher(self._augmented(x) if self.augment is not None else x)
         target = hard_sample_loss(out, self.labels, self.beta, self.gamma)
         total = self.stat.loss("distill") + target                   # mean/L + var/L + target, :259-265
         self.images.grad = torch.autograd.grad(total, [x])[0]

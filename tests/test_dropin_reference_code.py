@@ -375,3 +375,81 @@ def test_distill_step_equals_the_reference_loop_source(monkeypatch):
         assert torch.equal(mine.images.detach(), gaussian.detach()), it
         assert mine.opt.param_groups[0]["lr"] == optimizer.param_groups[0]["lr"]
     assert not torch.equal(gaussian.detach(), start)
+
+
+def test_augmented_distill_step_equals_the_reference_loop_source(monkeypatch):
+    """The 224-pixel branch of the same loop (distill_data.py:205-227): on every other iteration each image goes
+    through torchvision's ``RHF(RRC(gaussian_data[j]))`` before the teacher, and autograd carries the gradient back
+    through the resize.  ``DistillStep(augment=...)`` with the oracle's torch augmentation consumes Python's and
+    torch's generators the same way: images, loss and learning rate stay bit-identical over iterations of both kinds."""
+    import random
+
+    import numpy as np
+    import torch.nn.functional as F
+    import torchvision.transforms as transforms
+    from torch import optim
+
+    from ood_dfq_b200 import nets, step
+    from oracle import augment_torch, bns_torch
+    sys.path.insert(0, REF)
+    try:
+        from data_generate.distill_data import DistillData
+    finally:
+        sys.path.remove(REF)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    path = os.path.join(REF, "data_generate", "distill_data.py")
+    with open(path) as f:
+        body = "".join(f.readlines()[196:275])
+    src = ("def iteration(self, teacher_model, gaussian_data, labels, gt, beta, gamma, CE_loss, MSE_loss, optimizer, "
+           "scheduler, RRC, RHF, i, it):\n" + textwrap.indent(textwrap.dedent(body.expandtabs(4)), "    ") +
+           "    return total_loss\n")
+    ns = {"torch": torch, "np": np, "F": F, "random": random, "print": lambda *a, **k: None}
+    exec(compile(src, f"{path}:197-275", "exec"), ns)
+
+    torch.manual_seed(2)
+    teacher = nets.resnet20_cifar(num_classes=10)                     # no img_size attribute: the loop's 224 branch (:217-227)
+    nets.perturb_bn_stats(teacher)
+    teacher.eval()
+    side = 32                                                        # the branch is chosen by the missing attribute, not by the size
+    g = torch.Generator().manual_seed(6)
+    start = torch.randn(3, 3, side, side, generator=g) / 5.0
+    labels = torch.randint(0, 10, (3,), generator=g)
+
+    ref_teacher = copy.deepcopy(teacher)
+    dd = DistillData()
+    for m in ref_teacher.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.register_forward_hook(dd.hook_fn_forward)
+    gaussian = start.clone()
+    gaussian.requires_grad = True
+    optimizer = optim.Adam([gaussian], lr=0.5)
+    scheduler = optim.lr_scheduler.ReduceLROnPlateau(optimizer, min_lr=1e-4, patience=50)
+    ce, mse = nn.CrossEntropyLoss(reduction="none"), nn.MSELoss()
+    rrc = transforms.RandomResizedCrop(size=side, scale=(0.4, 1.0))   # :166-172 with augMargin = 0.4 (:87)
+    rhf = transforms.RandomHorizontalFlip()                          # :173
+
+    def oracle_augment(x, boxes, flips):
+        return augment_torch.batch(x, range(x.shape[0]), boxes, flips, x.shape[2:], channels=3)
+
+    mine = step.DistillStep(copy.deepcopy(teacher), None, start, labels, lr=0.5, beta=0.1, gamma=0.5,
+                            augment=oracle_augment, augment_p=0.5, aug_margin=0.4)
+    mine.stat = bns_torch.StatTap(mine.teacher)
+    iters, kinds = 6, []
+    random.seed(11)
+    torch.manual_seed(12)
+    want, ref_images = [], []
+    for it in range(iters):
+        state = random.getstate()
+        kinds.append(random.random() < 0.5)                           # peek at the coin the loop is about to toss
+        random.setstate(state)
+        want.append(ns["iteration"](dd, ref_teacher, gaussian, labels, labels.numpy(), 0.1, 0.5, ce, mse, optimizer,
+                                    scheduler, rrc, rhf, 0, it).detach().clone())
+        ref_images.append(gaussian.detach().clone())
+    assert any(kinds) and not all(kinds)                             # both kinds of iteration were exercised
+    random.seed(11)
+    torch.manual_seed(12)
+    for it in range(iters):
+        got = mine()
+        assert torch.equal(got.reshape(-1), want[it].reshape(-1)), (it, kinds[it])
+        assert torch.equal(mine.images.detach(), ref_images[it]), (it, kinds[it])
+    assert mine.opt.param_groups[0]["lr"] == optimizer.param_groups[0]["lr"]

@@ -154,3 +154,40 @@ def test_differentiable_augmentation_matches_oracle_autograd(src_cl):
     assert xd.grad.shape == xd.shape and xd.grad.stride() == xd.stride()
     scale = leaf.grad.abs().max().item()
     assert (xd.grad.cpu() - leaf.grad.float()).abs().max().item() <= 2e-6 * scale
+
+
+def test_augmented_distillation_iteration_matches_the_cpu_arm():
+    """step.DistillStep(augment=augment.batch_augmenter()) on the GPU against the same iteration with the oracle's
+    torch augmentation on CPU: equal seeds give equal crops, losses agree, gradients point the same way."""
+    import copy
+    import random
+
+    from ood_dfq_b200 import augment, bns, nets, step
+    from oracle import bns_torch
+    torch.manual_seed(4)
+    teacher = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(teacher)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(8, 3, 32, 32, generator=g) / 5
+    labels = torch.randint(0, 10, (8,), generator=g)
+    torch.backends.cudnn.allow_tf32 = False
+
+    def oracle_augment(t, boxes, flips):
+        return augment_torch.batch(t, range(t.shape[0]), boxes, flips, t.shape[2:], channels=3)
+    cpu = copy.deepcopy(teacher)
+    ref = step.DistillStep(cpu, bns_torch.StatTap(cpu), x, labels, augment=oracle_augment, augment_p=1.0)
+    gpu = copy.deepcopy(teacher).to(DEV)
+    ours = step.DistillStep(gpu, bns.BNStatLoss(gpu), x.to(DEV), labels.to(DEV), augment=augment.batch_augmenter(),
+                            augment_p=1.0)
+    random.seed(1)
+    torch.manual_seed(2)
+    l_ref = ref().item()
+    random.seed(1)
+    torch.manual_seed(2)
+    l_ours = ours().item()
+    assert abs(l_ours - l_ref) <= 1e-3 * abs(l_ref), (l_ours, l_ref)
+    cos = torch.nn.functional.cosine_similarity(ref.images.grad.flatten(), ours.images.grad.cpu().flatten(), dim=0).item()
+    assert cos > 0.999, cos
+    with pytest.raises(ValueError, match="cannot be captured"):
+        step.DistillStep(gpu, bns.BNStatLoss(gpu), x.to(DEV), labels.to(DEV), augment=augment.batch_augmenter(),
+                         capturable=True)
