@@ -453,3 +453,38 @@ def test_augmented_distill_step_equals_the_reference_loop_source(monkeypatch):
         assert torch.equal(got.reshape(-1), want[it].reshape(-1)), (it, kinds[it])
         assert torch.equal(mine.images.detach(), ref_images[it]), (it, kinds[it])
     assert mine.opt.param_groups[0]["lr"] == optimizer.param_groups[0]["lr"]
+
+
+def test_carrier_resnet18_loads_what_the_reference_key_conversion_produces():
+    """``convert_state_dict`` (main_direct.py:212-301), compiled from the reference file, maps a torchvision ResNet-18
+    checkpoint onto pytorchcv's key names.  The bench's carrier network (ood_dfq_b200/nets.py, shape-faithful stand-in
+    for ``ptcv_get_model('resnet18')``) must accept exactly that state dict -- same keys, same shapes -- and then
+    computes the same function as the torchvision network."""
+    tv = pytest.importorskip("torchvision")
+    from collections import OrderedDict
+
+    from ood_dfq_b200 import nets
+    path = os.path.join(REF, "main_direct.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "convert_state_dict")
+    ns = {"OrderedDict": OrderedDict, "print": lambda *a, **k: None}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+
+    torch.manual_seed(0)
+    source = tv.models.resnet18(num_classes=1000)
+    for m in source.modules():                                       # non-trivial BN state
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.1)
+            m.running_var.uniform_(0.5, 1.5)
+    carrier = nets.resnet18_imagenet(num_classes=1000)
+    converted = ns["convert_state_dict"](source.state_dict(), carrier, model_type="standard")
+    want = carrier.state_dict()
+    assert set(converted) == set(want)
+    assert all(converted[k].shape == want[k].shape for k in want)
+    carrier.load_state_dict(converted, strict=True)
+    source.eval()
+    carrier.eval()
+    x = torch.randn(2, 3, 224, 224)
+    with torch.no_grad():
+        assert torch.allclose(carrier(x), source(x), rtol=1e-4, atol=1e-5)
