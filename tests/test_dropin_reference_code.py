@@ -488,3 +488,26 @@ def test_carrier_resnet18_loads_what_the_reference_key_conversion_produces():
     x = torch.randn(2, 3, 224, 224)
     with torch.no_grad():
         assert torch.allclose(carrier(x), source(x), rtol=1e-4, atol=1e-5)
+
+
+def test_carrier_small_resnet18_is_the_reference_model():
+    """``nets.resnet18_small`` (the MedMNIST-shape workload of the bench) against the reference's own ``models.ResNet18``
+    (importable): identical state-dict keys and shapes, and the same function once the weights are copied."""
+    from ood_dfq_b200 import nets
+    sys.path.insert(0, REF)
+    try:
+        import models as ref_models
+    finally:
+        sys.path.remove(REF)
+    torch.manual_seed(1)
+    theirs = ref_models.ResNet18(3, 9, img_size=28)
+    mine = nets.resnet18_small(3, 9)
+    sd = theirs.state_dict()
+    assert list(sd) == list(mine.state_dict())
+    assert all(sd[k].shape == v.shape for k, v in mine.state_dict().items())
+    mine.load_state_dict(sd, strict=True)
+    theirs.eval()
+    mine.eval()
+    x = torch.randn(3, 3, 28, 28)
+    with torch.no_grad():
+        assert torch.equal(mine(x), theirs(x))
