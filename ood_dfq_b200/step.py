@@ -197,6 +197,49 @@ class QATStep:
         return total.detach()
 
 
+# ------------------------------------------------------------------------------ generator warm-up phase
+class GeneratorStep:
+    """One iteration of the warm-up epochs 0-3 (trainer_direct.py:458-488): the phase in which the activation ranges
+    are calibrated and the BN-statistics loss (trainer flavour) drives the generator.
+
+        z, labels -> images = G(z, labels) -> teacher(images) with the BN-input hooks
+        -> loss_G = CE(teacher logits, labels) + 0.1 * BNS  -> Adam step on G          (:459-487, backward_G :342-348)
+        -> student(images.detach())   # no loss: every QuantAct tracks its range on 16 generated images (:488)
+
+    ``stat`` is ``bns.BNStatLoss(teacher)`` on the GPU or the oracle's ``StatTap`` on CPU.  The generator itself is
+    the reference's (main_direct.py:52-127; out of scope here, any ``G(z, labels)`` module works).  ``z`` and the labels
+    are drawn on the host and moved, as in the reference, so equal seeds give equal batches on every device.
+    """
+
+    def __init__(self, generator, teacher, student, stat, latent_dim: int, n_classes: int, batch: int = 16,
+                 lr: float = 1e-3, betas=(0.5, 0.999), bns_weight: float = 0.1):
+        self.generator, self.teacher, self.student, self.stat = generator, teacher, student, stat
+        self.latent_dim, self.n_classes, self.batch, self.bns_weight = latent_dim, n_classes, batch, bns_weight
+        self.opt = torch.optim.Adam(generator.parameters(), lr=lr, betas=betas)         # trainer_direct.py:87-88
+        for p in teacher.parameters():
+            p.requires_grad_(False)
+        student.eval()            # :411-413
+        teacher.eval()
+        generator.train()
+
+    def __call__(self):
+        dev = next(self.generator.parameters()).device
+        z = torch.randn(self.batch, self.latent_dim).to(dev)                             # :459
+        labels = torch.randint(0, self.n_classes, (self.batch,)).to(dev)                 # :460
+        images = self.generator(z.contiguous(), labels.contiguous())
+        self.stat.clear()
+        logits = self.teacher(images)
+        one_hot = F.cross_entropy(logits, labels)                                        # :471
+        bns = self.stat.loss("trainer")                                                  # :473-484
+        loss_g = one_hot + self.bns_weight * bns                                         # :486
+        self.opt.zero_grad()
+        loss_g.backward()
+        self.opt.step()
+        with torch.no_grad():
+            self.student(images.detach())                                                # :488 (range tracking only)
+        return loss_g.detach(), one_hot.detach(), bns.detach()
+
+
 # ------------------------------------------------------------------------------ BN-statistics distillation
 def hard_sample_loss(logits, labels, beta: float, gamma: float):
     """Focal cross-entropy of the image-distillation loop (data_generate/distill_data.py:236-249).

@@ -511,3 +511,69 @@ def test_carrier_small_resnet18_is_the_reference_model():
     x = torch.randn(3, 3, 28, 28)
     with torch.no_grad():
         assert torch.equal(mine(x), theirs(x))
+
+
+def test_generator_phase_equals_the_reference_iteration_source():
+    """The warm-up branch of ``Trainer.train`` (trainer_direct.py:459-488: generator forward, teacher forward with the
+    BN-input hooks, ``CE + 0.1 * BNS``, ``backward_G`` :342-348, then the student's range-tracking forward), compiled
+    from the reference file with the reference's own ``Generator_32`` (main_direct.py:52-88), against
+    ``step.GeneratorStep`` on CPU oracle modules: losses, the updated generator and every calibrated activation range
+    bit for bit."""
+    from ood_dfq_b200 import nets, step, surgery
+    from oracle import bns_torch, fq_torch
+    tpath = os.path.join(REF, "trainer_direct.py")
+    ns = {}
+    for first, last in ((342, 348), (388, 397)):                     # backward_G, hook_fn_forward
+        ns.update(lines_of(tpath, first, last))
+    with open(tpath) as f:
+        body = "".join(f.readlines()[458:488])
+    src = "def iteration(self):\n" + textwrap.indent(textwrap.dedent(body.expandtabs(4)), "    ") + \
+          "    return loss_G, loss_one_hot, BNS_loss\n"
+    exec(compile(src, f"{tpath}:459-488", "exec"), ns)
+    mpath = os.path.join(REF, "main_direct.py")
+    with open(mpath) as f:
+        tree = ast.parse(f.read(), filename=mpath)
+    gen_cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Generator_32")
+    gns = {"nn": nn, "torch": torch, "Option": None}
+    exec(compile(ast.Module(body=[gen_cls], type_ignores=[]), mpath, "exec"), gns)
+
+    settings = types.SimpleNamespace(nClasses=10, latent_dim=100, img_size=32, channels=3)   # cifar10_resnet20.hocon
+    torch.manual_seed(7)
+    generator = gns["Generator_32"](options=settings)
+    teacher = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(teacher)
+    student = surgery.quantize_model(copy.deepcopy(teacher), 4, 4, namespace=fq_torch)
+
+    # ---- the reference's iteration -------------------------------------------------------------------------------
+    r_gen, r_teacher, r_student = copy.deepcopy(generator), copy.deepcopy(teacher), copy.deepcopy(student)
+    r_teacher.eval(), r_student.eval(), r_gen.train()                 # :411-413
+    trainer = types.SimpleNamespace(
+        settings=settings, args=types.SimpleNamespace(local_rank="cpu"), generator=r_gen, model_teacher=r_teacher,
+        model=r_student, criterion=nn.CrossEntropyLoss(), MSE_loss=nn.MSELoss(), mean_list=[], var_list=[],
+        teacher_running_mean=[], teacher_running_var=[],
+        optimizer_G=torch.optim.Adam(r_gen.parameters(), lr=0.001, betas=(0.5, 0.999)))              # :87-88
+    for name in ("backward_G", "hook_fn_forward", "iteration"):
+        setattr(trainer, name, types.MethodType(ns[name], trainer))
+    for m in r_teacher.modules():                                     # :418-423 (BatchNorm2d here, SyncBatchNorm there)
+        if isinstance(m, nn.BatchNorm2d):
+            m.register_forward_hook(trainer.hook_fn_forward)
+    torch.manual_seed(21)
+    want = [tuple(t.detach().clone() for t in trainer.iteration()) for _ in range(3)]
+
+    # ---- this repository's step -----------------------------------------------------------------------------------
+    m_gen, m_teacher, m_student = copy.deepcopy(generator), copy.deepcopy(teacher), copy.deepcopy(student)
+    gstep = step.GeneratorStep(m_gen, m_teacher, m_student, bns_torch.StatTap(m_teacher), latent_dim=100, n_classes=10,
+                               batch=16, lr=0.001, betas=(0.5, 0.999))
+    torch.manual_seed(21)
+    for it in range(3):
+        got = gstep()
+        for a, b in zip(got, want[it]):
+            assert torch.equal(a.reshape(-1), b.reshape(-1)), it
+    for (name, a), (_, b) in zip(m_gen.state_dict().items(), r_gen.state_dict().items()):
+        assert torch.equal(a, b), name
+    acts_m = [m for m in m_student.modules() if isinstance(m, fq_torch.OracleQuantAct)]
+    acts_r = [m for m in r_student.modules() if isinstance(m, fq_torch.OracleQuantAct)]
+    assert len(acts_m) == len(acts_r) > 10
+    for a, b in zip(acts_m, acts_r):
+        assert torch.equal(a.x_min, b.x_min) and torch.equal(a.x_max, b.x_max) and torch.equal(a.beta_t, b.beta_t)
+        assert a.x_max.item() > 0 and a.beta_t.item() < 1            # the ranges really were calibrated
