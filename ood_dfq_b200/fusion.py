@@ -213,10 +213,19 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
     pairs = []
     ref_out = None
     if example is not None and absorb_tails and (tails or relus):
-        produced = {}     # id(tensor) -> (module, tensor): the tensor is kept alive so ids cannot be recycled
-        handles = [b.register_forward_hook(lambda mod, i, o: produced.__setitem__(id(o), (mod, o))) for b in bns]
+        # id(tensor) -> (module, tensor, version): the tensor is kept alive so ids cannot be recycled, and its version
+        # counter tells whether something wrote into it between the BatchNorm and the consumer -- the reference's
+        # BasicBlock does ``out += self.shortcut(x)`` on the very tensor bn2 returned (models.py:40-41), so relu2
+        # receives the same object without being fed by bn2
+        produced = {}
+
+        def direct(table, t):
+            ent = table.get(id(t))
+            return ent if ent is not None and t._version == ent[2] else None
+
+        handles = [b.register_forward_hook(lambda mod, i, o: produced.__setitem__(id(o), (mod, o, o._version))) for b in bns]
         handles += [t.register_forward_pre_hook(
-            lambda mod, i: pairs.append((produced[id(i[0])][0], mod)) if id(i[0]) in produced else None)
+            lambda mod, i: pairs.append((direct(produced, i[0])[0], mod)) if direct(produced, i[0]) else None)
             for t in tails + relus]
         with torch.no_grad():
             ref_out = model(example)
@@ -229,9 +238,9 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
     if example is not None and absorb_tails and pools and pairs:
         tail_of = {id(t): b for b, t in pairs}
         made = {}
-        handles = [t.register_forward_hook(lambda mod, i, o: made.__setitem__(id(o), (mod, o))) for _, t in pairs]
+        handles = [t.register_forward_hook(lambda mod, i, o: made.__setitem__(id(o), (mod, o, o._version))) for _, t in pairs]
         handles += [p.register_forward_pre_hook(
-            lambda mod, i: stems.append((tail_of[id(made[id(i[0])][0])], mod)) if id(i[0]) in made else None)
+            lambda mod, i: stems.append((tail_of[id(direct(made, i[0])[0])], mod)) if direct(made, i[0]) else None)
             for p in pools]
         with torch.no_grad():
             model(example)

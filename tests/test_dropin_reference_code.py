@@ -577,3 +577,30 @@ def test_generator_phase_equals_the_reference_iteration_source():
     for a, b in zip(acts_m, acts_r):
         assert torch.equal(a.x_min, b.x_min) and torch.equal(a.x_max, b.x_max) and torch.equal(a.beta_t, b.beta_t)
         assert a.x_max.item() > 0 and a.beta_t.item() < 1            # the ranges really were calibrated
+
+
+def test_fusion_passes_recognise_the_reference_model_classes():
+    """The passes find the BatchNorm / residual-unit layout of the reference's OWN ``models.ResNet18`` (BasicBlock:
+    conv1..bn2 / shortcut / relu2, models.py:21-47), swap classes without touching keys, and -- off the GPU, where the
+    fused modules run their class's own forward -- leave the function unchanged."""
+    from ood_dfq_b200 import fusion, nets
+    sys.path.insert(0, REF)
+    try:
+        import models as ref_models
+    finally:
+        sys.path.remove(REF)
+    torch.manual_seed(5)
+    model = ref_models.ResNet18(3, 9, img_size=28).eval()
+    nets.perturb_bn_stats(model)
+    x = torch.randn(2, 3, 28, 28)
+    with torch.no_grad():
+        ref = model(x)
+    keys = list(model.state_dict())
+    units_before = [type(m) for m in model.modules() if isinstance(m, ref_models.BasicBlock)]
+    fusion.fuse_eval_bn(model, x)
+    assert fusion.fuse_residual_tails(model, x) == len(units_before) == 8
+    assert all(isinstance(m, fusion.FusedEvalBN) for m in model.modules() if isinstance(m, nn.BatchNorm2d))
+    assert sum(isinstance(m, ref_models.BasicBlock) for m in model.modules()) == 8          # still BasicBlocks
+    with torch.no_grad():
+        assert torch.equal(model(x), ref)
+    assert list(model.state_dict()) == keys
