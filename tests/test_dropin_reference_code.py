@@ -604,3 +604,60 @@ def test_fusion_passes_recognise_the_reference_model_classes():
     with torch.no_grad():
         assert torch.equal(model(x), ref)
     assert list(model.state_dict()) == keys
+
+
+def test_checkpoints_move_between_the_reference_classes_and_the_mirror(surgery_ns):
+    """A model quantised with the reference's OWN classes and one quantised with the mirror's have the same state dict
+    (keys, shapes, values), load each other's checkpoints strictly, survive ``convert_sync_batchnorm``
+    (main_direct.py:483) and wrap into DDP (:484) -- on CPU, gloo, no forward."""
+    import importlib
+    pkg = types.ModuleType("_live_reference_qu2")
+    pkg.__path__ = [os.path.join(REF, "quantization_utils")]
+    sys.modules["_live_reference_qu2"] = pkg
+    ref_qm = importlib.import_module("_live_reference_qu2.quant_modules")
+
+    # the reference's quantize_model, once bound to its own classes and once to the mirror's
+    path = os.path.join(REF, "main_direct.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ExperimentDesign")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "quantize_model")
+    ns_ref = {"nn": nn, "torch": torch, "copy": copy}
+    ns_ref.update({k: getattr(ref_qm, k) for k in ("Quant_Conv2d", "Quant_Linear", "QuantAct")})
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns_ref)
+    exp_ref = types.SimpleNamespace(settings=types.SimpleNamespace(qw=4, qa=4))
+    exp_ref.quantize_model = types.MethodType(ns_ref["quantize_model"], exp_ref)
+    exp_mine = experiment(surgery_ns, 4, 4)
+
+    net = reference_models()["reference models.ResNet18 (28x28)"]
+    theirs, mine = exp_ref.quantize_model(net), exp_mine.quantize_model(net)
+    assert type(next(m for m in theirs.modules() if "QuantAct" in type(m).__name__)).__module__.startswith("_live_reference")
+    sd_t, sd_m = theirs.state_dict(), mine.state_dict()
+    assert list(sd_t) == list(sd_m) and all(sd_t[k].shape == sd_m[k].shape and torch.equal(sd_t[k], sd_m[k]) for k in sd_t)
+    for m in theirs.modules():                              # a "trained" checkpoint: non-default ranges
+        if hasattr(m, "x_min"):
+            m.x_min.fill_(-0.125)
+            m.x_max.fill_(3.5)
+            m.beta_t.fill_(0.25)
+    mine.load_state_dict(theirs.state_dict(), strict=True)
+    assert all(m.x_max.item() == 3.5 and m.beta_t.item() == 0.25 for m in mine.modules() if hasattr(m, "x_min"))
+    theirs.load_state_dict(mine.state_dict(), strict=True)
+
+    sync = torch.nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(mine))
+    assert list(sync.state_dict()) == list(sd_m)
+    assert sum(isinstance(m, nn.SyncBatchNorm) for m in sync.modules()) == sum(isinstance(m, nn.BatchNorm2d) for m in mine.modules())
+
+    own_group = not dist.is_initialized()
+    if own_group:
+        import socket
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        ddp = torch.nn.parallel.DistributedDataParallel(mine, broadcast_buffers=False)
+        assert [k[len("module."):] for k in ddp.state_dict()] == list(sd_m)
+        assert sum(p.numel() for p in ddp.parameters()) == sum(p.numel() for p in net.parameters())
+    finally:
+        if own_group:
+            dist.destroy_process_group()
