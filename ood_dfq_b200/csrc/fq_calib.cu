@@ -406,12 +406,12 @@ act_calib_onchip_tma_kernel(const float* __restrict__ x, float* __restrict__ y, 
     }
 }
 
-// true if the launch was made (the caller falls back to the two-kernel path otherwise)
-struct CoopProbe {
+struct CoopProbe {                   // per kernel variant: can it be launched cooperatively here, and how wide
     int state = 0;                   // 0 = not probed, 1 = usable, -1 = unavailable on this device / driver
     int grid = 0;
 };
 
+// true if the launch was made (the caller falls back to the two-kernel path otherwise)
 static bool try_onchip_calib(const float* x, float* y, long long numel, void* workspace, float* x_min, float* x_max,
                              const float* beta, float* beta_t, int k, bool tma, cudaStream_t st, int* rc) {
     static CoopProbe probes[2];
