@@ -661,3 +661,98 @@ def test_checkpoints_move_between_the_reference_classes_and_the_mirror(surgery_n
     finally:
         if own_group:
             dist.destroy_process_group()
+
+
+def test_reference_training_code_drives_the_mirror_modules(surgery_ns):
+    """The whole consumer chain at once: the reference's own ``quantize_model`` builds a student from the MIRROR
+    classes, its own warm-up iteration (:459-488) calibrates it, its own ``freeze_model`` freezes it and its own QAT
+    iteration (:500-518) trains it for several steps -- with the mirror's kernel launches swapped for oracle arithmetic
+    (tests/cpu_ops_shim.py), so that everything else is the product's host code: autograd Functions, in-place range
+    updates, the WeightBank across ``optimizer_S.step()``.  A student built from the reference's OWN classes goes
+    through the same code; ranges, losses and weights must stay bit-identical all the way."""
+    import importlib
+
+    import cpu_ops_shim
+    from ood_dfq_b200 import nets
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    pkg = types.ModuleType("_live_reference_qu4")
+    pkg.__path__ = [os.path.join(REF, "quantization_utils")]
+    sys.modules["_live_reference_qu4"] = pkg
+    ref_qm = importlib.import_module("_live_reference_qu4.quant_modules")
+
+    tpath, mpath = os.path.join(REF, "trainer_direct.py"), os.path.join(REF, "main_direct.py")
+    with open(mpath) as f:
+        tree = ast.parse(f.read(), filename=mpath)
+    exp_cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ExperimentDesign")
+    wanted = [n for n in exp_cls.body if isinstance(n, ast.FunctionDef) and n.name in ("quantize_model", "freeze_model")]
+    gen_cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Generator_32")
+    with open(tpath) as f:
+        lines = f.readlines()
+    warm = "def warm_up(self):\n" + textwrap.indent(textwrap.dedent("".join(lines[458:488]).expandtabs(4)), "    ") + \
+           "    return loss_G\n"
+    train = "def train_step(self, images, labels):\n" + \
+            textwrap.indent(textwrap.dedent("".join(lines[499:518]).expandtabs(4)), "    ") + "    return loss_total\n"
+
+    def side(classes):
+        """One complete trainer stand-in whose namespace binds the quantisation names to ``classes``."""
+        ns = {"nn": nn, "torch": torch, "copy": copy, "Option": None}
+        exec("from torch.autograd import Variable\nimport torch.nn.functional as F", ns)
+        ns.update({k: getattr(classes, k) for k in ("Quant_Conv2d", "Quant_Linear", "QuantAct")})
+        exec(compile(ast.Module(body=wanted + [gen_cls], type_ignores=[]), mpath, "exec"), ns)
+        for first, last in ((308, 340), (342, 348), (350, 356), (379, 397)):
+            exec(compile(textwrap.dedent("".join(lines[first - 1:last]).expandtabs(4)), tpath, "exec"), ns)
+        exec(compile(warm, tpath, "exec"), ns)
+        exec(compile(train, tpath, "exec"), ns)
+        settings = types.SimpleNamespace(qw=4, qa=4, nClasses=10, latent_dim=100, img_size=32, channels=3, alpha=20.0,
+                                         temperature=20.0, lam=1000.0, eps=0.01)
+        torch.manual_seed(9)
+        teacher = nets.resnet20_cifar(num_classes=10)
+        nets.perturb_bn_stats(teacher)
+        t = types.SimpleNamespace(settings=settings, args=types.SimpleNamespace(local_rank="cpu"), model_teacher=teacher.eval(),
+                                  generator=ns["Generator_32"](options=settings).train(), criterion=nn.CrossEntropyLoss(),
+                                  MSE_loss=nn.MSELoss(), KLloss=nn.KLDivLoss(reduction="batchmean"), mean_list=[], var_list=[],
+                                  teacher_running_mean=[], teacher_running_var=[], activation=[], activation_teacher=[])
+        for name in ("quantize_model", "freeze_model", "loss_fn_kd", "loss_fa", "forward", "backward_G", "backward_S",
+                     "channel_attention", "hook_activation", "hook_activation_teacher", "hook_fn_forward", "warm_up",
+                     "train_step"):
+            setattr(t, name, types.MethodType(ns[name], t))
+        t.model = t.quantize_model(copy.deepcopy(teacher)).eval()
+        t.optimizer_G = torch.optim.Adam(t.generator.parameters(), lr=1e-3, betas=(0.5, 0.999))
+        t.optimizer_S = torch.optim.SGD(t.model.parameters(), lr=1e-5, momentum=0.9, weight_decay=1e-4, nesterov=True)   # lr_S of cifar10_resnet20.hocon
+        handles = [m.register_forward_hook(t.hook_fn_forward) for m in teacher.modules() if isinstance(m, nn.BatchNorm2d)]
+        return t, handles
+
+    def run(t, handles):
+        out = []
+        torch.manual_seed(33)
+        for _ in range(2):                                           # epochs 0-3: generator + range calibration
+            out.append(t.warm_up().detach().clone())
+        for h in handles:                                            # epoch 4 (:425-440): hooks off, feature taps on
+            h.remove()
+        t.freeze_model(t.model)
+        for m in t.model_teacher.modules():
+            if isinstance(m, nets.ResUnit):
+                m.body.register_forward_hook(t.hook_activation_teacher)
+        for m in t.model.modules():
+            if isinstance(m, nets.ResUnit):
+                m.body.register_forward_hook(t.hook_activation)
+        g = torch.Generator().manual_seed(34)
+        for _ in range(3):
+            images, labels = torch.randn(4, 3, 32, 32, generator=g), torch.randint(0, 10, (4,), generator=g)
+            out.append(t.train_step(images, labels).detach().clone())
+        return out
+
+    ref_side, ref_handles = side(ref_qm)
+    want = run(ref_side, ref_handles)
+    with cpu_ops_shim.installed():
+        my_side, my_handles = side(qm)
+        assert type(next(m for m in my_side.model.modules() if type(m).__name__ == "QuantAct")) is qm.QuantAct
+        got = run(my_side, my_handles)
+        for i, (a, b) in enumerate(zip(got, want)):
+            assert torch.equal(a.reshape(-1), b.reshape(-1)), i
+        sd_a, sd_b = my_side.model.state_dict(), ref_side.model.state_dict()
+        assert list(sd_a) == list(sd_b)
+        for k in sd_a:
+            assert torch.equal(sd_a[k].reshape(-1), sd_b[k].reshape(-1)), k
+        assert any(k.endswith("x_max") and sd_a[k].item() > 0 for k in sd_a)
+        assert all(torch.isfinite(v).all() for v in sd_a.values())

@@ -1,0 +1,156 @@
+"""Host logic of the mirror modules (ood_dfq_b200/quantization_utils) exercised on CPU.
+
+The modules launch kernels for every tensor operation, so they cannot run here as shipped.  With the launch
+wrappers swapped for oracle arithmetic of the same contract (tests/cpu_ops_shim.py, test-only) everything ELSE is
+the product's own code: which autograd Function runs in which mode, the in-place updates of ``x_min / x_max /
+beta_t``, ``fix`` / ``unfix`` / ``full_precision_flag``, the straight-through gradients, and the ``WeightBank`` that
+decides when weights are re-quantised.  Each scenario is run against the LIVE reference classes where the tree is
+mounted, against the oracle modules otherwise: bit-identical results are required.
+"""
+import copy
+import os
+import sys
+import types
+
+import pytest
+import torch
+from torch import nn
+
+import cpu_ops_shim
+from oracle import fq_torch
+
+REF = os.environ.get("OODFQ_REFERENCE", "/root/reference")
+
+
+def twin_classes():
+    """(QuantAct, QuantAct_DSG, QuantAct_MSE, Quant_Conv2d, Quant_Linear, QuantConv2d_DSG, QuantLinear_DSG) of the
+    comparison side: the live reference when present."""
+    if os.path.isdir(os.path.join(REF, "quantization_utils")):
+        import importlib
+        pkg = types.ModuleType("_live_reference_qu3")
+        pkg.__path__ = [os.path.join(REF, "quantization_utils")]
+        sys.modules["_live_reference_qu3"] = pkg
+        m = importlib.import_module("_live_reference_qu3.quant_modules")
+        return (m.QuantAct, m.QuantAct_DSG, m.QuantAct_MSE, m.Quant_Conv2d, m.Quant_Linear, m.QuantConv2d_DSG,
+                m.QuantLinear_DSG), "live reference"
+    o = fq_torch
+    return (o.OracleQuantAct, o.OracleQuantActSym, o.OracleQuantActMSE, o.OracleQuantConv2d, o.OracleQuantLinear,
+            o.OracleQuantConv2dSym, o.OracleQuantLinearSym), "oracle"
+
+
+TWIN, TWIN_NAME = twin_classes()
+
+
+@pytest.fixture()
+def mirror():
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    with cpu_ops_shim.installed():
+        yield qm
+
+
+def same(a, b):
+    return torch.equal(a.detach(), b.detach())
+
+
+@pytest.mark.parametrize("which", [0, 1, 2])
+def test_activation_modules_follow_the_reference_through_every_mode(mirror, which):
+    """Calibrating, frozen, full-precision and re-enabled tracking in one sequence; output, gradient and state."""
+    ours = [mirror.QuantAct, mirror.QuantAct_DSG, mirror.QuantAct_MSE][which](4)
+    ref = TWIN[which](4)
+    g = torch.Generator().manual_seed(which)
+    script = ["track", "track", "fix", "frozen", "fp", "fp-track", "unfix", "track"]
+    for step, what in enumerate(script):
+        if what == "fix":
+            ours.fix(), ref.fix()
+            continue
+        if what == "unfix":
+            ours.unfix(), ref.unfix()
+            ours.full_precision_flag = ref.full_precision_flag = False
+            continue
+        if what == "fp":
+            ours.full_precision_flag = ref.full_precision_flag = True
+        if what == "fp-track":
+            ours.unfix(), ref.unfix()
+        x = (torch.randn(3, 4, 5, 5, generator=g) * (1 + step)).requires_grad_(True)
+        xr = x.detach().clone().requires_grad_(True)
+        y, yr = ours(x), ref(xr)
+        assert same(y, yr), (what, step)
+        if what == "fp":
+            assert y is x                                     # quant_modules.py:95-96: the input object itself
+        cot = torch.randn(y.shape, generator=g)
+        (y * cot).sum().backward()
+        (yr * cot).sum().backward()
+        assert same(x.grad, xr.grad), (what, step)
+        for name in ("x_min", "x_max", "beta_t"):
+            assert same(getattr(ours, name).reshape(-1), getattr(ref, name).reshape(-1)), (name, what, step)
+        assert ours.x_min.shape == (1,) and "x_min" in dict(ours.named_buffers())
+
+
+@pytest.mark.parametrize("which,layer", [(3, "conv"), (4, "linear"), (5, "conv"), (6, "linear")])
+def test_weight_modules_requantise_exactly_when_the_weights_change(mirror, which, layer):
+    """Forward + backward + SGD for several steps: the cached fake-quantised weight must follow every optimiser update
+    (``_version``), two forwards between updates must reuse it, and results equal the reference's per-forward
+    recomputation bit for bit."""
+    torch.manual_seed(which)
+    src = nn.Conv2d(3, 6, 3, padding=1, bias=True) if layer == "conv" else nn.Linear(12, 5)
+    ours = [None, None, None, mirror.Quant_Conv2d, mirror.Quant_Linear, mirror.QuantConv2d_DSG, mirror.QuantLinear_DSG][which](weight_bit=4)
+    ref = TWIN[which](weight_bit=4)
+    ours.set_param(src), ref.set_param(src)
+    opt_o = torch.optim.SGD(ours.parameters(), lr=0.05, momentum=0.9)
+    opt_r = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9)
+    g = torch.Generator().manual_seed(10)
+    calls = []
+    real = cpu_ops_shim.weight_fq_multi
+    from ood_dfq_b200 import ops
+    ops.weight_fq_multi = lambda *a, **k: (calls.append(len(a[0])), real(*a, **k))[1]
+    for step in range(4):
+        x = torch.randn(2, 3, 6, 6, generator=g) if layer == "conv" else torch.randn(4, 12, generator=g)
+        out_a, out_b = ours(x), ours(x * 0.5)                 # two forwards per step, as the QAT iteration does
+        ref_a, ref_b = ref(x), ref(x * 0.5)
+        assert same(out_a, ref_a) and same(out_b, ref_b), step
+        assert len(calls) == step + 1, calls                  # one re-quantisation per optimiser step, not per forward
+        opt_o.zero_grad(), opt_r.zero_grad()
+        (out_a.square().sum() + out_b.sum()).backward()
+        (ref_a.square().sum() + ref_b.sum()).backward()
+        assert same(ours.weight.grad, ref.weight.grad) and same(ours.bias.grad, ref.bias.grad)
+        opt_o.step(), opt_r.step()
+        assert same(ours.weight, ref.weight)
+    # a copy of the module owns its own cache; a disabled bank re-quantises on every forward like the reference
+    twin = copy.deepcopy(ours)
+    with torch.no_grad():
+        twin.weight.mul_(2.0)
+    assert not same(twin(x), ours(x))
+    mirror.WeightBank.enabled = False
+    try:
+        n = len(calls)
+        ours(x), ours(x)
+        assert len(calls) == n + 2
+    finally:
+        mirror.WeightBank.enabled = True
+    ours.full_precision_flag = ref.full_precision_flag = True
+    assert same(ours(x), ref(x))
+
+
+def test_quant_utils_functions_match(mirror):
+    """The function-level API (quant_utils.py) through the same shim: parameters, quantise, dequantise, STE."""
+    from ood_dfq_b200.quantization_utils import quant_utils as qu
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, 3, 5, 5, generator=g)
+    lo, hi = torch.tensor([-1.5]), torch.tensor([2.25])
+    s, z = qu.asymmetric_linear_quantization_params(4, lo, hi)
+    s_ref, z_ref = fq_torch.quant_params(4, lo, hi)
+    assert same(s, s_ref) and same(z, z_ref)
+    q = qu.linear_quantize(x, s, z)
+    assert same(q, fq_torch.quantize(x, s_ref, z_ref))
+    assert same(qu.linear_dequantize(q, s, z), fq_torch.dequantize(q, s_ref, z_ref))
+    keep = x.clone()
+    assert qu.linear_quantize(keep, s, z, inplace=True) is keep and same(keep, q)
+    xr = x.clone().requires_grad_(True)
+    y = qu.AsymmetricQuantFunction.apply(xr, 4, lo, hi)
+    assert same(y, fq_torch.fake_quant(x, 4, lo, hi))
+    y.sum().backward()
+    assert same(xr.grad, torch.ones_like(x))                  # identity STE, no clip mask (quant_utils.py:159-161)
+    with pytest.raises(NotImplementedError):
+        qu.asymmetric_linear_quantization_params(4, lo, hi, integral_zero_point=False)
+    assert same(qu.find_MSESmallest(x, 4, lo, hi), fq_torch.fake_quant(x, 4, lo, hi))
+    assert abs(qu.lp_loss(x, x * 0.5, p=2.4, reduction="all").item() - (x * 0.5).abs().pow(2.4).mean().item()) < 1e-6
