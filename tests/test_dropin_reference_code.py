@@ -756,3 +756,37 @@ def test_reference_training_code_drives_the_mirror_modules(surgery_ns):
             assert torch.equal(sd_a[k].reshape(-1), sd_b[k].reshape(-1)), k
         assert any(k.endswith("x_max") and sd_a[k].item() > 0 for k in sd_a)
         assert all(torch.isfinite(v).all() for v in sd_a.values())
+
+
+def test_fusion_passes_on_the_reference_model_quantised_by_the_reference_code(surgery_ns):
+    """``models.ResNet18`` (in-place shortcut add, in-place ReLUs) -> the reference's ``quantize_model`` with mirror
+    classes -> calibrate -> the reference's ``freeze_model`` -> all fusion passes.  Nine BN-fed tails absorbed, the eight
+    tails behind the in-place adds fused as ReLU+QuantAct pairs (NOT swallowed by bn2), eight units recognised; results
+    and keys unchanged off the GPU."""
+    import cpu_ops_shim
+    from ood_dfq_b200 import fusion, nets
+    sys.path.insert(0, REF)
+    try:
+        import models as ref_models
+    finally:
+        sys.path.remove(REF)
+    torch.manual_seed(6)
+    net = ref_models.ResNet18(3, 9, img_size=28)
+    nets.perturb_bn_stats(net)
+    exp = experiment(surgery_ns, 4, 4)
+    x = torch.randn(2, 3, 28, 28)
+    with cpu_ops_shim.installed():
+        student = exp.quantize_model(net).eval()
+        with torch.no_grad():
+            student(x)
+        exp.freeze_model(student)
+        with torch.no_grad():
+            ref = student(x)
+        keys = list(student.state_dict())
+        fusion.fuse_eval_bn(student, x)
+        units = fusion.fuse_residual_tails(student, x)
+        count = lambda cls: sum(type(m) is cls for m in student.modules())
+        assert (count(fusion.AbsorbedTail), count(fusion.FusedReLUQuant), units) == (9, 8, 8)
+        with torch.no_grad():
+            assert torch.equal(student(x), ref)
+        assert list(student.state_dict()) == keys

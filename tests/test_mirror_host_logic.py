@@ -154,3 +154,46 @@ def test_quant_utils_functions_match(mirror):
         qu.asymmetric_linear_quantization_params(4, lo, hi, integral_zero_point=False)
     assert same(qu.find_MSESmallest(x, 4, lo, hi), fq_torch.fake_quant(x, 4, lo, hi))
     assert abs(qu.lp_loss(x, x * 0.5, p=2.4, reduction="all").item() - (x * 0.5).abs().pow(2.4).mean().item()) < 1e-6
+
+
+@pytest.mark.parametrize("net_name,side,expect", [
+    # (BN-fed tails absorbed, tails behind a residual add, stem pools absorbed, residual units)
+    ("resnet18_imagenet", 224, (9, 8, 1, 8)),
+    ("resnet20_cifar", 32, (10, 9, 0, 9)),
+    ("resnet18_small", 28, (9, 8, 0, 8)),
+])
+def test_fusion_passes_on_a_quantised_student(mirror, net_name, side, expect):
+    """The passes trace the QUANTISED student (Sequential(ReLU(inplace), QuantAct) tails) -- possible on CPU with the
+    shim: every BatchNorm that directly feeds a tail absorbs it, the tails behind residual adds become the fused
+    ReLU+QuantAct pair, the ImageNet stem absorbs its max-pool, every residual unit is recognised; off the GPU the
+    fused modules run the original chain, so outputs, ranges and keys are unchanged."""
+    from ood_dfq_b200 import fusion, nets, surgery
+    torch.manual_seed(2)
+    base = nets.resnet18_small(3, 9) if net_name == "resnet18_small" else getattr(nets, net_name)(num_classes=10)
+    nets.perturb_bn_stats(base)
+    student = surgery.quantize_model(base, 4, 4).eval()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, side, side, generator=g)
+    with torch.no_grad():
+        student(x)                                            # one calibrating forward, then freeze
+    surgery.freeze_model(student)
+    with torch.no_grad():
+        ref = student(x)
+    keys = list(student.state_dict())
+    state = {k: v.clone() for k, v in student.state_dict().items()}
+    fusion.fuse_eval_bn(student, x)
+    units = fusion.fuse_residual_tails(student, x)
+    fusion.space_to_depth_stem(student, x)
+    count = lambda cls: sum(type(m) is cls for m in student.modules())
+    assert (count(fusion.AbsorbedTail), count(fusion.FusedReLUQuant), count(fusion.AbsorbedPool), units) == expect
+    with torch.no_grad():
+        out = student(x)
+    assert torch.equal(out, ref) and list(student.state_dict()) == keys
+    assert all(torch.equal(v, state[k]) for k, v in student.state_dict().items())
+    # calibration keeps working through the fused modules (they step aside while a QuantAct tracks its range)
+    surgery.unfreeze_model(student)
+    plain = surgery.quantize_model(base, 4, 4).eval()
+    plain.load_state_dict(state)
+    with torch.no_grad():
+        assert torch.equal(student(x * 1.5), plain(x * 1.5))
+    assert all(torch.equal(a, b) for a, b in zip(student.state_dict().values(), plain.state_dict().values()))
