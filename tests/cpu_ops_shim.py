@@ -95,7 +95,64 @@ def act_mse_search(x, k, x_min, x_max, beta, beta_t, cur_min=None, cur_max=None,
     x_max.copy_(x_max * beta + keep_hi * (1 - beta))
 
 
-PATCHED = ("quant_params", "fake_quant", "elementwise", "minmax", "act_calib_forward", "weight_fq_multi", "act_mse_search")
+# ---- BN-statistics loss (csrc/bn_stats.cu contracts: shifted fp64 sums, packed layer blocks [S1 | S2]) ----------------
+def bn_stats_forward(x, shift=None, sums=None, fq=None):
+    c = x.shape[1]
+    sh = torch.zeros(c, dtype=torch.float64) if shift is None else shift.detach().double()
+    d = x.detach().double() - sh.view(1, c, 1, 1)
+    block = torch.cat([d.sum([0, 2, 3]), (d * d).sum([0, 2, 3])])
+    if sums is None:
+        sums = block
+    else:
+        sums.copy_(block)
+    return (sums, fake_quant(x, fq[0], fq[1], fq[2])) if fq is not None else sums
+
+
+def bn_stats_finalize(sums, shift, count):
+    c = sums.numel() // 2
+    m1 = sums[:c] / count
+    mean = m1 if shift is None else shift.double() + m1
+    return mean.float(), (sums[c:] / count - m1 * m1).float()
+
+
+def bns_loss(sums, shift, run_mean, run_var, ch_off, counts):
+    n_layers, ctot = len(counts), ch_off[-1]
+    mean, var = torch.empty(ctot, dtype=torch.float64), torch.empty(ctot, dtype=torch.float64)
+    gmean, gvar = torch.empty(ctot, dtype=torch.float64), torch.empty(ctot, dtype=torch.float64)
+    t_mean = t_var = 0.0
+    for l in range(n_layers):
+        a, b = ch_off[l], ch_off[l + 1]
+        c = b - a
+        block = sums[2 * a: 2 * b]
+        m1 = block[:c] / counts[l]
+        mean[a:b] = (shift[a:b].double() if shift is not None else 0.0) + m1
+        var[a:b] = block[c:] / counts[l] - m1 * m1
+        dm, dv = mean[a:b] - run_mean[a:b].double(), var[a:b] - run_var[a:b].double()
+        t_mean = t_mean + (dm * dm).mean()
+        t_var = t_var + (dv * dv).mean()
+        gmean[a:b] = 2.0 * dm / (c * n_layers)
+        gvar[a:b] = 2.0 * dv / (c * n_layers)
+    loss3 = torch.stack([(t_mean + t_var) / n_layers, t_mean / n_layers, t_var / n_layers]).float()
+    return loss3, mean.float(), var.float(), gmean.float(), gvar.float()
+
+
+def bn_stats_backward(x, grad_in, mean, gmean, gvar, count, gscale=None, out=None):
+    c = x.shape[1]
+    g = 1.0 if gscale is None else gscale.double().reshape(())
+    v = lambda t: t.double().view(1, c, 1, 1)
+    r = g * (v(gmean) / count + v(gvar) * 2.0 * (x.detach().double() - v(mean)) / count)
+    if grad_in is not None:
+        r = r + grad_in.double()
+    r = r.float().contiguous(memory_format=torch.channels_last if x.is_contiguous(memory_format=torch.channels_last)
+                             and not x.is_contiguous() else torch.contiguous_format)
+    if out is not None:
+        out.copy_(r)
+        return out
+    return r
+
+
+PATCHED = ("quant_params", "fake_quant", "elementwise", "minmax", "act_calib_forward", "weight_fq_multi", "act_mse_search",
+           "bn_stats_forward", "bn_stats_finalize", "bns_loss", "bn_stats_backward")
 
 
 @contextlib.contextmanager

@@ -159,3 +159,51 @@ def test_bn_partial_sums_allreduce_gives_global_statistics():
     for r in (0, 1):
         np.testing.assert_allclose(out[r][0], mean.numpy(), rtol=1e-6)
         np.testing.assert_allclose(out[r][1], var.numpy(), rtol=1e-5)
+
+
+# ------------------------------------------------------------------ BNStatLoss(sync=True): the product's own manager
+def _sync_net():
+    torch.manual_seed(4)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1, bias=False), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                              torch.nn.Conv2d(8, 12, 3, stride=2, padding=1, bias=False), torch.nn.BatchNorm2d(12)).eval()
+    g = torch.Generator().manual_seed(5)
+    for m in net:
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.3)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    return net
+
+
+def _sync_batch():
+    return torch.randn(8, 3, 10, 10, generator=torch.Generator().manual_seed(6)) * 1.5 + 0.3
+
+
+def _w_bns_sync(rank, world):
+    """``bns.BNStatLoss(sync=True)`` itself -- hooks, packed fp64 sums, the all-reduce, the fused backward -- with its
+    kernel launches swapped for oracle arithmetic (tests/cpu_ops_shim.py, test-only)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import cpu_ops_shim
+    from ood_dfq_b200 import bns, dist as ddist
+    net = _sync_net()
+    x = ddist.shard_batch(_sync_batch(), rank, world).clone().requires_grad_(True)
+    with cpu_ops_shim.installed():
+        mgr = bns.BNStatLoss(net, sync=True)
+        net(x)
+        loss = mgr.loss()
+        loss.backward()
+    return loss.item(), x.grad.numpy().copy()
+
+
+def test_synced_bn_stat_loss_is_the_global_batch_loss():
+    out = _spawn(_w_bns_sync, 2)
+    net = _sync_net()
+    x = _sync_batch().requires_grad_(True)
+    tap = bns_torch.StatTap(net)
+    net(x)
+    loss = tap.loss("trainer")
+    loss.backward()
+    assert abs(out[0][0] - loss.item()) <= 1e-6 * abs(loss.item()) and out[0][0] == out[1][0]
+    # every rank holds d(global loss)/d(its own images): together the global gradient
+    got = np.concatenate([out[0][1], out[1][1]])
+    np.testing.assert_allclose(got, x.grad.numpy(), rtol=1e-5, atol=1e-9)

@@ -197,3 +197,61 @@ def test_fusion_passes_on_a_quantised_student(mirror, net_name, side, expect):
     with torch.no_grad():
         assert torch.equal(student(x * 1.5), plain(x * 1.5))
     assert all(torch.equal(a, b) for a, b in zip(student.state_dict().values(), plain.state_dict().values()))
+
+
+# ------------------------------------------------------------------------------------------------ BN-statistics loss
+def _bn_net(seed=4):
+    torch.manual_seed(seed)
+    net = nn.Sequential(nn.Conv2d(3, 8, 3, padding=1, bias=False), nn.BatchNorm2d(8), nn.ReLU(),
+                        nn.Conv2d(8, 12, 3, stride=2, padding=1, bias=False), nn.BatchNorm2d(12), nn.ReLU(),
+                        nn.Conv2d(12, 5, 1, bias=False), nn.BatchNorm2d(5)).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    for m in net:
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.3)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+    return net
+
+
+def test_bn_stat_loss_manager_matches_the_hook_and_loss_of_the_reference(mirror):
+    """``bns.BNStatLoss`` (hooks, packed sums, token plumbing, fused backward) with shimmed kernels against the
+    reference's hook + loss lines restated by the oracle (trainer flavour and distillation parts)."""
+    from ood_dfq_b200 import bns
+    from oracle import bns_torch
+    net = _bn_net()
+    x = torch.randn(6, 3, 10, 10, generator=torch.Generator().manual_seed(9)) * 1.5 + 0.3
+    xr = x.clone().requires_grad_(True)
+    tap = bns_torch.StatTap(net)
+    out_ref = net(xr)
+    loss_ref = tap.loss("trainer")
+    (out_ref.square().mean() + 0.1 * loss_ref).backward()
+    tap.remove()
+    xo = x.clone().requires_grad_(True)
+    mgr = bns.BNStatLoss(net)
+    out = net(xo)
+    loss = mgr.loss()
+    (out.square().mean() + 0.1 * loss).backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item())
+    assert torch.allclose(xo.grad, xr.grad, rtol=1e-5, atol=1e-8)
+    m_term, v_term = mgr.parts()
+    assert abs((m_term + v_term).item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item())
+    for a, b in zip(mgr.means(), tap.means):
+        assert torch.allclose(a, b.detach(), rtol=1e-5, atol=1e-6)
+    for a, b in zip(mgr.variances(), tap.vars):
+        assert torch.allclose(a, b.detach(), rtol=1e-5, atol=1e-6)
+    # a pass in which a hooked module runs twice is refused, and the manager recovers
+    net(x), net[1](torch.randn(2, 8, 4, 4))
+    with pytest.raises(RuntimeError, match="fired"):
+        mgr.loss()
+    net(x)
+    assert abs(mgr.loss().item() - loss_ref.item()) <= 1e-6 * abs(loss_ref.item())
+    mgr.remove()
+    # the function-level drop-in for the two reductions of the hook
+    xs = x[:, :3].clone().requires_grad_(True)
+    mean, var = bns.bn_channel_stats(xs)
+    (mean.sum() + 2 * var.sum()).backward()
+    xt = x[:, :3].clone().requires_grad_(True)
+    mt, vt = bns_torch.channel_stats(xt)
+    (mt.sum() + 2 * vt.sum()).backward()
+    assert torch.allclose(mean, mt, rtol=1e-5, atol=1e-6) and torch.allclose(var, vt, rtol=1e-5)
+    assert torch.allclose(xs.grad, xt.grad, rtol=1e-5, atol=1e-8)
