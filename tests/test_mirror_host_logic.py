@@ -255,3 +255,27 @@ def test_bn_stat_loss_manager_matches_the_hook_and_loss_of_the_reference(mirror)
     (mt.sum() + 2 * vt.sum()).backward()
     assert torch.allclose(mean, mt, rtol=1e-5, atol=1e-6) and torch.allclose(var, vt, rtol=1e-5)
     assert torch.allclose(xs.grad, xt.grad, rtol=1e-5, atol=1e-8)
+
+
+def test_quantact_with_channel_statistics_in_the_same_pass(mirror):
+    """north_star (b): ``collect_channel_stats`` makes the quantising pass also leave per-channel sums of its input.
+    Output, range state and gradient must be those of the plain module in both modes; the statistics those of the hook."""
+    ours, plain = mirror.QuantAct(4), TWIN[0](4)
+    ours.collect_channel_stats = True
+    g = torch.Generator().manual_seed(8)
+    for step in range(4):
+        if step == 2:
+            ours.fix(), plain.fix()
+        x = torch.relu(torch.randn(5, 6, 7, 7, generator=g) * (1 + step)).requires_grad_(True)
+        xr = x.detach().clone().requires_grad_(True)
+        y, yr = ours(x), plain(xr)
+        assert same(y, yr), step
+        for name in ("x_min", "x_max", "beta_t"):
+            assert same(getattr(ours, name).reshape(-1), getattr(plain, name).reshape(-1)), (name, step)
+        y.sum().backward(), yr.sum().backward()
+        assert same(x.grad, xr.grad)
+        mean, var = ours.channel_mean_var()
+        assert torch.allclose(mean, x.detach().mean([0, 2, 3]), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(var, x.detach().var([0, 2, 3], unbiased=False), rtol=1e-5, atol=1e-6)
+    with pytest.raises(RuntimeError, match="no statistics"):
+        mirror.QuantAct(4).channel_mean_var()
