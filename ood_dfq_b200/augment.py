@@ -205,6 +205,11 @@ class DeviceShards:
     def set_epoch(self, epoch: int):
         self.epoch = epoch
 
+    @property
+    def sampler(self):
+        """``direct_dataload.sampler.set_epoch(epoch)`` (trainer_direct.py:447) keeps working on this object."""
+        return self
+
     def __len__(self):
         per_rank = -(-len(self.labels) // self.world)
         return per_rank // self.batch if self.drop_last else -(-per_rank // self.batch)

@@ -92,3 +92,22 @@ def test_grayscale_and_transform(tmp_path):
     crop = shards.ShardBatches(data, lab, batch=4, shuffle=False, transform=lambda t: t[:, :4, :4], out_size=(4, 4))
     xc, _ = next(iter(crop))
     assert xc.shape == (4, 3, 4, 4) and torch.equal(xc, x[:, :, :4, :4])
+
+
+def test_batch_stream_stands_in_for_the_dataloader_interface(tmp_path):
+    """What ``Trainer.train`` does with ``direct_dataload`` (trainer_direct.py:446-448, :492-497): ``.sampler.set_epoch``,
+    ``iter`` / ``next`` with re-iteration on exhaustion, ``len``."""
+    from ood_dfq_b200 import shards
+    rng = np.random.default_rng(1)
+    images, labels = rng.standard_normal((10, 3, 8, 8)).astype(np.float32), np.arange(10, dtype=np.int64)
+    stream = shards.ShardBatches(images, labels, batch=4, seed=3)
+    stream.sampler.set_epoch(2)
+    assert stream.epoch == 2 and len(stream) == 2
+    first = [y.clone() for _, y in stream]
+    stream.sampler.set_epoch(3)
+    second = [y.clone() for _, y in stream]
+    assert len(first) == len(second) == 2 and not all(torch.equal(a, b) for a, b in zip(first, second))
+    it = iter(stream)
+    next(it), next(it)
+    with pytest.raises(StopIteration):
+        next(it)
