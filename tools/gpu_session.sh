@@ -54,8 +54,8 @@ fi
 if has ncu; then
   # one full capture per headline family, on the microbenchmark (a single tensor per launch, a few launches)
   log "ncu --set full (tail, bn, stem, augment)"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'res_tail|bn_nhwc|bn_pool|crop_resize' -c 24 \
-      -o gpurun_out/full_kernels -f python tools/microbench.py --only tail,bn_fwd,bn_bwd,pool,augment --shapes 0,1 --iters 1 --flush none \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'res_tail|bn_nhwc|bn_pool|crop_resize' -c 80 \
+      -o gpurun_out/full_kernels -f python tools/microbench.py --only tail,bn_fwd,bn_bwd,pool,augment --shapes 0,1 --iters 1 --warmup 0 --flush none \
       > gpurun_out/ncu_full.log 2>&1
   log "ncu full exit $?"
   ncu -i gpurun_out/full_kernels.ncu-rep --page raw --csv \

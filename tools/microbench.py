@@ -35,12 +35,12 @@ class Timer:
     """flush = "write": fill a 512 MB buffer (L2 left full of DIRTY lines whose write-back then competes with the
     timed kernel -- the harsher convention); "read": sum a 512 MB buffer (L2 left full of clean foreign lines)."""
 
-    def __init__(self, iters, flush="write"):
-        self.iters, self.mode = iters, flush
+    def __init__(self, iters, flush="write", warmup=3):
+        self.iters, self.mode, self.warmup = iters, flush, warmup
         self.flush = torch.ones(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda") if flush != "none" else None
 
     def __call__(self, fn):
-        for _ in range(3):
+        for _ in range(self.warmup):
             fn()
         times = []
         for _ in range(self.iters):
@@ -65,11 +65,12 @@ def main():
     ap.add_argument("--json", default="")
     ap.add_argument("--shapes", default="", help="indices into the activation shape list, e.g. 0,4")
     ap.add_argument("--flush", choices=["write", "read", "none"], default="write")
+    ap.add_argument("--warmup", type=int, default=3, help="untimed launches per kernel (0 under ncu: one launch per variant)")
     args = ap.parse_args()
     only = set(args.only.split(","))
     shapes = ACT_SHAPES if not args.shapes else [ACT_SHAPES[int(i)] for i in args.shapes.split(",")]
     pk = peak()
-    timer = Timer(args.iters, flush=args.flush)
+    timer = Timer(args.iters, flush=args.flush, warmup=args.warmup)
     print(f"# L2 flush between timed launches: {args.flush}", flush=True)
     rows = []
 
