@@ -207,3 +207,45 @@ def test_synced_bn_stat_loss_is_the_global_batch_loss():
     # every rank holds d(global loss)/d(its own images): together the global gradient
     got = np.concatenate([out[0][1], out[1][1]])
     np.testing.assert_allclose(got, x.grad.numpy(), rtol=1e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------ packed reduce_minmax == the reference's own code
+_REF_TRAINER = "/root/reference/trainer_direct.py"
+
+
+def _w_reduce_minmax_vs_reference(rank, world):
+    """Each rank calibrates on its own data; then the reference's ``Trainer.reduce_minmax`` (its source, lines 368-374,
+    2 all-reduces per QuantAct) and the packed one-call version are applied to copies of the same MIRROR student."""
+    import textwrap
+    import types
+    import ood_dfq_b200
+    from ood_dfq_b200 import dist as ddist, nets, surgery
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    ood_dfq_b200.install()
+    ns = {"dist": dist}
+    exec("from quantization_utils.quant_modules import *", ns)
+    with open(_REF_TRAINER) as f:
+        exec(compile(textwrap.dedent("".join(f.readlines()[367:374]).expandtabs(4)), _REF_TRAINER, "exec"), ns)
+    torch.manual_seed(1)
+    student = surgery.quantize_model(nets.resnet20_cifar(num_classes=10), 4, 4)      # mirror classes, CPU buffers only
+    g = torch.Generator().manual_seed(200 + rank)
+    for m in student.modules():
+        if isinstance(m, qm.QuantAct):
+            m.x_min.copy_(-torch.rand(1, generator=g))
+            m.x_max.copy_(torch.rand(1, generator=g) * 5)
+    theirs, ours = copy.deepcopy(student), copy.deepcopy(student)
+    ns["reduce_minmax"](types.SimpleNamespace(model=types.SimpleNamespace(module=theirs)))
+    ddist.reduce_minmax(ours)
+    pack = lambda net: torch.stack([torch.cat([m.x_min, m.x_max]) for m in net.modules() if isinstance(m, qm.QuantAct)])
+    return pack(theirs).numpy(), pack(ours).numpy(), pack(student).numpy()
+
+
+@pytest.mark.skipif(not os.path.isfile(_REF_TRAINER), reason="reference tree not mounted (GPU box)")
+def test_packed_reduce_minmax_equals_the_reference_source_on_two_ranks():
+    out = _spawn(_w_reduce_minmax_vs_reference, 2)
+    for r in (0, 1):
+        theirs, ours, _ = out[r]
+        np.testing.assert_array_equal(theirs, ours)                     # bit-identical to the reference's own code
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    np.testing.assert_array_equal(out[0][1], ((out[0][2] + out[1][2]) / np.float32(2)).astype(np.float32))
+    assert not np.array_equal(out[0][2], out[1][2])
