@@ -52,6 +52,18 @@ def test_bad_arguments_return_error_codes_without_a_gpu(lib_path):
     assert lib.oodfq_bn_stats_forward(1, 0, 4, 4, None, 1, None, None, None, 0, 0, 1, None) == -1
     with pytest.raises(RuntimeError, match="null pointer"):
         _native.check(lib.oodfq_quant_params(None, None, None, None, 1, 4, None), "quant_params")
+    # batch assembly: (images, M, C_in, H, W, index, boxes, flips, out, N, C_out, OH, OW, flags, stream)
+    crop = lib.oodfq_crop_resize_flip
+    assert crop(1, 4, 3, 8, 8, 1, 1, 1, 1, 0, 3, 8, 8, 0, None) == 0               # empty batch: no launch
+    assert crop(None, 4, 3, 8, 8, 1, 1, 1, 1, 2, 3, 8, 8, 0, None) == -1 and b"null pointer" in lib.oodfq_last_error()
+    assert crop(1, 4, 3, 8, 8, 1, 1, 1, 1, 2, 1, 8, 8, 0, None) == -1 and b"channels 3 -> 1" in lib.oodfq_last_error()
+    assert crop(1, 0, 3, 8, 8, 1, 1, 1, 1, 2, 3, 8, 8, 0, None) == -1 and b"empty image set" in lib.oodfq_last_error()
+    assert crop(1, 4, 3, 8, 20000, 1, 1, 1, 1, 2, 3, 8, 8, 0, None) == -1 and b"sides above" in lib.oodfq_last_error()
+    assert crop(1, 4, 3, 8, 8, 1, 1, 1, 1, 40000, 3, 8192, 8192, 0, None) == -1 and b"2^31" in lib.oodfq_last_error()
+    back = lib.oodfq_crop_resize_flip_backward
+    assert back(1, None, 4, 3, 8, 8, 1, 1, 1, 2, 3, 8, 8, 0, None) == -1 and b"null pointer" in lib.oodfq_last_error()
+    assert back(1, 1, 4, 1, 8, 8, 1, 1, 1, 2, 2, 8, 8, 0, None) == -1 and b"channels 1 -> 2" in lib.oodfq_last_error()
+    assert back(1, 1, 4, 3, 8, 8, 1, 1, 1, 0, 3, 8, 8, 0, None) == 0
 
 
 def test_mirror_exports_reference_names():
