@@ -312,7 +312,11 @@ def main_ours(args):
         _native.reset_launch_count()
         qat(resident[0])
         launches_per_step = _native.launch_count()
-        qat = step_mod.GraphedStep(dstep, None) if kind == "distill" else step_mod.GraphedStep(qat, resident[0])
+        # --graph-collective (experiment, N > 1): capture the NCCL gradient all-reduce and the optimiser update inside the
+        # graph as well (default: replay forward + backward, run the exchange and the update eagerly behind it)
+        cap = True if (args.graph_collective and world > 1) else None
+        qat = step_mod.GraphedStep(dstep, None) if kind == "distill" else \
+            step_mod.GraphedStep(qat, resident[0], capture_update=cap)
     else:
         ops.PROFILE = []                            # event pairs around every streaming launch
     _native.reset_launch_count()
@@ -455,6 +459,7 @@ def main_ours(args):
                        "stem_space_to_depth": not (args.no_fuse or args.no_s2d),
                        "memory_format": "channels_last" if channels_last else "NCHW (as the reference)",
                        "cuda_graph": use_graph,
+                       "graph_collective": bool(use_graph and args.graph_collective and world > 1),
                        **({"distill_batch": "global (BN statistics all-reduced)" if (args.distill_sync and world > 1)
                            else "independent per rank", "distill_augment": bool(args.distill_augment)}
                           if kind == "distill" else {})},
@@ -544,6 +549,8 @@ def main():
     ap.add_argument("--e2e-input", choices=["host", "device_shards"], default="host",
                     help="end-to-end arm: pinned host batches copied every step (default, the reference's data flow) or "
                          "batches assembled on the device from an HBM-resident image set (opt-in)")
+    ap.add_argument("--graph-collective", action="store_true",
+                    help="N > 1: capture the gradient all-reduce and the optimiser update inside the CUDA graph (experiment)")
     ap.add_argument("--distill-augment", action="store_true",
                     help="distillation workload: apply the loop's per-image RandomResizedCrop / flip on every other "
                          "iteration (distill_data.py:205-227; eager)")
