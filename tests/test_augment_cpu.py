@@ -274,3 +274,34 @@ def test_oracle_gradient_reproduces_torchvision_autograd(golden):
     y = augment_torch.batch(leaf, c["index"], c["boxes"], c["flips"], c["out"].shape[2:], channels=3)
     (y * torch.from_numpy(c["cotangent"]).double()).sum().backward()
     assert torch.equal(leaf.grad.float(), torch.from_numpy(c["grad_exact"]))
+
+
+def test_kernel_body_random_geometries(host_kernel):
+    """hypothesis: any image / box / output geometry (up- AND down-scaling, one-pixel sides, flips, every channel mode
+    and layout) against the plain bilinear filter (``F.interpolate(..., antialias=False)``) evaluated in double."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import HealthCheck, given, settings, strategies as st
+
+    @settings(deadline=None, max_examples=150, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+    @given(seed=st.integers(0, 2 ** 31), h=st.integers(1, 33), w=st.integers(1, 33), oh=st.integers(1, 40),
+           ow=st.integers(1, 40), mode=st.sampled_from([(3, 3), (1, 3), (1, 1)]), nhwc=st.booleans(), src_nhwc=st.booleans())
+    def check(seed, h, w, oh, ow, mode, nhwc, src_nhwc):
+        rng = np.random.default_rng(seed)
+        c_in, c_out = mode
+        m, n = 3, 5
+        images = rng.standard_normal((m, c_in, h, w)).astype(np.float32)
+        index = rng.integers(0, m, n).astype(np.int64)
+        bh, bw = rng.integers(1, h + 1, n), rng.integers(1, w + 1, n)
+        top, left = rng.integers(0, h - bh + 1), rng.integers(0, w - bw + 1)
+        boxes = np.stack([top, left, bh, bw], 1).astype(np.int32)
+        flips = rng.integers(0, 2, n).astype(np.uint8)
+        y = host_kernel(images, index, boxes, flips, (oh, ow), c_out, nhwc, 4 if nhwc else 1, src_nhwc=src_nhwc)
+        want = torch.stack([augment_torch.resized_crop_flip(torch.from_numpy(images[index[j]]).double(), boxes[j], bool(flips[j]),
+                                                            (oh, ow), antialias=False)[:c_out] for j in range(n)]).float().numpy()
+        assert np.abs(y - want).max() <= 1e-6 * max(1.0, float(np.abs(images).max()))
+        # and the gradient scatter is the exact adjoint of that map
+        g = rng.standard_normal(y.shape).astype(np.float32)
+        gx = host_kernel.backward(g, images.shape, index, boxes, flips, nhwc, src_nhwc)
+        lhs, rhs = float((y.astype(np.float64) * g).sum()), float((images.astype(np.float64) * gx).sum())
+        assert abs(lhs - rhs) <= 2e-5 * max(1.0, float(np.abs(y.astype(np.float64) * g).sum()))
+    check()
