@@ -165,8 +165,6 @@ class BNStatLoss:
         self._sync, self._group = sync, process_group
         self._run = None          # the pass being collected
         self._last = None         # the pass loss() was last called on
-        self._rm = self._rv = None
-        self._stat_versions = None
         self._handles = [lay.module.register_forward_pre_hook(self._make_hook(i))
                          for i, lay in enumerate(self._layers)]
 
@@ -191,13 +189,13 @@ class BNStatLoss:
 
     # ------------------------------------------------------------------ evaluation
     def _packed_running_stats(self, device):
-        versions = tuple((lay.module.running_mean._version, lay.module.running_var._version,
-                          lay.module.running_mean.data_ptr()) for lay in self._layers)
-        if self._rm is None or versions != self._stat_versions or self._rm.device != device:
-            self._rm = torch.cat([lay.module.running_mean.detach().reshape(-1) for lay in self._layers]).float()
-            self._rv = torch.cat([lay.module.running_var.detach().reshape(-1) for lay in self._layers]).float()
-            self._stat_versions = versions
-        return self._rm, self._rv
+        # Re-packed on every evaluation (two small concatenations): a cache keyed on the buffers' version counters
+        # would miss writes made through ``.data`` -- which is exactly how the reference's BN-statistic delta
+        # correction rewrites running statistics (trainer_direct.py:292-297) -- and the loss would silently keep
+        # matching against the old targets.
+        rm = torch.cat([lay.module.running_mean.detach().reshape(-1) for lay in self._layers]).float()
+        rv = torch.cat([lay.module.running_var.detach().reshape(-1) for lay in self._layers]).float()
+        return rm.to(device), rv.to(device)
 
     def _reduce_and_evaluate(self, run):
         if self._sync:

@@ -62,6 +62,16 @@ def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _written(t: torch.Tensor) -> torch.Tensor:
+    """Tell torch that a kernel wrote into a caller-provided tensor through its raw pointer: an in-place op on an
+    empty slice bumps the (shared) version counter without launching anything.  Autograd's saved-tensor checks and the
+    caches keyed on ``_version`` (the space-to-depth stem input, fusion.py) then see the write."""
+    if t.dim() > 0:
+        with torch.no_grad():                 # only the counter matters: no autograd node for this no-op
+            t[:0].zero_()
+    return t
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -133,6 +143,8 @@ def elementwise(x, p0, p1, k, mode, symmetric=False, params_given=False, out=Non
                                        p0.contiguous().data_ptr(), p1.contiguous().data_ptr(), rows,
                                        int(k), mode, flags, _stream(x.device))
         N.check(rc, "fq_forward")
+    if out is not None:
+        _written(y)
     return (y, cd) if codes else y
 
 
@@ -647,6 +659,7 @@ def crop_resize_flip(images, index, boxes, flips, size, channels=None, channels_
     c_out = int(channels) if channels is not None else (3 if c_in == 1 else c_in)
     oh, ow = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
     fmt = torch.channels_last if channels_last else torch.contiguous_format
+    given = out is not None
     if out is None:
         out = torch.empty((n, c_out, oh, ow), dtype=torch.float32, device=images.device, memory_format=fmt)
     else:
@@ -661,7 +674,7 @@ def crop_resize_flip(images, index, boxes, flips, size, channels=None, channels_
                                              flips.data_ptr(), out.data_ptr(), n, c_out, oh, ow,
                                              (N.BN_NHWC if channels_last else 0) | src_flag, _stream(images.device))
         N.check(rc, "crop_resize_flip")
-    return out
+    return _written(out) if given else out
 
 
 def crop_resize_flip_backward(grad_out, like, index, boxes, flips, accumulate_into=None):
@@ -692,4 +705,4 @@ def crop_resize_flip_backward(grad_out, like, index, boxes, flips, accumulate_in
                                                       index.data_ptr(), boxes.data_ptr(), flips.data_ptr(), n, c_out, oh,
                                                       ow, out_flag | src_flag, _stream(like.device))
         N.check(rc, "crop_resize_flip_backward")
-    return grad_images
+    return _written(grad_images) if accumulate_into is not None else grad_images

@@ -279,3 +279,26 @@ def test_quantact_with_channel_statistics_in_the_same_pass(mirror):
         assert torch.allclose(var, x.detach().var([0, 2, 3], unbiased=False), rtol=1e-5, atol=1e-6)
     with pytest.raises(RuntimeError, match="no statistics"):
         mirror.QuantAct(4).channel_mean_var()
+
+
+def test_bn_stat_loss_sees_running_statistics_rewritten_through_data(mirror):
+    """The reference's BN-statistic delta correction rewrites running statistics with ``running_mean.data.copy_(...)``
+    (trainer_direct.py:292-297), which does not bump the buffer's version counter; the loss must follow anyway."""
+    from ood_dfq_b200 import bns
+    from oracle import bns_torch
+    net = _bn_net()
+    x = torch.randn(4, 3, 10, 10, generator=torch.Generator().manual_seed(2))
+    mgr = bns.BNStatLoss(net)
+    net(x)
+    before = mgr.loss().item()
+    for m in net:
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.data.copy_(m.running_mean * 0.5 + 1.0)
+            m.running_var.data.copy_(m.running_var * 2.0)
+    net(x)
+    after = mgr.loss().item()
+    mgr.remove()
+    tap = bns_torch.StatTap(net)
+    net(x)
+    want = tap.loss("trainer").item()
+    assert abs(after - want) <= 1e-6 * abs(want) and abs(after - before) > 1e-3
