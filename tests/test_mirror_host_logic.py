@@ -302,3 +302,59 @@ def test_bn_stat_loss_sees_running_statistics_rewritten_through_data(mirror):
     net(x)
     want = tap.loss("trainer").item()
     assert abs(after - want) <= 1e-6 * abs(want) and abs(after - before) > 1e-3
+
+
+class _PretendCudaNHWC:
+    """What ``_fused_setup`` asks of its input, answered like a channels_last fp32 CUDA tensor (decision logic only)."""
+    is_cuda, dtype = True, torch.float32
+
+    def dim(self):
+        return 4
+
+    def is_contiguous(self, memory_format=torch.contiguous_format):
+        return memory_format is torch.channels_last
+
+
+def test_fused_units_step_aside_for_foreign_hooks_and_calibration(mirror):
+    """The decision whether a residual unit takes its one-kernel tail is host logic: it must say yes for a frozen,
+    eval-mode, hook-free unit, and no as soon as (a) a BatchNorm it would bypass carries a forward hook -- the
+    reference's BN-statistic delta correction hangs one on EVERY BatchNorm (trainer_direct.py:176-199, :215-240) --,
+    (b) its QuantAct tracks the range again, (c) the model trains; the trainer's own feature hook on ``body`` is the
+    one hook it serves itself."""
+    from ood_dfq_b200 import fusion, nets, step, surgery
+    torch.manual_seed(2)
+    base = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(base)
+    student = surgery.quantize_model(base, 4, 4).eval()
+    x = torch.randn(2, 3, 32, 32)
+    with torch.no_grad():
+        student(x)
+    surgery.freeze_model(student)
+    fusion.fuse_eval_bn(student, x)
+    assert fusion.fuse_residual_tails(student, x) == 9
+    units = [m for m in student.modules() if isinstance(m, fusion._FusedUnitMixin)]
+    fake = _PretendCudaNHWC()
+    assert all(u._fused_setup(fake) is not None for u in units)
+    assert all(u._fused_setup(torch.zeros(1, 16, 4, 4)) is None for u in units)          # a CPU tensor: never
+
+    u = units[3]
+    plan = u._tail_plan
+    h = plan.bn1.register_forward_hook(lambda m, i, o: None)                              # (a) BSDC-style statistics hook
+    assert u._fused_setup(fake) is None and units[4]._fused_setup(fake) is not None
+    h.remove()
+    assert u._fused_setup(fake) is not None
+    qact = plan.act[1]
+    qact.unfix()                                                                          # (b) calibrating again
+    assert u._fused_setup(fake) is None
+    qact.fix()
+    student.train()                                                                       # (c) training mode
+    assert u._fused_setup(fake) is None
+    student.eval()
+    tap = step.FeatureTap(student, (nets.ResUnit,), fused=True)                           # the trainer's feature hook
+    setup = u._fused_setup(fake)
+    assert setup is not None and setup[2] == [tap]
+    other = u.body.register_forward_hook(lambda m, i, o: None)                            # any other hook there: no
+    assert u._fused_setup(fake) is None
+    other.remove()
+    qact.full_precision_flag = True                                                       # fp activations: fused, no quantiser
+    assert u._fused_setup(fake)[1] is None
