@@ -790,3 +790,102 @@ def test_fusion_passes_on_the_reference_model_quantised_by_the_reference_code(su
         with torch.no_grad():
             assert torch.equal(student(x), ref)
         assert list(student.state_dict()) == keys
+
+
+def test_reference_bsdc_correction_runs_on_a_fused_mirror_student(surgery_ns):
+    """``Trainer._init_bn_tracking`` / ``_create_bn_stat_hook`` / ``apply_bsdc_correction`` (trainer_direct.py:135-307,
+    the BN-statistic delta correction: forward hooks on EVERY BatchNorm of teacher and student, both nets switched to
+    ``train()`` under ``no_grad``, running statistics rewritten through ``.data.copy_``), compiled from the reference
+    file -- whose lines 275-277 are the space-indented ones that make the file as a whole a TabError; tabs are expanded
+    to 8 columns for this cut, nothing else is touched -- against (a) a student built from the reference's own
+    classes and (b) a mirror-built student AFTER all fusion passes (kernel launches swapped for oracle arithmetic).
+    The fused modules must step aside (training mode, hooked BatchNorms) so that every statistic BSDC collects and
+    every running statistic it writes is bit-identical."""
+    import importlib
+    from collections import OrderedDict
+
+    import cpu_ops_shim
+    from ood_dfq_b200 import fusion, nets
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    pkg = types.ModuleType("_live_reference_qu5")
+    pkg.__path__ = [os.path.join(REF, "quantization_utils")]
+    sys.modules["_live_reference_qu5"] = pkg
+    ref_qm = importlib.import_module("_live_reference_qu5.quant_modules")
+    sys.path.insert(0, REF)
+    try:
+        import models as ref_models
+    finally:
+        sys.path.remove(REF)
+    tpath = os.path.join(REF, "trainer_direct.py")
+    with open(tpath) as f:
+        text = "".join(f.readlines()[134:307])
+    ns = {"torch": torch, "nn": nn, "dist": dist, "OrderedDict": OrderedDict}
+    exec(compile(textwrap.dedent(text.expandtabs(8)), f"{tpath}:135-307", "exec"), ns)
+
+    class Wrapped(nn.Module):                                         # stands in for DistributedDataParallel (.module)
+        def __init__(self, module):
+            super().__init__()
+            self.module = module
+
+        def forward(self, x):
+            return self.module(x)
+
+    def trainer_for(classes, fuse):
+        torch.manual_seed(3)
+        # the reference's own 28x28 ResNet-18: BSDC pairs teacher and student BatchNorms BY NAME (:137-151), which only
+        # works where quantize_model keeps the names -- index-named Sequentials, as in models.py
+        teacher = ref_models.ResNet18(3, 9, img_size=28)
+        nets.perturb_bn_stats(teacher)
+        path = os.path.join(REF, "main_direct.py")
+        with open(path) as f:
+            tree = ast.parse(f.read(), filename=path)
+        cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ExperimentDesign")
+        fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "quantize_model")
+        qns = {"nn": nn, "torch": torch, "copy": copy}
+        qns.update({k: getattr(classes, k) for k in ("Quant_Conv2d", "Quant_Linear", "QuantAct")})
+        exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), qns)
+        exp = types.SimpleNamespace(settings=types.SimpleNamespace(qw=4, qa=4))
+        exp.quantize_model = types.MethodType(qns["quantize_model"], exp)
+        student = exp.quantize_model(copy.deepcopy(teacher)).eval()
+        teacher.eval()
+        x = torch.randn(2, 3, 28, 28, generator=torch.Generator().manual_seed(4))
+        with torch.no_grad():
+            student(x)                                                # calibrate once, then freeze
+        for m in student.modules():
+            if type(m).__name__ == "QuantAct":
+                m.fix()
+        if fuse:
+            for net in (student, teacher):
+                fusion.fuse_eval_bn(net, x)
+                assert fusion.fuse_residual_tails(net, x) == 8
+        t = types.SimpleNamespace(
+            model=Wrapped(student).eval(), model_teacher=Wrapped(teacher).eval(), logger=None, args=types.SimpleNamespace(local_rank="cpu"),
+            settings=types.SimpleNamespace(nEpochs=150), bsdc_num_batches=None, bsdc_correction_applied=False,
+            bn_layer_names=[], teacher_bn_layers=[], student_bn_layers=[], teacher_bn_source_stats=[], bsdc_delta_means=[],
+            bsdc_delta_vars=[], bsdc_teacher_ood_stats=[], bsdc_student_ood_stats=[])
+        for name in ("_init_bn_tracking", "_create_bn_stat_hook", "apply_bsdc_correction"):
+            setattr(t, name, types.MethodType(ns[name], t))
+        t._init_bn_tracking()
+        return t, student, teacher
+
+    g = torch.Generator().manual_seed(5)
+    loader = [(torch.randn(4, 3, 28, 28, generator=g) * 1.5 + 0.2, torch.zeros(4, dtype=torch.long)) for _ in range(3)]
+
+    ref_t, ref_student, ref_teacher = trainer_for(ref_qm, fuse=False)
+    ref_t.apply_bsdc_correction(loader, epoch=149)
+    with cpu_ops_shim.installed():
+        my_t, my_student, my_teacher = trainer_for(qm, fuse=True)
+        assert any(isinstance(m, fusion._FusedUnitMixin) for m in my_student.modules())
+        before = {k: v.clone() for k, v in my_student.state_dict().items()}
+        my_t.apply_bsdc_correction(loader, epoch=149)
+    assert len(ref_t.student_bn_layers) == len(my_t.student_bn_layers) == 20 and my_t.bsdc_correction_applied
+    sd_ref, sd_my = ref_student.state_dict(), my_student.state_dict()
+    assert list(sd_ref) == list(sd_my)
+    for k in sd_ref:
+        assert torch.equal(sd_ref[k].reshape(-1), sd_my[k].reshape(-1)), k
+    for a, b in zip(ref_t.bsdc_delta_means + ref_t.bsdc_delta_vars, my_t.bsdc_delta_means + my_t.bsdc_delta_vars):
+        assert torch.equal(a, b)
+    assert any(k.endswith("running_mean") and not torch.equal(before[k], sd_my[k]) for k in sd_my)   # BSDC did write
+    for (k, a), (_, b) in zip(ref_teacher.state_dict().items(), my_teacher.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert not my_student.training and not my_teacher.training
