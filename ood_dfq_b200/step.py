@@ -385,12 +385,30 @@ class GraphedStep:
                 step(*args)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._body, self._args = body, args
+        self._capture()
+
+    def _capture(self):
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.static_out = body(*args)
+            self.static_out = self._body(*self._args)
         self._bank.invalidate()
+        self._hyper_at_capture = self._hyper()
+
+    def _hyper(self):
+        """Python-number hyper-parameters of an optimiser whose update is INSIDE the graph.  They are baked into the
+        captured launches (``alpha=-lr`` of the foreach update), so ``Trainer.update_lr`` (trainer_direct.py:122-133,
+        ``param_group['lr'] = ...`` once per epoch) would otherwise be ignored by every replay.  Tensor-valued ones
+        (the capturable Adam of the distillation step) live on the device and need no tracking."""
+        opt = getattr(self.step, "opt", None)
+        if opt is None or self._eager_tail is not None:
+            return None
+        return [tuple((k, v) for k, v in sorted(g.items()) if k != "params" and isinstance(v, (bool, int, float)))
+                for g in opt.param_groups]
 
     def __call__(self, batch=None, non_blocking=True):
+        if self._hyper_at_capture is not None and self._hyper() != self._hyper_at_capture:
+            self._capture()                                       # a learning-rate milestone: capture once more
         if batch is not None and self.static_in is not None:      # steps without an input (distillation) ignore it
             self.static_in.copy_(batch, non_blocking=non_blocking)
         self.graph.replay()

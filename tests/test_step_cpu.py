@@ -71,3 +71,88 @@ def test_device_side_plateau_scheduler_follows_torchs():
             reductions += int(after != before)
             assert abs(after - float(lr)) <= 1e-7 * after, (seed, it, after, float(lr))
         assert reductions >= 3 and float(lr) >= 1e-4 * (1 - 1e-6)
+
+
+def test_graphed_step_recaptures_when_the_learning_rate_changes(monkeypatch):
+    """Host logic of ``GraphedStep`` with the CUDA-graph machinery replaced by stand-ins (capture = run the body once,
+    replay = nothing): a change of ``param_group['lr']`` -- ``Trainer.update_lr`` does that every epoch,
+    trainer_direct.py:122-133 -- must trigger exactly one new capture when the optimiser update is inside the graph,
+    and none when it runs eagerly behind the graph or when the learning rate is a device tensor."""
+    from ood_dfq_b200 import step
+
+    class FakeGraph:
+        replays = 0
+
+        def replay(self):
+            FakeGraph.replays += 1
+
+    class FakeCtx:
+        def __init__(self, *a):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    class FakeStream:
+        def wait_stream(self, other):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", FakeGraph)
+    monkeypatch.setattr(torch.cuda, "graph", FakeCtx)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "stream", FakeCtx)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: FakeStream())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+
+    class Toy:
+        """compute / apply split like QATStep, counting body runs."""
+
+        def __init__(self, lr):
+            self.w = torch.zeros(3, requires_grad=True)
+            self.opt = torch.optim.SGD([self.w], lr=lr, momentum=0.9)
+            self.group, self.computes = None, 0
+
+        def compute(self, x):
+            self.computes += 1
+            return x.sum()
+
+        def apply(self):
+            pass
+
+        def __call__(self, x):
+            out = self.compute(x)
+            self.apply()
+            return out
+
+    x = torch.ones(2)
+    toy = Toy(0.1)
+    g = step.GraphedStep(toy, x, warmup=1)                       # world 1: update inside the graph
+    captured = toy.computes
+    g(x), g(x)
+    assert toy.computes == captured and FakeGraph.replays == 2    # replays only
+    toy.opt.param_groups[0]["lr"] = 0.01                          # an epoch boundary
+    g(x)
+    assert toy.computes == captured + 1                           # one new capture ...
+    g(x)
+    assert toy.computes == captured + 1                           # ... and replays again
+    toy.opt.param_groups[0]["weight_decay"] = 1e-4
+    g(x)
+    assert toy.computes == captured + 2
+
+    toy2 = Toy(0.1)
+    g2 = step.GraphedStep(toy2, x, warmup=1, capture_update=False)   # update runs eagerly behind the graph
+    n = toy2.computes
+    toy2.opt.param_groups[0]["lr"] = 0.5
+    g2(x)
+    assert toy2.computes == n
+
+    toy3 = Toy(0.1)
+    toy3.opt.param_groups[0]["lr"] = torch.tensor(0.1)             # device-side learning rate: nothing to track
+    g3 = step.GraphedStep(toy3, x, warmup=1)
+    n = toy3.computes
+    toy3.opt.param_groups[0]["lr"].mul_(0.1)
+    g3(x)
+    assert toy3.computes == n
