@@ -386,7 +386,15 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self._body, self._args = body, args
+        # what the captured launches depend on besides tensors: the mode flags the modules branch on in Python
+        self._nets = [v for v in vars(step).values() if isinstance(v, nn.Module)]
+        self._flagged = [m for net in self._nets for m in net.modules() if hasattr(m, "running_stat")]
         self._capture()
+        self._modes_at_capture = self._modes()
+
+    def _modes(self):
+        return (tuple(net.training for net in self._nets),
+                tuple((m.running_stat, getattr(m, "full_precision_flag", False)) for m in self._flagged))
 
     def _capture(self):
         self.graph = torch.cuda.CUDAGraph()
@@ -409,6 +417,11 @@ class GraphedStep:
     def __call__(self, batch=None, non_blocking=True):
         if self._hyper_at_capture is not None and self._hyper() != self._hyper_at_capture:
             self._capture()                                       # a learning-rate milestone: capture once more
+        if self._modes() != self._modes_at_capture:
+            # freeze_model / unfreeze_model / train() / eval() change which kernels a forward launches; a replay would
+            # keep running the old ones (e.g. frozen ranges while the caller believes it is calibrating)
+            raise RuntimeError("GraphedStep: the models' mode flags (train/eval, QuantAct.running_stat, "
+                               "full_precision_flag) changed since the graph was captured; build a new GraphedStep")
         if batch is not None and self.static_in is not None:      # steps without an input (distillation) ignore it
             self.static_in.copy_(batch, non_blocking=non_blocking)
         self.graph.replay()

@@ -156,3 +156,46 @@ def test_graphed_step_recaptures_when_the_learning_rate_changes(monkeypatch):
     toy3.opt.param_groups[0]["lr"].mul_(0.1)
     g3(x)
     assert toy3.computes == n
+
+
+def test_graphed_step_refuses_to_replay_after_a_mode_change(monkeypatch):
+    """freeze / unfreeze / train / eval decide in Python which kernels a forward launches; a captured graph must not be
+    replayed across such a change (same stand-in graph machinery as above)."""
+    from ood_dfq_b200 import step
+
+    class FakeGraph:
+        def replay(self):
+            pass
+
+    class FakeCtx:
+        def __init__(self, *a):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    class FakeStream:
+        def wait_stream(self, other):
+            pass
+
+    for name, obj in (("CUDAGraph", FakeGraph), ("graph", FakeCtx), ("Stream", FakeStream), ("stream", FakeCtx)):
+        monkeypatch.setattr(torch.cuda, name, obj)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: FakeStream())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    import pytest
+    teacher, student, _ = _pair()
+    qat = step.QATStep(student, teacher, lr=1e-3, unit_types=(nets.ResUnit,))
+    g = step.GraphedStep(qat, torch.randn(2, 3, 32, 32), warmup=0)
+    g(torch.randn(2, 3, 32, 32))
+    act = next(m for m in student.modules() if isinstance(m, fq_torch.OracleQuantAct))
+    act.unfix()
+    with pytest.raises(RuntimeError, match="mode flags"):
+        g(torch.randn(2, 3, 32, 32))
+    act.fix()
+    g(torch.randn(2, 3, 32, 32))
+    student.train()
+    with pytest.raises(RuntimeError, match="mode flags"):
+        g(torch.randn(2, 3, 32, 32))
