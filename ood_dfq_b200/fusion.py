@@ -86,7 +86,18 @@ class _ReLUQuantSTE(torch.autograd.Function):
         return torch.ops.aten.threshold_backward(grad_y, x, 0), None
 
 
-class FusedReLUQuant(nn.Sequential):
+class _WalkableSequential(nn.Sequential):
+    """The reference's ``freeze_model`` / ``unfreeze_model`` (main_direct.py:486-516) recurse into an EXACT
+    ``nn.Sequential`` through ``named_children()`` and into anything else through ``dir()`` + ``getattr``.  A class-swapped
+    Sequential is "anything else", and ``Module.__dir__`` hides children whose names start with a digit -- the ``'1'`` that
+    holds the QuantAct -- so that walk would silently stop short of it.  Listing the child keys keeps every QuantAct
+    reachable (``getattr(seq, '1')`` already works)."""
+
+    def __dir__(self):
+        return list(super().__dir__()) + [k for k in self._modules if k[:1].isdigit()]
+
+
+class FusedReLUQuant(_WalkableSequential):
     """A ``Sequential(ReLU, QuantAct)`` that no BatchNorm could absorb (it follows a residual add): still one
     kernel instead of two once the range is frozen."""
 
@@ -151,7 +162,7 @@ class AbsorbedPool(nn.MaxPool2d):
         return nn.MaxPool2d.forward(self, x)
 
 
-class AbsorbedTail(nn.Sequential):
+class AbsorbedTail(_WalkableSequential):
     """The ``Sequential(ReLU, QuantAct)`` whose work the preceding FusedEvalBN has taken over."""
 
     def forward(self, x):

@@ -790,6 +790,13 @@ def test_fusion_passes_on_the_reference_model_quantised_by_the_reference_code(su
         with torch.no_grad():
             assert torch.equal(student(x), ref)
         assert list(student.state_dict()) == keys
+        # the reference's attribute walk (dir() / getattr over every module, exact-type checks) still reaches every
+        # QuantAct through the class-swapped containers
+        acts = [m for m in student.modules() if type(m).__name__ == "QuantAct"]
+        exp.unfreeze_model(student)
+        assert len(acts) == 17 and all(m.running_stat for m in acts)
+        exp.freeze_model(student)
+        assert not any(m.running_stat for m in acts)
 
 
 def test_reference_bsdc_correction_runs_on_a_fused_mirror_student(surgery_ns):
@@ -889,3 +896,31 @@ def test_reference_bsdc_correction_runs_on_a_fused_mirror_student(surgery_ns):
     for (k, a), (_, b) in zip(ref_teacher.state_dict().items(), my_teacher.state_dict().items()):
         assert torch.equal(a, b), k
     assert not my_student.training and not my_teacher.training
+
+
+@pytest.mark.parametrize("net_name,side", [("resnet18_imagenet", 224), ("resnet20_cifar", 32), ("resnet18_small", 28)])
+def test_reference_freeze_walk_reaches_every_quantact_of_a_fused_model(surgery_ns, net_name, side):
+    """``freeze_model`` / ``unfreeze_model`` run after (and before) EVERY epoch (main_direct.py:533-538) on whatever the
+    fusion passes left behind: the walk must still reach each QuantAct -- also through a DDP-style wrapper."""
+    import cpu_ops_shim
+    from ood_dfq_b200 import fusion, nets
+    torch.manual_seed(1)
+    base = nets.resnet18_small(3, 9) if net_name == "resnet18_small" else getattr(nets, net_name)(num_classes=10)
+    exp = experiment(surgery_ns, 4, 4)
+    x = torch.randn(2, 3, side, side)
+    with cpu_ops_shim.installed():
+        student = exp.quantize_model(base).eval()
+        with torch.no_grad():
+            student(x)
+        exp.freeze_model(student)
+        fusion.fuse_eval_bn(student, x)
+        fusion.fuse_residual_tails(student, x)
+        fusion.space_to_depth_stem(student, x)
+    acts = [m for m in student.modules() if type(m).__name__ == "QuantAct"]
+    wrapped = nn.Sequential()                                         # any container with a `.module`-like child
+    wrapped.module = student
+    for target in (student, wrapped):
+        exp.unfreeze_model(target)
+        assert len(acts) >= 17 and all(m.running_stat for m in acts), net_name
+        exp.freeze_model(target)
+        assert not any(m.running_stat for m in acts), net_name
