@@ -110,10 +110,19 @@ class FusedReLUQuant(_WalkableSequential):
 
 
 class AbsorbedReLU(nn.ReLU):
-    """A plain ReLU whose work the preceding FusedEvalBN has taken over (full-precision teacher)."""
+    """A plain ReLU whose work the preceding FusedEvalBN has taken over (full-precision teacher).
+
+    It only passes its input through for the call its BatchNorm has just announced (``_done``): should that
+    BatchNorm ever be replaced behind the pass's back -- ``convert_sync_batchnorm`` after fusion builds fresh modules
+    -- the ReLU simply does its own work again instead of silently vanishing from the network."""
+
+    _done = False
 
     def forward(self, x):
-        return x
+        if self._done:
+            self._done = False
+            return x
+        return nn.ReLU.forward(self, x)
 
     def run(self, x):
         return nn.ReLU.forward(self, x)
@@ -163,10 +172,16 @@ class AbsorbedPool(nn.MaxPool2d):
 
 
 class AbsorbedTail(_WalkableSequential):
-    """The ``Sequential(ReLU, QuantAct)`` whose work the preceding FusedEvalBN has taken over."""
+    """The ``Sequential(ReLU, QuantAct)`` whose work the preceding FusedEvalBN has taken over (same ``_done``
+    handshake as ``AbsorbedReLU``: without its BatchNorm's announcement it runs ReLU and QuantAct itself)."""
+
+    _done = False
 
     def forward(self, x):
-        return x
+        if self._done:
+            self._done = False
+            return x
+        return nn.Sequential.forward(self, x)
 
     def run(self, x):
         return nn.Sequential.forward(self, x)
@@ -191,6 +206,8 @@ class _FusedEvalMixin:
             and self.track_running_stats and self.running_mean is not None
         if has_tail and qact is not None and (qact.running_stat or type(qact) is not QuantAct):
             fusable = False                       # still calibrating (or not the asymmetric QuantAct): exact old path
+        if has_tail:
+            self._tail._done = True               # the tail module right behind this BatchNorm hands our result through
         if not fusable:
             y = super().forward(x)
             return self._tail.run(y) if has_tail else y

@@ -81,3 +81,34 @@ def test_space_to_depth_pass_on_cpu_and_weight_reindexing():
         out = F.conv2d(xs, fusion._s2d_weight(w), None, 1, 0)
         want = F.conv2d(xx, w, None, 2, p)
         assert out.shape == want.shape and torch.allclose(out, want, rtol=1e-4, atol=1e-4)
+
+
+def test_absorbed_modules_do_their_own_work_without_their_batchnorm():
+    """An absorbed ReLU / Sequential(ReLU, QuantAct) passes its input through only for the call its BatchNorm has just
+    announced.  (a) torchvision's BasicBlock uses ONE ReLU module behind bn1 and behind the residual add: the second
+    use must stay a ReLU.  (b) ``convert_sync_batchnorm`` after the pass replaces the fused BatchNorms by fresh
+    modules: the absorbed ReLUs must go back to work instead of vanishing from the network."""
+    import pytest
+    tv = pytest.importorskip("torchvision")
+    torch.manual_seed(0)
+    model = tv.models.resnet18(num_classes=10).eval()
+    nets.perturb_bn_stats(model)
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        ref = model(x)
+    fusion.fuse_eval_bn(model, x)
+    assert sum(isinstance(m, fusion.AbsorbedReLU) for m in model.modules()) == 9      # stem + one shared ReLU per block
+    with torch.no_grad():
+        assert torch.equal(model(x), ref)
+    sync = torch.nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(model)).eval()
+    assert not any(isinstance(m, fusion.FusedEvalBN) for m in sync.modules())
+    with torch.no_grad():
+        assert torch.allclose(sync(x), ref, rtol=1e-5, atol=1e-6)
+
+    student, x2 = _student("resnet20_cifar")
+    with torch.no_grad():
+        ref2 = student(x2)
+    fusion.fuse_eval_bn(student, x2)
+    sync2 = torch.nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(student)).eval()
+    with torch.no_grad():
+        assert torch.equal(student(x2), ref2) and torch.allclose(sync2(x2), ref2, rtol=1e-5, atol=1e-6)
