@@ -416,6 +416,12 @@ class _FusedUnitMixin:
             return None
         if not x.is_contiguous(memory_format=torch.channels_last):
             return None
+        # the plan holds module references: if something re-built part of the unit after the pass (e.g.
+        # ``convert_sync_batchnorm`` swaps every BatchNorm for a fresh module), the class's own forward -- which goes
+        # through the attributes -- is the only correct one
+        live = {id(m) for m in self.modules()}
+        if any(m is not None and id(m) not in live for m in (p.conv, p.bn1, p.idconv, p.bn2, p.act, *p.front)):
+            return None
         for bn in (p.bn1, p.bn2):
             if bn is None:
                 continue

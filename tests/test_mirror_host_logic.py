@@ -358,3 +358,27 @@ def test_fused_units_step_aside_for_foreign_hooks_and_calibration(mirror):
     other.remove()
     qact.full_precision_flag = True                                                       # fp activations: fused, no quantiser
     assert u._fused_setup(fake)[1] is None
+
+
+def test_fused_units_notice_when_their_modules_were_rebuilt(mirror):
+    """``convert_sync_batchnorm`` after the passes replaces every BatchNorm object; a fused unit whose plan still points
+    at the old ones must take its class's own forward (which goes through the attributes)."""
+    from ood_dfq_b200 import fusion, nets, surgery
+    torch.manual_seed(2)
+    student = surgery.quantize_model(nets.resnet20_cifar(num_classes=10), 4, 4).eval()
+    x = torch.randn(2, 3, 32, 32)
+    with torch.no_grad():
+        student(x)
+    surgery.freeze_model(student)
+    fusion.fuse_eval_bn(student, x)
+    fusion.fuse_residual_tails(student, x)
+    with torch.no_grad():
+        ref = student(x)
+    fake = _PretendCudaNHWC()
+    units = [m for m in student.modules() if isinstance(m, fusion._FusedUnitMixin)]
+    assert all(u._fused_setup(fake) is not None for u in units)
+    sync = torch.nn.SyncBatchNorm.convert_sync_batchnorm(student).eval()
+    units = [m for m in sync.modules() if isinstance(m, fusion._FusedUnitMixin)]
+    assert len(units) == 9 and all(u._fused_setup(fake) is None for u in units)
+    with torch.no_grad():
+        assert torch.allclose(sync(x), ref, rtol=1e-5, atol=1e-6)
