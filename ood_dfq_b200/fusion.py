@@ -275,35 +275,67 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
         for h in handles:
             h.remove()
         made.clear()
+    swapped, linked = [], []                      # (object, class before the pass) / BatchNorms given a tail or pool
+
+    def swap(obj, cls):
+        if type(obj) is not cls:
+            swapped.append((obj, type(obj)))
+            obj.__class__ = cls
+
     for b in bns:
-        b.__class__ = _FUSED_CLASS.get(type(b), type(b))
+        swap(b, _FUSED_CLASS.get(type(b), type(b)))
+    n_bn_swaps = len(swapped)
     taken = set()
     for b, t in pairs:
         if id(b) in taken or getattr(b, "_tail", None) is not None:
             continue                              # one tail per BatchNorm
         if type(t) is nn.ReLU:
-            t.__class__ = AbsorbedReLU
+            swap(t, AbsorbedReLU)
         elif type(t[0]) is nn.ReLU6:
             continue                              # ReLU6 clamps from above as well: leave it unfused
         else:
-            t.__class__ = AbsorbedTail
+            swap(t, AbsorbedTail)
         object.__setattr__(b, "_tail", t)
+        linked.append(b)
         taken.add(id(b))
     for b, p in stems:
         if getattr(b, "_tail", None) is not None and getattr(b, "_pool", None) is None:
-            p.__class__ = AbsorbedPool
+            swap(p, AbsorbedPool)
             object.__setattr__(b, "_pool", p)
     if absorb_tails:
         for t in tails:                           # ReLU + QuantAct behind a residual add: fuse the pair itself
             if type(t) is nn.Sequential and type(t[0]) is nn.ReLU:
-                t.__class__ = FusedReLUQuant
-    if verify and ref_out is not None:
+                swap(t, FusedReLUQuant)
+
+    def deviation():
         with torch.no_grad():
             new_out = model(example)
-        err = (new_out - ref_out).abs().max().item()
-        scale = ref_out.abs().max().item() + 1e-12
+        return (new_out - ref_out).abs().max().item(), ref_out.abs().max().item() + 1e-12
+
+    if verify and ref_out is not None:
+        err, scale = deviation()
+        if not err <= 0.05 * scale and linked:
+            # Absorbing an activation is only right when the BatchNorm's output has no other consumer (the trace sees
+            # who reads the tensor first, not who else does).  Keep the always-safe part -- the BatchNorms themselves --
+            # and put the activations back.
+            import warnings
+            for b in linked:
+                object.__setattr__(b, "_tail", None)
+                object.__setattr__(b, "_pool", None)
+            for obj, cls in swapped[n_bn_swaps:]:
+                obj.__class__ = cls
+            del swapped[n_bn_swaps:]
+            first = err
+            err, scale = deviation()
+            if err <= 0.05 * scale:
+                warnings.warn(f"fuse_eval_bn: absorbing the activations changed the result ({first:.3e} vs scale {scale:.3e}); "
+                              "only the BatchNorms themselves were fused")
         if not err <= 0.05 * scale:
-            raise RuntimeError(f"fuse_eval_bn: fused model deviates from the original ({err:.3e} vs scale {scale:.3e})")
+            for obj, cls in swapped:              # leave the model exactly as it was handed in
+                obj.__class__ = cls
+            model.train(was_training)
+            raise RuntimeError(f"fuse_eval_bn: fused model deviates from the original ({err:.3e} vs scale {scale:.3e}); "
+                               "the pass has been undone")
     model.train(was_training)
     return model
 

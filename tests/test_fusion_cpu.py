@@ -112,3 +112,33 @@ def test_absorbed_modules_do_their_own_work_without_their_batchnorm():
     sync2 = torch.nn.SyncBatchNorm.convert_sync_batchnorm(copy.deepcopy(student)).eval()
     with torch.no_grad():
         assert torch.equal(student(x2), ref2) and torch.allclose(sync2(x2), ref2, rtol=1e-5, atol=1e-6)
+
+
+def test_pass_keeps_only_the_safe_part_when_a_batchnorm_output_has_two_readers():
+    """The trace sees who reads a BatchNorm's output first, not who else does: absorbing the ReLU would hand the other
+    reader post-ReLU values.  The self-check notices, puts the activations back, keeps the BatchNorm fusion and warns;
+    results are unchanged."""
+    import pytest
+
+    class TwoReaders(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(3, 6, 3, padding=1)
+            self.bn = torch.nn.BatchNorm2d(6)
+            self.relu = torch.nn.ReLU()
+            self.mix = torch.nn.Conv2d(6, 4, 1)
+
+        def forward(self, x):
+            y = self.bn(self.conv(x))
+            return self.mix(self.relu(y) - 0.5 * y)               # y is read again after the ReLU
+    torch.manual_seed(0)
+    m = TwoReaders().eval()
+    nets.perturb_bn_stats(m)
+    x = torch.randn(2, 3, 8, 8)
+    with torch.no_grad():
+        ref = m(x)
+    with pytest.warns(UserWarning, match="only the BatchNorms"):
+        fusion.fuse_eval_bn(m, x)
+    assert type(m.bn) is fusion.FusedEvalBN and type(m.relu) is torch.nn.ReLU and m.bn._tail is None
+    with torch.no_grad():
+        assert torch.equal(m(x), ref)
