@@ -227,6 +227,39 @@ def _is_stem_pool(m):
             and two(m.dilation) == (1, 1) and not m.ceil_mode and not m.return_indices)
 
 
+def _single_reader(model, example, candidates):
+    """ids of the BatchNorms among ``candidates`` whose output is read by exactly ONE autograd node in a forward of
+    ``example`` (None when that cannot be established).  Absorbing the activation behind a BatchNorm changes what the
+    BatchNorm returns, which is only right if nothing else reads that tensor: ``y = bn(x); relu(y) + 0.25 * y`` has two
+    readers, and a deviation of a per cent at the output is not something a tolerance-based self-check can tell from a
+    flipped quantisation code.  (An in-place ReLU rewrites ``y`` for every later reader anyway: one reader.)"""
+    from collections import Counter
+    nodes, handles = {}, []
+    try:
+        handles = [b.register_forward_hook(lambda mod, i, o: nodes.__setitem__(id(mod), getattr(o, "grad_fn", None)))
+                   for b in candidates]
+        with torch.enable_grad():
+            out = model(example.detach().clone().requires_grad_(True))
+    except Exception:
+        return None
+    finally:
+        for h in handles:
+            h.remove()
+    if not isinstance(out, torch.Tensor) or out.grad_fn is None:
+        return None
+    readers, seen, stack = Counter(), set(), [out.grad_fn]
+    while stack:
+        node = stack.pop()
+        if node in seen:
+            continue
+        seen.add(node)
+        for fn, _ in node.next_functions:
+            if fn is not None:
+                readers[fn] += 1
+                stack.append(fn)
+    return {id(b) for b in candidates if nodes.get(id(b)) is not None and readers[nodes[id(b)]] == 1}
+
+
 def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=True, verify=True):
     """Apply the fusion in place and return the model.  ``example``: a (small) input batch used to trace which
     BatchNorm feeds which ``Sequential(ReLU, QuantAct)``; without it only the BatchNorms themselves are fused."""
@@ -260,6 +293,10 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
         for h in handles:
             h.remove()
         produced.clear()
+        if pairs and example.is_floating_point():
+            single = _single_reader(model, example, list({id(b): b for b, _ in pairs}.values()))
+            if single is not None:
+                pairs = [(b, t) for b, t in pairs if id(b) in single]
     # stem: a MaxPool2d(3, 2, 1) fed directly by a tail (found with a second traced forward)
     stems = []
     pools = [m for m in model.modules() if type(m) is nn.MaxPool2d and _is_stem_pool(m)]

@@ -114,29 +114,47 @@ def test_absorbed_modules_do_their_own_work_without_their_batchnorm():
         assert torch.equal(student(x2), ref2) and torch.allclose(sync2(x2), ref2, rtol=1e-5, atol=1e-6)
 
 
-def test_pass_keeps_only_the_safe_part_when_a_batchnorm_output_has_two_readers():
+def test_pass_keeps_only_the_safe_part_when_a_batchnorm_output_has_two_readers(monkeypatch):
     """The trace sees who reads a BatchNorm's output first, not who else does: absorbing the ReLU would hand the other
-    reader post-ReLU values.  The self-check notices, puts the activations back, keeps the BatchNorm fusion and warns;
-    results are unchanged."""
+    reader post-ReLU values.  The reader count taken from the autograd graph of the example declines such a pair up
+    front; should that analysis be unavailable, the self-check notices, puts the activations back, keeps the BatchNorm
+    fusion and warns.  Either way the results are unchanged."""
+    import warnings
+
     import pytest
 
     class TwoReaders(torch.nn.Module):
-        def __init__(self):
+        def __init__(self, scale):
             super().__init__()
             self.conv = torch.nn.Conv2d(3, 6, 3, padding=1)
             self.bn = torch.nn.BatchNorm2d(6)
             self.relu = torch.nn.ReLU()
             self.mix = torch.nn.Conv2d(6, 4, 1)
+            self.scale = scale
 
         def forward(self, x):
             y = self.bn(self.conv(x))
-            return self.mix(self.relu(y) - 0.5 * y)               # y is read again after the ReLU
-    torch.manual_seed(0)
-    m = TwoReaders().eval()
-    nets.perturb_bn_stats(m)
-    x = torch.randn(2, 3, 8, 8)
-    with torch.no_grad():
-        ref = m(x)
+            return self.mix(self.relu(y) - self.scale * y)        # y is read again after the ReLU
+
+    def build(scale):
+        torch.manual_seed(0)
+        m = TwoReaders(scale).eval()
+        nets.perturb_bn_stats(m)
+        x = torch.randn(2, 3, 8, 8)
+        with torch.no_grad():
+            return m, x, m(x)
+
+    for scale in (0.5, 0.01):                                     # 0.01: far below what an output tolerance could see
+        m, x, ref = build(scale)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")                        # declined up front: nothing to warn about
+            fusion.fuse_eval_bn(m, x)
+        assert type(m.bn) is fusion.FusedEvalBN and type(m.relu) is torch.nn.ReLU and m.bn._tail is None
+        with torch.no_grad():
+            assert torch.equal(m(x), ref)
+
+    monkeypatch.setattr(fusion, "_single_reader", lambda *a: None)   # analysis unavailable: the backstop
+    m, x, ref = build(0.5)
     with pytest.warns(UserWarning, match="only the BatchNorms"):
         fusion.fuse_eval_bn(m, x)
     assert type(m.bn) is fusion.FusedEvalBN and type(m.relu) is torch.nn.ReLU and m.bn._tail is None

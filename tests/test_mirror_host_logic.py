@@ -382,3 +382,91 @@ def test_fused_units_notice_when_their_modules_were_rebuilt(mirror):
     assert len(units) == 9 and all(u._fused_setup(fake) is None for u in units)
     with torch.no_grad():
         assert torch.allclose(sync(x), ref, rtol=1e-5, atol=1e-6)
+
+
+def _random_net(rng, width=8):
+    """A small CNN assembled from the patterns the passes have to cope with (and some they must leave alone)."""
+    class Res(nn.Module):
+        def __init__(self, c, style):
+            super().__init__()
+            self.conv1, self.bn1 = nn.Conv2d(c, c, 3, padding=1, bias=False), nn.BatchNorm2d(c)
+            self.conv2, self.bn2 = nn.Conv2d(c, c, 3, padding=1, bias=False), nn.BatchNorm2d(c)
+            self.style = style
+            if style == "shared":                              # torchvision BasicBlock: one ReLU module, two sites
+                self.relu = nn.ReLU(inplace=True)
+            else:
+                self.relu1, self.relu2 = nn.ReLU(inplace=True), nn.ReLU(inplace=bool(rng.integers(2)))
+
+        def forward(self, x):
+            r1 = self.relu if self.style == "shared" else self.relu1
+            r2 = self.relu if self.style == "shared" else self.relu2
+            out = self.bn2(self.conv2(r1(self.bn1(self.conv1(x)))))
+            if self.style == "inplace":
+                out += x                                       # reference models.py:40-41
+            else:
+                out = out + x
+            return r2(out)
+
+    class TwoReaders(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.conv, self.bn, self.relu = nn.Conv2d(c, c, 1, bias=False), nn.BatchNorm2d(c), nn.ReLU()
+
+        def forward(self, x):
+            y = self.bn(self.conv(x))
+            return self.relu(y) + 0.25 * y
+
+    layers, c = [nn.Conv2d(3, width, 3, padding=1, bias=False), nn.BatchNorm2d(width), nn.ReLU(inplace=True)], width
+    for _ in range(int(rng.integers(2, 6))):
+        kind = rng.choice(["cbr", "cb", "cbr6", "pool", "res_out", "res_inplace", "res_shared", "two"])
+        if kind == "cbr":
+            layers += [nn.Conv2d(c, c, 3, padding=1, bias=False), nn.BatchNorm2d(c), nn.ReLU(inplace=bool(rng.integers(2)))]
+        elif kind == "cb":
+            layers += [nn.Conv2d(c, c, 1, bias=False), nn.BatchNorm2d(c)]
+        elif kind == "cbr6":
+            layers += [nn.Conv2d(c, c, 1, bias=False), nn.BatchNorm2d(c), nn.ReLU6()]
+        elif kind == "pool":
+            layers += [nn.MaxPool2d(3, 2, 1)]
+        elif kind == "two":
+            layers += [TwoReaders(c)]
+        else:
+            layers += [Res(c, kind.split("_")[1])]
+    layers += [nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(c, 5)]
+    return nn.Sequential(*layers)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fusion_passes_never_change_a_random_network(mirror, seed):
+    """Full-precision and quantised: whatever the layout, after ``fuse_eval_bn`` + ``fuse_residual_tails`` the network
+    computes what it computed before (the passes may decline, warn, or keep only the BatchNorm part)."""
+    import warnings
+
+    import numpy as np
+
+    from ood_dfq_b200 import fusion, nets, surgery
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    net = _random_net(rng).eval()
+    nets.perturb_bn_stats(net, seed=seed)
+    x = torch.randn(3, 3, 16, 16)
+    for quantised in (False, True):
+        model = copy.deepcopy(net)
+        if quantised:
+            model = surgery.quantize_model(model, 4, 4).eval()
+            with torch.no_grad():
+                model(x)
+            surgery.freeze_model(model)
+        with torch.no_grad():
+            ref = model(x)
+        keys = list(model.state_dict())
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            fusion.fuse_eval_bn(model, x)
+            fusion.fuse_residual_tails(model, x)
+        with torch.no_grad():
+            out = model(x)
+        assert torch.equal(out, ref), (seed, quantised)
+        assert list(model.state_dict()) == keys
+        twin = copy.deepcopy(model)
+        with torch.no_grad():
+            assert torch.equal(twin(x), ref)
