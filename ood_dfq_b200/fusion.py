@@ -559,15 +559,39 @@ def fuse_residual_tails(model: nn.Module, example: torch.Tensor = None, verify=T
     was_training = model.training
     model.eval()
     ref = None
+    plans = {id(u): (u, _plan_of(u)) for u in model.modules() if not isinstance(u, _FusedUnitMixin)}
+    plans = {k: v for k, v in plans.items() if v[1] is not None}
+    seen = {}
     if verify and example is not None:
+        # what every candidate unit received and returned in the unfused model: the plan is only trusted for a unit
+        # whose own forward really is  act(bn1(conv(front(x))) + [bn2(idconv(x)) | x])  -- evaluated with the unit's own
+        # modules, so the comparison is exact arithmetic, not a tolerance that a quantisation flip could hide behind
+        handles = [u.register_forward_hook(
+            lambda mod, i, o: seen.__setitem__(id(mod), (i[0].detach().clone(), o.detach().clone()))
+            if isinstance(o, torch.Tensor) and len(i) == 1 and isinstance(i[0], torch.Tensor) else None)
+            for u, _ in plans.values()]
         with torch.no_grad():
             ref = model(example)
+        for h in handles:
+            h.remove()
+
+    def follows_plan(u, p):
+        if id(u) not in seen:
+            return ref is None                    # no example: trust the layout; with one: the unit never ran
+        x, y_ref = seen[id(u)]
+        try:
+            with torch.no_grad():
+                z = p.bn1(p.conv(p.head(x)))
+                r = x if p.idconv is None else (p.bn2(p.idconv(x)) if p.bn2 is not None else p.idconv(x))
+                y = p.act(z + r)
+        except Exception:
+            return False
+        scale = y_ref.abs().max().item() + 1e-12
+        return y.shape == y_ref.shape and (y - y_ref).abs().max().item() <= 1e-4 * scale   # same modules, same order: exact
+
     swapped = []
-    for u in list(model.modules()):
-        if isinstance(u, _FusedUnitMixin):
-            continue
-        plan = _plan_of(u)
-        if plan is None:
+    for u, plan in plans.values():
+        if not follows_plan(u, plan):
             continue
         cls = type(u)
         fused_cls = _FUSED_UNIT_CLASSES.get(cls)

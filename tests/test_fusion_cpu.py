@@ -160,3 +160,30 @@ def test_pass_keeps_only_the_safe_part_when_a_batchnorm_output_has_two_readers(m
     assert type(m.bn) is fusion.FusedEvalBN and type(m.relu) is torch.nn.ReLU and m.bn._tail is None
     with torch.no_grad():
         assert torch.equal(m(x), ref)
+
+
+def test_units_that_only_look_like_the_layout_are_not_swapped():
+    """Same attribute names as the reference BasicBlock, different dataflow (the body is damped by 1 % before the
+    add): the per-unit check evaluates the plan's formula with the unit's own modules against what the unit really
+    returned, exactly, and declines -- a 1 % deviation is below anything an output tolerance could separate from a
+    flipped quantisation code."""
+    class Damped(nets.SmallBlock):
+        def forward(self, x):
+            y = self.relu1(self.bn1(self.conv1(x)))
+            y = self.bn2(self.conv2(y)) * 0.99
+            return self.relu2(y + self.shortcut(x))
+    torch.manual_seed(3)
+    model = nets.resnet18_small(3, 9).eval()
+    nets.perturb_bn_stats(model)
+    blocks = [m for m in model.modules() if type(m) is nets.SmallBlock]
+    for b in blocks[::2]:
+        b.__class__ = Damped
+    x = torch.randn(2, 3, 28, 28)
+    with torch.no_grad():
+        ref = model(x)
+    fusion.fuse_eval_bn(model, x)
+    assert fusion.fuse_residual_tails(model, x) == len(blocks) - len(blocks[::2]) == 4
+    assert all(not isinstance(b, fusion._FusedUnitMixin) for b in blocks[::2])
+    assert all(isinstance(b, fusion._FusedUnitMixin) for b in blocks[1::2])
+    with torch.no_grad():
+        assert torch.equal(model(x), ref)
