@@ -227,6 +227,34 @@ def _is_stem_pool(m):
             and two(m.dilation) == (1, 1) and not m.ceil_mode and not m.return_indices)
 
 
+class _RangesPreserved:
+    """The passes run the example through the model a few times.  A QuantAct that is still calibrating would take an
+    EMA step on every one of those forwards; its state is put back on exit, so applying a pass never moves a range."""
+
+    def __init__(self, model):
+        self.saved = [(m, name, getattr(m, name).detach().clone()) for m in model.modules()
+                      if getattr(m, "running_stat", False) for name in ("x_min", "x_max", "beta_t", "cur_x_min", "cur_x_max")
+                      if isinstance(getattr(m, name, None), torch.Tensor)]
+
+    def __enter__(self):
+        return self
+
+    def restore(self):
+        """Also called before every traced forward, so that all of them start from the same ranges and can be
+        compared with each other."""
+        with torch.no_grad():
+            for m, name, value in self.saved:
+                cur = getattr(m, name)
+                if cur.shape == value.shape:
+                    cur.copy_(value)
+                else:
+                    setattr(m, name, value.clone())
+
+    def __exit__(self, *exc):
+        self.restore()
+        return False
+
+
 def _single_reader(model, example, candidates):
     """ids of the BatchNorms among ``candidates`` whose output is read by exactly ONE autograd node in a forward of
     ``example`` (None when that cannot be established).  Absorbing the activation behind a BatchNorm changes what the
@@ -261,6 +289,12 @@ def _single_reader(model, example, candidates):
 
 
 def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=True, verify=True):
+    """See ``_fuse_eval_bn``; range state of calibrating QuantActs is left exactly as it was."""
+    with _RangesPreserved(model) as keep:
+        return _fuse_eval_bn(model, example, absorb_tails, verify, keep)
+
+
+def _fuse_eval_bn(model: nn.Module, example, absorb_tails, verify, keep):
     """Apply the fusion in place and return the model.  ``example``: a (small) input batch used to trace which
     BatchNorm feeds which ``Sequential(ReLU, QuantAct)``; without it only the BatchNorms themselves are fused."""
     was_training = model.training
@@ -289,11 +323,13 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
             lambda mod, i: pairs.append((direct(produced, i[0])[0], mod)) if direct(produced, i[0]) else None)
             for t in tails + relus]
         with torch.no_grad():
+            keep.restore()
             ref_out = model(example)
         for h in handles:
             h.remove()
         produced.clear()
         if pairs and example.is_floating_point():
+            keep.restore()
             single = _single_reader(model, example, list({id(b): b for b, _ in pairs}.values()))
             if single is not None:
                 pairs = [(b, t) for b, t in pairs if id(b) in single]
@@ -308,6 +344,7 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
             lambda mod, i: stems.append((tail_of[id(direct(made, i[0])[0])], mod)) if direct(made, i[0]) else None)
             for p in pools]
         with torch.no_grad():
+            keep.restore()
             model(example)
         for h in handles:
             h.remove()
@@ -346,6 +383,7 @@ def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=Tr
 
     def deviation():
         with torch.no_grad():
+            keep.restore()
             new_out = model(example)
         return (new_out - ref_out).abs().max().item(), ref_out.abs().max().item() + 1e-12
 
@@ -551,6 +589,12 @@ _FUSED_UNIT_CLASSES = {}
 
 
 def fuse_residual_tails(model: nn.Module, example: torch.Tensor = None, verify=True):
+    """See ``_fuse_residual_tails``; range state of calibrating QuantActs is left exactly as it was."""
+    with _RangesPreserved(model) as keep:
+        return _fuse_residual_tails(model, example, verify, keep)
+
+
+def _fuse_residual_tails(model: nn.Module, example, verify, keep):
     """Class-swap every residual unit whose layout ``_plan_of`` recognises to a subclass with the fused tail
     (parameters, buffers, state_dict keys and ``isinstance`` checks untouched).  Call after ``fuse_eval_bn`` (the
     tail needs the BatchNorms already in their fused form) and before hooks such as ``step.FeatureTap`` are
@@ -571,6 +615,7 @@ def fuse_residual_tails(model: nn.Module, example: torch.Tensor = None, verify=T
             if isinstance(o, torch.Tensor) and len(i) == 1 and isinstance(i[0], torch.Tensor) else None)
             for u, _ in plans.values()]
         with torch.no_grad():
+            keep.restore()
             ref = model(example)
         for h in handles:
             h.remove()
@@ -579,6 +624,7 @@ def fuse_residual_tails(model: nn.Module, example: torch.Tensor = None, verify=T
         if id(u) not in seen:
             return ref is None                    # no example: trust the layout; with one: the unit never ran
         x, y_ref = seen[id(u)]
+        keep.restore()
         try:
             with torch.no_grad():
                 z = p.bn1(p.conv(p.head(x)))
@@ -603,6 +649,7 @@ def fuse_residual_tails(model: nn.Module, example: torch.Tensor = None, verify=T
         swapped.append((u, cls))
     if ref is not None and swapped:
         with torch.no_grad():
+            keep.restore()
             out = model(example)
         err, scale = (out - ref).abs().max().item(), ref.abs().max().item() + 1e-12
         if not err <= 0.05 * scale:

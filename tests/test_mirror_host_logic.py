@@ -470,3 +470,20 @@ def test_fusion_passes_never_change_a_random_network(mirror, seed):
         twin = copy.deepcopy(model)
         with torch.no_grad():
             assert torch.equal(twin(x), ref)
+
+
+def test_passes_do_not_move_the_ranges_of_a_calibrating_student(mirror):
+    """Applied before ``freeze_model`` the passes still run the example through the model several times; every
+    calibrating QuantAct must come out with exactly the state it went in with."""
+    from ood_dfq_b200 import fusion, nets, surgery
+    torch.manual_seed(4)
+    student = surgery.quantize_model(nets.resnet20_cifar(num_classes=10), 4, 4).eval()
+    x = torch.randn(2, 3, 32, 32)
+    with torch.no_grad():
+        student(x)
+    before = {k: v.clone() for k, v in student.state_dict().items()}
+    fusion.fuse_eval_bn(student, x)
+    assert fusion.fuse_residual_tails(student, x) == 9
+    after = student.state_dict()
+    assert all(torch.equal(before[k], after[k]) for k in before)
+    assert any(k.endswith("beta_t") and 0 < float(v) < 1 for k, v in after.items())      # it WAS calibrating
