@@ -741,6 +741,11 @@ def space_to_depth_stem(model: nn.Module, example: torch.Tensor = None, verify=T
     """Class-swap the image-side stride-2 convolution(s) of ``model`` (``nn.Conv2d`` or this package's
     ``Quant_Conv2d``) to the space-to-depth form.  Returns how many were swapped; with ``example`` the result is
     checked against the original and undone if it deviates."""
+    with _RangesPreserved(model) as keep:
+        return _space_to_depth_stem(model, example, verify, keep)
+
+
+def _space_to_depth_stem(model, example, verify, keep):
     was_training = model.training
     model.eval()
     ref = None
@@ -760,6 +765,7 @@ def space_to_depth_stem(model: nn.Module, example: torch.Tensor = None, verify=T
         swapped.append((m, cls))
     if ref is not None and swapped:
         _S2DCache.clear()
+        keep.restore()
         with torch.no_grad():
             out = model(example)
         err, scale = (out - ref).abs().max().item(), ref.abs().max().item() + 1e-12
