@@ -289,14 +289,14 @@ def _single_reader(model, example, candidates):
 
 
 def fuse_eval_bn(model: nn.Module, example: torch.Tensor = None, absorb_tails=True, verify=True):
-    """See ``_fuse_eval_bn``; range state of calibrating QuantActs is left exactly as it was."""
+    """Apply the fusion in place and return the model.  ``example``: a (small) input batch used to trace which
+    BatchNorm feeds which ``Sequential(ReLU, QuantAct)``; without it only the BatchNorms themselves are fused.
+    The range state of QuantActs that are still calibrating is left exactly as it was."""
     with _RangesPreserved(model) as keep:
         return _fuse_eval_bn(model, example, absorb_tails, verify, keep)
 
 
 def _fuse_eval_bn(model: nn.Module, example, absorb_tails, verify, keep):
-    """Apply the fusion in place and return the model.  ``example``: a (small) input batch used to trace which
-    BatchNorm feeds which ``Sequential(ReLU, QuantAct)``; without it only the BatchNorms themselves are fused."""
     was_training = model.training
     model.eval()
     fusable = (nn.BatchNorm2d, nn.SyncBatchNorm, FusedEvalBN, FusedEvalSyncBN)
@@ -589,17 +589,17 @@ _FUSED_UNIT_CLASSES = {}
 
 
 def fuse_residual_tails(model: nn.Module, example: torch.Tensor = None, verify=True):
-    """See ``_fuse_residual_tails``; range state of calibrating QuantActs is left exactly as it was."""
+    """Class-swap every residual unit whose layout ``_plan_of`` recognises to a subclass with the fused tail
+    (parameters, buffers, state_dict keys and ``isinstance`` checks untouched).  Call after ``fuse_eval_bn`` (the
+    tail needs the BatchNorms already in their fused form) and before hooks such as ``step.FeatureTap`` are
+    attached.  With ``example`` the fused model is checked against the unfused one and the swap is undone if they
+    disagree (an unknown unit class whose forward is not the layout its attributes suggest).
+    The range state of QuantActs that are still calibrating is left exactly as it was."""
     with _RangesPreserved(model) as keep:
         return _fuse_residual_tails(model, example, verify, keep)
 
 
 def _fuse_residual_tails(model: nn.Module, example, verify, keep):
-    """Class-swap every residual unit whose layout ``_plan_of`` recognises to a subclass with the fused tail
-    (parameters, buffers, state_dict keys and ``isinstance`` checks untouched).  Call after ``fuse_eval_bn`` (the
-    tail needs the BatchNorms already in their fused form) and before hooks such as ``step.FeatureTap`` are
-    attached.  With ``example`` the fused model is checked against the unfused one and the swap is undone if they
-    disagree (an unknown unit class whose forward is not the layout its attributes suggest)."""
     was_training = model.training
     model.eval()
     ref = None
