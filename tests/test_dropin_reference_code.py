@@ -924,3 +924,36 @@ def test_reference_freeze_walk_reaches_every_quantact_of_a_fused_model(surgery_n
         assert len(acts) >= 17 and all(m.running_stat for m in acts), net_name
         exp.freeze_model(target)
         assert not any(m.running_stat for m in acts), net_name
+
+
+def test_reference_option_class_runs_on_our_hocon_reader():
+    """``Option.__init__`` (options.py:12-71), compiled from the reference file with ``ConfigFactory.parse_file`` served by
+    ``ood_dfq_b200.hocon.load`` (pyhocon is not installed): every one of the reference's config files must give the
+    reference's own option object every key it asks for, and ``QuantSettings`` must agree with it on the fields that
+    reach the quantisation path."""
+    import glob
+    import shutil
+    import uuid
+
+    from ood_dfq_b200 import hocon
+    path = os.path.join(REF, "options.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), filename=path)
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "Option")
+
+    class Conf(dict):                                                 # pyhocon's ConfigTree: mapping with .get
+        pass
+
+    ns = {"os": os, "shutil": shutil, "uuid": uuid, "NetOption": object,
+          "ConfigFactory": types.SimpleNamespace(parse_file=lambda p: Conf(hocon.load(p)))}
+    exec(compile(ast.Module(body=[cls], type_ignores=[]), path, "exec"), ns)
+    files = sorted(glob.glob(os.path.join(REF, "config", "*.hocon")))
+    assert len(files) == 15
+    for f in files:
+        opt = ns["Option"](f)
+        mine = hocon.QuantSettings.from_file(f)
+        for name in ("model_name", "dataset", "batchSize", "nClasses", "img_size", "channels", "qw", "qa", "temperature",
+                     "alpha", "lr_S", "momentum", "weightDecay", "lam", "eps"):
+            assert getattr(mine, name) == getattr(opt, name), (os.path.basename(f), name)
+        assert isinstance(opt.step_S, list) and opt.lrPolicy_S == "multi_step" and opt.nEpochs > 0
+        assert opt.latent_dim > 0 and 0 < opt.b1 < 1 and opt.bsdc_start_epoch == opt.nEpochs - 1
