@@ -487,3 +487,34 @@ def test_passes_do_not_move_the_ranges_of_a_calibrating_student(mirror):
     after = student.state_dict()
     assert all(torch.equal(before[k], after[k]) for k in before)
     assert any(k.endswith("beta_t") and 0 < float(v) < 1 for k, v in after.items())      # it WAS calibrating
+
+
+def test_qat_step_on_a_fused_mirror_student_equals_the_oracle_step(mirror):
+    """``step.QATStep`` (flat gradient buffer, pruned backward, feature taps) over a mirror-built student that went
+    through every fusion pass, against the same step over the oracle-built student: identical losses and weights for
+    several iterations (off the GPU the fused modules run the chains they replace; the bookkeeping around them --
+    class swaps, absorbed containers, WeightBank -- is what is exercised)."""
+    from ood_dfq_b200 import fusion, nets, step, surgery
+    torch.manual_seed(6)
+    teacher = nets.resnet20_cifar(num_classes=10)
+    nets.perturb_bn_stats(teacher)
+    g = torch.Generator().manual_seed(7)
+    calib = torch.randn(4, 3, 32, 32, generator=g)
+    batches = [torch.randn(4, 3, 32, 32, generator=g) for _ in range(3)]
+    results = []
+    for namespace, fuse in ((fq_torch, False), (None, True)):
+        student = surgery.quantize_model(copy.deepcopy(teacher), 4, 4, namespace=namespace).eval()
+        t = copy.deepcopy(teacher).eval()
+        with torch.no_grad():
+            student(calib)
+        surgery.freeze_model(student, namespace)
+        if fuse:
+            for net in (student, t):
+                fusion.fuse_eval_bn(net, calib[:2])
+                assert fusion.fuse_residual_tails(net, calib[:2]) == 9
+        qat = step.QATStep(student, t, lr=1e-4, unit_types=(nets.ResUnit,))
+        losses = [qat(b).clone() for b in batches]
+        results.append((losses, [p.detach().clone() for p in student.parameters()]))
+    (l_a, p_a), (l_b, p_b) = results
+    assert all(torch.equal(a, b) for a, b in zip(l_a, l_b))
+    assert all(torch.equal(a, b) for a, b in zip(p_a, p_b))
