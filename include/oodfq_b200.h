@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OODFQ_ABI_VERSION 3
+#define OODFQ_ABI_VERSION 4
 
 #define OODFQ_OK 0
 #define OODFQ_EINVAL (-1)  /* bad argument (null pointer, k out of range, misaligned ...) */
@@ -48,7 +48,7 @@ extern "C" {
 #define OODFQ_RELU_FIRST 4     /* x <- max(x, 0) before quantising: the nn.Sequential(ReLU, QuantAct) of
                                   main_direct.py:464-465 in one pass (scalar range, FAKEQUANT mode) */
 #define OODFQ_NO_ONCHIP 8      /* act_calib_forward: always take the two-kernel path (tests, comparisons) */
-#define OODFQ_ONCHIP_TMA 16    /* act_calib_forward: on-chip kernel variant fed by TMA bulk copies (opt-in, experimental) */
+#define OODFQ_ONCHIP_TMA 16    /* accepted and ignored since ABI 4: the on-chip kernel is always fed by TMA bulk copies */
 
 /* flags of the per-channel (BatchNorm) entry points */
 #define OODFQ_BN_RELU 1
@@ -93,14 +93,30 @@ int oodfq_fq_forward(const float* x, float* y, int8_t* codes, long long numel,
  * One call = data min/max of x, the bias-corrected running-range update of
  * (x_min, x_max, beta_t) IN PLACE on the device, then the fake-quantised y
  * with the UPDATED range.  y == NULL: range update only (full_precision_flag).
- * Tensors of up to 96 MB (asymmetric, k <= 8, numel % 4 == 0) run as ONE cooperative kernel that keeps x in
- * shared memory across the grid-wide range reduction, so x crosses HBM once; larger ones (or OODFQ_NO_ONCHIP)
- * as a reducing kernel followed by the streaming fake-quant.  Results are bit-identical either way.
+ * Tensors of up to 96 MB (asymmetric, k <= 8, numel % 4 == 0) run as ONE cooperative kernel that stages x into
+ * shared memory with TMA bulk copies and keeps it there across the grid-wide range reduction, so x crosses HBM
+ * once; larger ones (or OODFQ_NO_ONCHIP) as a reducing kernel followed by the streaming fake-quant.  Results are
+ * bit-identical either way.
  * workspace: oodfq_workspace_bytes() of device memory, zeroed once by the
  * caller and then owned by this library between calls on one stream. */
 int oodfq_act_calib_forward(const float* x, float* y, int8_t* codes, long long numel,
                             float* x_min, float* x_max, const float* beta, float* beta_t,
                             int k, int flags, void* workspace, oodfq_stream_t stream);
+
+/* ---- a6 + a11 in one pass (BASELINE.json north_star (b)) --------------------
+ * replaces: QuantAct.forward with running_stat=True, quant_modules.py:80-94, AND the two per-channel
+ *           reductions of the BN-statistics hook on the same tensor, trainer_direct.py:388-393
+ *           (input.mean([0,2,3]), input.var([0,2,3], unbiased=False)) -- the reference never combines them.
+ * x, y: [N, C, HW] NCHW, or channels_last [N*HW rows][C] with OODFQ_BN_NHWC (C % 4 == 0).  One call = data
+ * min/max, the in-place running-range update, y = fakequant(x) with the UPDATED range (bit-identical to
+ * oodfq_act_calib_forward) and sums[2*C] fp64 = (sum_c x, then sum_c x^2) over N and HW.
+ * Up to 96 MB (k <= 8; NCHW: C <= 1024; channels_last: C a power of two in [4, 1024]) this is ONE cooperative
+ * kernel / ONE read of x from HBM; otherwise (or with OODFQ_NO_ONCHIP) the range reduction followed by one pass
+ * that quantises and accumulates (12 B/elem, the floor once 4*numel exceeds L2).  flags: OODFQ_BN_NHWC,
+ * OODFQ_NO_ONCHIP. */
+int oodfq_act_calib_stats_forward(const float* x, float* y, int N, int C, long long HW,
+                                  float* x_min, float* x_max, const float* beta, float* beta_t,
+                                  int k, int flags, double* sums, void* workspace, oodfq_stream_t stream);
 
 /* data min / max only (NaN-propagating like torch.min/max): out[0]=min, out[1]=max
  * replaces: x.data.min(), x.data.max(), quant_modules.py:81-82 */

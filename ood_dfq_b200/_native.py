@@ -15,7 +15,7 @@ MODE_FAKEQUANT, MODE_QUANTIZE, MODE_DEQUANTIZE = 0, 1, 2
 SYMMETRIC, PARAMS_GIVEN, RELU_FIRST, NO_ONCHIP, ONCHIP_TMA = 1, 2, 4, 8, 16
 BN_RELU, BN_QUANT, BN_NHWC = 1, 2, 4
 AUG_SRC_NHWC = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _vp, _ll, _i, _d = C.c_void_p, C.c_longlong, C.c_int, C.c_double
 
@@ -36,6 +36,7 @@ SIGNATURES = {
     "oodfq_quant_params": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "oodfq_fq_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "oodfq_act_calib_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "oodfq_act_calib_stats_forward": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "oodfq_minmax": (_i, [_vp, _ll, _vp, _vp, _vp]),
     "oodfq_weight_fq_multi": (_i, [C.POINTER(WeightDesc), _i, _vp]),
     "oodfq_bn_stats_forward": (_i, [_vp, _i, _i, _ll, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),

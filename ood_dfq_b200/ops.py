@@ -173,9 +173,8 @@ def act_calib_forward(x, k, x_min, x_max, beta, beta_t, symmetric=False, quantiz
 
     quant_modules.py:80-94 (DSG :365-386).  ``quantize=False`` only tracks the range
     (full_precision_flag) and returns None.  ``onchip=False`` forces the two-kernel path (tensors up to 96 MB
-    otherwise run as one cooperative kernel that keeps x in shared memory; same bits either way).
-    ``onchip="tma"`` selects the experimental variant of that kernel whose shared-memory tile is filled by TMA bulk
-    copies (opt-in until measured on hardware).
+    otherwise run as one cooperative kernel that stages x into shared memory with TMA bulk copies and keeps it there;
+    same bits either way).  ``onchip="tma"`` is accepted for round-1 callers and means ``True``.
     """
     _need(x, "input")
     for t, nme in ((x_min, "x_min"), (x_max, "x_max"), (beta, "beta"), (beta_t, "beta_t")):
@@ -187,11 +186,39 @@ def act_calib_forward(x, k, x_min, x_max, beta, beta_t, symmetric=False, quantiz
     cd = torch.empty_like(xd, dtype=torch.int8) if (codes and quantize) else None
     rc = N.load().oodfq_act_calib_forward(xd.data_ptr(), _ptr(y), _ptr(cd), xd.numel(), x_min.data_ptr(),
                                           x_max.data_ptr(), beta.data_ptr(), beta_t.data_ptr(), int(k),
-                                          (N.SYMMETRIC if symmetric else 0) | (0 if onchip else N.NO_ONCHIP) |
-                                          (N.ONCHIP_TMA if onchip == "tma" else 0),
+                                          (N.SYMMETRIC if symmetric else 0) | (0 if onchip else N.NO_ONCHIP),
                                           workspace(x.device).data_ptr(), _stream(x.device))
     N.check(rc, "act_calib_forward")
     return (y, cd) if codes else y
+
+
+def act_calib_stats_forward(x, k, x_min, x_max, beta, beta_t, sums=None, onchip=True):
+    """Calibrating QuantAct forward that ALSO leaves the per-channel sums of its input (north_star (b)): updates
+    (x_min, x_max, beta_t) in place, returns ``(y, sums)`` with ``y`` bit-identical to ``act_calib_forward`` and
+    ``sums`` fp64 ``[2*C]`` = (sum_c x, sum_c x^2) -- what ``x.mean([0,2,3])`` / ``x.var([0,2,3], unbiased=False)``
+    of the BN-statistics hook (trainer_direct.py:388-393) need, from the same read.
+
+    4-D NCHW-contiguous or channels_last input, k <= 8.  Up to 96 MB one cooperative kernel (x crosses HBM once);
+    larger tensors: range reduction + one quantising / accumulating pass.  ``onchip=False`` forces the latter.
+    """
+    _need(x, "input")
+    for t, nme in ((x_min, "x_min"), (x_max, "x_max"), (beta, "beta"), (beta_t, "beta_t")):
+        _need(t, nme)
+        if t.numel() != 1 or not t.is_contiguous():
+            raise RuntimeError(f"ood_dfq_b200: {nme} must be a contiguous 1-element buffer")
+    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
+    if sums is None:
+        sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+    elif sums.dtype != torch.float64 or sums.numel() != 2 * c or not sums.is_contiguous():
+        raise RuntimeError("ood_dfq_b200: sums must be a contiguous float64 [2*C] tensor")
+    y = torch.empty_like(xc)
+    with _Timed("act_calib_stats (single-pass calibrating QuantAct + channel sums, 8 B/elem on chip)", 8 * xc.numel()):
+        rc = N.load().oodfq_act_calib_stats_forward(xc.data_ptr(), y.data_ptr(), n, c, hw, x_min.data_ptr(),
+                                                    x_max.data_ptr(), beta.data_ptr(), beta_t.data_ptr(), int(k),
+                                                    (N.BN_NHWC if nhwc else 0) | (0 if onchip else N.NO_ONCHIP),
+                                                    sums.data_ptr(), workspace(x.device).data_ptr(), _stream(x.device))
+        N.check(rc, "act_calib_stats_forward")
+    return y, sums
 
 
 # ----------------------------------------------------------------------------- a7 / a8

@@ -48,6 +48,22 @@ class _CalibratingSTE(torch.autograd.Function):
         return grad_output, None
 
 
+class _CalibratingStatsSTE(torch.autograd.Function):
+    """min/max -> running range (in place) -> fake-quant, and the per-channel sums of the input from the same
+    read (BASELINE.json north_star (b)); identity backward."""
+
+    @staticmethod
+    def forward(ctx, x, owner):
+        y, owner.channel_sums = _ops.act_calib_stats_forward(x, owner.activation_bit, owner.x_min, owner.x_max,
+                                                             owner.beta, owner.beta_t)
+        owner.channel_count = float(x.numel() // x.shape[1])
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output, None
+
+
 class _StatsSTE(torch.autograd.Function):
     """Frozen fake-quant that also leaves the per-channel sums of its input on the module (one read)."""
 
@@ -112,10 +128,12 @@ class _ActQuantBase(Module):
         fused_stats = (self.collect_channel_stats and quantise and not self._symmetric and x.dim() == 4
                        and self.activation_bit <= 8)
         if fused_stats:
-            if self.running_stat:       # pass 1: range; pass 2: quantise + channel sums with the updated range
+            if self.running_stat:
+                # ONE call: range update, fake-quant with the updated range and the channel sums.  Tensors the chip
+                # can hold (<= 96 MB) are one cooperative kernel and one HBM read; larger ones read x twice (the
+                # range depends on the whole tensor), the second pass quantising and accumulating together
                 self._state_ready()
-                _ops.act_calib_forward(x.detach(), self.activation_bit, self.x_min, self.x_max, self.beta,
-                                       self.beta_t, quantize=False)
+                return _CalibratingStatsSTE.apply(x, self)
             return _StatsSTE.apply(x, self)
         if self.running_stat:
             self._state_ready()

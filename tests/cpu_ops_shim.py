@@ -63,6 +63,12 @@ def act_calib_forward(x, k, x_min, x_max, beta, beta_t, symmetric=False, quantiz
     return fake_quant(x, k, x_min, x_max, symmetric=symmetric, codes=codes)
 
 
+def act_calib_stats_forward(x, k, x_min, x_max, beta, beta_t, sums=None, onchip=True):
+    """Range update + fake-quant + raw per-channel fp64 sums of the same input (csrc/fq_calib.cu contract)."""
+    y = act_calib_forward(x, k, x_min, x_max, beta, beta_t)
+    return y, bn_stats_forward(x, None, sums=sums)
+
+
 def weight_fq_multi(weights, ks, symmetric, outs=None, want_range=False, want_codes=False):
     res = []
     for i, w in enumerate(weights):
@@ -151,7 +157,7 @@ def bn_stats_backward(x, grad_in, mean, gmean, gvar, count, gscale=None, out=Non
     return r
 
 
-PATCHED = ("quant_params", "fake_quant", "elementwise", "minmax", "act_calib_forward", "weight_fq_multi", "act_mse_search",
+PATCHED = ("quant_params", "fake_quant", "elementwise", "minmax", "act_calib_forward", "act_calib_stats_forward", "weight_fq_multi", "act_mse_search",
            "bn_stats_forward", "bn_stats_finalize", "bns_loss", "bn_stats_backward")
 
 

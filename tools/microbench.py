@@ -107,11 +107,22 @@ def main():
                 st[3].fill_(1.0)
                 ops.act_calib_forward(x, 4, st[0], st[1], st[2], st[3], onchip=False)
             report("calib_2k", shape, 12 * n, *timer(calib2))
-            if os.environ.get("OODFQ_EXPERIMENTAL"):
-                def calib3():
+        if "calib_stats" in only:
+            # north_star (b): range update + fake-quant + per-channel sums.  On chip (<= 96 MB) x crosses HBM once:
+            # 8 B/elem; above that the floor is 12 B/elem (the fraction printed is against the bytes stated here)
+            st = [torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda"),
+                  torch.full((1,), 0.9, device="cuda"), torch.ones(1, device="cuda")]
+            per = 8 if 4 * n <= (96 << 20) else 12
+            for fmt, tag in ((torch.contiguous_format, "nchw"), (torch.channels_last, "nhwc")):
+                xf = x.contiguous(memory_format=fmt)
+                sums = torch.empty(2 * shape[1], dtype=torch.float64, device="cuda")
+
+                def cs(onchip=True):
                     st[3].fill_(1.0)
-                    ops.act_calib_forward(x, 4, st[0], st[1], st[2], st[3], onchip="tma")
-                report("calib_tma", shape, 12 * n, *timer(calib3))
+                    ops.act_calib_stats_forward(xf, 4, st[0], st[1], st[2], st[3], sums=sums, onchip=onchip)
+                report(f"cstat_{tag}", shape, per * n, *timer(cs))
+                report(f"cstat2_{tag}", shape, 12 * n, *timer(lambda: cs(False)))
+                del xf
         c = shape[1]
         shift = torch.zeros(c, device="cuda")
         if "stats" in only:
