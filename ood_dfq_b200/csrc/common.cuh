@@ -99,6 +99,50 @@ __device__ __forceinline__ void st_out(float4* p, float4 v) {
                  :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- TMA bulk copies (cp.async.bulk, 1-D) and the mbarrier that counts their bytes ------------------------
+// Used where a CTA stages a contiguous run of global memory in shared memory (the single-pass calibrating
+// QuantAct, the stem re-layout): one thread issues the copy, the copy engine moves the data without passing
+// through registers, every consumer waits on the barrier's phase.  SASS: UBLKCP.S.G, SYNCS.ARRIVE.TRANS64,
+// SYNCS.PHASECHK.TRANS64.TRYWAIT.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" :: "r"(count), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" :: "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// global -> shared bulk copy (size and both addresses multiples of 16 bytes), completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a byte count that never completes must end in a trap (a CUDA error), not in a hung device
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    const uint32_t a = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(phase) : "memory");
+        if (ok) return;
+    }
+    asm volatile("trap;");
+}
+
+// shared -> global bulk copy (size and both addresses multiples of 16 bytes); completion via bulk groups
+__device__ __forceinline__ void bulk_s2g(void* gmem, const void* smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gmem), "r"(smem_u32(smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N bulk groups of this thread are still READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
+// make generic-proxy writes to shared memory visible to the async proxy (before a shared -> global bulk copy)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- quantisation parameters ----------------------------------------------------------
 struct QParams {
     float scale;  // n / clamp(hi - lo, 1e-8)  evaluated as reciprocal * n

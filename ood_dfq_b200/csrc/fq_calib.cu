@@ -179,31 +179,6 @@ constexpr int kStatsMaxC = 1024;
 constexpr int kThreadPlaneMax = 256;                       // kStatsNCHW: planes up to this size are walked by one thread
 static_assert(kTChunkVec == kCThreads, "one vector per thread and chunk");
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" :: "r"(count), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" :: "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// global -> shared bulk copy (size and both addresses multiples of 16 bytes), completion counted on `bar`
-__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// bounded wait: a byte count that never completes must end in a trap (a CUDA error), not in a hung device
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    const uint32_t a = smem_u32(bar);
-    for (int spin = 0; spin < (1 << 22); ++spin) {
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(phase) : "memory");
-        if (ok) return;
-    }
-    asm volatile("trap;");
-}
-
 __device__ __forceinline__ void minmax4(float& mn, float& mx, const float4& v) {
     mn = min_nan(min_nan(mn, v.x), min_nan(v.y, min_nan(v.z, v.w)));
     mx = max_nan(max_nan(mx, v.x), max_nan(v.y, max_nan(v.z, v.w)));

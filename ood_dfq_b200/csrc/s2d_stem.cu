@@ -100,6 +100,144 @@ s2d_stem_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, con
     }
 }
 
+// TMA-staged row form (the default for C = 1 / 3 / 4 when rows are 16-byte multiples).  The scalar row kernel above
+// keeps one 4-byte load per thread in flight and sat at 50 % of the HBM rate (profiles/r1 bench table).  Here a
+// persistent CTA walks its xs rows through a ring of kS2dStages shared-memory stages: one thread issues the bulk
+// copies of the NEXT rows' sources (cp.async.bulk global -> shared, completion on an mbarrier) while all threads
+// permute the current source into the destination row inside shared memory (LDS / STS only), and the finished row
+// leaves as one bulk store (shared -> global).  No data passes through registers on its way from or to HBM, and
+// kS2dStages rows per CTA are in flight.
+//   forward : source = the two image rows 2i-pad, 2i+1-pad (W*C floats each), destination = xs row (n, i)
+//   backward: source = xs row (n, i), destination = the same two image rows of the input gradient
+// Rows outside the image are neither copied nor stored; their elements read as zero.
+constexpr int kS2dStages = 4;
+constexpr int kS2dThreads = 256;
+
+template <int C, bool BWD>
+__global__ void __launch_bounds__(kS2dThreads)
+s2d_stem_tma_kernel(const float* __restrict__ src, float* __restrict__ dst, const S2dGeom G) {
+    extern __shared__ __align__(128) float s2d_smem[];
+    __shared__ __align__(8) uint64_t full[kS2dStages];
+    const int wlen = G.W * C, xlen = 4 * C * G.Ws, shift = G.pad * C;
+    const int in_len = BWD ? xlen : 2 * wlen, out_len = BWD ? 2 * wlen : xlen;
+    const int stage_len = in_len + out_len;                         // floats; both parts are 16-byte multiples
+    const long long rows = (long long)G.N * G.Hs;
+    const long long mine = rows > blockIdx.x ? (rows - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    auto issue = [&](long long t) {                                 // thread 0: sources of this CTA's t-th row
+        const long long ni = blockIdx.x + t * gridDim.x;
+        const int st = (int)(t % kS2dStages);
+        float* in = s2d_smem + (size_t)st * stage_len;
+        const int i = (int)(ni % G.Hs);
+        const long long n = ni / G.Hs;
+        if (BWD) {
+            mbar_arrive_expect_tx(&full[st], (uint32_t)xlen * 4u);
+            bulk_g2s(in, src + ni * (long long)xlen, (uint32_t)xlen * 4u, &full[st]);
+        } else {
+            const int h0 = 2 * i - G.pad;
+            const bool v0 = h0 >= 0 && h0 < G.H, v1 = h0 + 1 >= 0 && h0 + 1 < G.H;
+            mbar_arrive_expect_tx(&full[st], (uint32_t)((v0 ? wlen : 0) + (v1 ? wlen : 0)) * 4u);
+            if (v0) bulk_g2s(in, src + (n * G.H + h0) * (long long)wlen, (uint32_t)wlen * 4u, &full[st]);
+            if (v1) bulk_g2s(in + wlen, src + (n * G.H + h0 + 1) * (long long)wlen, (uint32_t)wlen * 4u, &full[st]);
+        }
+    };
+
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < kS2dStages; ++k) mbar_init(&full[k], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (long long t = 0; t < mine && t < kS2dStages; ++t) issue(t);
+
+    for (long long t = 0; t < mine; ++t) {
+        const int st = (int)(t % kS2dStages);
+        const uint32_t phase = (uint32_t)((t / kS2dStages) & 1);
+        float* in = s2d_smem + (size_t)st * stage_len;
+        float* out = in + in_len;
+        const long long ni = blockIdx.x + t * gridDim.x;
+        const int i = (int)(ni % G.Hs);
+        const long long n = ni / G.Hs;
+        const int h0 = 2 * i - G.pad;
+        const bool v0 = h0 >= 0 && h0 < G.H, v1 = h0 + 1 >= 0 && h0 + 1 < G.H;
+        // the bulk store that last left from this stage's `out` (kS2dStages rows ago) must have read it completely
+        if (threadIdx.x == 0) bulk_wait_read<kS2dStages - 1>();
+        __syncthreads();
+        mbar_wait(&full[st], phase);
+        if (!BWD) {
+            for (int q4 = threadIdx.x; q4 < xlen / 4; q4 += kS2dThreads) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = 4 * q4 + u;
+                    const int r = q % (4 * C), s = r / (2 * C);
+                    const int m = (q / (4 * C)) * (2 * C) + r % (2 * C) - shift;
+                    const bool ok = (s ? v1 : v0) && m >= 0 && m < wlen;
+                    v[u] = ok ? in[s * wlen + m] : 0.0f;
+                }
+                reinterpret_cast<float4*>(out)[q4] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        } else {
+            for (int m4 = threadIdx.x; m4 < (2 * wlen) / 4; m4 += kS2dThreads) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = 4 * m4 + u;
+                    const int s = e >= wlen ? 1 : 0;
+                    const int q = e - s * wlen + shift;
+                    v[u] = in[(q / (2 * C)) * (4 * C) + s * 2 * C + q % (2 * C)];
+                }
+                reinterpret_cast<float4*>(out)[m4] = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        fence_async_smem();                                          // our STS before the async proxy reads `out`
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (!BWD) {
+                bulk_s2g(dst + ni * (long long)xlen, out, (uint32_t)xlen * 4u);
+            } else {
+                if (v0) bulk_s2g(dst + (n * G.H + h0) * (long long)wlen, out, (uint32_t)wlen * 4u);
+                if (v1) bulk_s2g(dst + (n * G.H + h0 + 1) * (long long)wlen, out + wlen, (uint32_t)wlen * 4u);
+            }
+            bulk_commit();
+            if (t + kS2dStages < mine) issue(t + kS2dStages);        // every thread is done reading `in` (barrier above)
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait<0>();                            // stores complete before the CTA's memory goes away
+}
+
+template <int C, bool BWD>
+static bool launch_tma_c(const float* src, float* dst, const S2dGeom& G, cudaStream_t st) {
+    const int wlen = G.W * C, xlen = 4 * C * G.Ws;
+    const size_t smem = (size_t)kS2dStages * (2 * wlen + xlen) * sizeof(float);
+    if ((wlen & 3) || !aligned16(src) || !aligned16(dst) || smem > 160 * 1024) return false;
+    auto kernel = s2d_stem_tma_kernel<C, BWD>;
+    static int per_sm = -1;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return false;
+        }
+        smem_set = smem;
+        per_sm = -1;
+    }
+    if (per_sm < 0) per_sm = resident_ctas(kernel, kS2dThreads, smem);
+    const long long rows = (long long)G.N * G.Hs, cap = (long long)kNumSM * per_sm;
+    kernel<<<(unsigned)(rows < cap ? rows : cap), kS2dThreads, smem, st>>>(src, dst, G);
+    return true;
+}
+
+template <bool BWD>
+static bool launch_tma(const float* src, float* dst, const S2dGeom& G, cudaStream_t st) {
+    switch (G.C) {
+        case 1: return launch_tma_c<1, BWD>(src, dst, G, st);
+        case 3: return launch_tma_c<3, BWD>(src, dst, G, st);
+        case 4: return launch_tma_c<4, BWD>(src, dst, G, st);
+        default: return false;
+    }
+}
+
 template <bool BWD>
 static bool launch_rows(const float* src, float* dst, const S2dGeom& G, cudaStream_t st) {
     const long long rows = BWD ? (long long)G.N * G.H : (long long)G.N * G.Hs, cap = (long long)kNumSM * 32;
@@ -131,7 +269,7 @@ extern "C" int oodfq_s2d_stem_forward(const float* x, float* xs, int N, int H, i
     if (s2d_geom(N, H, W, C, pad, G) != OODFQ_OK)
         return fail(OODFQ_EINVAL, "s2d_stem_forward: needs a non-empty tensor with even H + 2*pad and W + 2*pad");
     const long long total = (long long)N * G.Hs * G.Ws * 4 * C;
-    if (!launch_rows<false>(x, xs, G, (cudaStream_t)stream)) {
+    if (!launch_tma<false>(x, xs, G, (cudaStream_t)stream) && !launch_rows<false>(x, xs, G, (cudaStream_t)stream)) {
         static const int per_sm = resident_ctas(s2d_stem_kernel<false>, 256);
         long long want = (total + 255) / 256, cap = (long long)kNumSM * per_sm * 4;
         s2d_stem_kernel<false><<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(x, xs, G, total);
@@ -147,7 +285,8 @@ extern "C" int oodfq_s2d_stem_backward(const float* grad_xs, float* grad_x, int 
     if (s2d_geom(N, H, W, C, pad, G) != OODFQ_OK)
         return fail(OODFQ_EINVAL, "s2d_stem_backward: needs a non-empty tensor with even H + 2*pad and W + 2*pad");
     const long long total = (long long)N * H * W * C;
-    if (!launch_rows<true>(grad_xs, grad_x, G, (cudaStream_t)stream)) {
+    if (!launch_tma<true>(grad_xs, grad_x, G, (cudaStream_t)stream) &&
+        !launch_rows<true>(grad_xs, grad_x, G, (cudaStream_t)stream)) {
         static const int per_sm = resident_ctas(s2d_stem_kernel<true>, 256);
         long long want = (total + 255) / 256, cap = (long long)kNumSM * per_sm * 4;
         s2d_stem_kernel<true><<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(grad_xs, grad_x, G, total);

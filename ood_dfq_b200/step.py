@@ -119,6 +119,13 @@ class FlatGrads:
             self.flat.div_(dist.get_world_size(group))
 
 
+def _drop_stem_cache():
+    """The space-to-depth stem keeps the re-laid-out batch of the last call so that teacher and student share it
+    within an iteration (fusion._S2DCache); nothing may outlive the iteration (a batch and its copy, 300 MB)."""
+    from .fusion import _S2DCache
+    _S2DCache.clear()
+
+
 class QATStep:
     """One data-free QAT iteration (see module docstring).  ``__call__`` returns the detached losses."""
 
@@ -128,6 +135,9 @@ class QATStep:
         self.student, self.teacher = student, teacher
         self.T, self.alpha, self.lam, self.eps = temperature, alpha, lam, eps
         self.group, self.perturb = group, perturb
+        # False: never exchange gradients, even with an initialised process group (a single-process run of the GLOBAL
+        # batch inside a multi-rank job: the oracle of the data-parallel parity checks)
+        self.exchange = True
         # The final backward only has to deliver the student's parameter gradients.  ``loss.backward()`` as the
         # reference writes it (trainer_direct.py:350-356) also walks the teacher's graph and the student's stem
         # dgrad down to ``images.grad``, which nothing reads after the sign perturbation; with
@@ -167,7 +177,8 @@ class QATStep:
 
     def apply(self):
         """Gradient exchange over the data-parallel group, then the optimiser update."""
-        self.grads.all_reduce_mean(self.group)
+        if self.exchange:
+            self.grads.all_reduce_mean(self.group)
         self.opt.step()
 
     def compute(self, images):
@@ -194,6 +205,7 @@ class QATStep:
             total.backward(inputs=self.grads.params)
         else:
             total.backward()
+        _drop_stem_cache()
         return total.detach()
 
 
@@ -347,6 +359,7 @@ class DistillStep:
         self.opt.step()
         if self.scheduler is not None:                               # :275
             self.scheduler.step(total if self._on_device else total.item())
+        _drop_stem_cache()
         return total.detach()
 
 

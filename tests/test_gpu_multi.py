@@ -122,3 +122,80 @@ def test_reduce_minmax_nccl():
     b1, a1, _ = out[1]
     np.testing.assert_array_equal(a0, a1)
     np.testing.assert_array_equal(a0, ((b0 + b1) / np.float32(2)).astype(np.float32))
+
+
+def _qat_pair(dev):
+    """A small W4A4 student / teacher with frozen ranges, identical on every caller (same seeds, same calibration)."""
+    import copy
+    from ood_dfq_b200 import nets, surgery
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    torch.manual_seed(11)
+    teacher = nets.perturb_bn_stats(nets.resnet20_cifar(num_classes=10))
+    student = surgery.quantize_model(copy.deepcopy(teacher), 4, 4, namespace=qm)
+    teacher, student = teacher.to(dev), student.to(dev)
+    calib = torch.randn(8, 3, 32, 32, generator=torch.Generator().manual_seed(12)).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            student(calib)
+    surgery.freeze_model(student, qm)
+    return teacher, student
+
+
+def _qat_step(teacher, student):
+    from ood_dfq_b200 import nets, step
+    return step.QATStep(student, teacher, lr=1e-3, momentum=0.9, weight_decay=1e-4, temperature=20.0, alpha=20.0,
+                        lam=1000.0, eps=0.01, unit_types=(nets.ResUnit,))
+
+
+def _global_batches(n, steps):
+    g = torch.Generator().manual_seed(13)
+    return [torch.randn(n, 3, 32, 32, generator=g) for _ in range(steps)]
+
+
+def _deterministic():
+    torch.backends.cudnn.benchmark = False
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _w_grad_exchange(rank, world):
+    """Two SGD steps, each rank on its shard, gradients exchanged by ``FlatGrads.all_reduce_mean`` over NCCL."""
+    from ood_dfq_b200 import dist as ddist
+    _deterministic()
+    dev = torch.device("cuda", rank)
+    qat = _qat_step(*_qat_pair(dev))
+    grads = []
+    for glob in _global_batches(8 * world, 2):
+        qat.compute(ddist.shard_batch(glob, rank, world).to(dev))
+        qat.grads.all_reduce_mean(qat.group)
+        grads.append(qat.grads.flat.cpu().numpy().copy())
+        qat.opt.step()
+    weights = torch.cat([p.detach().reshape(-1) for p in qat.student.parameters()]).cpu().numpy()
+    return grads, weights
+
+
+def test_gradient_exchange_nccl_equals_the_global_batch():
+    """Row a15 (DDP of main_direct.py:484, backward_S trainer_direct.py:350-356) over NCCL: the all-reduced mean
+    gradient of two ranks equals the gradient of the global batch walked shard by shard in ONE process with the
+    exchange switched off, step after step; the updated weights are bit-identical on both ranks."""
+    world = 2
+    out = _spawn(_w_grad_exchange, world)
+    from ood_dfq_b200 import dist as ddist
+    _deterministic()
+    dev = torch.device("cuda", 0)
+    solo = _qat_step(*_qat_pair(dev))
+    solo.exchange = False
+    for it, glob in enumerate(_global_batches(8 * world, 2)):
+        acc = torch.zeros_like(solo.grads.flat)
+        for r in range(world):
+            solo.compute(ddist.shard_batch(glob, r, world).to(dev))
+            acc += solo.grads.flat
+        want = (acc / world).cpu().numpy()
+        for r in range(world):
+            np.testing.assert_allclose(out[r][0][it], want, rtol=1e-5, atol=1e-6 * np.abs(want).max())
+        solo.grads.flat.copy_(acc / world)
+        solo.opt.step()
+    assert np.array_equal(out[0][1].view(np.int32), out[1][1].view(np.int32))          # replicas stay bit-identical
+    want_w = torch.cat([p.detach().reshape(-1) for p in solo.student.parameters()]).cpu().numpy()
+    np.testing.assert_allclose(out[0][1], want_w, rtol=1e-5, atol=1e-7)
