@@ -473,10 +473,11 @@ def bench_workload(args, env, workload, full=True, namespace=None, fuse=True, ch
         _native.reset_launch_count()
         qat(resident[0])
         launches_per_step = _native.launch_count()
-        # N > 1: the NCCL gradient all-reduce and the optimiser update are captured INSIDE the graph as well (NCCL
-        # collectives are capturable), so a replay is the whole iteration and the host only enqueues one graph launch;
-        # --no-graph-collective replays forward + backward and runs exchange and update eagerly behind it
-        graph_collective = bool(world > 1 and kind != "distill" and not args.no_graph_collective)
+        # N > 1: replay forward + backward, run the NCCL gradient all-reduce and the optimiser update eagerly behind the
+        # graph.  --graph-collective captures them inside the graph as well (NCCL collectives are capturable); measured
+        # at N = 2 it is the slower of the two (36.56 vs 36.32 ms at 224x224, 8.47 vs 8.37 ms at 32x32,
+        # profiles/r2_n2_graph_collective.txt), so it stays an option
+        graph_collective = bool(world > 1 and kind != "distill" and args.graph_collective)
         cap = True if graph_collective else None
         qat = step_mod.GraphedStep(dstep, None) if kind == "distill" else \
             step_mod.GraphedStep(qat, resident[0], capture_update=cap)
@@ -815,8 +816,9 @@ def main():
     ap.add_argument("--e2e-input", choices=["host", "device_shards"], default="host",
                     help="end-to-end arm: pinned host batches copied every step (default, the reference's data flow) or "
                          "batches assembled on the device from an HBM-resident image set (opt-in)")
-    ap.add_argument("--no-graph-collective", action="store_true",
-                    help="N > 1: keep the gradient all-reduce and the optimiser update outside the CUDA graph (eager tail)")
+    ap.add_argument("--graph-collective", action="store_true",
+                    help="N > 1: capture the gradient all-reduce and the optimiser update inside the CUDA graph too "
+                         "(default: eager behind the replay, which measured faster)")
     ap.add_argument("--distill-augment", action="store_true",
                     help="distillation workload: apply the loop's per-image RandomResizedCrop / flip on every other "
                          "iteration (distill_data.py:205-227; eager)")
