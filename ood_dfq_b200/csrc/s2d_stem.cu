@@ -111,7 +111,7 @@ s2d_stem_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, con
 //   backward: source = xs row (n, i), destination = the same two image rows of the input gradient
 // Rows outside the image are neither copied nor stored; their elements read as zero.
 constexpr int kS2dStages = 4;
-constexpr int kS2dThreads = 256;
+constexpr int kS2dThreads = 128;
 
 template <int C, bool BWD>
 __global__ void __launch_bounds__(kS2dThreads)
@@ -164,30 +164,38 @@ s2d_stem_tma_kernel(const float* __restrict__ src, float* __restrict__ dst, cons
         if (threadIdx.x == 0) bulk_wait_read<kS2dStages - 1>();
         __syncthreads();
         mbar_wait(&full[st], phase);
+        // One thread per xs pixel j: its 4C floats are 2C consecutive floats of image row 2i-pad followed by the same
+        // 2C columns of row 2i+1-pad (columns 2C*j - pad*C ...), so neither direction needs a division.
         if (!BWD) {
-            for (int q4 = threadIdx.x; q4 < xlen / 4; q4 += kS2dThreads) {
-                float v[4];
+            for (int j = threadIdx.x; j < G.Ws; j += kS2dThreads) {
+                const int m0 = 2 * C * j - shift;
+                float v[4 * C];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int q = 4 * q4 + u;
-                    const int r = q % (4 * C), s = r / (2 * C);
-                    const int m = (q / (4 * C)) * (2 * C) + r % (2 * C) - shift;
-                    const bool ok = (s ? v1 : v0) && m >= 0 && m < wlen;
-                    v[u] = ok ? in[s * wlen + m] : 0.0f;
+                for (int k = 0; k < 2 * C; ++k) {
+                    const bool ok = (unsigned)(m0 + k) < (unsigned)wlen;
+                    v[k] = (ok && v0) ? in[m0 + k] : 0.0f;
+                    v[2 * C + k] = (ok && v1) ? in[wlen + m0 + k] : 0.0f;
                 }
-                reinterpret_cast<float4*>(out)[q4] = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+                for (int u = 0; u < C; ++u)
+                    reinterpret_cast<float4*>(out)[C * j + u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
             }
         } else {
-            for (int m4 = threadIdx.x; m4 < (2 * wlen) / 4; m4 += kS2dThreads) {
-                float v[4];
+            for (int j = threadIdx.x; j < G.Ws; j += kS2dThreads) {
+                const int m0 = 2 * C * j - shift;
+                float v[4 * C];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int e = 4 * m4 + u;
-                    const int s = e >= wlen ? 1 : 0;
-                    const int q = e - s * wlen + shift;
-                    v[u] = in[(q / (2 * C)) * (4 * C) + s * 2 * C + q % (2 * C)];
+                for (int u = 0; u < C; ++u) {
+                    const float4 t = reinterpret_cast<const float4*>(in)[C * j + u];
+                    v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
                 }
-                reinterpret_cast<float4*>(out)[m4] = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+                for (int k = 0; k < 2 * C; ++k) {
+                    if ((unsigned)(m0 + k) < (unsigned)wlen) {
+                        out[m0 + k] = v[k];
+                        out[wlen + m0 + k] = v[2 * C + k];
+                    }
+                }
             }
         }
         fence_async_smem();                                          // our STS before the async proxy reads `out`

@@ -206,6 +206,14 @@ def main():
                        *timer(lambda: ops.crop_resize_flip(images, index, boxes, flips, side, channels_last=cl, out=out)))
             del images
             torch.cuda.empty_cache()
+    if "s2d" in only:
+        # stem input re-layout (csrc/s2d_stem.cu): the 154 MB image batch -> 2x2 space-to-depth (12 channels), and back
+        xi = torch.randn(256, 3, 224, 224, device="cuda").contiguous(memory_format=torch.channels_last)
+        xs = ops.s2d_stem_forward(xi, 3)
+        gs = torch.randn_like(xs)
+        report("s2d_fwd", (256, 3, 224, 224), 4 * (xi.numel() + xs.numel()), *timer(lambda: ops.s2d_stem_forward(xi, 3)))
+        report("s2d_bwd", (256, 3, 224, 224), 4 * (xi.numel() + xs.numel()), *timer(lambda: ops.s2d_stem_backward(gs, xi.shape, 3)))
+        del xi, xs, gs
     if "weights" in only:
         ws = [torch.randn(s, device="cuda") * 0.02 for s in R18_WEIGHTS]
         outs = [torch.empty_like(w) for w in ws]
