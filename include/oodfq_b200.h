@@ -249,20 +249,25 @@ int oodfq_act_mse_search(const float* x, long long numel, const float* data_minm
  * channels_last only (flags must contain OODFQ_BN_NHWC, optionally OODFQ_BN_QUANT): x1, r, y, grads [N,H,W,C].
  * rv2 == NULL: the identity is r itself; otherwise identity = BN2(r) with (w2, b2, rm2, rv2, eps2).
  * energy (nullable) [N, C] = mean_hw BN1(x1)^2; scratch: oodfq_res_tail_scratch_floats(N, C) floats.
+ * relu_mask (nullable, forward output / backward input): one byte per 128-bit column, [N*H*W*C/4] bytes in storage
+ *           order; bit j = the ReLU behind the add lets the gradient of channel j of that column through.  With it
+ *           the backward never re-derives the mask, so `r` may be NULL unless the identity BatchNorm's parameter
+ *           gradients are wanted (rv2 && dwdb), and `x1` may be NULL when neither grad_energy nor dwdb is given:
+ *           16.25 instead of 20 B/elem for the common case.
  * backward: grad_y2 (nullable) is a second gradient w.r.t. y, added to grad_y in registers (the output fed two
  *           consumers); grad_energy nullable; dwdb nullable, else [2*Ct] doubles with Ct = C (or 2C with BN2):
  *           dW of BN1 (then BN2), followed by dB of BN1 (then BN2). */
 size_t oodfq_res_tail_scratch_floats(int N, int C);
-int oodfq_res_tail_forward(const float* x1, const float* r, float* y, float* energy, float* scratch, int N, int C,
-                           long long HW, const float* w1, const float* b1, const float* rm1, const float* rv1,
-                           float eps1, const float* w2, const float* b2, const float* rm2, const float* rv2,
-                           float eps2, int flags, const float* fq_lo, const float* fq_hi, int fq_k,
-                           oodfq_stream_t stream);
+int oodfq_res_tail_forward(const float* x1, const float* r, float* y, float* energy, float* scratch,
+                           uint8_t* relu_mask, int N, int C, long long HW, const float* w1, const float* b1,
+                           const float* rm1, const float* rv1, float eps1, const float* w2, const float* b2,
+                           const float* rm2, const float* rv2, float eps2, int flags, const float* fq_lo,
+                           const float* fq_hi, int fq_k, oodfq_stream_t stream);
 int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2, const float* grad_energy, const float* x1, const float* r,
-                            float* grad_x1, float* grad_r, int N, int C, long long HW, const float* w1,
-                            const float* b1, const float* rm1, const float* rv1, float eps1, const float* w2,
-                            const float* b2, const float* rm2, const float* rv2, float eps2, int flags,
-                            double* dwdb, void* workspace, oodfq_stream_t stream);
+                            const uint8_t* relu_mask, float* grad_x1, float* grad_r, int N, int C, long long HW,
+                            const float* w1, const float* b1, const float* rm1, const float* rv1, float eps1,
+                            const float* w2, const float* b2, const float* rm2, const float* rv2, float eps2,
+                            int flags, double* dwdb, void* workspace, oodfq_stream_t stream);
 
 /* ---- space-to-depth re-layout in front of the ImageNet stem convolution ---------------------------------
  * replaces: nothing in the reference -- it is the data format on the input side of Quant_Conv2d's F.conv2d call

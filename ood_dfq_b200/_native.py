@@ -50,9 +50,9 @@ SIGNATURES = {
     "oodfq_channel_energy_forward": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp, _vp]),
     "oodfq_channel_energy_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _i, _vp]),
     "oodfq_res_tail_scratch_floats": (C.c_size_t, [_i, _i]),
-    "oodfq_res_tail_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float,
+    "oodfq_res_tail_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float,
                                     _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
-    "oodfq_res_tail_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float,
+    "oodfq_res_tail_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float,
                                      _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
     "oodfq_act_mse_scratch_doubles": (C.c_size_t, [_i]),
     "oodfq_act_mse_search": (_i, [_vp, _ll, _vp, _i, _i, _d, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -28,6 +28,8 @@
 // image -- and a thread one 128-bit column (4 channels) of those rows, as plane_energy.cu.  Parameter-gradient
 // partials stay in registers across the items of a CTA and are folded in CTA order (deterministic, no atomics).
 // Roofline: HBM.
+#include <type_traits>
+
 #include "bn_geom.cuh"
 
 namespace oodfq {
@@ -56,8 +58,9 @@ constexpr int kTailBwdDepth = 2;    // 6 loads backward (more state in registers
 template <bool QUANT, bool IDBN, bool ENERGY>
 __global__ void __launch_bounds__(kBThreads)
 res_tail_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ r, float* __restrict__ y,
-                    float* __restrict__ epart, const TailGeom G, const TailBn P1, const TailBn P2, float inv_hw,
-                    const float* __restrict__ fq_lo, const float* __restrict__ fq_hi, int fq_k) {
+                    float* __restrict__ epart, uint8_t* __restrict__ mask, const TailGeom G, const TailBn P1,
+                    const TailBn P2, float inv_hw, const float* __restrict__ fq_lo, const float* __restrict__ fq_hi,
+                    int fq_k) {
     __shared__ float lut[QUANT ? kLutMax : 1];
     __shared__ float red[ENERGY ? kBThreads * 4 : 1];
     QParams qp = given_qparams(1.0f, 0.0f, 1);
@@ -87,6 +90,7 @@ res_tail_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ r, f
         const float4* p1 = reinterpret_cast<const float4*>(x1) + base;
         const float4* p2 = reinterpret_cast<const float4*>(r) + base;
         float4* py = reinterpret_cast<float4*>(y) + base;
+        uint8_t* pm = mask ? mask + base : nullptr;
         float s[4] = {0.f, 0.f, 0.f, 0.f};
         if (active) {
             for (int row = r_begin + rsub; row < r_end; row += kTailFwdDepth * G.lanes_r) {
@@ -106,16 +110,19 @@ res_tail_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ r, f
                         const float xs[4] = {u[d].x, u[d].y, u[d].z, u[d].w};
                         const float rs[4] = {v[d].x, v[d].y, v[d].z, v[d].w};
                         float o[4];
+                        unsigned open = 0;              // bit j: the ReLU lets the gradient of channel j through
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float z1 = fmaf(xs[j], a1[j], b1[j]);
                             if (ENERGY) s[j] = fmaf(z1, z1, s[j]);
                             const float id = IDBN ? fmaf(rs[j], a2[j], b2[j]) : rs[j];
                             float t = __fadd_rn(z1, id);
+                            open |= (t <= 0.0f) ? 0u : (1u << j);     // aten::threshold_backward: NaN passes
                             t = (t != t) ? t : fmaxf(t, 0.0f);
                             o[j] = QUANT ? fake_quant_lut(t, qp, lut, qh, qmask) : t;
                         }
                         st_out(py + (long long)rr * G.cols, make_float4(o[0], o[1], o[2], o[3]));
+                        if (pm) pm[(long long)rr * G.cols] = (uint8_t)open;
                     }
                 }
             }
@@ -146,12 +153,17 @@ __global__ void res_tail_fold_energy_kernel(const float* __restrict__ partial, f
     e[i] = t;
 }
 
-template <bool IDBN, bool ENERGY, bool REDUCE>
+// MASK: the forward left one byte per 128-bit column (bit j = the ReLU of channel j is open), so the identity `r` is
+// only read when its BatchNorm's weight gradient needs it (IDBN && REDUCE) and the body output `x1` only when the
+// energy gradient or BN1's weight gradient does: 16.25 instead of 20 B/elem for the common case.
+template <bool IDBN, bool ENERGY, bool REDUCE, bool MASK>
 __global__ void __launch_bounds__(kBThreads)
 res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2, const float* __restrict__ ge,
-                    const float* __restrict__ x1, const float* __restrict__ r, float* __restrict__ gx1,
-                    float* __restrict__ gr, const TailGeom G, const TailBn P1, const TailBn P2, float two_inv_hw,
-                    Workspace* ws) {
+                    const float* __restrict__ x1, const float* __restrict__ r, const uint8_t* __restrict__ mask,
+                    float* __restrict__ gx1, float* __restrict__ gr, const TailGeom G, const TailBn P1,
+                    const TailBn P2, float two_inv_hw, Workspace* ws) {
+    constexpr bool NEED_X1 = ENERGY || REDUCE || !MASK;
+    constexpr bool NEED_R = !MASK || (IDBN && REDUCE);
     __shared__ float red[REDUCE ? (IDBN ? 4 : 2) * kBThreads * 4 : 1];
     const bool active = (int)threadIdx.x < G.lanes_r * G.cols;
     const int col = threadIdx.x % G.cols, rsub = threadIdx.x / G.cols;
@@ -178,6 +190,7 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2,
             const float4* pg2 = gy2 ? reinterpret_cast<const float4*>(gy2) + base : nullptr;
             const float4* p1 = reinterpret_cast<const float4*>(x1) + base;
             const float4* p2 = reinterpret_cast<const float4*>(r) + base;
+            const uint8_t* pm = MASK ? mask + base : nullptr;
             float4* o1 = reinterpret_cast<float4*>(gx1) + base;
             float4* o2 = reinterpret_cast<float4*>(gr) + base;
             float ce[4] = {0.f, 0.f, 0.f, 0.f};
@@ -187,14 +200,18 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2,
             }
             for (int row = r_begin + rsub; row < r_end; row += kTailBwdDepth * G.lanes_r) {
                 float4 g[kTailBwdDepth], g2[kTailBwdDepth], u[kTailBwdDepth], v[kTailBwdDepth];
+                unsigned open[kTailBwdDepth];
 #pragma unroll
                 for (int d = 0; d < kTailBwdDepth; ++d) {
                     const int rr = row + d * G.lanes_r;
+                    u[d] = v[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    open[d] = 0;
                     if (rr < r_end) {
                         g[d] = ld_stream(pg + (long long)rr * G.cols);
                         if (pg2) g2[d] = ld_stream(pg2 + (long long)rr * G.cols);
-                        u[d] = ld_stream(p1 + (long long)rr * G.cols);
-                        v[d] = ld_stream(p2 + (long long)rr * G.cols);
+                        if (NEED_X1) u[d] = ld_stream(p1 + (long long)rr * G.cols);
+                        if (NEED_R) v[d] = ld_stream(p2 + (long long)rr * G.cols);
+                        if (MASK) open[d] = __ldg(pm + (long long)rr * G.cols);
                     }
                 }
 #pragma unroll
@@ -212,9 +229,14 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2,
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const float z1 = fmaf(xs[j], a1[j], b1[j]);
-                            const float id = IDBN ? fmaf(rs[j], a2[j], b2[j]) : rs[j];
-                            const float s = __fadd_rn(z1, id);
-                            const float gm = (s <= 0.0f) ? 0.0f : gs[j];          // aten::threshold_backward
+                            float gm;
+                            if (MASK) {
+                                gm = ((open[d] >> j) & 1u) ? gs[j] : 0.0f;
+                            } else {
+                                const float id = IDBN ? fmaf(rs[j], a2[j], b2[j]) : rs[j];
+                                const float s = __fadd_rn(z1, id);
+                                gm = (s <= 0.0f) ? 0.0f : gs[j];                  // aten::threshold_backward
+                            }
                             const float dz = ENERGY ? __fadd_rn(gm, __fmul_rn(ce[j], z1)) : gm;
                             if (REDUCE) {
                                 sb1[j] += dz; sw1[j] = fmaf(dz, xs[j] - rm1[j], sw1[j]);
@@ -289,18 +311,44 @@ static int make_tail_geom(int N, int C, long long HW, long long slots, int depth
 
 template <bool QUANT, bool IDBN>
 static void launch_tail_fwd(bool energy, unsigned grid, cudaStream_t st, const float* x1, const float* r, float* y,
-                            float* epart, const TailGeom& G, const TailBn& P1, const TailBn& P2, float inv_hw,
-                            const float* lo, const float* hi, int k) {
-    if (energy) res_tail_fwd_kernel<QUANT, IDBN, true><<<grid, kBThreads, 0, st>>>(x1, r, y, epart, G, P1, P2, inv_hw, lo, hi, k);
-    else res_tail_fwd_kernel<QUANT, IDBN, false><<<grid, kBThreads, 0, st>>>(x1, r, y, epart, G, P1, P2, inv_hw, lo, hi, k);
+                            float* epart, uint8_t* mask, const TailGeom& G, const TailBn& P1, const TailBn& P2,
+                            float inv_hw, const float* lo, const float* hi, int k) {
+    if (energy) res_tail_fwd_kernel<QUANT, IDBN, true><<<grid, kBThreads, 0, st>>>(x1, r, y, epart, mask, G, P1, P2, inv_hw, lo, hi, k);
+    else res_tail_fwd_kernel<QUANT, IDBN, false><<<grid, kBThreads, 0, st>>>(x1, r, y, epart, mask, G, P1, P2, inv_hw, lo, hi, k);
 }
 
-template <bool IDBN, bool ENERGY>
-static void launch_tail_bwd(bool reduce, unsigned grid, cudaStream_t st, const float* gy, const float* gy2,
-                            const float* ge, const float* x1, const float* r, float* gx1, float* gr,
-                            const TailGeom& G, const TailBn& P1, const TailBn& P2, float two_inv_hw, Workspace* ws) {
-    if (reduce) res_tail_bwd_kernel<IDBN, ENERGY, true><<<grid, kBThreads, 0, st>>>(gy, gy2, ge, x1, r, gx1, gr, G, P1, P2, two_inv_hw, ws);
-    else res_tail_bwd_kernel<IDBN, ENERGY, false><<<grid, kBThreads, 0, st>>>(gy, gy2, ge, x1, r, gx1, gr, G, P1, P2, two_inv_hw, ws);
+template <bool IDBN, bool ENERGY, bool REDUCE, bool MASK>
+static int tail_bwd_occupancy() {
+    static const int n = resident_ctas(res_tail_bwd_kernel<IDBN, ENERGY, REDUCE, MASK>, kBThreads);
+    return n;
+}
+
+// (resident CTAs per SM, launcher) of one variant
+struct TailBwdArgs {
+    const float *gy, *gy2, *ge, *x1, *r;
+    const uint8_t* mask;
+    float *gx1, *gr;
+    TailGeom G;
+    TailBn P1, P2;
+    float two_inv_hw;
+    Workspace* ws;
+};
+
+template <bool IDBN, bool ENERGY, bool REDUCE, bool MASK>
+static void tail_bwd_go(unsigned grid, cudaStream_t st, const TailBwdArgs& a) {
+    res_tail_bwd_kernel<IDBN, ENERGY, REDUCE, MASK><<<grid, kBThreads, 0, st>>>(a.gy, a.gy2, a.ge, a.x1, a.r, a.mask, a.gx1,
+                                                                              a.gr, a.G, a.P1, a.P2, a.two_inv_hw, a.ws);
+}
+
+template <typename F>
+static auto tail_bwd_dispatch(bool idbn, bool energy, bool reduce, bool mask, F&& f) {
+#define OODFQ_TB(I, E, R, M) if (idbn == I && energy == E && reduce == R && mask == M) return f(std::integral_constant<int, (I << 3) | (E << 2) | (R << 1) | M>{});
+    OODFQ_TB(0, 0, 0, 0) OODFQ_TB(0, 0, 0, 1) OODFQ_TB(0, 0, 1, 0) OODFQ_TB(0, 0, 1, 1)
+    OODFQ_TB(0, 1, 0, 0) OODFQ_TB(0, 1, 0, 1) OODFQ_TB(0, 1, 1, 0) OODFQ_TB(0, 1, 1, 1)
+    OODFQ_TB(1, 0, 0, 0) OODFQ_TB(1, 0, 0, 1) OODFQ_TB(1, 0, 1, 0) OODFQ_TB(1, 0, 1, 1)
+    OODFQ_TB(1, 1, 0, 0) OODFQ_TB(1, 1, 0, 1) OODFQ_TB(1, 1, 1, 0)
+#undef OODFQ_TB
+    return f(std::integral_constant<int, 15>{});
 }
 
 }  // namespace oodfq
@@ -309,8 +357,8 @@ using namespace oodfq;
 
 extern "C" size_t oodfq_res_tail_scratch_floats(int N, int C) { return (size_t)16 * (size_t)N * (size_t)C; }
 
-extern "C" int oodfq_res_tail_forward(const float* x1, const float* r, float* y, float* energy, float* scratch, int N,
-                                      int C, long long HW, const float* w1, const float* b1, const float* rm1,
+extern "C" int oodfq_res_tail_forward(const float* x1, const float* r, float* y, float* energy, float* scratch,
+                                      uint8_t* relu_mask, int N, int C, long long HW, const float* w1, const float* b1, const float* rm1,
                                       const float* rv1, float eps1, const float* w2, const float* b2,
                                       const float* rm2, const float* rv2, float eps2, int flags, const float* fq_lo,
                                       const float* fq_hi, int fq_k, oodfq_stream_t stream) {
@@ -337,10 +385,10 @@ extern "C" int oodfq_res_tail_forward(const float* x1, const float* r, float* y,
     const unsigned grid = (unsigned)(items < cap ? items : cap);
     const float inv_hw = (float)(1.0 / (double)HW);
     float* epart = energy ? (G.chunks == 1 ? energy : scratch) : nullptr;
-    if (quant && idbn) launch_tail_fwd<true, true>(energy, grid, st, x1, r, y, epart, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
-    else if (quant) launch_tail_fwd<true, false>(energy, grid, st, x1, r, y, epart, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
-    else if (idbn) launch_tail_fwd<false, true>(energy, grid, st, x1, r, y, epart, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
-    else launch_tail_fwd<false, false>(energy, grid, st, x1, r, y, epart, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
+    if (quant && idbn) launch_tail_fwd<true, true>(energy, grid, st, x1, r, y, epart, relu_mask, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
+    else if (quant) launch_tail_fwd<true, false>(energy, grid, st, x1, r, y, epart, relu_mask, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
+    else if (idbn) launch_tail_fwd<false, true>(energy, grid, st, x1, r, y, epart, relu_mask, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
+    else launch_tail_fwd<false, false>(energy, grid, st, x1, r, y, epart, relu_mask, G, P1, P2, inv_hw, fq_lo, fq_hi, fq_k);
     count_launch();
     int rc = check_launch("res_tail_forward");
     if (rc != OODFQ_OK || !energy || G.chunks == 1) return rc;
@@ -351,40 +399,42 @@ extern "C" int oodfq_res_tail_forward(const float* x1, const float* r, float* y,
 }
 
 extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2, const float* grad_energy, const float* x1, const float* r,
-                                       float* grad_x1, float* grad_r, int N, int C, long long HW, const float* w1,
+                                       const uint8_t* relu_mask, float* grad_x1, float* grad_r, int N, int C, long long HW, const float* w1,
                                        const float* b1, const float* rm1, const float* rv1, float eps1,
                                        const float* w2, const float* b2, const float* rm2, const float* rv2,
                                        float eps2, int flags, double* dwdb, void* workspace, oodfq_stream_t stream) {
-    if (!grad_y || !x1 || !r || !grad_x1 || !grad_r || !rm1 || !rv1) return fail(OODFQ_EINVAL, "res_tail_backward: null pointer");
+    if (!grad_y || !grad_x1 || !grad_r || !rm1 || !rv1) return fail(OODFQ_EINVAL, "res_tail_backward: null pointer");
     if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "res_tail_backward: empty tensor");
     if (!(flags & OODFQ_BN_NHWC)) return fail(OODFQ_EINVAL, "res_tail_backward: channels_last only");
-    const bool idbn = rv2 != nullptr, energy = grad_energy != nullptr, reduce = dwdb != nullptr;
+    const bool idbn = rv2 != nullptr, energy = grad_energy != nullptr, reduce = dwdb != nullptr, mask = relu_mask != nullptr;
     if (idbn && !rm2) return fail(OODFQ_EINVAL, "res_tail_backward: identity BatchNorm needs both running statistics");
     if (reduce && !workspace) return fail(OODFQ_EINVAL, "res_tail_backward: parameter gradients need the workspace");
-    static const int occ[8] = {
-        resident_ctas(res_tail_bwd_kernel<false, false, false>, kBThreads), resident_ctas(res_tail_bwd_kernel<false, false, true>, kBThreads),
-        resident_ctas(res_tail_bwd_kernel<false, true, false>, kBThreads), resident_ctas(res_tail_bwd_kernel<false, true, true>, kBThreads),
-        resident_ctas(res_tail_bwd_kernel<true, false, false>, kBThreads), resident_ctas(res_tail_bwd_kernel<true, false, true>, kBThreads),
-        resident_ctas(res_tail_bwd_kernel<true, true, false>, kBThreads), resident_ctas(res_tail_bwd_kernel<true, true, true>, kBThreads)};
-    const int per_sm = occ[(idbn ? 4 : 0) + (energy ? 2 : 0) + (reduce ? 1 : 0)];
+    // what the chosen variant dereferences: x1 unless the mask makes it redundant, r likewise
+    if (!x1 && (energy || reduce || !mask)) return fail(OODFQ_EINVAL, "res_tail_backward: x1 is needed (energy / parameter gradients / no mask)");
+    if (!r && (!mask || (idbn && reduce))) return fail(OODFQ_EINVAL, "res_tail_backward: r is needed (no mask, or the identity BatchNorm's weight gradient)");
+    const int per_sm = tail_bwd_dispatch(idbn, energy, reduce, mask, [](auto tag) {
+        constexpr int v = decltype(tag)::value;
+        return tail_bwd_occupancy<(v >> 3) & 1, (v >> 2) & 1, (v >> 1) & 1, v & 1>();
+    });
     const int Ct = (idbn ? 2 : 1) * C;
     long long cap = (long long)kNumSM * per_sm;
     const long long table = (long long)kMaxBnSplit * kMaxBnChannels / Ct;     // rows of ws->bn_partial
     if (reduce && cap > table) cap = table;
     TailGeom G;
-    if (make_tail_geom(N, C, HW, cap, kTailBwdDepth, G) != OODFQ_OK || !aligned16(grad_y) || !aligned16(x1) ||
-        !aligned16(r) || !aligned16(grad_x1) || !aligned16(grad_r) || (grad_y2 && !aligned16(grad_y2)))
+    if (make_tail_geom(N, C, HW, cap, kTailBwdDepth, G) != OODFQ_OK || !aligned16(grad_y) || (x1 && !aligned16(x1)) ||
+        (r && !aligned16(r)) || !aligned16(grad_x1) || !aligned16(grad_r) || (grad_y2 && !aligned16(grad_y2)))
         return fail(OODFQ_EINVAL, "res_tail_backward: needs C %% 4 == 0, C <= 1024 and 16-byte aligned buffers");
     cudaStream_t st = (cudaStream_t)stream;
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
-    const TailBn P1{w1, b1, rm1, rv1, eps1}, P2{w2, b2, rm2, rv2, eps2};
     const long long items = (long long)N * G.chunks;
     const unsigned grid = (unsigned)(items < cap ? items : cap);
-    const float two_inv_hw = (float)(2.0 / (double)HW);
-    if (idbn && energy) launch_tail_bwd<true, true>(reduce, grid, st, grad_y, grad_y2, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
-    else if (idbn) launch_tail_bwd<true, false>(reduce, grid, st, grad_y, grad_y2, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
-    else if (energy) launch_tail_bwd<false, true>(reduce, grid, st, grad_y, grad_y2, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
-    else launch_tail_bwd<false, false>(reduce, grid, st, grad_y, grad_y2, grad_energy, x1, r, grad_x1, grad_r, G, P1, P2, two_inv_hw, ws);
+    const TailBwdArgs args{grad_y, grad_y2, grad_energy, x1, r, relu_mask, grad_x1, grad_r, G,
+                           TailBn{w1, b1, rm1, rv1, eps1}, TailBn{w2, b2, rm2, rv2, eps2}, (float)(2.0 / (double)HW), ws};
+    tail_bwd_dispatch(idbn, energy, reduce, mask, [&](auto tag) {
+        constexpr int v = decltype(tag)::value;
+        tail_bwd_go<(v >> 3) & 1, (v >> 2) & 1, (v >> 1) & 1, v & 1>(grid, st, args);
+        return 0;
+    });
     count_launch();
     int rc = check_launch("res_tail_backward");
     if (rc != OODFQ_OK || !reduce) return rc;

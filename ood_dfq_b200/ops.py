@@ -523,12 +523,14 @@ def _tail_bn(bn, c):
     return _bn_ptrs(weight, bias, running_mean, running_var, c) + (float(eps),)
 
 
-def res_tail_forward(x1, r, bn1, bn2=None, fq=None, want_energy=False):
+def res_tail_forward(x1, r, bn1, bn2=None, fq=None, want_energy=False, want_mask=False):
     """``y = [fakequant](relu(BN1(x1) + id))`` with ``id = r`` or ``BN2(r)``, and optionally the per-(image,
     channel) mean of squares of ``BN1(x1)`` (the feature-alignment tap of the body output) from the same read.
 
     ``bn1`` / ``bn2``: ``(weight, bias, running_mean, running_var, eps)``; ``fq = (k, lo, hi)``.
-    Returns ``(y, energy or None)``.
+    Returns ``(y, energy or None)``; with ``want_mask`` ``(y, energy or None, mask)`` where ``mask`` is one byte per
+    four channels saying where the ReLU is open -- handed to ``res_tail_backward`` it spares that pass the read of
+    ``r`` (and of ``x1`` when neither energy nor parameter gradients are wanted).
     """
     _need(x1, "body output")
     _need(r, "identity")
@@ -542,24 +544,27 @@ def res_tail_forward(x1, r, bn1, bn2=None, fq=None, want_energy=False):
     if want_energy:
         energy = torch.empty((n, c), dtype=torch.float32, device=x1.device)
         scratch = torch.empty(int(N.load().oodfq_res_tail_scratch_floats(n, c)), dtype=torch.float32, device=x1.device)
+    mask = torch.empty(x1.numel() // 4, dtype=torch.uint8, device=x1.device) if want_mask else None
     flags, k, lo, hi = N.BN_NHWC, 0, None, None
     if fq is not None:
         k, lo, hi = fq
         flags |= N.BN_QUANT
-    with _Timed("res_tail_fwd_kernel (BN + residual add + ReLU + QuantAct [+ energy], 12 B/elem)", 12 * x1.numel()):
+    with _Timed("res_tail_fwd_kernel (BN + residual add + ReLU + QuantAct [+ energy], 12 B/elem)",
+                12 * x1.numel() + (x1.numel() // 4 if want_mask else 0)):
         rc = N.load().oodfq_res_tail_forward(x1.data_ptr(), r.data_ptr(), y.data_ptr(), _ptr(energy), _ptr(scratch),
-                                             n, c, h * w, *p1, *p2, flags, _ptr(lo), _ptr(hi), int(k),
+                                             _ptr(mask), n, c, h * w, *p1, *p2, flags, _ptr(lo), _ptr(hi), int(k),
                                              _stream(x1.device))
         N.check(rc, "res_tail_forward")
-    return y, energy
+    return (y, energy, mask) if want_mask else (y, energy)
 
 
-def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grads=True, grad_y2=None):
+def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grads=True, grad_y2=None, mask=None):
     """Backward of ``res_tail_forward``: ``(grad_x1, grad_r, dW1, dB1, dW2, dB2)`` (parameter gradients None
     unless wanted; dW2 / dB2 None without ``bn2``).  ``grad_y2``: a second gradient w.r.t. ``y`` (the output fed
-    two consumers), added to ``grad_y`` inside the kernel."""
+    two consumers), added to ``grad_y`` inside the kernel.  ``mask``: the forward's ReLU mask; with it ``r`` may be
+    None unless ``bn2``'s parameter gradients are wanted, ``x1`` may be None without energy / parameter gradients."""
     _need(grad_y, "grad_output")
-    n, c, h, w = x1.shape
+    n, c, h, w = grad_y.shape
     gy = grad_y.contiguous(memory_format=torch.channels_last)
     gy2 = None
     if grad_y2 is not None:
@@ -569,16 +574,26 @@ def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grad
     if grad_energy is not None:
         _need(grad_energy, "grad_energy")
         ge = grad_energy.contiguous()
+    if mask is not None:
+        _need(mask, "relu mask", torch.uint8)
+        if mask.numel() != gy.numel() // 4 or not mask.is_contiguous():
+            raise RuntimeError("ood_dfq_b200: the ReLU mask must be the forward's contiguous [numel / 4] byte tensor")
+    reads_x1 = mask is None or ge is not None or want_param_grads
+    reads_r = mask is None or (bn2 is not None and want_param_grads)
+    if (reads_x1 and x1 is None) or (reads_r and r is None):
+        raise RuntimeError("ood_dfq_b200: res_tail_backward needs x1 / r for this combination (see the docstring)")
     p1, p2 = _tail_bn(bn1, c), _tail_bn(bn2, c)
-    gx1, gr = torch.empty_like(x1), torch.empty_like(r)
+    gx1, gr = torch.empty_like(gy), torch.empty_like(gy)
     ct = c * (2 if bn2 is not None else 1)
-    dwdb = torch.empty(2 * ct, dtype=torch.float64, device=x1.device) if want_param_grads else None
-    ws = workspace(x1.device).data_ptr() if want_param_grads else None
-    with _Timed("res_tail_bwd_kernel (ReLU mask + energy gradient + BN backward(s), 20 B/elem)",
-                (24 if gy2 is not None else 20) * x1.numel()):
-        rc = N.load().oodfq_res_tail_backward(gy.data_ptr(), _ptr(gy2), _ptr(ge), x1.data_ptr(), r.data_ptr(), gx1.data_ptr(),
+    dwdb = torch.empty(2 * ct, dtype=torch.float64, device=gy.device) if want_param_grads else None
+    ws = workspace(gy.device).data_ptr() if want_param_grads else None
+    per_elem = 12 + (4 if gy2 is not None else 0) + (4 if reads_x1 else 0) + (4 if reads_r else 0) + (0.25 if mask is not None else 0)
+    with _Timed("res_tail_bwd_kernel (ReLU mask + energy gradient + BN backward(s), 16.25 - 24 B/elem)",
+                int(per_elem * gy.numel())):
+        rc = N.load().oodfq_res_tail_backward(gy.data_ptr(), _ptr(gy2), _ptr(ge), _ptr(x1) if reads_x1 else None,
+                                              _ptr(r) if reads_r else None, _ptr(mask), gx1.data_ptr(),
                                               gr.data_ptr(), n, c, h * w, *p1, *p2, N.BN_NHWC, _ptr(dwdb), ws,
-                                              _stream(x1.device))
+                                              _stream(gy.device))
         N.check(rc, "res_tail_backward")
     if not want_param_grads:
         return gx1, gr, None, None, None, None

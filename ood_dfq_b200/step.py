@@ -190,7 +190,11 @@ class QATStep:
         loss = kl + fa
         total = loss
         if self.perturb:
-            sign = torch.sgn(torch.autograd.grad(loss, images, retain_graph=True)[0])
+            # only the images' gradient is asked for: the fused backward kernels skip their parameter-gradient
+            # reductions in this sweep (the engine would discard them anyway)
+            from .fusion import input_gradient_only
+            with input_gradient_only():
+                sign = torch.sgn(torch.autograd.grad(loss, images, retain_graph=True)[0])
             self._clear_taps()
             with torch.no_grad():
                 images_p = images + self.eps * sign

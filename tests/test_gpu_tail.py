@@ -71,6 +71,20 @@ def test_tail_matches_the_kernel_chain(shape, idbn, k):
         gx1b, grb, dw1b, _, _, _ = ops.res_tail_backward(gy, ge if with_energy else None, x1, r, bn1, bn2,
                                                          want_param_grads=False)
         assert dw1b is None and torch.equal(gx1b, gx1) and torch.equal(grb, gr)
+        # with the forward's ReLU mask the backward no longer re-derives it: same bits, and the tensors the variant
+        # does not need may be withheld altogether
+        y3, _, mask = ops.res_tail_forward(x1, r, bn1, bn2, fq=fq, want_energy=False, want_mask=True)
+        assert torch.equal(y3, y) and mask.dtype == torch.uint8 and mask.numel() == x1.numel() // 4
+        m = ops.res_tail_backward(gy, ge if with_energy else None, x1, r if idbn else None, bn1, bn2, mask=mask)
+        assert torch.equal(m[0], gx1) and torch.equal(m[1], gr)
+        assert torch.equal(m[2], dw1) and torch.equal(m[3], db1)
+        if idbn:
+            assert torch.equal(m[4], dw2) and torch.equal(m[5], db2)
+        m = ops.res_tail_backward(gy, ge if with_energy else None, x1 if with_energy else None, None, bn1, bn2,
+                                  want_param_grads=False, mask=mask)
+        assert torch.equal(m[0], gx1) and torch.equal(m[1], gr) and m[2] is None
+    with pytest.raises(RuntimeError, match="needs x1 / r"):
+        ops.res_tail_backward(gy, None, x1, None, bn1, bn2)                      # no mask: r is indispensable
 
 
 @pytest.mark.parametrize("idbn", [False, True])
@@ -272,3 +286,42 @@ def test_qat_step_with_fused_tails_matches_step_without():
     for (n0, p0), (n1, p1) in zip(s0.named_parameters(), s1.named_parameters()):
         assert torch.allclose(p0, p1, rtol=1e-4, atol=1e-6), n0
     torch.backends.cudnn.deterministic = False
+
+
+def test_input_gradient_only_sweep_skips_parameter_reductions_and_keeps_the_image_gradient():
+    """``fusion.input_gradient_only()`` around ``autograd.grad(loss, images)`` (the sign perturbation of
+    trainer_direct.py:508-512): the fused backwards run their gradient-only variants -- fewer launches (no fold
+    kernels), same image gradient bit for bit."""
+    import copy
+    from ood_dfq_b200 import _native, fusion, nets, surgery
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    torch.manual_seed(3)
+    base = nets.perturb_bn_stats(nets.resnet18_imagenet(num_classes=10))
+    net = surgery.quantize_model(copy.deepcopy(base), 4, 4, namespace=qm).to(DEV).to(memory_format=torch.channels_last).eval()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 3, 224, 224, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        for _ in range(2):
+            net(x)
+    surgery.freeze_model(net, qm)
+    fusion.fuse_eval_bn(net, x[:2])
+    fusion.fuse_residual_tails(net, x[:2])
+    torch.backends.cudnn.deterministic = True
+
+    def sweep(skip):
+        xi = x.detach().clone().requires_grad_(True)
+        loss = net(xi).square().mean()
+        torch.cuda.synchronize()
+        _native.reset_launch_count()
+        if skip:
+            with fusion.input_gradient_only():
+                gx = torch.autograd.grad(loss, xi)[0]
+        else:
+            gx = torch.autograd.grad(loss, xi)[0]
+        return gx, _native.launch_count()
+
+    g_full, n_full = sweep(False)
+    g_skip, n_skip = sweep(True)
+    assert torch.equal(g_full.view(torch.int32), g_skip.view(torch.int32))
+    assert n_skip < n_full, (n_skip, n_full)
+    assert not fusion._SKIP_PARAM_GRADS

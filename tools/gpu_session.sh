@@ -19,9 +19,6 @@ if has tests; then
   log "pytest -m gpu"
   timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
   log "pytest exit $? : $(tail -1 gpurun_out/pytest_gpu.log)"
-  log "pytest experimental (opt-in kernels)"
-  OODFQ_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_zz_experimental.py -q > gpurun_out/pytest_experimental.log 2>&1
-  log "experimental exit $? : $(tail -1 gpurun_out/pytest_experimental.log)"
 fi
 if has smoke; then
   log "smoke"
@@ -30,7 +27,7 @@ if has smoke; then
 fi
 if has bench; then
   log "bench N=1"
-  timeout 900 python bench.py --gpus 1 --steps 8 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
+  timeout 900 python bench.py --gpus 1 --steps 20 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
   log "bench exit $? : $(head -c 300 gpurun_out/bench_n1.json)"
   log "bench N=1, batches assembled on the device (opt-in e2e input)"
   timeout 900 python bench.py --gpus 1 --steps 8 --warmup 3 --no-cpu-baseline --e2e-input device_shards \
@@ -39,7 +36,7 @@ if has bench; then
 fi
 if has ref; then
   log "reference arm"
-  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+  timeout 900 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
   log "reference exit $?"
 fi
 if has launches; then
@@ -47,24 +44,26 @@ if has launches; then
   log "ncu launch list"
   timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'oodfq|fq_|bn_|res_tail|s2d|weight_fq|minmax|energy|crop_resize' \
       -c 4000 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --graph off > gpurun_out/launches_run.log 2>&1
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-baselines --no-other-configs --graph off > gpurun_out/launches_run.log 2>&1
   log "launch list exit $?"
   python tools/launch_list.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1 || true
 fi
 if has ncu; then
   # one full capture per headline family, on the microbenchmark (a single tensor per launch, a few launches)
-  log "ncu --set full (tail, bn, stem, augment)"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'res_tail|bn_nhwc|bn_pool|crop_resize' -c 80 \
-      -o gpurun_out/full_kernels -f python tools/microbench.py --only tail,bn_fwd,bn_bwd,pool,augment --shapes 0,1 --iters 1 --warmup 0 --flush none \
+  log "ncu --set full (tail, bn, stem, s2d, fq, single-pass calibration)"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'res_tail|bn_nhwc|bn_pool|s2d_stem|fq_flat|act_calib_onchip' -c 120 \
+      -o gpurun_out/full_kernels -f python tools/microbench.py --only fq,tail,bn_fwd,bn_bwd,pool,s2d,calib_stats --shapes 0,1,4 --iters 1 --warmup 0 --flush none \
       > gpurun_out/ncu_full.log 2>&1
   log "ncu full exit $?"
   ncu -i gpurun_out/full_kernels.ncu-rep --page raw --csv \
       --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active \
       > gpurun_out/full_kernels_raw.csv 2>/dev/null || true
+  python tools/ncu_traffic.py gpurun_out/full_kernels_raw.csv "profiles/r2_full_kernels_raw.csv (ncu --set full on tools/microbench.py, this build)" \
+      > gpurun_out/ncu_traffic.json 2> gpurun_out/ncu_traffic.err || true
 fi
 if has micro; then
   log "microbench (read-flush)"
-  OODFQ_EXPERIMENTAL=1 timeout 900 python tools/microbench.py --only copy,fq,calib,tail,pool,bn_fwd,bn_bwd,stats_nhwc,weights,augment --flush read \
+  timeout 900 python tools/microbench.py --only copy,fq,calib,calib_stats,tail,pool,s2d,bn_fwd,bn_bwd,stats_nhwc,weights,augment --flush read \
       --json gpurun_out/microbench.json > gpurun_out/microbench.txt 2>&1
   log "microbench exit $?"
 fi

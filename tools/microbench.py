@@ -174,6 +174,12 @@ def main():
             report("tailbw_ep", shape, 20 * n, *timer(lambda: ops.res_tail_backward(gy, ge, x1, r, bn1, None)))
             report("tailbw_idp", shape, 20 * n, *timer(lambda: ops.res_tail_backward(gy, ge, x1, r, bn1, bn2)))
             report("tailbw_e", shape, 20 * n, *timer(lambda: ops.res_tail_backward(gy, ge, x1, r, bn1, None, want_param_grads=False)))
+            _, _, mask = ops.res_tail_forward(x1, r, bn1, None, fq=(4, lo, hi), want_energy=True, want_mask=True)
+            report("tail_fq_em", shape, 12 * n + n // 4, *timer(lambda: ops.res_tail_forward(x1, r, bn1, None, fq=(4, lo, hi), want_energy=True, want_mask=True)))
+            report("tailbwm_ep", shape, 16 * n + n // 4, *timer(lambda: ops.res_tail_backward(gy, ge, x1, None, bn1, None, mask=mask)))
+            report("tailbwm_e", shape, 16 * n + n // 4, *timer(lambda: ops.res_tail_backward(gy, ge, x1, None, bn1, None, want_param_grads=False, mask=mask)))
+            report("tailbwm_e2", shape, 20 * n + n // 4, *timer(lambda: ops.res_tail_backward(gy, ge, x1, None, bn1, None, want_param_grads=False, mask=mask, grad_y2=gy)))
+            del mask
             del x1, r, gy
         if "pool" in only and shape[2] >= 56:
             w, b = torch.rand(c, device="cuda") + 0.5, torch.randn(c, device="cuda") * 0.3
