@@ -189,15 +189,19 @@ int oodfq_bn_stats_backward(const float* x, const float* grad_in, float* grad_x,
  *           dwdb[c] = sum g'*(x-rm_c)/sqrt(rv_c+eps), dwdb[C+c] = sum g'   (fp64, NULL: skip)
  * flags: OODFQ_BN_RELU | OODFQ_BN_QUANT (QUANT: scalar range fq_lo/fq_hi, k = fq_k <= 8; its
  * backward is the identity STE).  z_debug (nullable): the fp32 value handed to the quantiser.
- * weight / bias may be NULL (1 / 0). */
+ * weight / bias may be NULL (1 / 0).
+ * relu_mask (nullable; channels_last + OODFQ_BN_RELU only): forward output / backward input, one byte per 128-bit
+ * column ([N*H*W*C/4] bytes in storage order), bit j = a_c*x+b_c > 0 for channel j of the column.  A backward that is
+ * given the mask and no dwdb never reads x (x may be NULL): 8.25 instead of 12 B/elem. */
 int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, int N, int C, long long HW,
                           const float* weight, const float* bias, const float* running_mean,
                           const float* running_var, float eps, int flags, const float* fq_lo,
-                          const float* fq_hi, int fq_k, oodfq_stream_t stream);
+                          const float* fq_hi, int fq_k, uint8_t* relu_mask, oodfq_stream_t stream);
 int oodfq_bn_eval_backward(const float* x, const float* grad_y, float* grad_x, int N, int C,
                            long long HW, const float* weight, const float* bias,
                            const float* running_mean, const float* running_var, float eps,
-                           int flags, double* dwdb, void* workspace, oodfq_stream_t stream);
+                           int flags, double* dwdb, void* workspace, const uint8_t* relu_mask,
+                           oodfq_stream_t stream);
 
 /* ---- the reduction inside the feature-alignment loss ----------------------
  * replaces: x.pow(2).mean([2,3]) of Trainer.channel_attention, trainer_direct.py:382-383 (hooks :432-440,

@@ -43,7 +43,7 @@ SIGNATURES = {
     "oodfq_bn_stats_finalize": (_i, [_vp, _vp, _i, _d, _vp, _vp, _vp]),
     "oodfq_bns_loss": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_i), C.POINTER(_d), _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "oodfq_bn_stats_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _d, _vp, _i, _vp]),
-    "oodfq_bn_eval_forward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
+    "oodfq_bn_eval_forward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp, _vp]),
     "oodfq_bn_pool_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
     "oodfq_bn_pool_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp]),
     "oodfq_channel_energy_scratch_floats": (C.c_size_t, [_i, _i]),
@@ -61,7 +61,7 @@ SIGNATURES = {
     "oodfq_s2d_stem_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_crop_resize_flip": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_crop_resize_flip_backward": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "oodfq_bn_eval_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp]),
+    "oodfq_bn_eval_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

@@ -304,8 +304,9 @@ bn_group_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
 // the CTA's 256 threads cover `lanes_r = 256 / (C/4)` rows at a time as ONE contiguous run of memory.
 template <bool RELU, bool QUANT>
 __global__ void __launch_bounds__(kBThreads)
-bn_nhwc_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ zdbg, const NhwcGeom G,
-                   const BnParams P, const float* __restrict__ fq_lo, const float* __restrict__ fq_hi, int fq_k) {
+bn_nhwc_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ zdbg,
+                   uint8_t* __restrict__ mask, const NhwcGeom G, const BnParams P, const float* __restrict__ fq_lo,
+                   const float* __restrict__ fq_hi, int fq_k) {
     __shared__ float lut[QUANT ? kLutMax : 1];
     QParams qp;
     const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
@@ -342,7 +343,50 @@ bn_nhwc_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __
                     o.w = head<RELU, QUANT>(v[d].w, a[3], b[3], qp, lut, qh, qmask, z.w);
                     st_out(reinterpret_cast<float4*>(y) + rr * G.cols + col, o);
                     if (zdbg) reinterpret_cast<float4*>(zdbg)[rr * G.cols + col] = z;
+                    // one byte per 128-bit column: bit j = the ReLU of channel j is open (what the backward re-derives
+                    // from x otherwise: a*x + b > 0)
+                    if (RELU && mask)
+                        mask[rr * G.cols + col] = (uint8_t)((z.x > 0.0f ? 1 : 0) | (z.y > 0.0f ? 2 : 0) | (z.z > 0.0f ? 4 : 0) |
+                                                            (z.w > 0.0f ? 8 : 0));
                 }
+            }
+        }
+    }
+}
+
+// Backward through BN + ReLU (+ identity STE) when only grad_x is wanted and the forward left its ReLU mask:
+// grad_x = [open] * grad_y * a_c -- x is not read at all (8.25 instead of 12 B/elem).
+__global__ void __launch_bounds__(kBThreads)
+bn_nhwc_bwdx_mask_kernel(const uint8_t* __restrict__ mask, const float* __restrict__ gy, float* __restrict__ gx,
+                         const NhwcGeom G, const BnParams P) {
+    const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
+    if ((int)threadIdx.x >= G.lanes_r * wcols) return;
+    const int rsub = threadIdx.x / wcols;
+    for (int cb = 0; cb < G.col_blocks; ++cb) {
+        const int col = cb * kBThreads + threadIdx.x % wcols;
+        if (col >= G.cols) continue;
+        float a[4], b, invstd;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) affine_of(P, 4 * col + j, a[j], b, invstd);
+        const long long rstep = (long long)G.lanes_r * gridDim.x;
+        for (long long r = (long long)blockIdx.x * G.lanes_r + rsub; r < G.R; r += kDepth * rstep) {
+            float4 g[kDepth];
+            unsigned open[kDepth];
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const long long rr = r + d * rstep;
+                if (rr < G.R) {
+                    g[d] = ld_stream(reinterpret_cast<const float4*>(gy) + rr * G.cols + col);
+                    open[d] = __ldg(mask + rr * G.cols + col);
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const long long rr = r + d * rstep;
+                if (rr < G.R)
+                    st_out(reinterpret_cast<float4*>(gx) + rr * G.cols + col,
+                           make_float4(((open[d] & 1u) ? g[d].x : 0.0f) * a[0], ((open[d] & 2u) ? g[d].y : 0.0f) * a[1],
+                                       ((open[d] & 4u) ? g[d].z : 0.0f) * a[2], ((open[d] & 8u) ? g[d].w : 0.0f) * a[3]));
             }
         }
     }
@@ -430,8 +474,10 @@ using namespace oodfq;
 extern "C" int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, int N, int C, long long HW,
                                      const float* weight, const float* bias, const float* running_mean,
                                      const float* running_var, float eps, int flags, const float* fq_lo,
-                                     const float* fq_hi, int fq_k, oodfq_stream_t stream) {
+                                     const float* fq_hi, int fq_k, uint8_t* relu_mask, oodfq_stream_t stream) {
     if (!x || !y || !running_mean || !running_var) return fail(OODFQ_EINVAL, "bn_eval_forward: null pointer");
+    if (relu_mask && !((flags & OODFQ_BN_NHWC) && (flags & OODFQ_BN_RELU)))
+        return fail(OODFQ_EINVAL, "bn_eval_forward: the ReLU mask output exists for channels_last tensors with OODFQ_BN_RELU only");
     if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "bn_eval_forward: empty tensor");
     const bool relu = flags & OODFQ_BN_RELU, quant = flags & OODFQ_BN_QUANT;
     if (quant && (!fq_lo || !fq_hi || fq_k < 1 || fq_k > 8))
@@ -446,10 +492,10 @@ extern "C" int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, i
         long long want = (G.R + (long long)G.lanes_r * kDepth - 1) / ((long long)G.lanes_r * kDepth);
         long long cap = (long long)kNumSM * per_sm;
         const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
-        if (relu && quant) bn_nhwc_fwd_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
-        else if (relu) bn_nhwc_fwd_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
-        else if (quant) bn_nhwc_fwd_kernel<false, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
-        else bn_nhwc_fwd_kernel<false, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, G, P, fq_lo, fq_hi, fq_k);
+        if (relu && quant) bn_nhwc_fwd_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, relu_mask, G, P, fq_lo, fq_hi, fq_k);
+        else if (relu) bn_nhwc_fwd_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, relu_mask, G, P, fq_lo, fq_hi, fq_k);
+        else if (quant) bn_nhwc_fwd_kernel<false, true><<<grid, kBThreads, 0, st>>>(x, y, z_debug, relu_mask, G, P, fq_lo, fq_hi, fq_k);
+        else bn_nhwc_fwd_kernel<false, false><<<grid, kBThreads, 0, st>>>(x, y, z_debug, relu_mask, G, P, fq_lo, fq_hi, fq_k);
         count_launch();
         return check_launch("bn_eval_forward");
     }
@@ -486,8 +532,10 @@ extern "C" int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, i
 extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float* grad_x, int N, int C,
                                       long long HW, const float* weight, const float* bias,
                                       const float* running_mean, const float* running_var, float eps,
-                                      int flags, double* dwdb, void* workspace, oodfq_stream_t stream) {
-    if (!x || !grad_y || !grad_x || !running_mean || !running_var) return fail(OODFQ_EINVAL, "bn_eval_backward: null pointer");
+                                      int flags, double* dwdb, void* workspace, const uint8_t* relu_mask,
+                                      oodfq_stream_t stream) {
+    const bool by_mask = relu_mask && (flags & OODFQ_BN_NHWC) && (flags & OODFQ_BN_RELU) && !dwdb;
+    if ((!x && !by_mask) || !grad_y || !grad_x || !running_mean || !running_var) return fail(OODFQ_EINVAL, "bn_eval_backward: null pointer");
     if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "bn_eval_backward: empty tensor");
     if (dwdb && !workspace) return fail(OODFQ_EINVAL, "bn_eval_backward: parameter gradients need the workspace");
     if (C > kMaxBnChannels) return fail(OODFQ_EINVAL, "bn_eval_backward: C=%d exceeds %d", C, kMaxBnChannels);
@@ -495,10 +543,18 @@ extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float
     cudaStream_t st = (cudaStream_t)stream;
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
     const BnParams P{weight, bias, running_mean, running_var, eps};
-    const bool vec_ok = aligned16(x) && aligned16(grad_y) && aligned16(grad_x);
+    const bool vec_ok = (!x || aligned16(x)) && aligned16(grad_y) && aligned16(grad_x);
     if (flags & OODFQ_BN_NHWC) {
         if (!vec_ok || (C % 4) != 0) return fail(OODFQ_EINVAL, "bn_eval_backward: NHWC needs C %% 4 == 0 and 16-byte alignment");
         const NhwcGeom G = make_nhwc((long long)N * HW, C);
+        if (by_mask) {
+            static const int per_sm = resident_ctas(bn_nhwc_bwdx_mask_kernel, kBThreads);
+            long long want = (G.R + (long long)G.lanes_r * kDepth - 1) / ((long long)G.lanes_r * kDepth);
+            const long long cap = (long long)kNumSM * per_sm;
+            bn_nhwc_bwdx_mask_kernel<<<(unsigned)(want < 1 ? 1 : (want < cap ? want : cap)), kBThreads, 0, st>>>(relu_mask, grad_y, grad_x, G, P);
+            count_launch();
+            return check_launch("bn_eval_backward(mask)");
+        }
         // resident CTAs differ a lot between the variants (97 vs 48 registers): size each grid by its own
         static const int occ[4] = {resident_ctas(bn_nhwc_bwdx_kernel<false, false>, kBThreads),
                                    resident_ctas(bn_nhwc_bwdx_kernel<false, true>, kBThreads),

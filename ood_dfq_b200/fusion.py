@@ -79,18 +79,25 @@ class _FusedBN(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, bn, relu, qact):
         fq = (qact.activation_bit, qact.x_min, qact.x_max) if qact is not None else None
-        y = ops.bn_eval_forward(x, weight, bias, bn.running_mean, bn.running_var, bn.eps, relu=relu, fq=fq)
-        ctx.save_for_backward(x, weight, bias)
+        # with a ReLU inside, leave its mask (1 byte per 4 channels): a sweep that wants no parameter gradients then
+        # never reads x again
+        mask = None
+        if relu and any(ctx.needs_input_grad[:3]):
+            y, mask = ops.bn_eval_forward(x, weight, bias, bn.running_mean, bn.running_var, bn.eps, relu=relu, fq=fq,
+                                          want_mask=True)
+        else:
+            y = ops.bn_eval_forward(x, weight, bias, bn.running_mean, bn.running_var, bn.eps, relu=relu, fq=fq)
+        ctx.save_for_backward(x, weight, bias, mask)
         ctx.bn, ctx.relu = bn, relu
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
-        x, weight, bias = ctx.saved_tensors
+        x, weight, bias, mask = ctx.saved_tensors
         need_p = ((weight is not None and ctx.needs_input_grad[1]) or (bias is not None and ctx.needs_input_grad[2])) \
             and not _SKIP_PARAM_GRADS
         gx, dw, db = ops.bn_eval_backward(x, grad_y, weight, bias, ctx.bn.running_mean, ctx.bn.running_var,
-                                          ctx.bn.eps, relu=ctx.relu, want_param_grads=need_p)
+                                          ctx.bn.eps, relu=ctx.relu, want_param_grads=need_p, mask=mask)
         return (gx,
                 dw if (need_p and weight is not None and ctx.needs_input_grad[1]) else None,
                 db if (need_p and bias is not None and ctx.needs_input_grad[2]) else None,

@@ -364,16 +364,20 @@ def _bn_ptrs(weight, bias, running_mean, running_var, c):
     return _ptr(weight), _ptr(bias), running_mean.data_ptr(), running_var.data_ptr()
 
 
-def bn_eval_forward(x, weight, bias, running_mean, running_var, eps, relu=False, fq=None, want_z=False):
+def bn_eval_forward(x, weight, bias, running_mean, running_var, eps, relu=False, fq=None, want_z=False, want_mask=False):
     """``[fakequant]([relu](BN_eval(x)))`` in one pass.  ``fq = (k, lo, hi)`` with a scalar range.
 
     NCHW-contiguous and channels_last inputs both run natively; the output keeps the input's memory format.
+    ``want_mask`` (channels_last + ``relu``): also return the one-byte-per-four-channels ReLU mask that lets
+    ``bn_eval_backward`` skip the read of ``x`` when no parameter gradients are wanted (None where unsupported).
+    Returns ``y``, or a tuple ``(y[, z][, mask])`` in that order for the extras asked for.
     """
     _need(x, "input")
     xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
     y = torch.empty_like(xc)
     z = torch.empty_like(xc) if want_z else None
+    mask = torch.empty(xc.numel() // 4, dtype=torch.uint8, device=x.device) if (want_mask and nhwc and relu) else None
     flags, k, lo, hi = (N.BN_RELU if relu else 0) | (N.BN_NHWC if nhwc else 0), 0, None, None
     if fq is not None:
         k, lo, hi = fq
@@ -382,29 +386,42 @@ def bn_eval_forward(x, weight, bias, running_mean, running_var, eps, relu=False,
         flags |= N.BN_QUANT
     name = "bn_*_fwd_kernel<relu,quant> (BN+ReLU+QuantAct forward, 8 B/elem)" if fq is not None else \
         "bn_*_fwd_kernel (eval BN forward, 8 B/elem)"
-    with _Timed(name, 8 * xc.numel()):
+    with _Timed(name, 8 * xc.numel() + (xc.numel() // 4 if mask is not None else 0)):
         rc = N.load().oodfq_bn_eval_forward(xc.data_ptr(), y.data_ptr(), _ptr(z), n, c, hw, pw, pb, prm, prv,
-                                            float(eps), flags, _ptr(lo), _ptr(hi), int(k), _stream(x.device))
+                                            float(eps), flags, _ptr(lo), _ptr(hi), int(k), _ptr(mask), _stream(x.device))
         N.check(rc, "bn_eval_forward")
-    return (y, z) if want_z else y
+    if not (want_z or want_mask):
+        return y
+    return (y,) + ((z,) if want_z else ()) + ((mask,) if want_mask else ())
 
 
-def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, relu=False, want_param_grads=True):
-    """Backward of ``bn_eval_forward`` (identity STE through the quantiser): (grad_x, dweight, dbias)."""
-    _need(x, "input")
+def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, relu=False, want_param_grads=True, mask=None):
+    """Backward of ``bn_eval_forward`` (identity STE through the quantiser): (grad_x, dweight, dbias).
+    ``mask``: the forward's ReLU mask; with it and without parameter gradients ``x`` is not read (may be None)."""
     _need(grad_y, "grad_output")
-    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
-    gy = grad_y.contiguous(memory_format=torch.channels_last) if nhwc else grad_y.contiguous()
+    by_mask = mask is not None and relu and not want_param_grads
+    if x is None and not by_mask:
+        raise RuntimeError("ood_dfq_b200: bn_eval_backward needs x unless the ReLU mask replaces it")
+    if by_mask:
+        _need(mask, "relu mask", torch.uint8)
+        gc, n, c, hw, nhwc = _nchw_or_nhwc(grad_y)
+        if not nhwc or mask.numel() != gc.numel() // 4 or not mask.is_contiguous():
+            raise RuntimeError("ood_dfq_b200: the ReLU mask belongs to a channels_last tensor of the gradient's shape")
+        xc, gy = None, gc
+    else:
+        _need(x, "input")
+        xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
+        gy = grad_y.contiguous(memory_format=torch.channels_last) if nhwc else grad_y.contiguous()
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
-    gx = torch.empty_like(xc)
-    dwdb = torch.empty(2 * c, dtype=torch.float64, device=x.device) if want_param_grads else None
-    ws = workspace(x.device).data_ptr() if want_param_grads else None
-    reads_x = relu or want_param_grads          # otherwise grad_x = grad_y * a_c and x is never touched
+    gx = torch.empty_like(gy)
+    dwdb = torch.empty(2 * c, dtype=torch.float64, device=gy.device) if want_param_grads else None
+    ws = workspace(gy.device).data_ptr() if want_param_grads else None
+    reads_x = (relu or want_param_grads) and not by_mask   # otherwise grad_x = grad_y * a_c and x is never touched
     with _Timed("bn_*_bwdx_kernel (fused BN backward, 12 B/elem; 8 without ReLU mask and parameter grads)",
-                (12 if reads_x else 8) * xc.numel()):
-        rc = N.load().oodfq_bn_eval_backward(xc.data_ptr(), gy.data_ptr(), gx.data_ptr(), n, c, hw, pw, pb, prm, prv,
+                int((12 if reads_x else (8.25 if by_mask else 8)) * gy.numel())):
+        rc = N.load().oodfq_bn_eval_backward(_ptr(xc), gy.data_ptr(), gx.data_ptr(), n, c, hw, pw, pb, prm, prv,
                                              float(eps), (N.BN_RELU if relu else 0) | (N.BN_NHWC if nhwc else 0),
-                                             _ptr(dwdb), ws, _stream(x.device))
+                                             _ptr(dwdb), ws, _ptr(mask) if by_mask else None, _stream(gy.device))
         N.check(rc, "bn_eval_backward")
     if not want_param_grads:
         return gx, None, None

@@ -488,3 +488,35 @@ def test_fused_stem_in_the_imagenet_student():
     with torch.no_grad():
         yc = fused(xs[2].contiguous())
     assert torch.allclose(yc, yb.detach(), rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("shape", [(4, 64, 12, 12), (32, 128, 28, 28), (3, 8, 5, 7), (2, 512, 7, 7)])
+@pytest.mark.parametrize("k", [4, 0])
+def test_fused_bn_relu_mask_replaces_x_in_the_gradient_only_backward(shape, k):
+    """channels_last + ReLU: the forward can leave one byte per four channels saying where the ReLU is open; a
+    backward that wants no parameter gradients then takes the mask INSTEAD of x -- same bits as the pass that
+    re-derives the mask from x (NaN closes the ReLU in both)."""
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + k)
+    x = (torch.randn(shape, generator=g) * 1.4)
+    x[0, 0, 0, 0] = float("nan")
+    x = cu(x).contiguous(memory_format=torch.channels_last)
+    w, b, rm, rv = (cu(t) for t in make_bn(shape[1], g))
+    fq = (k, cu(torch.zeros(1)), cu(torch.tensor([1.9]))) if k else None
+    y, mask = ops.bn_eval_forward(x, w, b, rm, rv, 1e-5, relu=True, fq=fq, want_mask=True)
+    assert torch.equal(y.view(torch.int32), ops.bn_eval_forward(x, w, b, rm, rv, 1e-5, relu=True, fq=fq).view(torch.int32))
+    assert mask.dtype == torch.uint8 and mask.numel() == x.numel() // 4
+    gy = cu(torch.randn(shape, generator=g)).contiguous(memory_format=torch.channels_last)
+    ref, _, _ = ops.bn_eval_backward(x, gy, w, b, rm, rv, 1e-5, relu=True, want_param_grads=False)
+    got, dw, db = ops.bn_eval_backward(None, gy, w, b, rm, rv, 1e-5, relu=True, want_param_grads=False, mask=mask)
+    assert dw is None and db is None and got.stride() == ref.stride()
+    assert torch.equal(got.view(torch.int32), ref.view(torch.int32))
+    # with parameter gradients the mask is simply not used (x is needed for dW anyway)
+    full = ops.bn_eval_backward(x, gy, w, b, rm, rv, 1e-5, relu=True, mask=mask)
+    base = ops.bn_eval_backward(x, gy, w, b, rm, rv, 1e-5, relu=True)
+    assert all(torch.equal(a.view(torch.int32), b_.view(torch.int32)) for a, b_ in zip(full, base))     # (NaN-safe)
+    # NCHW tensors have no mask variant: the forward says so by returning None
+    _, none = ops.bn_eval_forward(x.contiguous(), w, b, rm, rv, 1e-5, relu=True, fq=fq, want_mask=True)
+    assert none is None
+    with pytest.raises(RuntimeError, match="needs x"):
+        ops.bn_eval_backward(None, gy, w, b, rm, rv, 1e-5, relu=True)
