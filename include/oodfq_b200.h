@@ -273,6 +273,22 @@ int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2, const flo
                             const float* w2, const float* b2, const float* rm2, const float* rv2, float eps2,
                             int flags, double* dwdb, void* workspace, oodfq_stream_t stream);
 
+/* ---- feature-alignment loss over all residual units, one kernel each way -------------------------------
+ * replaces: Trainer.loss_fa (trainer_direct.py:325-330) over the maps of Trainer.channel_attention
+ *           (trainer_direct.py:382-383): fa = lam * sum_l mean((F.normalize(Es_l) - F.normalize(Et_l))^2), and the
+ *           autograd tape behind it (~20 element-wise / reduction launches per unit and pass in eager PyTorch).
+ * e_student / e_teacher / grad_*: HOST arrays of L device pointers to [N, channels[l]] fp32 row-major tensors
+ * (the per-(image, channel) energies of oodfq_res_tail_forward / oodfq_channel_energy_forward); channels: host ints.
+ * forward : loss[0] (device) receives fa; row_scratch: L*N device doubles; workspace as everywhere.
+ * backward: grad tables receive grad_loss[0] * d fa / d E (grad_loss: device scalar, NULL = 1); either table may be
+ *           NULL, as may single entries (that side / unit gets no gradient).  L <= oodfq_fa_loss_max_layers(). */
+int oodfq_fa_loss_max_layers(void);
+int oodfq_fa_loss_forward(const float* const* e_student, const float* const* e_teacher, const int* channels, int L,
+                          int N, float lam, float* loss, double* row_scratch, void* workspace, oodfq_stream_t stream);
+int oodfq_fa_loss_backward(const float* const* e_student, const float* const* e_teacher, const int* channels, int L,
+                           int N, float lam, const float* grad_loss, float* const* grad_student,
+                           float* const* grad_teacher, oodfq_stream_t stream);
+
 /* ---- space-to-depth re-layout in front of the ImageNet stem convolution ---------------------------------
  * replaces: nothing in the reference -- it is the data format on the input side of Quant_Conv2d's F.conv2d call
  *           (quant_modules.py:279-281) for the 3-channel 7x7 stride-2 stem (main_direct.py:380-397), where a

@@ -635,7 +635,7 @@ class _FusedUnitMixin:
                                       bn2.bias if bn2 is not None else None, bn1, bn2, qact, bool(taps))
         setattr(y, _TWIN, twin)
         for t in taps:
-            t.maps.append(F.normalize(e))
+            t.maps.append(e)                      # raw energies: step.feature_alignment_loss(raw=True) normalises them
         return y
 
 

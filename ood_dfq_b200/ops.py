@@ -460,6 +460,58 @@ def channel_energy_backward(x, grad_e):
     return gx
 
 
+# ----------------------------------------------------------------------------- 8(f)-2: feature-alignment loss
+def _fa_tables(es, et):
+    if len(es) != len(et) or not es:
+        raise RuntimeError("ood_dfq_b200: the feature-alignment loss needs as many student as teacher maps (>= 1)")
+    if len(es) > int(N.load().oodfq_fa_loss_max_layers()):
+        raise RuntimeError(f"ood_dfq_b200: at most {int(N.load().oodfq_fa_loss_max_layers())} residual units per call")
+    n = es[0].shape[0]
+    keep = []
+    for i, (a, b) in enumerate(zip(es, et)):
+        _need(a, f"student energy[{i}]")
+        _need(b, f"teacher energy[{i}]")
+        if a.dim() != 2 or a.shape != b.shape or a.shape[0] != n:
+            raise RuntimeError("ood_dfq_b200: energies must be [N, C_l] tensors, pairwise of one shape")
+        keep.append((a.contiguous(), b.contiguous()))
+    L = len(keep)
+    ps = (C.c_void_p * L)(*[a.data_ptr() for a, _ in keep])
+    pt = (C.c_void_p * L)(*[b.data_ptr() for _, b in keep])
+    ch = (C.c_int * L)(*[a.shape[1] for a, _ in keep])
+    return keep, ps, pt, ch, L, n
+
+
+def fa_loss_forward(es, et, lam: float):
+    """``lam * sum_l mean((F.normalize(es[l]) - F.normalize(et[l]))**2)`` (trainer_direct.py:325-330, :382-383) of all
+    residual units in one launch.  ``es`` / ``et``: lists of ``[N, C_l]`` energies.  Returns a 1-element tensor."""
+    keep, ps, pt, ch, L, n = _fa_tables(es, et)
+    dev = keep[0][0].device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    scratch = torch.empty(L * n, dtype=torch.float64, device=dev)
+    rc = N.load().oodfq_fa_loss_forward(ps, pt, ch, L, n, float(lam), loss.data_ptr(), scratch.data_ptr(),
+                                        workspace(dev).data_ptr(), _stream(dev))
+    N.check(rc, "fa_loss_forward")
+    return loss
+
+
+def fa_loss_backward(es, et, lam: float, grad_loss, want_student=True, want_teacher=True):
+    """Gradients of ``fa_loss_forward`` w.r.t. every energy: ``(list for es, list for et)``; a side that is not
+    wanted comes back as a list of None."""
+    keep, ps, pt, ch, L, n = _fa_tables(es, et)
+    dev = keep[0][0].device
+    if grad_loss is not None:
+        _need(grad_loss, "grad_loss")
+        grad_loss = grad_loss.reshape(-1)[:1].contiguous()
+    gs = [torch.empty_like(a) for a, _ in keep] if want_student else [None] * L
+    gt = [torch.empty_like(b) for _, b in keep] if want_teacher else [None] * L
+    pgs = (C.c_void_p * L)(*[_ptr(g) for g in gs]) if want_student else None
+    pgt = (C.c_void_p * L)(*[_ptr(g) for g in gt]) if want_teacher else None
+    if want_student or want_teacher:
+        rc = N.load().oodfq_fa_loss_backward(ps, pt, ch, L, n, float(lam), _ptr(grad_loss), pgs, pgt, _stream(dev))
+        N.check(rc, "fa_loss_backward")
+    return gs, gt
+
+
 # ----------------------------------------------------------------------------- stem: BN -> ReLU -> [QuantAct] -> MaxPool(3,2,1)
 def bn_pool_supported(x) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0 and x.shape[1] <= 1024

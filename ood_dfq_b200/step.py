@@ -58,7 +58,9 @@ def channel_attention_fused(x):
 class FeatureTap:
     """Forward hooks collecting channel attention of the residual bodies (trainer_direct.py:432-440).
 
-    ``fused``: use the kernel (CUDA tensors); otherwise the reference's expression on a clone of the output.
+    ``fused``: use the kernels (CUDA tensors) -- ``maps`` then holds the RAW per-(image, channel) energies
+    ``x.pow(2).mean([2,3])`` and the normalisation happens inside the fused loss (``feature_alignment_loss(...,
+    raw=True)``); otherwise the reference's expression on a clone of the output, normalised as there.
     """
 
     def __init__(self, model: nn.Module, unit_types: tuple, fused=False):
@@ -67,14 +69,39 @@ class FeatureTap:
                         if isinstance(m, unit_types) and hasattr(m, "body")]
 
     def _hook(self, module, inputs, output):
-        self.maps.append(channel_attention_fused(output) if self.fused else channel_attention(output.clone()))
+        self.maps.append(_ChannelEnergy.apply(output) if self.fused else channel_attention(output.clone()))
 
     def clear(self):
         self.maps.clear()
 
 
-def feature_alignment_loss(student_maps, teacher_maps, lam: float, device):
-    """``lam * sum_l mean((A_s - A_t)^2)`` (trainer_direct.py:325-330)."""
+class _FusedFALoss(torch.autograd.Function):
+    """``lam * sum_l mean((normalize(Es_l) - normalize(Et_l))^2)`` and its gradient as one launch each
+    (csrc/fa_loss.cu) instead of ~20 element-wise / reduction launches per unit and pass."""
+
+    @staticmethod
+    def forward(ctx, lam, n_units, *energies):
+        from . import ops
+        es, et = list(energies[:n_units]), list(energies[n_units:])
+        ctx.save_for_backward(*energies)
+        ctx.lam, ctx.n_units = lam, n_units
+        return ops.fa_loss_forward(es, et, lam)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        from . import ops
+        L = ctx.n_units
+        es, et = list(ctx.saved_tensors[:L]), list(ctx.saved_tensors[L:])
+        need = ctx.needs_input_grad[2:]
+        gs, gt = ops.fa_loss_backward(es, et, ctx.lam, grad_loss, want_student=any(need[:L]), want_teacher=any(need[L:]))
+        return (None, None) + tuple(g if n else None for g, n in zip(gs + gt, need))
+
+
+def feature_alignment_loss(student_maps, teacher_maps, lam: float, device, raw=False):
+    """``lam * sum_l mean((A_s - A_t)^2)`` (trainer_direct.py:325-330).  ``raw``: the maps are un-normalised
+    energies (``FeatureTap(fused=True)``) and the whole expression, normalisation included, runs as one kernel."""
+    if raw and len(student_maps) > 0:
+        return _FusedFALoss.apply(float(lam), len(student_maps), *student_maps, *teacher_maps)
     fa = torch.zeros(1, device=device)
     for s, t in zip(student_maps, teacher_maps):
         fa = fa + (s - t).pow(2).mean()
@@ -119,6 +146,13 @@ class FlatGrads:
             self.flat.div_(dist.get_world_size(group))
 
 
+def _weight_bank(model):
+    """The ``WeightBank`` of this package's weight-quantising modules when ``model`` is built from them, else None
+    (the CPU arm drives oracle / reference modules, which re-quantise on every forward)."""
+    from .quantization_utils import quant_modules as qm
+    return qm.WeightBank if any(isinstance(m, qm._WeightQuantBase) for m in model.modules()) else None
+
+
 def _drop_stem_cache():
     """The space-to-depth stem keeps the re-laid-out batch of the last call so that teacher and student share it
     within an iteration (fusion._S2DCache); nothing may outlive the iteration (a batch and its copy, 300 MB)."""
@@ -131,7 +165,7 @@ class QATStep:
 
     def __init__(self, student, teacher, lr=1e-6, momentum=0.9, weight_decay=1e-4, temperature=20.0,
                  alpha=20.0, lam=1000.0, eps=0.01, unit_types: tuple = (), group=None, perturb=True,
-                 fused_attention=None, prune_backward=True):
+                 fused_attention=None, prune_backward=True, fused_optimizer=True):
         self.student, self.teacher = student, teacher
         self.T, self.alpha, self.lam, self.eps = temperature, alpha, lam, eps
         self.group, self.perturb = group, perturb
@@ -147,8 +181,12 @@ class QATStep:
         for p in teacher.parameters():
             p.requires_grad_(False)
         self.grads = FlatGrads(student.parameters())
+        # torch's multi-tensor ("fused") SGD where the parameters live on a GPU: the update of all 62 tensors is one
+        # launch per 2^n-tensor chunk instead of ~350 element-wise launches (0.9 ms of a 35 ms step); same formula as
+        # the reference's torch.optim.SGD(nesterov=True) (trainer_direct.py:59-65), stock PyTorch either way
+        on_gpu = self.grads.params[0].is_cuda
         self.opt = torch.optim.SGD(self.grads.params, lr=lr, momentum=momentum, weight_decay=weight_decay,
-                                   nesterov=True)
+                                   nesterov=True, **({"fused": True} if on_gpu and fused_optimizer else {}))
         if fused_attention is None:             # the kernel where the model lives on a GPU; the CPU arm keeps torch
             fused_attention = next(student.parameters()).is_cuda
         self.tap_s = FeatureTap(student, unit_types, fused_attention) if unit_types else None
@@ -160,7 +198,8 @@ class QATStep:
         out = self.student(images)
         kl = kd_loss(out, teacher_logits, self.T, self.alpha)
         if self.tap_s is not None:
-            fa = feature_alignment_loss(self.tap_s.maps, self.tap_t.maps, self.lam, images.device)
+            fa = feature_alignment_loss(self.tap_s.maps, self.tap_t.maps, self.lam, images.device,
+                                        raw=self.tap_s.fused and self.tap_t.fused)
         else:
             fa = torch.zeros(1, device=images.device)
         return out, kl, fa
@@ -180,6 +219,12 @@ class QATStep:
         if self.exchange:
             self.grads.all_reduce_mean(self.group)
         self.opt.step()
+        # The weights just changed: the modules' cached fake-quantised copies are stale whether or not the optimiser's
+        # in-place update bumped the parameters' version counters (torch's fused multi-tensor SGD does not, and a
+        # CUDA-graph capture that found the cache "fresh" would leave the re-quantisation out of the graph)
+        bank = _weight_bank(self.student)
+        if bank is not None:
+            bank.invalidate()
 
     def compute(self, images):
         """Both forwards and the backward of one iteration; leaves the gradients in the flat buffer."""
@@ -206,7 +251,12 @@ class QATStep:
                                "re-formatted after the step was built); create the step after model.to(...)")
         self.grads.zero()
         if self.prune_backward:
-            total.backward(inputs=self.grads.params)
+            # same pruned sweep as ``total.backward(inputs=params)``, but the gradients come back as fresh tensors and
+            # land in the flat buffer with ONE multi-tensor copy instead of one ``grad += g`` launch per parameter
+            got = torch.autograd.grad(total, self.grads.params, allow_unused=True)
+            dst = [p.grad for p, g in zip(self.grads.params, got) if g is not None]
+            if dst:
+                torch._foreach_copy_(dst, [g for g in got if g is not None])
         else:
             total.backward()
         _drop_stem_cache()
