@@ -293,10 +293,14 @@ int oodfq_fa_loss_backward(const float* const* e_student, const float* const* e_
  * replaces: nothing in the reference -- it is the data format on the input side of Quant_Conv2d's F.conv2d call
  *           (quant_modules.py:279-281) for the 3-channel 7x7 stride-2 stem (main_direct.py:380-397), where a
  *           stride-2 KxK convolution is run as the equal stride-1 convolution over the 2x2 space-to-depth image.
- * x [N,H,W,C] channels_last -> xs [N,(H+2*pad)/2,(W+2*pad)/2,4C], xs[n,i,j,(s,t,c)] = x[n,2i+s-pad,2j+t-pad,c]
- * (zero outside the image); backward is the inverse gather of the gradient. */
-int oodfq_s2d_stem_forward(const float* x, float* xs, int N, int H, int W, int C, int pad, oodfq_stream_t stream);
-int oodfq_s2d_stem_backward(const float* grad_xs, float* grad_x, int N, int H, int W, int C, int pad,
+ * x [N,H,W,C] channels_last -> xs [N,(H+2*pad)/2,(W+2*pad)/2,CP], xs[n,i,j,(s,t,c)] = x[n,2i+s-pad,2j+t-pad,c]
+ * (zero outside the image); CP = cpad floats per xs pixel: 0 or 4C for the plain form, or a larger multiple of 4 whose
+ * extra channels are written as zeros (16 for C = 3: cuDNN converts a 12-channel tensor before every use).
+ * backward is the inverse gather of the gradient (padding channels ignored).
+ * C = 1, 3, 4 with 16-byte-multiple rows run as a TMA-staged ring (bulk loads and stores). */
+int oodfq_s2d_stem_forward(const float* x, float* xs, int N, int H, int W, int C, int pad, int cpad,
+                           oodfq_stream_t stream);
+int oodfq_s2d_stem_backward(const float* grad_xs, float* grad_x, int N, int H, int W, int C, int pad, int cpad,
                             oodfq_stream_t stream);
 
 /* ---- batch assembly: gather -> RandomResizedCrop -> grey->RGB repeat -> RandomHorizontalFlip ----------------

@@ -61,8 +61,8 @@ SIGNATURES = {
     "oodfq_fa_loss_forward": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), _i, _i, C.c_float, _vp, _vp, _vp, _vp]),
     "oodfq_fa_loss_backward": (_i, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i), _i, _i, C.c_float, _vp,
                                     C.POINTER(_vp), C.POINTER(_vp), _vp]),
-    "oodfq_s2d_stem_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "oodfq_s2d_stem_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "oodfq_s2d_stem_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "oodfq_s2d_stem_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "oodfq_crop_resize_flip": (_i, [_vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_crop_resize_flip_backward": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "oodfq_bn_eval_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp, _vp]),

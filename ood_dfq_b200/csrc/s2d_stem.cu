@@ -22,18 +22,21 @@ namespace oodfq {
 
 struct S2dGeom {
     int N, H, W, C, pad, Hs, Ws;
+    int CP;             // floats per xs pixel: 4*C, or more (zero channels behind the 4*C real ones, e.g. 16 for C = 3:
+                        // cuDNN converts a 12-channel tensor before every use, a 16-channel one it takes as it is)
 };
 
 // generic channel counts: one thread per element (gather), runtime divisors
 template <bool BWD>
 __global__ void __launch_bounds__(256)
 s2d_stem_kernel(const float* __restrict__ src, float* __restrict__ dst, const S2dGeom G, long long total) {
-    const int c4 = 4 * G.C, c2 = 2 * G.C;
+    const int c4 = G.CP, c2 = 2 * G.C;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         if (!BWD) {
             // e indexes xs[n][i][j][ch]
             const int ch = (int)(e % c4);
             long long q = e / c4;
+            if (ch >= 4 * G.C) { dst[e] = 0.0f; continue; }          // padding channel
             const int j = (int)(q % G.Ws); q /= G.Ws;
             const int i = (int)(q % G.Hs);
             const long long n = q / G.Hs;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(kS2dThreads)
 s2d_stem_tma_kernel(const float* __restrict__ src, float* __restrict__ dst, const S2dGeom G) {
     extern __shared__ __align__(128) float s2d_smem[];
     __shared__ __align__(8) uint64_t full[kS2dStages];
-    const int wlen = G.W * C, xlen = 4 * C * G.Ws, shift = G.pad * C;
+    const int wlen = G.W * C, xlen = G.CP * G.Ws, shift = G.pad * C, cp4 = G.CP >> 2;
     const int in_len = BWD ? xlen : 2 * wlen, out_len = BWD ? 2 * wlen : xlen;
     const int stage_len = in_len + out_len;                         // floats; both parts are 16-byte multiples
     const long long rows = (long long)G.N * G.Hs;
@@ -178,7 +181,8 @@ s2d_stem_tma_kernel(const float* __restrict__ src, float* __restrict__ dst, cons
                 }
 #pragma unroll
                 for (int u = 0; u < C; ++u)
-                    reinterpret_cast<float4*>(out)[C * j + u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    reinterpret_cast<float4*>(out)[cp4 * j + u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                for (int u = C; u < cp4; ++u) reinterpret_cast<float4*>(out)[cp4 * j + u] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         } else {
             for (int j = threadIdx.x; j < G.Ws; j += kS2dThreads) {
@@ -186,7 +190,7 @@ s2d_stem_tma_kernel(const float* __restrict__ src, float* __restrict__ dst, cons
                 float v[4 * C];
 #pragma unroll
                 for (int u = 0; u < C; ++u) {
-                    const float4 t = reinterpret_cast<const float4*>(in)[C * j + u];
+                    const float4 t = reinterpret_cast<const float4*>(in)[cp4 * j + u];
                     v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
                 }
 #pragma unroll
@@ -216,9 +220,9 @@ s2d_stem_tma_kernel(const float* __restrict__ src, float* __restrict__ dst, cons
 
 template <int C, bool BWD>
 static bool launch_tma_c(const float* src, float* dst, const S2dGeom& G, cudaStream_t st) {
-    const int wlen = G.W * C, xlen = 4 * C * G.Ws;
+    const int wlen = G.W * C, xlen = G.CP * G.Ws;
     const size_t smem = (size_t)kS2dStages * (2 * wlen + xlen) * sizeof(float);
-    if ((wlen & 3) || !aligned16(src) || !aligned16(dst) || smem > 160 * 1024) return false;
+    if ((wlen & 3) || (G.CP & 3) || !aligned16(src) || !aligned16(dst) || smem > 160 * 1024) return false;
     auto kernel = s2d_stem_tma_kernel<C, BWD>;
     static int per_sm = -1;
     static size_t smem_set = 0;
@@ -248,6 +252,7 @@ static bool launch_tma(const float* src, float* dst, const S2dGeom& G, cudaStrea
 
 template <bool BWD>
 static bool launch_rows(const float* src, float* dst, const S2dGeom& G, cudaStream_t st) {
+    if (G.CP != 4 * G.C) return false;
     const long long rows = BWD ? (long long)G.N * G.H : (long long)G.N * G.Hs, cap = (long long)kNumSM * 32;
     const unsigned grid = (unsigned)(rows < cap ? rows : cap);
     switch (G.C) {
@@ -258,9 +263,11 @@ static bool launch_rows(const float* src, float* dst, const S2dGeom& G, cudaStre
     }
 }
 
-static int s2d_geom(int N, int H, int W, int C, int pad, S2dGeom& G) {
+static int s2d_geom(int N, int H, int W, int C, int pad, int cpad, S2dGeom& G) {
     if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || pad < 0 || ((H + 2 * pad) & 1) || ((W + 2 * pad) & 1)) return OODFQ_EINVAL;
-    G.N = N; G.H = H; G.W = W; G.C = C; G.pad = pad;
+    if (cpad == 0) cpad = 4 * C;
+    if (cpad < 4 * C) return OODFQ_EINVAL;
+    G.N = N; G.H = H; G.W = W; G.C = C; G.pad = pad; G.CP = cpad;
     G.Hs = (H + 2 * pad) / 2;
     G.Ws = (W + 2 * pad) / 2;
     return OODFQ_OK;
@@ -270,13 +277,13 @@ static int s2d_geom(int N, int H, int W, int C, int pad, S2dGeom& G) {
 
 using namespace oodfq;
 
-extern "C" int oodfq_s2d_stem_forward(const float* x, float* xs, int N, int H, int W, int C, int pad,
+extern "C" int oodfq_s2d_stem_forward(const float* x, float* xs, int N, int H, int W, int C, int pad, int cpad,
                                       oodfq_stream_t stream) {
     if (!x || !xs) return fail(OODFQ_EINVAL, "s2d_stem_forward: null pointer");
     S2dGeom G;
-    if (s2d_geom(N, H, W, C, pad, G) != OODFQ_OK)
-        return fail(OODFQ_EINVAL, "s2d_stem_forward: needs a non-empty tensor with even H + 2*pad and W + 2*pad");
-    const long long total = (long long)N * G.Hs * G.Ws * 4 * C;
+    if (s2d_geom(N, H, W, C, pad, cpad, G) != OODFQ_OK)
+        return fail(OODFQ_EINVAL, "s2d_stem_forward: needs a non-empty tensor with even H + 2*pad and W + 2*pad, cpad 0 or >= 4*C");
+    const long long total = (long long)N * G.Hs * G.Ws * G.CP;
     if (!launch_tma<false>(x, xs, G, (cudaStream_t)stream) && !launch_rows<false>(x, xs, G, (cudaStream_t)stream)) {
         static const int per_sm = resident_ctas(s2d_stem_kernel<false>, 256);
         long long want = (total + 255) / 256, cap = (long long)kNumSM * per_sm * 4;
@@ -287,11 +294,11 @@ extern "C" int oodfq_s2d_stem_forward(const float* x, float* xs, int N, int H, i
 }
 
 extern "C" int oodfq_s2d_stem_backward(const float* grad_xs, float* grad_x, int N, int H, int W, int C, int pad,
-                                       oodfq_stream_t stream) {
+                                       int cpad, oodfq_stream_t stream) {
     if (!grad_xs || !grad_x) return fail(OODFQ_EINVAL, "s2d_stem_backward: null pointer");
     S2dGeom G;
-    if (s2d_geom(N, H, W, C, pad, G) != OODFQ_OK)
-        return fail(OODFQ_EINVAL, "s2d_stem_backward: needs a non-empty tensor with even H + 2*pad and W + 2*pad");
+    if (s2d_geom(N, H, W, C, pad, cpad, G) != OODFQ_OK)
+        return fail(OODFQ_EINVAL, "s2d_stem_backward: needs a non-empty tensor with even H + 2*pad and W + 2*pad, cpad 0 or >= 4*C");
     const long long total = (long long)N * H * W * C;
     if (!launch_tma<true>(grad_xs, grad_x, G, (cudaStream_t)stream) &&
         !launch_rows<true>(grad_xs, grad_x, G, (cudaStream_t)stream)) {

@@ -752,11 +752,20 @@ def _fuse_residual_tails(model: nn.Module, example, verify, keep):
 
 
 # ------------------------------------------------------------------------------ stem convolution: space-to-depth input
+def _s2d_channels(c):
+    """Channels of the space-to-depth image handed to cuDNN.  The kernels can append zero channels (``cpad``), and a
+    16-channel image spares cuDNN the ``convertTensor_kernel`` it runs in front of every 12-channel fprop / dgrad /
+    wgrad (1.4 ms of the 224x224 step) -- but measured in the step the autotuner then picks a slower weight-gradient
+    kernel for the stem (1.4 instead of 0.84 ms per launch) and the iteration time does not move (33.72 vs 33.73 ms,
+    profiles/r2_exp_s2d_c16.txt).  So the plain 4*C form stays."""
+    return 4 * c
+
+
 class _S2D(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, pad):
         ctx.in_shape, ctx.pad = tuple(x.shape), pad
-        return ops.s2d_stem_forward(x, pad)
+        return ops.s2d_stem_forward(x, pad, cpad=_s2d_channels(x.shape[1]))
 
     @staticmethod
     def backward(ctx, grad_xs):
@@ -798,6 +807,9 @@ def _s2d_weight(w):
     w8 = F.pad(w, (0, kw % 2, 0, kh % 2))
     a, b = w8.shape[2] // 2, w8.shape[3] // 2
     w2 = w8.reshape(o, c, a, 2, b, 2).permute(0, 3, 5, 1, 2, 4).reshape(o, 4 * c, a, b)
+    cp = _s2d_channels(c)
+    if cp > 4 * c:
+        w2 = F.pad(w2, (0, 0, 0, 0, 0, cp - 4 * c))           # zero taps for the image's zero channels
     return w2.contiguous(memory_format=torch.channels_last)
 
 

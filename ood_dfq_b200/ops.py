@@ -679,29 +679,37 @@ def s2d_stem_supported(x, pad) -> bool:
             and x.is_contiguous(memory_format=torch.channels_last))
 
 
-def s2d_stem_forward(x, pad):
-    """channels_last ``[N,C,H,W]`` -> channels_last ``[N,4C,(H+2p)/2,(W+2p)/2]`` with channel order (s, t, c):
-    ``xs[n,(s,t,c),i,j] = x[n,c,2i+s-p,2j+t-p]``, zero outside the image."""
+def s2d_stem_forward(x, pad, cpad=None):
+    """channels_last ``[N,C,H,W]`` -> channels_last ``[N,CP,(H+2p)/2,(W+2p)/2]`` with channel order (s, t, c):
+    ``xs[n,(s,t,c),i,j] = x[n,c,2i+s-p,2j+t-p]``, zero outside the image.  ``CP = cpad`` (default ``4C``): a larger
+    multiple of 4 appends zero channels (cuDNN takes 16-channel tensors as they are, 12-channel ones it converts)."""
     _need(x, "input")
     if not s2d_stem_supported(x, pad):
         raise RuntimeError("ood_dfq_b200: space-to-depth needs a channels_last fp32 CUDA tensor with even H+2p, W+2p")
     n, c, h, w = x.shape
-    xs = torch.empty((n, 4 * c, (h + 2 * pad) // 2, (w + 2 * pad) // 2), dtype=torch.float32, device=x.device,
+    cp = 4 * c if cpad is None else int(cpad)
+    if cp < 4 * c or cp % 4:
+        raise RuntimeError("ood_dfq_b200: cpad must be a multiple of 4 that is >= 4*C")
+    xs = torch.empty((n, cp, (h + 2 * pad) // 2, (w + 2 * pad) // 2), dtype=torch.float32, device=x.device,
                      memory_format=torch.channels_last)
     with _Timed("s2d_stem_kernel (stem input re-layout, 8 B/elem)", 4 * (x.numel() + xs.numel())):
-        rc = N.load().oodfq_s2d_stem_forward(x.data_ptr(), xs.data_ptr(), n, h, w, c, int(pad), _stream(x.device))
+        rc = N.load().oodfq_s2d_stem_forward(x.data_ptr(), xs.data_ptr(), n, h, w, c, int(pad), cp, _stream(x.device))
         N.check(rc, "s2d_stem_forward")
     return xs
 
 
 def s2d_stem_backward(grad_xs, in_shape, pad):
-    """Gradient of ``s2d_stem_forward`` w.r.t. its input (channels_last ``in_shape``)."""
+    """Gradient of ``s2d_stem_forward`` w.r.t. its input (channels_last ``in_shape``); the channel padding, if any, is
+    read off ``grad_xs``."""
     _need(grad_xs, "grad_output")
     n, c, h, w = in_shape
     g = grad_xs.contiguous(memory_format=torch.channels_last)
+    cp = g.shape[1]
+    if cp < 4 * c or cp % 4:
+        raise RuntimeError("ood_dfq_b200: grad_output must have 4*C channels (or more, as a multiple of 4)")
     gx = torch.empty((n, c, h, w), dtype=torch.float32, device=g.device, memory_format=torch.channels_last)
     with _Timed("s2d_stem_kernel (stem input re-layout, 8 B/elem)", 4 * (gx.numel() + g.numel())):
-        rc = N.load().oodfq_s2d_stem_backward(g.data_ptr(), gx.data_ptr(), n, h, w, c, int(pad), _stream(g.device))
+        rc = N.load().oodfq_s2d_stem_backward(g.data_ptr(), gx.data_ptr(), n, h, w, c, int(pad), cp, _stream(g.device))
         N.check(rc, "s2d_stem_backward")
     return gx
 

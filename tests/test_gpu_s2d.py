@@ -34,6 +34,27 @@ def test_relayout_is_the_exact_gather_both_ways(shape, pad):
     assert gx.is_contiguous(memory_format=CL) and torch.equal(gx, xr.grad)
 
 
+@pytest.mark.parametrize("shape,pad,cpad", [((4, 3, 224, 224), 3, 16), ((3, 3, 32, 28), 3, 16), ((2, 1, 6, 8), 1, 8), ((2, 2, 6, 8), 1, 12),
+                                            ((3, 5, 4, 6), 2, 32)])
+def test_relayout_with_zero_channels_behind_the_real_ones(shape, pad, cpad):
+    """``cpad``: the space-to-depth image padded to a channel count cuDNN takes without converting (12 -> 16): the real
+    channels are the exact gather, the padding is zero, the backward ignores whatever gradient the padding carries."""
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + cpad)
+    x = torch.randn(shape, generator=g).to(DEV).contiguous(memory_format=CL)
+    c4 = 4 * shape[1]
+    xs = ops.s2d_stem_forward(x, pad, cpad=cpad)
+    ref = torch_s2d(x, pad)
+    assert xs.shape[1] == cpad and xs.is_contiguous(memory_format=CL)
+    assert torch.equal(xs[:, :c4], ref) and not xs[:, c4:].any()
+    gxs = torch.randn(xs.shape, generator=g).to(DEV).contiguous(memory_format=CL)
+    xr = x.clone().requires_grad_(True)
+    torch_s2d(xr, pad).backward(gxs[:, :c4])
+    assert torch.equal(ops.s2d_stem_backward(gxs, x.shape, pad), xr.grad)
+    with pytest.raises(RuntimeError, match="cpad"):
+        ops.s2d_stem_forward(x, pad, cpad=c4 - 4 if c4 > 4 else 2)
+
+
 def test_relayout_rejects_odd_extents_and_nchw():
     from ood_dfq_b200 import ops
     assert not ops.s2d_stem_supported(torch.zeros(1, 3, 7, 8, device=DEV).contiguous(memory_format=CL), 3)
