@@ -273,6 +273,20 @@ int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2, const flo
                             const float* w2, const float* b2, const float* rm2, const float* rv2, float eps2,
                             int flags, double* dwdb, void* workspace, oodfq_stream_t stream);
 
+/* ---- backward through an eval-mode BatchNorm whose input is tapped by the BN-statistics loss --------------
+ * replaces: the chain oodfq_bn_eval_backward -> oodfq_bn_stats_backward(grad_in = its result) for a BatchNorm that is
+ *           both fused and hooked by the statistics loss (distill_data.py:69-78, :252-265 put the
+ *           hook on EVERY BatchNorm): grad_x = [a_c*x+b_c > 0] * grad_y * a_c + g * (gmean_c/count +
+ *           gvar_c * 2*(x - mean_c)/count) in ONE pass over x and grad_y (12 B/elem instead of 8-12 + 12), same
+ *           roundings in the same order as the chain.  No parameter gradients (the hooked network is frozen).
+ * channels_last only (flags: OODFQ_BN_NHWC, optionally OODFQ_BN_RELU); mean, gmean, gvar, gscale as in
+ * oodfq_bn_stats_backward. */
+int oodfq_bn_eval_tap_backward(const float* x, const float* grad_y, float* grad_x, int N, int C, long long HW,
+                               const float* weight, const float* bias, const float* running_mean,
+                               const float* running_var, float eps, int flags, const float* mean,
+                               const float* gmean, const float* gvar, double count, const float* gscale,
+                               oodfq_stream_t stream);
+
 /* ---- feature-alignment loss over all residual units, one kernel each way -------------------------------
  * replaces: Trainer.loss_fa (trainer_direct.py:325-330) over the maps of Trainer.channel_attention
  *           (trainer_direct.py:382-383): fa = lam * sum_l mean((F.normalize(Es_l) - F.normalize(Et_l))^2), and the

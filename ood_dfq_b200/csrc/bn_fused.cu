@@ -392,6 +392,62 @@ bn_nhwc_bwdx_mask_kernel(const uint8_t* __restrict__ mask, const float* __restri
     }
 }
 
+// Backward through a BatchNorm whose INPUT is also tapped by the BN-statistics loss (every BatchNorm of the
+// distillation loop, distill_data.py:69-78 / :252-265): the chain is  grad_bn = [open] * grad_y * a_c  (kernel above)
+// followed by  grad_x = grad_bn + g * (gmean_c / M + gvar_c * 2 (x - mean_c) / M)  (bn_nhwc_bwd_kernel of bn_stats.cu):
+// 8-12 + 12 B/elem.  x is read by the second step anyway, so one pass does both -- 12 B/elem -- with the same
+// roundings in the same order (bit-identical to the chain).
+template <bool RELU>
+__global__ void __launch_bounds__(kBThreads)
+bn_nhwc_bwdx_tap_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                        const NhwcGeom G, const BnParams P, const float* __restrict__ mean,
+                        const float* __restrict__ gmean, const float* __restrict__ gvar, float inv_count,
+                        const float* __restrict__ gscale) {
+    const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
+    if ((int)threadIdx.x >= G.lanes_r * wcols) return;
+    const int rsub = threadIdx.x / wcols;
+    const float gs = gscale ? __ldg(gscale) : 1.0f;
+    const long long rstep = (long long)G.lanes_r * gridDim.x;
+    for (int cb = 0; cb < G.col_blocks; ++cb) {
+        const int col = cb * kBThreads + threadIdx.x % wcols;
+        if (col >= G.cols) continue;
+        float a[4], b[4], ca[4], cbv[4], mu[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float invstd;
+            affine_of(P, 4 * col + j, a[j], b[j], invstd);
+            ca[j] = gs * 2.0f * __ldg(gvar + 4 * col + j) * inv_count;
+            cbv[j] = gs * __ldg(gmean + 4 * col + j) * inv_count;
+            mu[j] = __ldg(mean + 4 * col + j);
+        }
+        for (long long r = (long long)blockIdx.x * G.lanes_r + rsub; r < G.R; r += kDepth * rstep) {
+            float4 v[kDepth], g[kDepth];
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const long long rr = r + d * rstep;
+                if (rr < G.R) {
+                    v[d] = ld_stream(reinterpret_cast<const float4*>(x) + rr * G.cols + col);
+                    g[d] = ld_stream(reinterpret_cast<const float4*>(gy) + rr * G.cols + col);
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const long long rr = r + d * rstep;
+                if (rr < G.R) {
+                    const float xs[4] = {v[d].x, v[d].y, v[d].z, v[d].w};
+                    float gsv[4] = {g[d].x, g[d].y, g[d].z, g[d].w}, o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (RELU && !(fmaf(xs[j], a[j], b[j]) > 0.0f)) gsv[j] = 0.0f;
+                        o[j] = __fadd_rn(fmaf(ca[j], xs[j] - mu[j], cbv[j]), __fmul_rn(gsv[j], a[j]));
+                    }
+                    st_out(reinterpret_cast<float4*>(gx) + rr * G.cols + col, make_float4(o[0], o[1], o[2], o[3]));
+                }
+            }
+        }
+    }
+}
+
 // Backward: every CTA leaves one fp64 partial (dW, dB) per channel in ws->bn_partial[cta][C][2];
 // bn_nhwc_fold_kernel then sums the partials of each channel in CTA order (deterministic).
 template <bool RELU, bool REDUCE>
@@ -608,4 +664,30 @@ extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float
     }
     count_launch();
     return check_launch("bn_eval_backward");
+}
+
+extern "C" int oodfq_bn_eval_tap_backward(const float* x, const float* grad_y, float* grad_x, int N, int C, long long HW,
+                                          const float* weight, const float* bias, const float* running_mean,
+                                          const float* running_var, float eps, int flags, const float* mean,
+                                          const float* gmean, const float* gvar, double count, const float* gscale,
+                                          oodfq_stream_t stream) {
+    if (!x || !grad_y || !grad_x || !running_mean || !running_var || !mean || !gmean || !gvar)
+        return fail(OODFQ_EINVAL, "bn_eval_tap_backward: null pointer");
+    if (N <= 0 || C <= 0 || HW <= 0 || !(count > 0)) return fail(OODFQ_EINVAL, "bn_eval_tap_backward: empty tensor");
+    if (!(flags & OODFQ_BN_NHWC) || (C % 4) != 0 || !aligned16(x) || !aligned16(grad_y) || !aligned16(grad_x))
+        return fail(OODFQ_EINVAL, "bn_eval_tap_backward: channels_last tensors with C %% 4 == 0 and 16-byte alignment only");
+    const BnParams P{weight, bias, running_mean, running_var, eps};
+    const NhwcGeom G = make_nhwc((long long)N * HW, C);
+    const bool relu = flags & OODFQ_BN_RELU;
+    static const int occ[2] = {resident_ctas(bn_nhwc_bwdx_tap_kernel<false>, kBThreads),
+                               resident_ctas(bn_nhwc_bwdx_tap_kernel<true>, kBThreads)};
+    long long want = (G.R + (long long)G.lanes_r * kDepth - 1) / ((long long)G.lanes_r * kDepth);
+    const long long cap = (long long)kNumSM * occ[relu ? 1 : 0];
+    const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+    const float ic = (float)(1.0 / count);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (relu) bn_nhwc_bwdx_tap_kernel<true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, mean, gmean, gvar, ic, gscale);
+    else bn_nhwc_bwdx_tap_kernel<false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, mean, gmean, gvar, ic, gscale);
+    count_launch();
+    return check_launch("bn_eval_tap_backward");
 }

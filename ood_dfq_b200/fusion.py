@@ -224,6 +224,8 @@ class _FusedEvalMixin:
 
     _tail = None          # AbsorbedTail / AbsorbedReLU or None (plain attribute: not a registered child)
     _pool = None          # AbsorbedPool or None: the stem max-pool behind the tail
+    _oodfq_accepts_tap = True     # bns.BNStatLoss leaves its tap in ``_pending_tap`` instead of hooking the input
+    _pending_tap = None
 
     def _tail_parts(self):
         if self._tail is None:
@@ -233,6 +235,9 @@ class _FusedEvalMixin:
         return True, self._tail[1]
 
     def forward(self, x):
+        tap = self._pending_tap
+        if tap is not None:
+            object.__setattr__(self, "_pending_tap", None)
         has_tail, qact = self._tail_parts()
         fusable = (not self.training) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 \
             and self.track_running_stats and self.running_mean is not None
@@ -243,14 +248,21 @@ class _FusedEvalMixin:
         if has_tail:
             self._tail._done = True               # the tail module right behind this BatchNorm hands our result through
         if not fusable:
+            if tap is not None:
+                x = tap.plain(x)
             y = super().forward(x)
             return self._tail.run(y) if has_tail else y
         q = qact if (qact is not None and not qact.full_precision_flag) else None
         if self._pool is not None and has_tail and ops.bn_pool_supported(x) and (q is None or q.activation_bit <= 8):
+            if tap is not None:
+                x = tap.plain(x)
             self._pool._bypass = True             # the pool module two steps downstream just hands this through
             out, twin = _FusedStem.apply(x, self.weight, self.bias, self, q)
             setattr(out, _TWIN, twin)
             return out
+        if tap is not None:
+            # statistics tap and BatchNorm as ONE autograd node: its backward is a single pass (bns._TapFusedBN)
+            return tap.fused(x, self.weight, self.bias, self, has_tail, q)
         return _FusedBN.apply(x, self.weight, self.bias, self, has_tail, q)
 
 

@@ -429,6 +429,27 @@ def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, re
     return gx, d[:c], d[c:]
 
 
+def bn_eval_tap_backward(x, grad_y, weight, bias, running_mean, running_var, eps, mean, gmean, gvar, count: float,
+                         relu=False, gscale=None):
+    """``bn_eval_backward`` (no parameter gradients) followed by ``bn_stats_backward`` accumulating into its result, as
+    ONE pass: the backward of a fused BatchNorm whose input is tapped by the BN-statistics loss.  channels_last only."""
+    _need(x, "input")
+    _need(grad_y, "grad_output")
+    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
+    if not nhwc:
+        raise RuntimeError("ood_dfq_b200: bn_eval_tap_backward takes channels_last tensors (C % 4 == 0) only")
+    gy = grad_y.contiguous(memory_format=torch.channels_last)
+    pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
+    gx = torch.empty_like(xc)
+    with _Timed("bn_*_bwdx_tap_kernel (fused BN backward + BNS-loss backward, 12 B/elem)", 12 * xc.numel()):
+        rc = N.load().oodfq_bn_eval_tap_backward(xc.data_ptr(), gy.data_ptr(), gx.data_ptr(), n, c, hw, pw, pb, prm, prv,
+                                                 float(eps), (N.BN_RELU if relu else 0) | N.BN_NHWC, mean.data_ptr(),
+                                                 gmean.data_ptr(), gvar.data_ptr(), float(count), _ptr(gscale),
+                                                 _stream(x.device))
+        N.check(rc, "bn_eval_tap_backward")
+    return gx
+
+
 # ----------------------------------------------------------------------------- 8(f)-2: feature-alignment reduction
 def channel_energy_forward(x):
     """``x.pow(2).mean([2, 3])`` of an NCHW / channels_last tensor in one read (trainer_direct.py:382-383)."""

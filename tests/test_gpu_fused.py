@@ -520,3 +520,51 @@ def test_fused_bn_relu_mask_replaces_x_in_the_gradient_only_backward(shape, k):
     assert none is None
     with pytest.raises(RuntimeError, match="needs x"):
         ops.bn_eval_backward(None, gy, w, b, rm, rv, 1e-5, relu=True)
+
+
+@pytest.mark.parametrize("quantised", [False, True])
+def test_statistics_tap_and_fused_batchnorm_share_one_backward_pass(quantised):
+    """``bns.BNStatLoss`` on a network whose BatchNorms are fused (the distillation loop hooks EVERY BatchNorm,
+    distill_data.py:69-78): tap and BatchNorm form one autograd node whose backward is a single kernel.  Loss and image
+    gradient must equal the two-kernel chain (a fused BatchNorm with the ordinary pre-hook tap) bit for bit."""
+    from ood_dfq_b200 import _native, bns, fusion, nets, surgery
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.manual_seed(5)
+    base = nets.perturb_bn_stats(nets.resnet20_cifar(num_classes=10))
+    if quantised:
+        base = surgery.quantize_model(base, 4, 4, namespace=qm)
+    net = base.to(DEV).to(memory_format=torch.channels_last).eval()
+    for p in net.parameters():
+        p.requires_grad_(False)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(8, 3, 32, 32, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    if quantised:
+        with torch.no_grad():
+            for _ in range(2):
+                net(x)
+        surgery.freeze_model(net, qm)
+    fusion.fuse_eval_bn(net, x[:2])
+
+    def run(one_node):
+        fusion._FusedEvalMixin._oodfq_accepts_tap = one_node
+        try:
+            stat = bns.BNStatLoss(net)
+            xi = x.detach().clone().requires_grad_(True)
+            out = net(xi)
+            loss = stat.loss() + out.square().mean()
+            torch.cuda.synchronize()
+            _native.reset_launch_count()
+            gx = torch.autograd.grad(loss, xi)[0]
+            n = _native.launch_count()
+            stat.remove()
+            return loss.detach(), gx, n
+        finally:
+            fusion._FusedEvalMixin._oodfq_accepts_tap = True
+
+    l_chain, g_chain, n_chain = run(False)
+    l_one, g_one, n_one = run(True)
+    assert torch.equal(l_chain, l_one)
+    assert torch.equal(g_chain.view(torch.int32), g_one.view(torch.int32))
+    assert n_one < n_chain, (n_one, n_chain)

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--nchw", action="store_true")
     ap.add_argument("--no-tail-fuse", action="store_true")
     ap.add_argument("--no-s2d", action="store_true")
+    ap.add_argument("--top", type=int, default=40)
     args = ap.parse_args()
     from ood_dfq_b200.quantization_utils import quant_modules as qm
     dev = torch.device("cuda:0")
@@ -54,7 +55,15 @@ def main():
         if not args.no_s2d:
             fusion.space_to_depth_stem(student, xs[0][:2])
             fusion.space_to_depth_stem(teacher, xs[0][:2])
-    qat = bench.make_step(args.workload, teacher, student, qm)
+    if bench.KINDS.get(args.workload) == "distill":
+        from ood_dfq_b200 import bns, step as step_mod
+        labels = torch.randint(0, bench.WORKLOADS[args.workload][1], (batch,), generator=g).to(dev)
+        dstep = step_mod.DistillStep(student, bns.BNStatLoss(student), xs[0] / 5, labels)
+
+        def qat(_batch=None):
+            return dstep()
+    else:
+        qat = bench.make_step(args.workload, teacher, student, qm)
     for i in range(3):
         qat(xs[i % 2])
     torch.cuda.synchronize()
@@ -72,7 +81,7 @@ def main():
     lines = [f"# {cfg}; batch {batch}; {args.steps} steps; device kernel time {total / args.steps / 1e3:.2f} ms/step",
              f"# {'share':>6s} {'ms/step':>9s} {'launches/step':>14s}  kernel"]
     ours = 0.0
-    for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+    for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.top]:
         mine = "oodfq::" in name
         ours += t if mine else 0.0
         lines.append(f"  {100 * t / total:6.2f} {t / args.steps / 1e3:9.3f} {n / args.steps:14.1f}  {'*' if mine else ' '} {name[:110]}")
