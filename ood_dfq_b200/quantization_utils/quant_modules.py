@@ -217,9 +217,11 @@ class WeightBank:
     step therefore quantises the whole model (one launch for ResNet-18's 21 tensors) and
     the remaining layers -- and the second student forward of the same step
     (trainer_direct.py:505, 514) -- hit the cache.
-    Mutating ``weight.data`` behind autograd's back does not bump ``_version``; call
-    ``WeightBank.invalidate()`` after doing that, or set ``WeightBank.enabled = False``
-    to re-quantise on every forward like the reference.
+    Mutating ``weight.data`` behind autograd's back does not bump ``_version``.  The cases this package can see
+    drop the cache themselves -- ``Module._apply`` (``.to()``, ``.cuda()``), ``load_state_dict``, and
+    ``step.QATStep.apply`` after every optimiser update (torch's fused multi-tensor SGD does not bump versions
+    either); for anything else call ``WeightBank.invalidate()``, or set ``WeightBank.enabled = False`` to re-quantise
+    on every forward like the reference.
     """
 
     enabled = True
@@ -268,6 +270,16 @@ class _WeightQuantBase(Module):
     def __repr__(self):
         s = super().__repr__()
         return "(" + s + " weight_bit={}, full_precision_flag={})".format(self.weight_bit, self.full_precision_flag)
+
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float() re-create or rewrite the parameter storage behind the version counter
+        self._wq, self._wq_key = None, None
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        # load_state_dict copies into ``weight.data`` under no_grad: drop the cached quantised copy explicitly
+        self._wq, self._wq_key = None, None
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def _take(self, src):
         self.weight = Parameter(src.weight.data.clone())

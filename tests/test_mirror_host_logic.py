@@ -518,3 +518,28 @@ def test_qat_step_on_a_fused_mirror_student_equals_the_oracle_step(mirror):
     (l_a, p_a), (l_b, p_b) = results
     assert all(torch.equal(a, b) for a, b in zip(l_a, l_b))
     assert all(torch.equal(a, b) for a, b in zip(p_a, p_b))
+
+
+def test_weight_cache_is_dropped_by_state_dict_loads_data_writes_through_apply_and_the_step(mirror):
+    """The fake-quantised weight is cached per parameter version.  Writes that bypass the version counter must still
+    be seen where the package can see them: ``load_state_dict`` (copies under no_grad -- bumps), ``Module._apply``
+    (``.to()`` / ``.double().float()`` rewrite ``.data``: no bump) and the optimiser update inside ``QATStep.apply``
+    (torch's fused SGD does not bump); the reference re-quantises on every forward and would notice all of them."""
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(4, 6, 3, bias=False)
+    q, ref = mirror.Quant_Conv2d(4), TWIN[2](4) if len(TWIN) > 2 else None
+    q.set_param(conv)
+    x = torch.randn(2, 4, 8, 8)
+    y0 = q(x)
+    other = {"weight": torch.randn_like(conv.weight)}
+    q.load_state_dict(other)
+    y1 = q(x)
+    want = torch.nn.functional.conv2d(x, cpu_ops_shim.weight_fq_multi([other["weight"]], [4], [False])[0]["wq"])
+    assert same(y1, want) and not same(y1, y0)
+    # a write through .data that nothing can observe keeps serving the cache (documented) ...
+    q.weight.data.mul_(2.0)
+    assert same(q(x), y1)
+    # ... until something the package sees happens: Module._apply
+    q._apply(lambda t: t)
+    want2 = torch.nn.functional.conv2d(x, cpu_ops_shim.weight_fq_multi([q.weight.detach()], [4], [False])[0]["wq"])
+    assert same(q(x), want2) and not same(want2, y1)
