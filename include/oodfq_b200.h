@@ -186,7 +186,7 @@ int oodfq_bn_stats_backward(const float* x, const float* grad_in, float* grad_x,
  *           followed by the nn.Sequential(ReLU, QuantAct) of main_direct.py:464-465
  * forward : y = [fakequant]( [relu]( a_c*x + b_c ) ),  a_c = w_c/sqrt(rv_c+eps), b_c = bias_c - rm_c*a_c
  * backward: g' = grad_y * [a_c*x+b_c > 0];  grad_x = g'*a_c;
- *           dwdb[c] = sum g'*(x-rm_c)/sqrt(rv_c+eps), dwdb[C+c] = sum g'   (fp64, NULL: skip)
+ *           dwdb[c] = sum g'*(x-rm_c)/sqrt(rv_c+eps), dwdb[C+c] = sum g'   (accumulated in fp64, stored as fp32; NULL: skip)
  * flags: OODFQ_BN_RELU | OODFQ_BN_QUANT (QUANT: scalar range fq_lo/fq_hi, k = fq_k <= 8; its
  * backward is the identity STE).  z_debug (nullable): the fp32 value handed to the quantiser.
  * weight / bias may be NULL (1 / 0).
@@ -200,7 +200,7 @@ int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, int N, int C
 int oodfq_bn_eval_backward(const float* x, const float* grad_y, float* grad_x, int N, int C,
                            long long HW, const float* weight, const float* bias,
                            const float* running_mean, const float* running_var, float eps,
-                           int flags, double* dwdb, void* workspace, const uint8_t* relu_mask,
+                           int flags, float* dwdb, void* workspace, const uint8_t* relu_mask,
                            oodfq_stream_t stream);
 
 /* ---- the reduction inside the feature-alignment loss ----------------------
@@ -229,7 +229,7 @@ int oodfq_bn_pool_forward(const float* x, float* out, uint8_t* idx, float* xhat,
 int oodfq_bn_pool_backward(const float* grad_out, const float* grad_out2, const uint8_t* idx, const float* xhat, float* grad_x,
                            int N, int C, int H, int W, const float* weight, const float* bias,
                            const float* running_mean, const float* running_var, float eps,
-                           double* dwdb, void* workspace, oodfq_stream_t stream);
+                           float* dwdb, void* workspace, oodfq_stream_t stream);
 
 /* ---- QuantAct_MSE: clip-ratio range search --------------------------------------------------------------
  * replaces: the 80-iteration loop of QuantAct_MSE.forward (quant_modules.py:160-178) with find_MSESmallest
@@ -259,7 +259,7 @@ int oodfq_act_mse_search(const float* x, long long numel, const float* data_minm
  *           gradients are wanted (rv2 && dwdb), and `x1` may be NULL when neither grad_energy nor dwdb is given:
  *           16.25 instead of 20 B/elem for the common case.
  * backward: grad_y2 (nullable) is a second gradient w.r.t. y, added to grad_y in registers (the output fed two
- *           consumers); grad_energy nullable; dwdb nullable, else [2*Ct] doubles with Ct = C (or 2C with BN2):
+ *           consumers); grad_energy nullable; dwdb nullable, else [2*Ct] floats (fp64 accumulation, rounded once) with Ct = C (or 2C with BN2):
  *           dW of BN1 (then BN2), followed by dB of BN1 (then BN2). */
 size_t oodfq_res_tail_scratch_floats(int N, int C);
 int oodfq_res_tail_forward(const float* x1, const float* r, float* y, float* energy, float* scratch,
@@ -271,7 +271,17 @@ int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2, const flo
                             const uint8_t* relu_mask, float* grad_x1, float* grad_r, int N, int C, long long HW,
                             const float* w1, const float* b1, const float* rm1, const float* rv1, float eps1,
                             const float* w2, const float* b2, const float* rm2, const float* rv2, float eps2,
-                            int flags, double* dwdb, void* workspace, oodfq_stream_t stream);
+                            int flags, float* dwdb, void* workspace, oodfq_stream_t stream);
+
+/* ---- eval-mode BatchNorm (+ReLU +QuantAct) AND the statistics of its input, one read ---------------------
+ * replaces: oodfq_bn_stats_forward(x, shift) followed by oodfq_bn_eval_forward(x) for a fused BatchNorm whose input is
+ *           tapped by the BN-statistics loss (distill_data.py:69-78 hooks every BatchNorm): y as oodfq_bn_eval_forward
+ *           (bit-identical), sums[2*C] fp64 as oodfq_bn_stats_forward, 8 instead of 4 + 8 B/elem.
+ * channels_last only (flags: OODFQ_BN_NHWC, optionally OODFQ_BN_RELU, OODFQ_BN_QUANT with a scalar range). */
+int oodfq_bn_eval_stats_forward(const float* x, float* y, int N, int C, long long HW, const float* weight,
+                                const float* bias, const float* running_mean, const float* running_var, float eps,
+                                int flags, const float* fq_lo, const float* fq_hi, int fq_k, const float* shift,
+                                double* sums, void* workspace, oodfq_stream_t stream);
 
 /* ---- backward through an eval-mode BatchNorm whose input is tapped by the BN-statistics loss --------------
  * replaces: the chain oodfq_bn_eval_backward -> oodfq_bn_stats_backward(grad_in = its result) for a BatchNorm that is

@@ -57,6 +57,8 @@ SIGNATURES = {
     "oodfq_act_mse_scratch_doubles": (C.c_size_t, [_i]),
     "oodfq_act_mse_search": (_i, [_vp, _ll, _vp, _i, _i, _d, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp]),
+    "oodfq_bn_eval_stats_forward": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp, _vp,
+                                         _vp, _vp]),
     "oodfq_bn_eval_tap_backward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _vp, _d,
                                         _vp, _vp]),
     "oodfq_fa_loss_max_layers": (_i, []),

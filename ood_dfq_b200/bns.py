@@ -128,11 +128,17 @@ class _TapFusedBN(torch.autograd.Function):
         if c != lay.channels:
             raise RuntimeError(f"BNStatLoss: layer {idx} saw {c} channels, expected {lay.channels}")
         xc = x if x.is_contiguous(memory_format=torch.channels_last) else x.contiguous()
-        ops.bn_stats_forward(xc, lay.module.running_mean, sums=run.sums[2 * lay.offset: 2 * (lay.offset + c)])
+        sums = run.sums[2 * lay.offset: 2 * (lay.offset + c)]
+        fq = (qact.activation_bit, qact.x_min, qact.x_max) if qact is not None else None
+        if xc.is_contiguous(memory_format=torch.channels_last) and not xc.is_contiguous() and c % 4 == 0:
+            # statistics and BatchNorm from ONE read of x (8 instead of 4 + 8 B/elem)
+            y = ops.bn_eval_stats_forward(xc, weight, bias, bn.running_mean, bn.running_var, bn.eps,
+                                          lay.module.running_mean, sums, relu=relu, fq=fq)
+        else:
+            ops.bn_stats_forward(xc, lay.module.running_mean, sums=sums)
+            y = ops.bn_eval_forward(xc, weight, bias, bn.running_mean, bn.running_var, bn.eps, relu=relu, fq=fq)
         run.counts[idx] = float(n * h * w)
         run.fired[idx] += 1
-        fq = (qact.activation_bit, qact.x_min, qact.x_max) if qact is not None else None
-        y = ops.bn_eval_forward(xc, weight, bias, bn.running_mean, bn.running_var, bn.eps, relu=relu, fq=fq)
         ctx.save_for_backward(xc, weight, bias)
         ctx.bn, ctx.relu, ctx.lay, ctx.idx, ctx.run = bn, relu, lay, idx, run
         ctx.set_materialize_grads(False)

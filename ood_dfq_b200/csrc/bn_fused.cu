@@ -20,29 +20,6 @@
 
 namespace oodfq {
 
-struct BnParams {
-    const float* w;    // [C] or NULL (1)
-    const float* b;    // [C] or NULL (0)
-    const float* rm;   // [C] running mean
-    const float* rv;   // [C] running var
-    float eps;
-};
-
-// one rounding per step, the same in every kernel (forward and the mask recomputed by backward)
-__device__ __forceinline__ void affine_of(const BnParams& P, int c, float& a, float& b, float& invstd) {
-    invstd = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(P.rv + c), P.eps)));
-    a = __fmul_rn(P.w ? __ldg(P.w + c) : 1.0f, invstd);
-    b = __fsub_rn(P.b ? __ldg(P.b + c) : 0.0f, __fmul_rn(__ldg(P.rm + c), a));
-}
-
-template <bool RELU, bool QUANT>
-__device__ __forceinline__ float head(float x, float a, float b, const QParams& qp, const float* lut, int qh,
-                                      int qmask, float& z) {
-    z = fmaf(x, a, b);
-    if (RELU) z = (z != z) ? z : fmaxf(z, 0.0f);      // clamp_min keeps NaN
-    return QUANT ? fake_quant_lut(z, qp, lut, qh, qmask) : z;
-}
-
 // =============================================================================== forward
 template <bool RELU, bool QUANT>
 __global__ void __launch_bounds__(kBThreads)
@@ -144,7 +121,7 @@ bn_group_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
 template <bool RELU, bool REDUCE>
 __global__ void __launch_bounds__(kBThreads)
 bn_plane_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx, int N,
-                     int C, long long HW, int split, const BnParams P, double* __restrict__ dwdb, Workspace* ws) {
+                     int C, long long HW, int split, const BnParams P, float* __restrict__ dwdb, Workspace* ws) {
     __shared__ float r1[kBThreads / 32], r2[kBThreads / 32];
     __shared__ int s_last;
     const int c = blockIdx.x / split, sp = blockIdx.x % split;
@@ -206,7 +183,7 @@ bn_plane_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, 
 template <int VEC, bool RELU, bool REDUCE>
 __global__ void __launch_bounds__(kBThreads)
 bn_group_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
-                     const BnGeom G, const BnParams P, double* __restrict__ dwdb, Workspace* ws) {
+                     const BnGeom G, const BnParams P, float* __restrict__ dwdb, Workspace* ws) {
     __shared__ float s1[REDUCE ? kBThreads * VEC : 1];
     __shared__ float s2[REDUCE ? kBThreads * VEC : 1];
     __shared__ int s_last;
@@ -588,7 +565,7 @@ extern "C" int oodfq_bn_eval_forward(const float* x, float* y, float* z_debug, i
 extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float* grad_x, int N, int C,
                                       long long HW, const float* weight, const float* bias,
                                       const float* running_mean, const float* running_var, float eps,
-                                      int flags, double* dwdb, void* workspace, const uint8_t* relu_mask,
+                                      int flags, float* dwdb, void* workspace, const uint8_t* relu_mask,
                                       oodfq_stream_t stream) {
     const bool by_mask = relu_mask && (flags & OODFQ_BN_NHWC) && (flags & OODFQ_BN_RELU) && !dwdb;
     if ((!x && !by_mask) || !grad_y || !grad_x || !running_mean || !running_var) return fail(OODFQ_EINVAL, "bn_eval_backward: null pointer");
@@ -628,7 +605,7 @@ extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float
         count_launch();
         int rc = check_launch("bn_eval_backward");
         if (rc != OODFQ_OK || !reduce) return rc;
-        bn_nhwc_fold_kernel<<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
+        bn_nhwc_fold_kernel<float><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
         count_launch();
         return check_launch("bn_eval_backward(fold)");
     }

@@ -23,9 +23,36 @@ constexpr long long kPlaneMin = 1024;               // planes at least this larg
 
 constexpr int kDepth = 4;                           // batch rows in flight per thread (group kernels)
 
+// ---- eval-mode BatchNorm as a per-channel affine (shared by bn_fused.cu and the statistics kernels) -----------
+struct BnParams {
+    const float* w;    // [C] or NULL (1)
+    const float* b;    // [C] or NULL (0)
+    const float* rm;   // [C] running mean
+    const float* rv;   // [C] running var
+    float eps;
+};
+
+// one rounding per step, the same in every kernel (forward and the mask recomputed by backward)
+__device__ __forceinline__ void affine_of(const BnParams& P, int c, float& a, float& b, float& invstd) {
+    invstd = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(P.rv + c), P.eps)));
+    a = __fmul_rn(P.w ? __ldg(P.w + c) : 1.0f, invstd);
+    b = __fsub_rn(P.b ? __ldg(P.b + c) : 0.0f, __fmul_rn(__ldg(P.rm + c), a));
+}
+
+template <bool RELU, bool QUANT>
+__device__ __forceinline__ float head(float x, float a, float b, const QParams& qp, const float* lut, int qh,
+                                      int qmask, float& z) {
+    z = fmaf(x, a, b);
+    if (RELU) z = (z != z) ? z : fmaxf(z, 0.0f);      // clamp_min keeps NaN
+    return QUANT ? fake_quant_lut(z, qp, lut, qh, qmask) : z;
+}
+
 // the last CTA of a channel folds that channel's `nparts` partials (one warp, fixed tree)
+// (OutT = double for the BN-input statistics, which cross NVLink as fp64; float for parameter gradients, which torch
+// consumes as fp32 -- rounding once here spares a conversion launch per backward)
+template <typename OutT>
 __device__ __forceinline__ void fold_partials(const double* partial, int C, int c, int nparts, int lane,
-                                              double* sums) {
+                                              OutT* sums) {
     double t1 = 0.0, t2 = 0.0;
     for (int p = lane; p < nparts; p += 32) {
         const double2 q = __ldcg(reinterpret_cast<const double2*>(partial + ((size_t)p * C + c) * 2));
@@ -35,8 +62,8 @@ __device__ __forceinline__ void fold_partials(const double* partial, int C, int 
     t1 = warp_sum(t1);
     t2 = warp_sum(t2);
     if (lane == 0) {
-        sums[c] = t1;
-        sums[C + c] = t2;
+        sums[c] = (OutT)t1;
+        sums[C + c] = (OutT)t2;
     }
 }
 
@@ -101,8 +128,9 @@ __host__ __device__ inline NhwcGeom make_nhwc(long long R, int C) {
 }
 
 // every CTA left one fp64 partial pair per channel in partial[cta][C][2]; sum them in CTA order
+template <typename OutT>
 static __global__ void __launch_bounds__(kBThreads)
-bn_nhwc_fold_kernel(const double* __restrict__ partial, int C, int nparts, double* __restrict__ dwdb) {
+bn_nhwc_fold_kernel(const double* __restrict__ partial, int C, int nparts, OutT* __restrict__ dwdb) {
     const int lane = threadIdx.x & 31;
     const int c = blockIdx.x * (kBThreads / 32) + (threadIdx.x >> 5);
     if (c < C) fold_partials(partial, C, c, nparts, lane, dwdb);

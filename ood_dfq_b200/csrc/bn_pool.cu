@@ -582,7 +582,7 @@ extern "C" int oodfq_bn_pool_forward(const float* x, float* out, uint8_t* idx, f
 extern "C" int oodfq_bn_pool_backward(const float* grad_out, const float* grad_out2, const uint8_t* idx, const float* xhat, float* grad_x,
                                       int N, int C, int H, int W, const float* weight, const float* bias,
                                       const float* running_mean, const float* running_var, float eps,
-                                      double* dwdb, void* workspace, oodfq_stream_t stream) {
+                                      float* dwdb, void* workspace, oodfq_stream_t stream) {
     if (!grad_out || !idx || !grad_x || !running_mean || !running_var) return fail(OODFQ_EINVAL, "bn_pool_backward: null pointer");
     if (dwdb && (!xhat || !workspace)) return fail(OODFQ_EINVAL, "bn_pool_backward: parameter gradients need xhat and the workspace");
     PoolGeom G;
@@ -615,7 +615,7 @@ extern "C" int oodfq_bn_pool_backward(const float* grad_out, const float* grad_o
             count_launch();
             int rc = check_launch("bn_pool_backward(tma)");
             if (rc != OODFQ_OK || !dwdb) return rc;
-            bn_nhwc_fold_kernel<<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
+            bn_nhwc_fold_kernel<float><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
             count_launch();
             return check_launch("bn_pool_backward(fold)");
         }
@@ -631,7 +631,7 @@ extern "C" int oodfq_bn_pool_backward(const float* grad_out, const float* grad_o
     count_launch();
     int rc = check_launch("bn_pool_backward");
     if (rc != OODFQ_OK || !dwdb) return rc;
-    bn_nhwc_fold_kernel<<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
+    bn_nhwc_fold_kernel<float><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
     count_launch();
     return check_launch("bn_pool_backward(fold)");
 }

@@ -326,11 +326,14 @@ bn_group_bwd_kernel(const float* __restrict__ x, const float* grad_in, float* gr
 }
 
 // =============================================================================== NHWC kernels
-template <bool QUANT>
+// HEAD: what the optional output y is -- 0: fakequant(x) (QuantAct with channel statistics, north_star (b)),
+// 1: [fakequant](BN_eval(x)), 2: [fakequant](relu(BN_eval(x))): the fused eval-mode BatchNorm (bn_fused.cu) whose INPUT is
+// tapped by the BN-statistics loss, statistics and BatchNorm from ONE read of x (8 instead of 4 + 8 B/elem).
+template <bool QUANT, int HEAD = 0>
 __global__ void __launch_bounds__(kBThreads)
 bn_nhwc_stats_kernel(const float* __restrict__ x, const NhwcGeom G, const float* __restrict__ shift,
                      float* __restrict__ y, const float* __restrict__ fq_lo, const float* __restrict__ fq_hi,
-                     int fq_k, Workspace* ws) {
+                     int fq_k, Workspace* ws, const BnParams P = BnParams{nullptr, nullptr, nullptr, nullptr, 0.f}) {
     __shared__ double dred[2 * kBThreads];
     __shared__ float lut[QUANT ? kLutMax : 1];
     QParams qp;
@@ -349,7 +352,12 @@ bn_nhwc_stats_kernel(const float* __restrict__ x, const NhwcGeom G, const float*
         const int col = cb * kBThreads + threadIdx.x % wcols;
         const bool on = active && col < G.cols && r0 < G.R;
         float pv[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+        float ha[4] = {1.f, 1.f, 1.f, 1.f}, hb[4] = {0.f, 0.f, 0.f, 0.f};
         long long cnt = 0;
+        if (HEAD && on) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { float invstd; affine_of(P, 4 * col + j, ha[j], hb[j], invstd); }
+        }
         if (on) {
             // pivot = this thread's first row: a sample of each of its 4 channels
             const float4 p4 = __ldg(reinterpret_cast<const float4*>(x) + r0 * G.cols + col);
@@ -373,10 +381,16 @@ bn_nhwc_stats_kernel(const float* __restrict__ x, const NhwcGeom G, const float*
                             a1[j] += dl;
                             a2[j] = fmaf(dl, dl, a2[j]);
                         }
-                        if (QUANT)
+                        if (HEAD) {
+                            float z, o[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) o[j] = head<HEAD == 2, QUANT>(xs[j], ha[j], hb[j], qp, lut, qh, qmask, z);
+                            st_out(reinterpret_cast<float4*>(y) + rr * G.cols + col, make_float4(o[0], o[1], o[2], o[3]));
+                        } else if (QUANT) {
                             st_out(reinterpret_cast<float4*>(y) + rr * G.cols + col,
                                    make_float4(fake_quant_lut(xs[0], qp, lut, qh, qmask), fake_quant_lut(xs[1], qp, lut, qh, qmask),
                                                fake_quant_lut(xs[2], qp, lut, qh, qmask), fake_quant_lut(xs[3], qp, lut, qh, qmask)));
+                        }
                     }
                 }
             }
@@ -541,7 +555,7 @@ extern "C" int oodfq_bn_stats_forward(const float* x, int N, int C, long long HW
         count_launch();
         int rc = check_launch("bn_stats_forward");
         if (rc != OODFQ_OK) return rc;
-        bn_nhwc_fold_kernel<<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, sums);
+        bn_nhwc_fold_kernel<double><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, sums);
         count_launch();
         return check_launch("bn_stats_forward(fold)");
     }
@@ -635,4 +649,40 @@ extern "C" int oodfq_bn_stats_backward(const float* x, const float* grad_in, flo
     else bn_group_bwd_kernel<1><<<grid, kBThreads, 0, st>>>(x, grad_in, grad_x, G, mean, gmean, gvar, ic, gscale);
     count_launch();
     return check_launch("bn_stats_backward");
+}
+
+extern "C" int oodfq_bn_eval_stats_forward(const float* x, float* y, int N, int C, long long HW, const float* weight,
+                                           const float* bias, const float* running_mean, const float* running_var,
+                                           float eps, int flags, const float* fq_lo, const float* fq_hi, int fq_k,
+                                           const float* shift, double* sums, void* workspace, oodfq_stream_t stream) {
+    if (!x || !y || !running_mean || !running_var || !sums || !workspace)
+        return fail(OODFQ_EINVAL, "bn_eval_stats_forward: null pointer");
+    if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "bn_eval_stats_forward: empty tensor");
+    if (C > kMaxBnChannels) return fail(OODFQ_EINVAL, "bn_eval_stats_forward: C=%d exceeds %d", C, kMaxBnChannels);
+    if (!(flags & OODFQ_BN_NHWC) || (C % 4) != 0 || !aligned16(x) || !aligned16(y))
+        return fail(OODFQ_EINVAL, "bn_eval_stats_forward: channels_last tensors with C %% 4 == 0 and 16-byte alignment only");
+    const bool relu = flags & OODFQ_BN_RELU, quant = flags & OODFQ_BN_QUANT;
+    if (quant && (!fq_lo || !fq_hi || fq_k < 1 || fq_k > 8))
+        return fail(OODFQ_EINVAL, "bn_eval_stats_forward: fused fake-quant needs a range and k in [1,8]");
+    cudaStream_t st = (cudaStream_t)stream;
+    Workspace* ws = reinterpret_cast<Workspace*>(workspace);
+    const BnParams P{weight, bias, running_mean, running_var, eps};
+    const NhwcGeom G = make_nhwc((long long)N * HW, C);
+    static const int occ[4] = {resident_ctas(bn_nhwc_stats_kernel<false, 1>, kBThreads), resident_ctas(bn_nhwc_stats_kernel<false, 2>, kBThreads),
+                               resident_ctas(bn_nhwc_stats_kernel<true, 1>, kBThreads), resident_ctas(bn_nhwc_stats_kernel<true, 2>, kBThreads)};
+    long long want = (G.R + (long long)G.lanes_r * kDepth - 1) / ((long long)G.lanes_r * kDepth);
+    long long cap = (long long)kNumSM * occ[(quant ? 2 : 0) + (relu ? 1 : 0)];
+    const long long table = (long long)kMaxBnSplit * kMaxBnChannels / C;
+    if (cap > table) cap = table;
+    const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+    if (quant && relu) bn_nhwc_stats_kernel<true, 2><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws, P);
+    else if (quant) bn_nhwc_stats_kernel<true, 1><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws, P);
+    else if (relu) bn_nhwc_stats_kernel<false, 2><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws, P);
+    else bn_nhwc_stats_kernel<false, 1><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws, P);
+    count_launch();
+    int rc = check_launch("bn_eval_stats_forward");
+    if (rc != OODFQ_OK) return rc;
+    bn_nhwc_fold_kernel<double><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, sums);
+    count_launch();
+    return check_launch("bn_eval_stats_forward(fold)");
 }

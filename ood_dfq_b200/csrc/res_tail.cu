@@ -402,7 +402,7 @@ extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2
                                        const uint8_t* relu_mask, float* grad_x1, float* grad_r, int N, int C, long long HW, const float* w1,
                                        const float* b1, const float* rm1, const float* rv1, float eps1,
                                        const float* w2, const float* b2, const float* rm2, const float* rv2,
-                                       float eps2, int flags, double* dwdb, void* workspace, oodfq_stream_t stream) {
+                                       float eps2, int flags, float* dwdb, void* workspace, oodfq_stream_t stream) {
     if (!grad_y || !grad_x1 || !grad_r || !rm1 || !rv1) return fail(OODFQ_EINVAL, "res_tail_backward: null pointer");
     if (N <= 0 || C <= 0 || HW <= 0) return fail(OODFQ_EINVAL, "res_tail_backward: empty tensor");
     if (!(flags & OODFQ_BN_NHWC)) return fail(OODFQ_EINVAL, "res_tail_backward: channels_last only");
@@ -439,7 +439,7 @@ extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2
     int rc = check_launch("res_tail_backward");
     if (rc != OODFQ_OK || !reduce) return rc;
     // dwdb[0 .. Ct) = dW (BN1 channels, then BN2), dwdb[Ct .. 2 Ct) = dB
-    bn_nhwc_fold_kernel<<<(Ct + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, Ct, (int)grid, dwdb);
+    bn_nhwc_fold_kernel<float><<<(Ct + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, Ct, (int)grid, dwdb);
     count_launch();
     return check_launch("res_tail_backward(fold)");
 }

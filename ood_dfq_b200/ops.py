@@ -414,7 +414,7 @@ def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, re
         gy = grad_y.contiguous(memory_format=torch.channels_last) if nhwc else grad_y.contiguous()
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
     gx = torch.empty_like(gy)
-    dwdb = torch.empty(2 * c, dtype=torch.float64, device=gy.device) if want_param_grads else None
+    dwdb = torch.empty(2 * c, dtype=torch.float32, device=gy.device) if want_param_grads else None
     ws = workspace(gy.device).data_ptr() if want_param_grads else None
     reads_x = (relu or want_param_grads) and not by_mask   # otherwise grad_x = grad_y * a_c and x is never touched
     with _Timed("bn_*_bwdx_kernel (fused BN backward, 12 B/elem; 8 without ReLU mask and parameter grads)",
@@ -425,8 +425,31 @@ def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, re
         N.check(rc, "bn_eval_backward")
     if not want_param_grads:
         return gx, None, None
-    d = dwdb.float()
+    d = dwdb
     return gx, d[:c], d[c:]
+
+
+def bn_eval_stats_forward(x, weight, bias, running_mean, running_var, eps, shift, sums, relu=False, fq=None):
+    """``bn_stats_forward(x, shift, sums=sums)`` and ``bn_eval_forward(x, ...)`` from ONE read of a channels_last ``x``:
+    returns ``y`` (bit-identical to ``bn_eval_forward``) and fills ``sums`` (fp64 ``[2*C]``, shifted by ``shift``)."""
+    _need(x, "input")
+    xc, n, c, hw, nhwc = _nchw_or_nhwc(x)
+    if not nhwc:
+        raise RuntimeError("ood_dfq_b200: bn_eval_stats_forward takes channels_last tensors (C % 4 == 0) only")
+    pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
+    if sums.dtype != torch.float64 or sums.numel() != 2 * c or not sums.is_contiguous():
+        raise RuntimeError("ood_dfq_b200: sums must be a contiguous float64 [2*C] tensor")
+    y = torch.empty_like(xc)
+    flags, k, lo, hi = (N.BN_RELU if relu else 0) | N.BN_NHWC, 0, None, None
+    if fq is not None:
+        k, lo, hi = fq
+        flags |= N.BN_QUANT
+    with _Timed("bn_*_stats_kernel + fused BN forward (8 B/elem)", 8 * xc.numel()):
+        rc = N.load().oodfq_bn_eval_stats_forward(xc.data_ptr(), y.data_ptr(), n, c, hw, pw, pb, prm, prv, float(eps), flags,
+                                                  _ptr(lo), _ptr(hi), int(k), _ptr(shift), sums.data_ptr(),
+                                                  workspace(x.device).data_ptr(), _stream(x.device))
+        N.check(rc, "bn_eval_stats_forward")
+    return y
 
 
 def bn_eval_tap_backward(x, grad_y, weight, bias, running_mean, running_var, eps, mean, gmean, gvar, count: float,
@@ -581,7 +604,7 @@ def bn_pool_backward(grad_out, idx, xhat, in_shape, weight, bias, running_mean, 
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
     gx = torch.empty((n, c, h, w), dtype=torch.float32, device=grad_out.device, memory_format=torch.channels_last)
     need = want_param_grads and xhat is not None
-    dwdb = torch.empty(2 * c, dtype=torch.float64, device=grad_out.device) if need else None
+    dwdb = torch.empty(2 * c, dtype=torch.float32, device=grad_out.device) if need else None
     ws = workspace(grad_out.device).data_ptr() if need else None
     with _Timed("bn_pool_bwd_kernel (stem backward, 4 B/elem out + 1/4 size inputs)",
                 4 * gx.numel() + ((9 if need else 5) + (4 if go2 is not None else 0)) * go.numel()):
@@ -591,7 +614,7 @@ def bn_pool_backward(grad_out, idx, xhat, in_shape, weight, bias, running_mean, 
         N.check(rc, "bn_pool_backward")
     if not need:
         return gx, None, None
-    d = dwdb.float()
+    d = dwdb
     return gx, d[:c], d[c:]
 
 
@@ -675,7 +698,7 @@ def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grad
     p1, p2 = _tail_bn(bn1, c), _tail_bn(bn2, c)
     gx1, gr = torch.empty_like(gy), torch.empty_like(gy)
     ct = c * (2 if bn2 is not None else 1)
-    dwdb = torch.empty(2 * ct, dtype=torch.float64, device=gy.device) if want_param_grads else None
+    dwdb = torch.empty(2 * ct, dtype=torch.float32, device=gy.device) if want_param_grads else None
     ws = workspace(gy.device).data_ptr() if want_param_grads else None
     per_elem = 12 + (4 if gy2 is not None else 0) + (4 if reads_x1 else 0) + (4 if reads_r else 0) + (0.25 if mask is not None else 0)
     with _Timed("res_tail_bwd_kernel (ReLU mask + energy gradient + BN backward(s), 16.25 - 24 B/elem)",
@@ -687,7 +710,7 @@ def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grad
         N.check(rc, "res_tail_backward")
     if not want_param_grads:
         return gx1, gr, None, None, None, None
-    d = dwdb.float()
+    d = dwdb
     if bn2 is None:
         return gx1, gr, d[:c], d[c:], None, None
     return gx1, gr, d[:c], d[2 * c:3 * c], d[c:2 * c], d[3 * c:]

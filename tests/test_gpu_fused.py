@@ -565,6 +565,38 @@ def test_statistics_tap_and_fused_batchnorm_share_one_backward_pass(quantised):
 
     l_chain, g_chain, n_chain = run(False)
     l_one, g_one, n_one = run(True)
-    assert torch.equal(l_chain, l_one)
-    assert torch.equal(g_chain.view(torch.int32), g_one.view(torch.int32))
+    # the statistics come out of another kernel (grid, hence fp32 partial grouping, differs): equal to fp64 accuracy
+    np.testing.assert_allclose(l_one.item(), l_chain.item(), rtol=1e-6)
+    scale = g_chain.abs().max().item()
+    np.testing.assert_allclose(g_one.cpu().numpy(), g_chain.cpu().numpy(), rtol=1e-4, atol=1e-6 * scale)
     assert n_one < n_chain, (n_one, n_chain)
+
+
+@pytest.mark.parametrize("shape", [(8, 64, 14, 14), (32, 128, 28, 28), (3, 8, 5, 7), (2, 512, 7, 7)])
+@pytest.mark.parametrize("relu,k", [(True, 4), (True, 0), (False, 0)])
+def test_tapped_batchnorm_kernels_equal_their_two_kernel_chains(shape, relu, k):
+    """Op level.  Forward: statistics of x and the fused BatchNorm output from one read -- y bit-identical to
+    ``bn_eval_forward``, sums equal to ``bn_stats_forward`` up to the fp32 grouping of another grid.  Backward: BN backward
+    and the BN-statistics loss gradient in one pass -- bit-identical to ``bn_eval_backward`` followed by
+    ``bn_stats_backward`` accumulating into its result."""
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + k + relu)
+    c = shape[1]
+    x = cu(torch.randn(shape, generator=g) * 1.4 + 0.3).contiguous(memory_format=torch.channels_last)
+    w, b, rm, rv = (cu(t) for t in make_bn(c, g))
+    fq = (k, cu(torch.zeros(1)), cu(torch.tensor([1.9]))) if k else None
+    sums = torch.empty(2 * c, dtype=torch.float64, device=DEV)
+    y = ops.bn_eval_stats_forward(x, w, b, rm, rv, 1e-5, rm, sums, relu=relu, fq=fq)
+    y_ref = ops.bn_eval_forward(x, w, b, rm, rv, 1e-5, relu=relu, fq=fq)
+    assert y.stride() == y_ref.stride() and torch.equal(y.view(torch.int32), y_ref.view(torch.int32))
+    sums_ref = ops.bn_stats_forward(x, rm)
+    np.testing.assert_allclose(sums.cpu().numpy(), sums_ref.cpu().numpy(), rtol=1e-6, atol=1e-6 * x.numel() / c)
+    count = float(x.numel() // c)
+    mean, var = ops.bn_stats_finalize(sums_ref, rm, count)
+    gmean, gvar = cu(torch.randn(c, generator=g)), cu(torch.randn(c, generator=g))
+    gy = cu(torch.randn(shape, generator=g)).contiguous(memory_format=torch.channels_last)
+    gs = cu(torch.tensor([0.37]))
+    chain, _, _ = ops.bn_eval_backward(x, gy, w, b, rm, rv, 1e-5, relu=relu, want_param_grads=False)
+    chain = ops.bn_stats_backward(x, chain, mean, gmean, gvar, count, gscale=gs)
+    one = ops.bn_eval_tap_backward(x, gy, w, b, rm, rv, 1e-5, mean, gmean, gvar, count, relu=relu, gscale=gs)
+    assert torch.equal(one.view(torch.int32), chain.view(torch.int32))

@@ -52,10 +52,11 @@ if has ncu; then
   # one full capture per headline family, on the microbenchmark (a single tensor per launch, a few launches)
   log "ncu --set full (tail, bn, stem, s2d, fq, single-pass calibration)"
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:'res_tail|bn_nhwc|bn_pool|s2d_stem|fq_flat|act_calib_onchip' -c 120 \
-      -o gpurun_out/full_kernels -f python tools/microbench.py --only fq,tail,bn_fwd,bn_bwd,pool,s2d,calib_stats --shapes 0,1,4 --iters 1 --warmup 0 --flush none \
+      -o /tmp/full_kernels -f python tools/microbench.py --only fq,tail,bn_fwd,bn_bwd,pool,s2d,calib_stats --shapes 0,1,4 --iters 1 --warmup 0 --flush none \
       > gpurun_out/ncu_full.log 2>&1
   log "ncu full exit $?"
-  ncu -i gpurun_out/full_kernels.ncu-rep --page raw --csv \
+  # the .ncu-rep itself (sources included) exceeds what gpurun copies back: it stays on the box, the tables come home
+  ncu -i /tmp/full_kernels.ncu-rep --page raw --csv \
       --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct_of_peak_sustained_active \
       > gpurun_out/full_kernels_raw.csv 2>/dev/null || true
   python tools/ncu_traffic.py gpurun_out/full_kernels_raw.csv "profiles/r2_full_kernels_raw.csv (ncu --set full on tools/microbench.py, this build)" \
