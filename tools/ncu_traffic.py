@@ -25,7 +25,10 @@ def family(name):
     plain, _, targs = fn.partition("<")
     targs = [t.strip() for t in targs.rstrip(">").split(",")] if targs else []
     if plain.startswith("res_tail_bwd"):
-        return "res_tail_bwd_kernel"
+        # the step only launches the variants that take the forward's ReLU mask (4th template argument); the variant
+        # that re-derives the mask from x1 and r is kept under its own key
+        masked = len(targs) >= 4 and targs[3].strip("()bool ") in ("1", "true")
+        return "res_tail_bwd_kernel" if masked else "res_tail_bwd_kernel<no mask>"
     if plain.startswith("res_tail_fwd"):
         return "res_tail_fwd_kernel"
     if plain.startswith("bn_pool_fwd"):
