@@ -61,15 +61,30 @@ __device__ __forceinline__ void scan_pixel(Cand& r, const float4 v, const int j,
     const float xs[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const float z = max_nan(fmaf(xs[c], a[c], b[c]), 0.0f);       // BN affine, ReLU (NaN stays NaN)
-        float key = z;
-        if (QUANT) {
-            key = code_of<false>(z, qp);
-            if (!STRICT) { const float y = lut[lut_index(key, qh, qmask)]; key = (key != key) ? key : y; }
+        const float zr = fmaf(xs[c], a[c], b[c]);                     // BN affine
+        float key;
+        if (QUANT && STRICT) {
+            // The code of relu(z) without the ReLU, the clamp-after-round and the FRND of code_of():
+            //   u = scale*z - zp  (the reference's two roundings); relu: s*z - zp is monotone in z and equals -zp at z = 0
+            //   (also at -0), so max(u, -zp) IS u(relu(z)); clamp and rint commute for integer bounds; rint of a value in
+            //   [-2^22, 2^22] is (u + 1.5*2^23) - 1.5*2^23 in round-to-nearest-even.  The biased sum orders like the code
+            //   and its low bits are the table index, so it is kept as the key: 6 FP32-pipe instructions, bit-identical
+            //   codes (tests/test_gpu_fused.py: stem vs the unfused chain, NaN and merged tables included).
+            float u = __fsub_rn(__fmul_rn(qp.scale, zr), qp.zp);
+            u = min_nan(max_nan(max_nan(u, -qp.zp), qp.qlo), qp.qhi);
+            key = __fadd_rn(u, kRoundMagic);
+        } else {
+            const float z = max_nan(zr, 0.0f);                         // ReLU (NaN stays NaN)
+            key = z;
+            if (QUANT) {
+                key = code_of<false>(z, qp);
+                const float y = lut[lut_index(key, qh, qmask)];
+                key = (key != key) ? key : y;
+            }
         }
         const bool t = takes_over(key, r.key[c]);
         r.key[c] = t ? key : r.key[c];
-        r.meta[c] = t ? (z > 0.0f ? (j | 128) : j) : r.meta[c];
+        r.meta[c] = t ? (zr > 0.0f ? (j | 128) : j) : r.meta[c];
         if (XHAT) r.x[c] = t ? xs[c] : r.x[c];
     }
 }
@@ -158,7 +173,8 @@ __device__ __forceinline__ void pool_fwd_body(const float* __restrict__ x, float
                 const bool t2 = takes_over(r2.key[c], key);
                 key = t2 ? r2.key[c] : key; meta = t2 ? r2.meta[c] + 6 : meta; bx = t2 ? r2.x[c] : bx;
                 if (QUANT && STRICT) {
-                    const float v = lut[lut_index(key, qh, qmask)];
+                    // key = code + 1.5*2^23 (see scan_pixel): its low bits index the table directly
+                    const float v = lut[(__float_as_int(key) + qh) & qmask];
                     y[c] = (key != key) ? key : v;
                 } else {
                     y[c] = key;
