@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- QAT images/sec of the OOD-DFQ quantisation path on B200 (see DESIGN.md section "Measurement").
 
-    python bench.py --gpus 1 --steps 8 --warmup 3                 # this repo's CUDA path
-    python bench.py --impl reference --steps 2 --warmup 1         # the reference algorithm on host cores
+    python bench.py --gpus 1 --steps 20 --warmup 3                # this repo's CUDA path
+    python bench.py --impl reference --steps 5 --warmup 1         # the reference's own modules on the host cores
+    python bench.py --impl reference-cuda --steps 5               # ... and eagerly on the GPU (the "before")
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W    # weak scaling, one rank per GPU
 
@@ -14,7 +15,15 @@ forward, backward, SGD.  Activation ranges are calibrated for 3 steps first and 
 as in the reference's epochs 0-3 / >= 4.
 
 One JSON line on stdout (rank 0).  value = images/s with the batches already in HBM; e2e = the
-same loop fed from pinned host memory with the loss read back every step.
+same loop fed from pinned host memory with the loss read back every step.  Beside the contract's
+keys the line carries
+  roofline            per-family event timing of the library's kernels, traffic parsed from profiles/r2_ncu_traffic.json
+  other_configs       BASELINE configs 2 (every N) and 3, 5 (N = 1) measured the same way, so the driver's runs hold them
+  dp_parity           N > 1: gradient exchange, synced BN-statistics loss and reduce_minmax against the single-process
+                      global batch computed on rank 0 in the same run, plus a cross-rank weight checksum
+  value_unfused       N = 1: ONLY the drop-in modules (NCHW, no fusion pass): the bit-exact configuration
+  gpu_eager_baseline  N = 1: the reference's own quantization_utils modules (oracle/_ref) on this GPU, eager, NCHW
+  cpu_baseline        N = 1: the same modules on the host cores, same 256-image batch (also: --impl reference)
 """
 import argparse
 import copy
