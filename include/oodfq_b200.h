@@ -54,6 +54,7 @@ extern "C" {
 #define OODFQ_BN_RELU 1
 #define OODFQ_BN_QUANT 2
 #define OODFQ_BN_NHWC 4        /* x, y, grads are channels_last: [N*H*W rows][C]; needs C % 4 == 0 */
+#define OODFQ_BN_POOL_REGISTER 16 /* bn_pool_forward: always take the register kernel (tests, comparisons) */
 #define OODFQ_AUG_SRC_NHWC 8   /* crop_resize_flip: the stored image set is channels_last too */
 
 typedef void* oodfq_stream_t;  /* cudaStream_t */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liboodfq_b200.so")
 
 MODE_FAKEQUANT, MODE_QUANTIZE, MODE_DEQUANTIZE = 0, 1, 2
 SYMMETRIC, PARAMS_GIVEN, RELU_FIRST, NO_ONCHIP, ONCHIP_TMA = 1, 2, 4, 8, 16
-BN_RELU, BN_QUANT, BN_NHWC = 1, 2, 4
+BN_RELU, BN_QUANT, BN_NHWC, BN_POOL_REGISTER = 1, 2, 4, 16
 AUG_SRC_NHWC = 8
 ABI_VERSION = 4
 

@@ -554,6 +554,8 @@ static int make_pool_geom(int N, int C, int H, int W, PoolGeom& G) {
 
 }  // namespace oodfq
 
+#include "bn_pool_ring.cuh"
+
 using namespace oodfq;
 
 extern "C" int oodfq_bn_pool_forward(const float* x, float* out, uint8_t* idx, float* xhat, int N, int C, int H,
@@ -572,6 +574,30 @@ extern "C" int oodfq_bn_pool_forward(const float* x, float* out, uint8_t* idx, f
         return fail(OODFQ_EINVAL, "bn_pool_forward: needs C %% 4 == 0, C <= 1024 and aligned buffers");
     cudaStream_t st = (cudaStream_t)stream;
     const BnParams2 P{weight, bias, running_mean, running_var, eps};
+    PoolFwdPlan L;
+    size_t smem = 0;
+    int threads = 0;
+    if (!(flags & OODFQ_BN_POOL_REGISTER) && make_pool_fwd_plan(G, L, smem, threads)) {
+        const void* kernels[4] = {(const void*)bn_pool_fwd_tma_kernel<false, false>, (const void*)bn_pool_fwd_tma_kernel<false, true>,
+                                  (const void*)bn_pool_fwd_tma_kernel<true, false>, (const void*)bn_pool_fwd_tma_kernel<true, true>};
+        const int v = (quant ? 2 : 0) + (xhat ? 1 : 0);
+        static size_t smem_set[4] = {0, 0, 0, 0};
+        bool ok = true;
+        if (smem > smem_set[v]) {
+            ok = cudaFuncSetAttribute(kernels[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+            if (ok) smem_set[v] = smem; else (void)cudaGetLastError();
+        }
+        if (ok) {
+            const long long items = (long long)N * L.nseg;
+            const unsigned grid = (unsigned)(items < kNumSM ? items : kNumSM);
+            if (v == 0) bn_pool_fwd_tma_kernel<false, false><<<grid, threads, smem, st>>>(x, out, idx, xhat, G, L, P, fq_lo, fq_hi, fq_k);
+            else if (v == 1) bn_pool_fwd_tma_kernel<false, true><<<grid, threads, smem, st>>>(x, out, idx, xhat, G, L, P, fq_lo, fq_hi, fq_k);
+            else if (v == 2) bn_pool_fwd_tma_kernel<true, false><<<grid, threads, smem, st>>>(x, out, idx, xhat, G, L, P, fq_lo, fq_hi, fq_k);
+            else bn_pool_fwd_tma_kernel<true, true><<<grid, threads, smem, st>>>(x, out, idx, xhat, G, L, P, fq_lo, fq_hi, fq_k);
+            count_launch();
+            return check_launch("bn_pool_forward(tma)");
+        }
+    }
     static const int occ[4] = {resident_ctas(bn_pool_fwd_kernel<false, false>, kBThreads), resident_ctas(bn_pool_fwd_kernel<false, true>, kBThreads),
                                resident_ctas(bn_pool_fwd_kernel<true, false>, kBThreads), resident_ctas(bn_pool_fwd_kernel<true, true>, kBThreads)};
     const int per_sm = occ[(quant ? 2 : 0) + (xhat ? 1 : 0)];

@@ -120,6 +120,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, uint32_t 
 // bounded wait: a byte count that never completes must end in a trap (a CUDA error), not in a hung device
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     const uint32_t a = smem_u32(bar);
+#pragma unroll 1
     for (int spin = 0; spin < (1 << 22); ++spin) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

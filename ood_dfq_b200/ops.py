@@ -562,11 +562,13 @@ def bn_pool_supported(x) -> bool:
             and x.is_contiguous(memory_format=torch.channels_last))
 
 
-def bn_pool_forward(x, weight, bias, running_mean, running_var, eps, fq=None, want_xhat=True):
+def bn_pool_forward(x, weight, bias, running_mean, running_var, eps, fq=None, want_xhat=True, register_kernel=False):
     """``max_pool2d(fakequant(relu(BN_eval(x))), 3, 2, 1)`` without ever writing the full-resolution tensor.
 
     channels_last input only.  Returns (out, idx, xhat): idx is the one-byte argmax code the backward needs,
     xhat the normalised input at the argmax (None unless ``want_xhat``; only BN parameter gradients use it).
+    ``register_kernel`` forces the register-staged kernel (the fallback for rows too wide for the TMA ring;
+    tests and comparisons).
     """
     _need(x, "input")
     if not bn_pool_supported(x):
@@ -581,6 +583,8 @@ def bn_pool_forward(x, weight, bias, running_mean, running_var, eps, fq=None, wa
     if fq is not None:
         k, lo, hi = fq
         flags |= N.BN_QUANT
+    if register_kernel:
+        flags |= N.BN_POOL_REGISTER
     with _Timed("bn_pool_fwd_kernel (BN+ReLU+QuantAct+MaxPool stem forward, 4 B/elem in + 1/4 size outputs)",
                 4 * x.numel() + (9 if want_xhat else 5) * out.numel()):
         rc = N.load().oodfq_bn_pool_forward(x.data_ptr(), out.data_ptr(), idx.data_ptr(), _ptr(xhat), n, c, h, w,

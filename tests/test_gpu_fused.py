@@ -388,11 +388,13 @@ def test_channel_energy_matches_reference_expression(shape):
         assert b.grad.stride() == b.stride()
 
 
+@pytest.mark.parametrize("register_kernel", [False, True])
 @pytest.mark.parametrize("shape", [(4, 64, 112, 112), (3, 16, 9, 11), (2, 8, 7, 7), (2, 128, 5, 6), (1, 4, 1, 1)])
 @pytest.mark.parametrize("k", [4, 2, 0])
-def test_fused_stem_matches_unfused_chain(shape, k):
+def test_fused_stem_matches_unfused_chain(shape, k, register_kernel):
     """BN -> ReLU -> [QuantAct] -> MaxPool2d(3,2,1) as one kernel vs the fused BN kernel followed by ATen's
-    max_pool2d: same values, same argmax tie-breaking (first maximum), hence the same gradient field."""
+    max_pool2d: same values, same argmax tie-breaking (first maximum), hence the same gradient field.  Both
+    forward kernels: the TMA-staged ring (default) and the register-staged fallback."""
     from ood_dfq_b200 import ops
     g = torch.Generator().manual_seed(sum(shape) + k)
     x = (torch.randn(shape, generator=g) * 1.4).to(DEV).contiguous(memory_format=torch.channels_last)
@@ -401,7 +403,7 @@ def test_fused_stem_matches_unfused_chain(shape, k):
     fq = (k, lo, hi) if k else None
     y = ops.bn_eval_forward(x, w, b, rm, rv, 1e-5, relu=True, fq=fq).requires_grad_(True)
     ref = torch.nn.functional.max_pool2d(y, 3, 2, 1)
-    out, idx, xhat = ops.bn_pool_forward(x, w, b, rm, rv, 1e-5, fq=fq)
+    out, idx, xhat = ops.bn_pool_forward(x, w, b, rm, rv, 1e-5, fq=fq, register_kernel=register_kernel)
     assert out.shape == ref.shape and out.is_contiguous(memory_format=torch.channels_last)
     assert torch.equal(out, ref)
     go = torch.randn(ref.shape, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
@@ -416,8 +418,9 @@ def test_fused_stem_matches_unfused_chain(shape, k):
     assert dw2 is None and torch.equal(gx2, gx)
 
 
+@pytest.mark.parametrize("register_kernel", [False, True])
 @pytest.mark.parametrize("case", ["merged_table", "nan", "odd_sizes_k2", "tall_segments"])
-def test_fused_stem_corner_cases(case):
+def test_fused_stem_corner_cases(case, register_kernel):
     """Degenerate dequantisation table (several codes share one value, so ties must be broken on the VALUE),
     NaN inputs (the last NaN of a window wins, as in ATen), odd extents, and a batch small enough that every
     window column is split into several row segments."""
@@ -443,7 +446,7 @@ def test_fused_stem_corner_cases(case):
     if case == "merged_table":
         assert y.detach().unique().numel() < 2 ** k          # the table really has merged entries
     ref = torch.nn.functional.max_pool2d(y, 3, 2, 1)
-    out, idx, xhat = ops.bn_pool_forward(x, w, b, rm, rv, 1e-5, fq=fq)
+    out, idx, xhat = ops.bn_pool_forward(x, w, b, rm, rv, 1e-5, fq=fq, register_kernel=register_kernel)
     assert np.array_equal(out.cpu().numpy().view(np.int32), ref.detach().cpu().numpy().view(np.int32)) or \
         (case == "nan" and torch.equal(torch.isnan(out), torch.isnan(ref)) and
          torch.equal(torch.nan_to_num(out), torch.nan_to_num(ref.detach())))
@@ -457,6 +460,40 @@ def test_fused_stem_corner_cases(case):
         assert torch.equal(gx[keep], gx_ref[keep])
     else:
         assert torch.equal(gx, gx_ref)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 112, 112), (5, 64, 56, 56), (3, 32, 33, 47), (2, 16, 14, 5), (7, 8, 2, 2),
+                                   (1, 12, 3, 1), (2, 256, 9, 16), (300, 16, 10, 10), (2, 64, 224, 224)])
+@pytest.mark.parametrize("mode", ["k4", "k8", "k1", "plain", "merged", "nan", "ties"])
+def test_stem_ring_kernel_equals_register_kernel(shape, mode):
+    """The TMA-staged stem forward (packed integer candidates, winner lookups in the ring) against the register
+    kernel: output bits, argmax / ReLU bytes and the normalised input at the argmax are identical -- many items per
+    CTA, rows that wrap the ring, odd extents, one-window rows, all-equal inputs (every tie), NaNs (the last NaN of
+    a window wins in both) and a table with merged entries (candidates compared on the value)."""
+    from ood_dfq_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape) + len(mode))
+    x = torch.randn(shape, generator=g) * 1.4
+    if mode == "ties":
+        x = torch.round(x)                       # few distinct values: ties inside most windows
+        x[0] = 0.25                              # and an image where every window is one big tie
+    if mode == "nan":
+        x.view(-1)[torch.randperm(x.numel(), generator=g)[:max(3, x.numel() // 50)]] = float("nan")
+    x = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    w, b, rm, rv = (cu(t) for t in make_bn(shape[1], g))
+    lo, hi, k = 0.0, 1.9, {"k8": 8, "k1": 1}.get(mode, 4)
+    if mode == "merged":
+        lo, hi = float(2 ** 23), float(2 ** 23 + 4)
+        b = b + float(2 ** 23 + 2)
+    fq = None if mode == "plain" else (k, torch.full((1,), lo, device=DEV), torch.full((1,), hi, device=DEV))
+    for want_xhat in (True, False):
+        o1, i1, x1 = ops.bn_pool_forward(x, w, b, rm, rv, 1e-5, fq=fq, want_xhat=want_xhat)
+        o2, i2, x2 = ops.bn_pool_forward(x, w, b, rm, rv, 1e-5, fq=fq, want_xhat=want_xhat, register_kernel=True)
+        assert torch.equal(o1.view(torch.int32), o2.view(torch.int32))
+        assert torch.equal(i1, i2)
+        if want_xhat:
+            assert torch.equal(x1.view(torch.int32), x2.view(torch.int32))
+        else:
+            assert x1 is None and x2 is None
 
 
 def test_fused_stem_in_the_imagenet_student():

@@ -190,6 +190,10 @@ def main():
             report("pool_fqx", shape, 4 * n + 9 * no, *timer(lambda: ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, fq=(4, lo, hi))))
             report("pool_fq", shape, 4 * n + 5 * no, *timer(lambda: ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, fq=(4, lo, hi), want_xhat=False)))
             report("pool_plain", shape, 4 * n + 5 * no, *timer(lambda: ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, want_xhat=False)))
+            # the register-staged fallback (round-2 default until the TMA ring)
+            report("poolr_fqx", shape, 4 * n + 9 * no, *timer(lambda: ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, fq=(4, lo, hi), register_kernel=True)))
+            report("poolr_fq", shape, 4 * n + 5 * no, *timer(lambda: ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, fq=(4, lo, hi), want_xhat=False, register_kernel=True)))
+            report("poolr_plain", shape, 4 * n + 5 * no, *timer(lambda: ops.bn_pool_forward(xf, w, b, rm, rv, 1e-5, want_xhat=False, register_kernel=True)))
             go = torch.randn_like(out)
             report("poolbw_p", shape, 4 * n + 9 * no, *timer(lambda: ops.bn_pool_backward(go, idx, xhat, xf.shape, w, b, rm, rv, 1e-5)))
             report("poolbw_x", shape, 4 * n + 5 * no, *timer(lambda: ops.bn_pool_backward(go, idx, None, xf.shape, w, b, rm, rv, 1e-5, want_param_grads=False)))
