@@ -425,6 +425,9 @@ def bench_workload(args, env, workload, full=True, namespace=None, fuse=True, ch
             # kernel for the 3-channel form); no-op for the networks without such a stem
             fusion.space_to_depth_stem(student, resident[0][:2])
             fusion.space_to_depth_stem(teacher, resident[0][:2])
+        # ... and the whole-plane average pool between the last QuantAct and Quant_Linear (bit-identical to ATen's)
+        fusion.fuse_global_avgpool(student)
+        fusion.fuse_global_avgpool(teacher)
     kind = KINDS.get(workload, "qat")
     graph_mode = args.graph if graph else "off"
     dstep = None

@@ -216,6 +216,17 @@ int oodfq_channel_energy_forward(const float* x, float* e, int N, int C, long lo
 int oodfq_channel_energy_backward(const float* x, const float* grad_e, float* grad_x, int N, int C,
                                   long long HW, int flags, oodfq_stream_t stream);
 
+/* ---- global average pool between the last QuantAct and Quant_Linear ------------------------------------
+ * replaces: features.final_pool = AvgPool2d(7 | 8) over a plane of exactly that size (pytorchcv ResNet behind
+ *           ptcv_get_model, main_direct.py:380-397; reference models.py avg_pool2d(out, 4)) and its backward
+ * channels_last only (flags must contain OODFQ_BN_NHWC; C % 4 == 0): x, grad_x [N, H*W, C]; y, grad_y [N, C].
+ * forward : y[n,c] = (fp32 running sum of x[n,hw,c] in hw order) / HW     -- bit-identical to ATen's avg_pool2d
+ * backward: grad_x[n,hw,c] = 0 + grad_y[n,c] / HW                          -- bit-identical to its backward */
+int oodfq_global_avgpool_forward(const float* x, float* y, int N, int C, long long HW, int flags,
+                                 oodfq_stream_t stream);
+int oodfq_global_avgpool_backward(const float* grad_y, float* grad_x, int N, int C, long long HW, int flags,
+                                  oodfq_stream_t stream);
+
 /* ---- stem fusion: eval BatchNorm -> ReLU -> [QuantAct] -> MaxPool2d(3, stride 2, padding 1) -----------
  * replaces: the first QuantAct site of the ImageNet ResNets together with the max-pool that consumes it
  *           (pytorchcv ResInitBlock behind ptcv_get_model, main_direct.py:380-397; quantize_model :464-465)

@@ -895,6 +895,62 @@ def _space_to_depth_stem(model, example, verify, keep):
     return len(swapped)
 
 
+# ----------------------------------------------------------------------------- the final average pool
+class _GlobalAvgPool(torch.autograd.Function):
+    """``avg_pool2d`` over the whole plane as one read forward and one write backward (csrc/gap.cu); nothing saved."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.in_shape = tuple(x.shape)
+        return ops.global_avgpool_forward(x)
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        return ops.global_avgpool_backward(grad_y, ctx.in_shape)
+
+
+def _covers_plane(m, x):
+    """Does this pooling module reduce ``x`` to 1x1 by averaging every pixel exactly once?"""
+    def two(v):
+        return (v, v) if isinstance(v, int) else tuple(v)
+    if isinstance(m, nn.AdaptiveAvgPool2d):
+        return two(m.output_size) == (1, 1)
+    return (two(m.kernel_size) == tuple(x.shape[2:]) and two(m.padding) == (0, 0) and not m.ceil_mode
+            and m.divisor_override is None)
+
+
+class _GlobalPoolMixin:
+    def forward(self, x):
+        if ops.global_avgpool_supported(x) and _covers_plane(self, x):
+            return _GlobalAvgPool.apply(x)
+        return super().forward(x)
+
+
+class GlobalAvgPool2d(_GlobalPoolMixin, nn.AvgPool2d):
+    """``nn.AvgPool2d`` whose window is the whole plane (the carriers' ``final_pool``); anything else, and any
+    tensor the kernel does not take (CPU, NCHW, C % 4 != 0), goes through ``nn.AvgPool2d.forward`` unchanged."""
+
+
+class GlobalAdaptiveAvgPool2d(_GlobalPoolMixin, nn.AdaptiveAvgPool2d):
+    """``nn.AdaptiveAvgPool2d(1)`` (reference ``models.ResNet18``): same kernel; ATen reduces this case with its
+    tree-ordered ``mean``, so results agree to fp32 rounding of a 49-term sum rather than bit for bit."""
+
+
+def fuse_global_avgpool(model: nn.Module) -> int:
+    """Class-swap every ``AvgPool2d`` / ``AdaptiveAvgPool2d(1)`` of ``model`` for the variant that takes the
+    whole-plane case through ``csrc/gap.cu``.  Whether a call qualifies is decided per call from the tensor it gets,
+    so the swap is safe for any module; returns the number of modules swapped (0 on a second application)."""
+    n = 0
+    for m in model.modules():
+        if type(m) is nn.AvgPool2d:
+            m.__class__ = GlobalAvgPool2d
+            n += 1
+        elif type(m) is nn.AdaptiveAvgPool2d and _covers_plane(m, None):
+            m.__class__ = GlobalAdaptiveAvgPool2d
+            n += 1
+    return n
+
+
 class FusedEvalBN(_FusedEvalMixin, nn.BatchNorm2d):
     """``nn.BatchNorm2d`` with the fused eval path."""
 

@@ -504,6 +504,40 @@ def channel_energy_backward(x, grad_e):
     return gx
 
 
+# ----------------------------------------------------------------------------- global average pool (final_pool)
+def global_avgpool_supported(x) -> bool:
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.numel() > 0
+            and x.shape[1] % 4 == 0 and x.shape[2] * x.shape[3] > 1
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def global_avgpool_forward(x):
+    """``avg_pool2d(x, (H, W))`` of a channels_last tensor -> ``[N, C, 1, 1]``: fp32 running sum in window order and
+    one division, i.e. the bits ATen's kernel produces."""
+    _need(x, "input")
+    if not global_avgpool_supported(x):
+        raise RuntimeError("ood_dfq_b200: the global average pool needs a channels_last fp32 tensor with C % 4 == 0")
+    n, c, h, w = x.shape
+    y = torch.empty((n, c, 1, 1), dtype=torch.float32, device=x.device)
+    with _Timed("gap_nhwc_fwd_kernel (global average pool, 4 B/elem)", 4 * x.numel()):
+        rc = N.load().oodfq_global_avgpool_forward(x.data_ptr(), y.data_ptr(), n, c, h * w, N.BN_NHWC, _stream(x.device))
+        N.check(rc, "global_avgpool_forward")
+    return y
+
+
+def global_avgpool_backward(grad_y, in_shape):
+    """``grad_x[n,c,h,w] = grad_y[n,c] / (H*W)`` as a channels_last tensor of ``in_shape``."""
+    _need(grad_y, "grad_output")
+    n, c, h, w = in_shape
+    gy = grad_y.reshape(n, c).contiguous()
+    gx = torch.empty((n, c, h, w), dtype=torch.float32, device=grad_y.device, memory_format=torch.channels_last)
+    with _Timed("gap_nhwc_bwd_kernel (global average pool backward, 4 B/elem)", 4 * gx.numel()):
+        rc = N.load().oodfq_global_avgpool_backward(gy.data_ptr(), gx.data_ptr(), n, c, h * w, N.BN_NHWC,
+                                                    _stream(grad_y.device))
+        N.check(rc, "global_avgpool_backward")
+    return gx
+
+
 # ----------------------------------------------------------------------------- 8(f)-2: feature-alignment loss
 def _fa_tables(es, et):
     if len(es) != len(et) or not es:

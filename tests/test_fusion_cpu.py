@@ -187,3 +187,21 @@ def test_units_that_only_look_like_the_layout_are_not_swapped():
     assert all(isinstance(b, fusion._FusedUnitMixin) for b in blocks[1::2])
     with torch.no_grad():
         assert torch.equal(model(x), ref)
+
+
+def test_global_avgpool_pass_on_cpu_swaps_classes_and_keeps_results():
+    """The whole-plane average pool pass is a class swap decided per call: on CPU tensors the module runs its own
+    class's forward, the swap is idempotent, survives deepcopy and leaves other pooling modules alone."""
+    from torch import nn
+    for name in ("resnet20_cifar", "resnet18_small"):
+        model, x = _student(name)
+        with torch.no_grad():
+            ref = model(x)
+        pools = [m for m in model.modules() if isinstance(m, (nn.AvgPool2d, nn.AdaptiveAvgPool2d))]
+        assert len(pools) == 1
+        assert fusion.fuse_global_avgpool(model) == 1 and fusion.fuse_global_avgpool(model) == 0
+        assert isinstance(pools[0], (fusion.GlobalAvgPool2d, fusion.GlobalAdaptiveAvgPool2d))
+        with torch.no_grad():
+            assert torch.equal(copy.deepcopy(model)(x), ref) and torch.equal(model(x), ref)
+    other = nn.Sequential(nn.AdaptiveAvgPool2d(3), nn.MaxPool2d(2))
+    assert fusion.fuse_global_avgpool(other) == 0 and type(other[0]) is nn.AdaptiveAvgPool2d

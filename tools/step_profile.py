@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--no-tail-fuse", action="store_true")
     ap.add_argument("--no-s2d", action="store_true")
     ap.add_argument("--top", type=int, default=40)
+    ap.add_argument("--by-shape", action="store_true",
+                    help="instead of the CUPTI table: CUDA-event pairs around every launch of the library (ops.PROFILE), "
+                         "grouped by (kernel family, algorithmic bytes) = one row per tensor size")
     args = ap.parse_args()
     from ood_dfq_b200.quantization_utils import quant_modules as qm
     dev = torch.device("cuda:0")
@@ -55,6 +58,8 @@ def main():
         if not args.no_s2d:
             fusion.space_to_depth_stem(student, xs[0][:2])
             fusion.space_to_depth_stem(teacher, xs[0][:2])
+        fusion.fuse_global_avgpool(student)
+        fusion.fuse_global_avgpool(teacher)
     if bench.KINDS.get(args.workload) == "distill":
         from ood_dfq_b200 import bns, step as step_mod
         labels = torch.randint(0, bench.WORKLOADS[args.workload][1], (batch,), generator=g).to(dev)
@@ -67,6 +72,31 @@ def main():
     for i in range(3):
         qat(xs[i % 2])
     torch.cuda.synchronize()
+    if args.by_shape:
+        from ood_dfq_b200 import ops
+        peak = bench.peaks()[0]
+        ops.PROFILE = []
+        for i in range(args.steps):
+            qat(xs[i % 2])
+        torch.cuda.synchronize()
+        rec, ops.PROFILE = ops.PROFILE, None
+        agg = defaultdict(lambda: [0.0, 0])
+        for name, e0, e1, nbytes in rec:
+            a = agg[(name.split(" (")[0], nbytes)]
+            a[0] += e0.elapsed_time(e1)
+            a[1] += 1
+        total = sum(a[0] for a in agg.values())
+        lines = [f"# {cfg}; batch {batch}; {args.steps} eager steps; event pairs around the library's launches: {total / args.steps:.2f} ms/step",
+                 f"# {'ms/step':>8s} {'launches':>9s} {'MB/launch':>10s} {'us/launch':>10s} {'GB/s':>7s} {'of peak':>8s}  kernel family"]
+        for (name, nbytes), (ms, n) in sorted(agg.items(), key=lambda kv: (kv[0][0], -kv[0][1])):
+            gbs = nbytes * n / (ms * 1e-3) / 1e9
+            lines.append(f"  {ms / args.steps:8.3f} {n / args.steps:9.1f} {nbytes / 1e6:10.1f} {1e3 * ms / n:10.1f} {gbs:7.0f} {100 * gbs / peak:7.1f}%  {name}")
+        text = "\n".join(lines)
+        print(text)
+        if args.out:
+            with open(args.out, "w") as f:
+                f.write(text + "\n")
+        return
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for i in range(args.steps):
             qat(xs[i % 2])
