@@ -82,6 +82,16 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    override = os.environ.get("OODFQ_LIB")       # A/B runs of two builds of the kernels (tools/): load exactly this file
+    if override:
+        lib = C.CDLL(override)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        if lib.oodfq_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"ood_dfq_b200: ABI {lib.oodfq_abi_version()} != expected {ABI_VERSION}; rebuild")
+        _lib = lib
+        return lib
     if os.path.exists(LIB_PATH):
         # a library older than its sources has the wrong ABI as often as not: rebuild it when nvcc is at hand
         # (one process at a time: the ranks of a torchrun job all come through here)

@@ -29,9 +29,11 @@ bn_plane_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
     __shared__ float lut[QUANT ? kLutMax : 1];
     const int c = blockIdx.x / split, sp = blockIdx.x % split;
     QParams qp;
+    float lowc = 0.0f;
     const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
     if (QUANT) {
         qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        lowc = relu_lower_bound(qp);
         build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
         __syncthreads();
     }
@@ -55,12 +57,12 @@ bn_plane_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
                 int i = i0 + u * kBThreads;
                 if (i < n4) {
                     float4 r, z;
-                    r.x = head<RELU, QUANT>(v[u].x, a, b, qp, lut, qh, qmask, z.x);
-                    r.y = head<RELU, QUANT>(v[u].y, a, b, qp, lut, qh, qmask, z.y);
-                    r.z = head<RELU, QUANT>(v[u].z, a, b, qp, lut, qh, qmask, z.z);
-                    r.w = head<RELU, QUANT>(v[u].w, a, b, qp, lut, qh, qmask, z.w);
+                    r.x = head<RELU, QUANT>(v[u].x, a, b, qp, lowc, lut, qh, qmask, z.x);
+                    r.y = head<RELU, QUANT>(v[u].y, a, b, qp, lowc, lut, qh, qmask, z.y);
+                    r.z = head<RELU, QUANT>(v[u].z, a, b, qp, lowc, lut, qh, qmask, z.z);
+                    r.w = head<RELU, QUANT>(v[u].w, a, b, qp, lowc, lut, qh, qmask, z.w);
                     st_out(q + i, r);
-                    if (zq) zq[i] = z;
+                    if (zq) zq[i] = RELU ? make_float4(relu_keep_nan(z.x), relu_keep_nan(z.y), relu_keep_nan(z.z), relu_keep_nan(z.w)) : z;
                 }
             }
         }
@@ -81,9 +83,11 @@ bn_group_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
     const long long row = (long long)G.C * G.HW;
     const int hw = (int)((G.cg > 1) ? G.HW : 0x7fffffff);
     QParams qp;
+    float lowc = 0.0f;
     const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
     if (QUANT) {
         qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        lowc = relu_lower_bound(qp);
         build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
         __syncthreads();
     }
@@ -108,9 +112,15 @@ bn_group_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* _
             if (nn < G.N) {
                 float r[VEC], z[VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) r[j] = head<RELU, QUANT>(v[d][j], a[j], b[j], qp, lut, qh, qmask, z[j]);
+                for (int j = 0; j < VEC; ++j) r[j] = head<RELU, QUANT>(v[d][j], a[j], b[j], qp, lowc, lut, qh, qmask, z[j]);
                 store_vec<VEC>(y + nn * row + off + e0, r);
-                if (zdbg) store_vec<VEC>(zdbg + nn * row + off + e0, z);
+                if (zdbg) {
+                    if (RELU) {
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j) z[j] = relu_keep_nan(z[j]);
+                    }
+                    store_vec<VEC>(zdbg + nn * row + off + e0, z);
+                }
             }
         }
     }
@@ -285,41 +295,60 @@ bn_nhwc_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, float* __
                    uint8_t* __restrict__ mask, const NhwcGeom G, const BnParams P, const float* __restrict__ fq_lo,
                    const float* __restrict__ fq_hi, int fq_k) {
     __shared__ float lut[QUANT ? kLutMax : 1];
+    // The first rows of this thread are requested BEFORE the parameter prologue (range -> table -> barrier, running
+    // statistics -> affine): three dependent memory latencies that a 10 us launch on a small plane otherwise pays
+    // in front of its first load (profiles/r2_microbench.txt: 7x7 planes at half the rate of the 56x56 ones).
+    const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
+    const bool active = (int)threadIdx.x < G.lanes_r * wcols;
+    const int rsub = threadIdx.x / wcols;
+    const long long rstep = (long long)G.lanes_r * gridDim.x;
+    const long long r0 = (long long)blockIdx.x * G.lanes_r + rsub;
+    const int col0 = threadIdx.x % wcols;
+    float4 v[kDepth];
+    if (active) {
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+            const long long rr = r0 + d * rstep;
+            if (rr < G.R) v[d] = ld_stream(reinterpret_cast<const float4*>(x) + rr * G.cols + col0);
+        }
+    }
     QParams qp;
+    float lowc = 0.0f;
     const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
     if (QUANT) {
         qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        lowc = relu_lower_bound(qp);
         build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
         __syncthreads();
     }
-    const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
-    if ((int)threadIdx.x >= G.lanes_r * wcols) return;
-    const int rsub = threadIdx.x / wcols;
+    if (!active) return;
     for (int cb = 0; cb < G.col_blocks; ++cb) {
-        const int col = cb * kBThreads + threadIdx.x % wcols;
+        const int col = cb * kBThreads + col0;
         if (col >= G.cols) continue;
         float a[4], b[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { float invstd; affine_of(P, 4 * col + j, a[j], b[j], invstd); }
-        const long long rstep = (long long)G.lanes_r * gridDim.x;
-        for (long long r = (long long)blockIdx.x * G.lanes_r + rsub; r < G.R; r += kDepth * rstep) {
-            float4 v[kDepth];
+        for (long long r = r0; r < G.R; r += kDepth * rstep) {
+            if (cb != 0 || r != r0) {
 #pragma unroll
-            for (int d = 0; d < kDepth; ++d) {
-                const long long rr = r + d * rstep;
-                if (rr < G.R) v[d] = ld_stream(reinterpret_cast<const float4*>(x) + rr * G.cols + col);
+                for (int d = 0; d < kDepth; ++d) {
+                    const long long rr = r + d * rstep;
+                    if (rr < G.R) v[d] = ld_stream(reinterpret_cast<const float4*>(x) + rr * G.cols + col);
+                }
             }
 #pragma unroll
             for (int d = 0; d < kDepth; ++d) {
                 const long long rr = r + d * rstep;
                 if (rr < G.R) {
                     float4 o, z;
-                    o.x = head<RELU, QUANT>(v[d].x, a[0], b[0], qp, lut, qh, qmask, z.x);
-                    o.y = head<RELU, QUANT>(v[d].y, a[1], b[1], qp, lut, qh, qmask, z.y);
-                    o.z = head<RELU, QUANT>(v[d].z, a[2], b[2], qp, lut, qh, qmask, z.z);
-                    o.w = head<RELU, QUANT>(v[d].w, a[3], b[3], qp, lut, qh, qmask, z.w);
+                    o.x = head<RELU, QUANT>(v[d].x, a[0], b[0], qp, lowc, lut, qh, qmask, z.x);
+                    o.y = head<RELU, QUANT>(v[d].y, a[1], b[1], qp, lowc, lut, qh, qmask, z.y);
+                    o.z = head<RELU, QUANT>(v[d].z, a[2], b[2], qp, lowc, lut, qh, qmask, z.z);
+                    o.w = head<RELU, QUANT>(v[d].w, a[3], b[3], qp, lowc, lut, qh, qmask, z.w);
                     st_out(reinterpret_cast<float4*>(y) + rr * G.cols + col, o);
-                    if (zdbg) reinterpret_cast<float4*>(zdbg)[rr * G.cols + col] = z;
+                    if (zdbg)
+                        reinterpret_cast<float4*>(zdbg)[rr * G.cols + col] =
+                            RELU ? make_float4(relu_keep_nan(z.x), relu_keep_nan(z.y), relu_keep_nan(z.z), relu_keep_nan(z.w)) : z;
                     // one byte per 128-bit column: bit j = the ReLU of channel j is open (what the backward re-derives
                     // from x otherwise: a*x + b > 0)
                     if (RELU && mask)

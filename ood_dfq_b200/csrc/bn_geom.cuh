@@ -39,11 +39,17 @@ __device__ __forceinline__ void affine_of(const BnParams& P, int c, float& a, fl
     b = __fsub_rn(P.b ? __ldg(P.b + c) : 0.0f, __fmul_rn(__ldg(P.rm + c), a));
 }
 
+// clamp_min(z, 0) keeps NaN
+__device__ __forceinline__ float relu_keep_nan(float z) { return (z != z) ? z : fmaxf(z, 0.0f); }
+
+// `zr` receives the PRE-activation value a*x + b (what the ReLU mask and the debug output derive from);
+// `lowc` = relu_lower_bound(qp), only read for RELU && QUANT
 template <bool RELU, bool QUANT>
-__device__ __forceinline__ float head(float x, float a, float b, const QParams& qp, const float* lut, int qh,
-                                      int qmask, float& z) {
-    z = fmaf(x, a, b);
-    if (RELU) z = (z != z) ? z : fmaxf(z, 0.0f);      // clamp_min keeps NaN
+__device__ __forceinline__ float head(float x, float a, float b, const QParams& qp, float lowc, const float* lut, int qh,
+                                      int qmask, float& zr) {
+    zr = fmaf(x, a, b);
+    if (RELU && QUANT) return relu_fake_quant_lut(zr, qp, lowc, lut, qh, qmask);
+    const float z = RELU ? relu_keep_nan(zr) : zr;
     return QUANT ? fake_quant_lut(z, qp, lut, qh, qmask) : z;
 }
 

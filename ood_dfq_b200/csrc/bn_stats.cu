@@ -337,9 +337,11 @@ bn_nhwc_stats_kernel(const float* __restrict__ x, const NhwcGeom G, const float*
     __shared__ double dred[2 * kBThreads];
     __shared__ float lut[QUANT ? kLutMax : 1];
     QParams qp;
+    float lowc = 0.0f;
     const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
     if (QUANT) {
         qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        lowc = relu_lower_bound(qp);
         build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
     }
     const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
@@ -384,7 +386,7 @@ bn_nhwc_stats_kernel(const float* __restrict__ x, const NhwcGeom G, const float*
                         if (HEAD) {
                             float z, o[4];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) o[j] = head<HEAD == 2, QUANT>(xs[j], ha[j], hb[j], qp, lut, qh, qmask, z);
+                            for (int j = 0; j < 4; ++j) o[j] = head<HEAD == 2, QUANT>(xs[j], ha[j], hb[j], qp, lowc, lut, qh, qmask, z);
                             st_out(reinterpret_cast<float4*>(y) + rr * G.cols + col, make_float4(o[0], o[1], o[2], o[3]));
                         } else if (QUANT) {
                             st_out(reinterpret_cast<float4*>(y) + rr * G.cols + col,

@@ -218,10 +218,30 @@ __device__ __forceinline__ int lut_index(float q, int h, int mask) {
     return (__float_as_int(__fadd_rn(q, kRoundMagic)) + h) & mask;
 }
 
+// The code only ever serves as the table index, so its rounding and clamping are done the cheap way round: clamp
+// and rint commute when the bounds are integers, and for |u| <= 2^22 the sum (u + 1.5*2^23) IS rint(u) (ties to
+// even) sitting in the low mantissa bits -- no FRND (a quarter-rate conversion-pipe instruction), one FADD fewer.
 __device__ __forceinline__ float fake_quant_lut(float x, const QParams& p, const float* lut, int h, int mask) {
-    float q = code_of<false>(x, p);
-    float y = lut[lut_index(q, h, mask)];
-    return (q != q) ? q : y;                 // NaN in, NaN out (as the ATen chain does)
+    float u = __fsub_rn(__fmul_rn(p.scale, x), p.zp);
+    u = min_nan(max_nan(u, p.qlo), p.qhi);
+    const float key = __fadd_rn(u, kRoundMagic);
+    const float y = lut[(__float_as_int(key) + h) & mask];
+    return (key != key) ? key : y;           // NaN in, NaN out (as the ATen chain does)
+}
+
+// fakequant(relu(z)) with the ReLU folded into the lower clamp.  u(z) = scale*z - zp (two roundings) is monotone
+// in z and u(+-0) = -zp exactly, so u(relu(z)) = max(u(z), -zp); zp is an integer (make_qparams rounds it), so that
+// max commutes with rint like the clamp does: code = min(max(rint(u), lowc), qhi) with lowc = max(-zp, qlo).
+// Bit-identical to relu -> fake_quant_lut (NaN stays NaN), three instructions shorter.  NOT valid for a zero-point
+// handed in from outside (OODFQ_PARAMS_GIVEN), which need not be an integer.
+__device__ __forceinline__ float relu_lower_bound(const QParams& p) { return fmaxf(-p.zp, p.qlo); }
+__device__ __forceinline__ float relu_fake_quant_lut(float z, const QParams& p, float lowc, const float* lut, int h,
+                                                     int mask) {
+    float u = __fsub_rn(__fmul_rn(p.scale, z), p.zp);
+    u = min_nan(max_nan(u, lowc), p.qhi);
+    const float key = __fadd_rn(u, kRoundMagic);
+    const float y = lut[(__float_as_int(key) + h) & mask];
+    return (key != key) ? key : y;
 }
 
 template <int MODE, bool SYM>

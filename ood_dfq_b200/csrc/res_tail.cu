@@ -65,8 +65,10 @@ res_tail_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ r, f
     __shared__ float red[ENERGY ? kBThreads * 4 : 1];
     QParams qp = given_qparams(1.0f, 0.0f, 1);
     const int qh = 1 << (fq_k - 1), qmask = (1 << fq_k) - 1;
+    float lowc = 0.0f;
     if (QUANT) {
         qp = make_qparams(__ldg(fq_lo), __ldg(fq_hi), fq_k);
+        lowc = relu_lower_bound(qp);
         build_lut(lut, qp, fq_k, threadIdx.x, kBThreads);
         __syncthreads();
     }
@@ -118,8 +120,8 @@ res_tail_fwd_kernel(const float* __restrict__ x1, const float* __restrict__ r, f
                             const float id = IDBN ? fmaf(rs[j], a2[j], b2[j]) : rs[j];
                             float t = __fadd_rn(z1, id);
                             open |= (t <= 0.0f) ? 0u : (1u << j);     // aten::threshold_backward: NaN passes
-                            t = (t != t) ? t : fmaxf(t, 0.0f);
-                            o[j] = QUANT ? fake_quant_lut(t, qp, lut, qh, qmask) : t;
+                            // ReLU (NaN kept) then the quantiser; with QUANT the ReLU is the quantiser's lower clamp
+                            o[j] = QUANT ? relu_fake_quant_lut(t, qp, lowc, lut, qh, qmask) : relu_keep_nan(t);
                         }
                         st_out(py + (long long)rr * G.cols, make_float4(o[0], o[1], o[2], o[3]));
                         if (pm) pm[(long long)rr * G.cols] = (uint8_t)open;

@@ -770,7 +770,9 @@ def _s2d_channels(c):
     wgrad (1.4 ms of the 224x224 step) -- but measured in the step the autotuner then picks a slower weight-gradient
     kernel for the stem (1.4 instead of 0.84 ms per launch) and the iteration time does not move (33.72 vs 33.73 ms,
     profiles/r2_exp_s2d_c16.txt).  So the plain 4*C form stays."""
-    return 4 * c
+    import os
+    pad_to = int(os.environ.get("OODFQ_S2D_CPAD", "0"))        # experiment switch (tools / profiles only)
+    return max(4 * c, pad_to)
 
 
 class _S2D(torch.autograd.Function):

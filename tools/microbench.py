@@ -20,7 +20,8 @@ import torch  # noqa: E402
 
 from ood_dfq_b200 import ops  # noqa: E402
 
-ACT_SHAPES = [(256, 64, 112, 112), (256, 64, 56, 56), (256, 128, 28, 28), (256, 256, 14, 14), (256, 512, 7, 7)]
+ACT_SHAPES = [(256, 64, 112, 112), (256, 64, 56, 56), (256, 128, 28, 28), (256, 256, 14, 14), (256, 512, 7, 7),
+              (256, 16, 32, 32), (256, 32, 16, 16), (256, 64, 8, 8)]      # 0-4: ResNet-18 / 224; 5-7: ResNet-20 / 32 (--shapes picks)
 R18_WEIGHTS = [(64, 3, 7, 7)] + [(64, 64, 3, 3)] * 4 + [(128, 64, 3, 3), (128, 128, 3, 3), (128, 64, 1, 1)] + \
               [(128, 128, 3, 3)] * 2 + [(256, 128, 3, 3), (256, 256, 3, 3), (256, 128, 1, 1)] + [(256, 256, 3, 3)] * 2 + \
               [(512, 256, 3, 3), (512, 512, 3, 3), (512, 256, 1, 1)] + [(512, 512, 3, 3)] * 2 + [(1000, 512)]
@@ -35,11 +36,47 @@ class Timer:
     """flush = "write": fill a 512 MB buffer (L2 left full of DIRTY lines whose write-back then competes with the
     timed kernel -- the harsher convention); "read": sum a 512 MB buffer (L2 left full of clean foreign lines)."""
 
-    def __init__(self, iters, flush="write", warmup=3):
-        self.iters, self.mode, self.warmup = iters, flush, warmup
+    def __init__(self, iters, flush="write", warmup=3, use_cupti=False):
+        self.iters, self.mode, self.warmup, self.use_cupti = iters, flush, warmup, use_cupti
         self.flush = torch.ones(512 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda") if flush != "none" else None
 
+    def cupti(self, fn):
+        """Device-side kernel durations from CUPTI (torch.profiler) instead of CUDA events: event timestamps tick every
+        ~2 us on this GPU, too coarse for the 5-20 us launches of the small planes.  The time of a call is the sum of
+        the kernels it launched (launch gaps excluded, as in a CUDA-graph replay); read-flush only."""
+        from torch.profiler import ProfilerActivity, profile
+        for _ in range(self.warmup):
+            fn()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(self.iters):
+                if self.flush is not None:
+                    self.flush.sum()
+                fn()
+            torch.cuda.synchronize()
+        evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA),
+                     key=lambda e: e.time_range.start)
+        times, cur = [], None
+        for e in evs:
+            if "reduce_kernel" in e.name:                 # the flush: a new timed call starts behind it
+                if cur:
+                    times.append(cur)
+                cur = 0.0
+                continue
+            if "Memset" in e.name or "Memcpy" in e.name:
+                continue
+            if cur is None:
+                cur = 0.0
+            cur += (getattr(e, "device_time_total", None) or getattr(e, "cuda_time_total", 0.0)) * 1e-3
+        if cur:
+            times.append(cur)
+        if self.flush is None:                            # no separators: everything is one segment
+            times = [times[0] / self.iters] if times else [0.0]
+        return statistics.median(times), min(times)
+
     def __call__(self, fn):
+        if self.use_cupti:
+            return self.cupti(fn)
         for _ in range(self.warmup):
             fn()
         times = []
@@ -65,13 +102,16 @@ def main():
     ap.add_argument("--json", default="")
     ap.add_argument("--shapes", default="", help="indices into the activation shape list, e.g. 0,4")
     ap.add_argument("--flush", choices=["write", "read", "none"], default="write")
+    ap.add_argument("--cupti", action="store_true", help="kernel durations from CUPTI instead of CUDA events (needs --flush read or none)")
     ap.add_argument("--warmup", type=int, default=3, help="untimed launches per kernel (0 under ncu: one launch per variant)")
     args = ap.parse_args()
     only = set(args.only.split(","))
-    shapes = ACT_SHAPES if not args.shapes else [ACT_SHAPES[int(i)] for i in args.shapes.split(",")]
+    shapes = ACT_SHAPES[:5] if not args.shapes else [ACT_SHAPES[int(i)] for i in args.shapes.split(",")]
     pk = peak()
-    timer = Timer(args.iters, flush=args.flush, warmup=args.warmup)
-    print(f"# L2 flush between timed launches: {args.flush}", flush=True)
+    if args.cupti and args.flush == "write":
+        raise SystemExit("--cupti separates the timed calls by the read-flush kernel: use --flush read (or none)")
+    timer = Timer(args.iters, flush=args.flush, warmup=args.warmup, use_cupti=args.cupti)
+    print(f"# L2 flush between timed launches: {args.flush}; timing: {'CUPTI kernel durations' if args.cupti else 'CUDA events'}", flush=True)
     rows = []
 
     def report(kernel, shape, nbytes, med, best):
