@@ -460,7 +460,7 @@ template <bool RELU, bool REDUCE>
 __global__ void __launch_bounds__(kBThreads)
 bn_nhwc_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
                     const NhwcGeom G, const BnParams P, Workspace* ws) {
-    __shared__ float red[REDUCE ? 2 * kBThreads * 4 : 1];
+    __shared__ __align__(16) float red[REDUCE ? 2 * kBThreads * 4 : 4];
     const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
     const bool active = (int)threadIdx.x < G.lanes_r * wcols;
     const int rsub = threadIdx.x / wcols;
@@ -503,26 +503,20 @@ bn_nhwc_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, f
             }
         }
         if (REDUCE) {
-            // fold the CTA's row-lanes in lane order, then one fp64 partial per channel
+            // fold the CTA's row-lanes (fixed tree over the lanes), then one fp64 partial per channel
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 red[threadIdx.x * 4 + j] = on ? sb[j] : 0.f;
                 red[kBThreads * 4 + threadIdx.x * 4 + j] = on ? sw[j] : 0.f;
             }
-            __syncthreads();
+            lane_tree_fold<2>(red, rsub, wcols, G.lanes_r);
             if (on && rsub == 0) {
-                const int lc = threadIdx.x % wcols;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float tb = 0.f, tw = 0.f;
-                    for (int l = 0; l < G.lanes_r; ++l) {
-                        tb += red[(l * wcols + lc) * 4 + j];
-                        tw += red[kBThreads * 4 + (l * wcols + lc) * 4 + j];
-                    }
                     double* p = ws->bn_partial + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
-                    p[0] = (double)tw * (double)inv[j];
-                    p[1] = (double)tb;
+                    p[0] = (double)red[kBThreads * 4 + threadIdx.x * 4 + j] * (double)inv[j];
+                    p[1] = (double)red[threadIdx.x * 4 + j];
                 }
             }
         }

@@ -73,6 +73,33 @@ __device__ __forceinline__ void fold_partials(const double* partial, int C, int 
     }
 }
 
+// ---- channels_last reducing kernels: CTA-level fold of the row-lanes ------------------------------------------
+// Every thread of a channels_last kernel holds partial sums for its 4 channels; thread t = rsub * wcols + lc shares
+// its column lc with the threads rsub' * wcols + lc.  lane_tree_fold adds them in a fixed binary tree over rsub
+// (deterministic; log2(lanes_r) barriers) and leaves the totals in the rsub == 0 entries of `red` -- the serial
+// loop it replaces cost 4-5 us for 16-channel tensors (4 columns, 64 row-lanes, 4 threads doing all the adding).
+//   red: [NV][kBThreads][4] floats; every thread has stored its NV x 4 values at red[(v * kBThreads + t) * 4 + j]
+template <int NV>
+__device__ __forceinline__ void lane_tree_fold(float* red, int rsub, int wcols, int lanes_r) {
+    int s = 1;
+    while (s * 2 < lanes_r) s *= 2;                  // largest power of two below lanes_r (lanes_r >= 2)
+    for (; s > 0; s >>= 1) {
+        __syncthreads();
+        if (rsub < s && rsub + s < lanes_r) {
+            const int t = threadIdx.x, u = t + s * wcols;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                float4* mine = reinterpret_cast<float4*>(red + ((size_t)v * kBThreads + t) * 4);
+                const float4 o = *reinterpret_cast<const float4*>(red + ((size_t)v * kBThreads + u) * 4);
+                float4 m = *mine;
+                m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+                *mine = m;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 struct BnGeom {
     int N, C;
     long long HW;

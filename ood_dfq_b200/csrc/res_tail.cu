@@ -166,7 +166,7 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2,
                     const TailBn P2, float two_inv_hw, Workspace* ws) {
     constexpr bool NEED_X1 = ENERGY || REDUCE || !MASK;
     constexpr bool NEED_R = !MASK || (IDBN && REDUCE);
-    __shared__ float red[REDUCE ? (IDBN ? 4 : 2) * kBThreads * 4 : 1];
+    __shared__ __align__(16) float red[REDUCE ? (IDBN ? 4 : 2) * kBThreads * 4 : 4];
     const bool active = (int)threadIdx.x < G.lanes_r * G.cols;
     const int col = threadIdx.x % G.cols, rsub = threadIdx.x / G.cols;
     float a1[4], b1[4], rm1[4], a2[4], b2[4], rm2[4];
@@ -265,18 +265,15 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2,
                 red[3 * kBThreads * 4 + threadIdx.x * 4 + j] = active ? sw2[j] : 0.f;
             }
         }
-        __syncthreads();
+        lane_tree_fold<2 * kSets>(red, rsub, G.cols, G.lanes_r);      // fixed tree over the row-lanes
+        const int Ct = kSets * G.C;              // partial[cta][Ct][2]: BN1 channels first, then BN2
         if (active && rsub == 0) {
-            const int Ct = kSets * G.C;          // partial[cta][Ct][2]: BN1 channels first, then BN2
 #pragma unroll
             for (int set = 0; set < kSets; ++set) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float tb = 0.f, tw = 0.f;
-                    for (int l = 0; l < G.lanes_r; ++l) {
-                        tb += red[(2 * set) * kBThreads * 4 + (l * G.cols + col) * 4 + j];
-                        tw += red[(2 * set + 1) * kBThreads * 4 + (l * G.cols + col) * 4 + j];
-                    }
+                    const float tb = red[(2 * set) * kBThreads * 4 + threadIdx.x * 4 + j];
+                    const float tw = red[(2 * set + 1) * kBThreads * 4 + threadIdx.x * 4 + j];
                     const TailBn& P = set ? P2 : P1;
                     const float inv = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(P.rv + 4 * col + j), P.eps)));
                     double* p = ws->bn_partial + ((size_t)blockIdx.x * Ct + (size_t)set * G.C + 4 * col + j) * 2;

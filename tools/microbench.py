@@ -63,7 +63,7 @@ class Timer:
                     times.append(cur)
                 cur = 0.0
                 continue
-            if "Memset" in e.name or "Memcpy" in e.name:
+            if "Memset" in e.name:
                 continue
             if cur is None:
                 cur = 0.0
