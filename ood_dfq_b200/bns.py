@@ -256,6 +256,9 @@ class BNStatLoss:
                 return None
             x_out, self._run.tokens[idx] = _Tap.apply(x, self, idx, self._run)
             return (x_out,) + tuple(inputs[1:])
+        # a module that bypasses this BatchNorm's forward (the fused residual tail, fusion._FusedUnitMixin) recognises
+        # the hook by this mark and runs the tap itself on the tensor the BatchNorm would have seen
+        hook._oodfq_bns_tap = True
         return hook
 
     def remove(self):

@@ -569,10 +569,29 @@ def _plan_of(u):
     return None
 
 
-def _no_hooks(m, allow_forward=()):
-    if m._forward_pre_hooks or m._backward_hooks or getattr(m, "_backward_pre_hooks", None):
+def _no_hooks(m, allow_forward=(), allow_stat_taps=False):
+    pre = list(m._forward_pre_hooks.values())
+    if allow_stat_taps:                          # bns.BNStatLoss marks its pre-hooks: the caller runs them itself
+        pre = [h for h in pre if not getattr(h, "_oodfq_bns_tap", False)]
+    if pre or m._backward_hooks or getattr(m, "_backward_pre_hooks", None):
         return False
     return all(h in allow_forward for h in m._forward_hooks.values())
+
+
+def _run_stat_taps(bn, x):
+    """The BN-statistics taps (``bns.BNStatLoss`` pre-hooks) of a BatchNorm whose forward the fused tail bypasses, run
+    on the tensor that BatchNorm would have received: statistics from one extra read, the loss gradient added into the
+    gradient of ``x`` on the way back (``bns._Tap``).  Returns the tapped tensor (``x`` itself without taps)."""
+    for h in list(bn._forward_pre_hooks.values()):
+        if getattr(h, "_oodfq_bns_tap", False):
+            res = h(bn, (x,))                                 # a fused BatchNorm gets its PendingTap ...
+            tap = bn._pending_tap
+            object.__setattr__(bn, "_pending_tap", None)
+            if tap is not None:
+                x = tap.plain(x)                              # ... which is run here, in front of the tail kernel
+            elif res is not None:                             # (the hook tapped the tensor itself)
+                x = res[0] if isinstance(res, tuple) else res
+    return x
 
 
 class _FusedUnitMixin:
@@ -600,7 +619,7 @@ class _FusedUnitMixin:
                 continue
             if not isinstance(bn, _FusedEvalMixin) or bn._tail is not None or bn.training \
                     or not bn.track_running_stats or bn.running_mean is None or bn.num_features % 4 \
-                    or bn.num_features > 1024 or not _no_hooks(bn):
+                    or bn.num_features > 1024 or not _no_hooks(bn, allow_stat_taps=True):
                 return None
         act, qact = p.act, None
         if isinstance(act, nn.Sequential):
@@ -637,6 +656,10 @@ class _FusedUnitMixin:
         xr = _pick_twin(x)                        # the producer's second handle, if it left one (see _twin_of)
         r = p.idconv(xr) if p.idconv is not None else xr
         bn1, bn2 = p.bn1, p.bn2
+        # BN-statistics taps on the two BatchNorms this path bypasses (the distillation loop hooks every BatchNorm)
+        x1 = _run_stat_taps(bn1, x1)
+        if bn2 is not None:
+            r = _run_stat_taps(bn2, r)
         if not ops.res_tail_supported(x1, r):
             # (a convolution handed back another layout) finish with the ordinary modules
             z = bn1(x1)

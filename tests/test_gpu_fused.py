@@ -637,3 +637,57 @@ def test_tapped_batchnorm_kernels_equal_their_two_kernel_chains(shape, relu, k):
     chain = ops.bn_stats_backward(x, chain, mean, gmean, gvar, count, gscale=gs)
     one = ops.bn_eval_tap_backward(x, gy, w, b, rm, rv, 1e-5, mean, gmean, gvar, count, relu=relu, gscale=gs)
     assert torch.equal(one.view(torch.int32), chain.view(torch.int32))
+
+
+@pytest.mark.parametrize("net_name", ["resnet20_cifar", "resnet18_small"])
+def test_fused_residual_tails_keep_running_under_the_statistics_taps(net_name):
+    """The distillation loop hooks EVERY BatchNorm (distill_data.py:69-78), including the two a fused residual tail
+    bypasses.  The fused unit runs those taps itself on the tensors the BatchNorms would have received: loss, per-layer
+    statistics and the image gradient equal those of the network whose units run their modules one by one."""
+    from ood_dfq_b200 import _native, bns, fusion, nets, surgery
+    from ood_dfq_b200.quantization_utils import quant_modules as qm
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+    torch.manual_seed(11)
+    base = nets.resnet18_small(3, 9) if net_name == "resnet18_small" else nets.resnet20_cifar(num_classes=10)
+    base = surgery.quantize_model(nets.perturb_bn_stats(base), 4, 4, namespace=qm)
+    net = base.to(DEV).to(memory_format=torch.channels_last).eval()
+    for p in net.parameters():
+        p.requires_grad_(False)
+    g = torch.Generator().manual_seed(12)
+    side = 28 if net_name == "resnet18_small" else 32
+    x = torch.randn(8, 3, side, side, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        for _ in range(2):
+            net(x)
+    surgery.freeze_model(net, qm)
+    fusion.fuse_eval_bn(net, x[:2])
+    plain = copy.deepcopy(net)
+    units = fusion.fuse_residual_tails(net, x[:2])
+    assert units >= 8
+
+    def run(model):
+        stat = bns.BNStatLoss(model)
+        xi = x.detach().clone().requires_grad_(True)
+        out = model(xi)
+        loss = stat.loss() + out.square().mean()
+        means = [m.clone() for m in stat.means()]
+        _native.reset_launch_count()
+        gx = torch.autograd.grad(loss, xi)[0]
+        n = _native.launch_count()
+        stat.remove()
+        return loss.detach(), means, gx, n
+
+    l_ref, m_ref, g_ref, n_ref = run(plain)
+    l_new, m_new, g_new, n_new = run(net)
+    np.testing.assert_allclose(l_new.item(), l_ref.item(), rtol=1e-5)
+    for a, b in zip(m_new, m_ref):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    scale = g_ref.abs().max().item()
+    # the fused tail rounds where the chain of fused BatchNorm, add and quantiser rounds (csrc/res_tail.cu), so
+    # activations agree bit for bit and the gradient differs only through the fp32 grouping of the statistics sums
+    np.testing.assert_allclose(g_new.cpu().numpy(), g_ref.cpu().numpy(), rtol=1e-4, atol=1e-6 * scale)
+    # and the units really took the fused path (the library then launches the tail kernels: its own count goes UP,
+    # what disappears are ATen's residual adds, ReLU masks and gradient-accumulation adds)
+    assert any(isinstance(m, fusion._FusedUnitMixin) for m in net.modules())
+    assert n_new != n_ref, (n_new, n_ref)
