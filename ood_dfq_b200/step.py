@@ -400,7 +400,7 @@ class DistillStep:
     """
 
     def __init__(self, teacher, stat, images, labels, lr=0.5, beta=0.1, gamma=0.5, capturable=False, plateau=True,
-                 augment=None, augment_p=0.5, aug_margin=0.4):
+                 augment=None, augment_p=0.5, aug_margin=0.4, fused_optimizer=True):
         if augment is not None and capturable:
             raise ValueError("DistillStep: the augmented iteration draws on the host every step and cannot be captured; "
                              "use capturable=False")
@@ -410,7 +410,11 @@ class DistillStep:
         # ``capturable``: keep Adam's step counter (and the learning rate) on the device so the iteration can be
         # replayed as a CUDA graph
         lr_arg = torch.tensor(float(lr), dtype=torch.float32, device=self.images.device) if capturable else lr
-        self.opt = torch.optim.Adam([self.images], lr=lr_arg, capturable=capturable)      # distill_data.py:183
+        # torch's single-kernel ("fused") Adam where the images live on a GPU: the update of the 154 MB batch is one
+        # pass over parameter, gradient and both moments (1.1 GB) instead of the ~20 multi-tensor launches of the
+        # default implementation (0.7 ms of a 9 ms iteration); same update rule, stock PyTorch either way
+        extra = {"fused": True} if self.images.is_cuda and fused_optimizer else {}
+        self.opt = torch.optim.Adam([self.images], lr=lr_arg, capturable=capturable, **extra)      # distill_data.py:183
         self.scheduler = None
         if plateau and capturable:
             self.scheduler = PlateauOnDevice(self.opt.param_groups[0]["lr"])
