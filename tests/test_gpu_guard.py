@@ -11,7 +11,7 @@ import torch
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 PAD = 512            # elements on each side (keeps 32-byte alignment for every dtype used)
-SENT = {torch.float32: 1234567.0, torch.float64: 1234567.0, torch.int8: 77}
+SENT = {torch.float32: 1234567.0, torch.float64: 1234567.0, torch.int8: 77, torch.uint8: 77}
 
 
 class Guard:
@@ -113,3 +113,63 @@ def test_per_channel_kernels_stay_in_bounds(guard, shape):
         ops.bn_eval_forward(xx, w, b, rm, rv, 1e-5)
         ops.bn_eval_backward(xx, gg, w, b, rm, rv, 1e-5, relu=True)
         ops.bn_eval_backward(xx, gg, w, b, rm, rv, 1e-5, relu=False, want_param_grads=False)
+
+
+def _bn(c, seed):
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(c, generator=g) + 0.5).to(DEV), torch.randn(c, generator=g).to(DEV) * 0.3,
+            (torch.randn(c, generator=g) * 0.1).to(DEV), (torch.rand(c, generator=g) + 0.5).to(DEV))
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 30, 30), (2, 16, 9, 11), (5, 8, 7, 7), (2, 128, 5, 6), (1, 4, 1, 1), (7, 12, 13, 3),
+                                   (2, 64, 112, 112), (150, 4, 6, 6)])
+def test_fused_stem_kernels_stay_in_bounds(guard, shape):
+    """Both stem forwards (TMA-staged ring and register kernel) and both backwards write out / idx / xhat / grad_x only
+    inside their tensors: odd extents, one-window rows, more items than CTAs, rows that wrap the ring."""
+    from ood_dfq_b200 import ops
+    x = rnd(shape, 3, relu=False).contiguous(memory_format=torch.channels_last)
+    w, b, rm, rv = _bn(shape[1], 4)
+    lo, hi = torch.zeros(1, device=DEV), torch.ones(1, device=DEV) * 2
+    for fq in (None, (4, lo, hi)):
+        for reg in (False, True):
+            out, idx, xhat = ops.bn_pool_forward(x, w, b, rm, rv, 1e-5, fq=fq, register_kernel=reg)
+            ops.bn_pool_forward(x, w, b, rm, rv, 1e-5, fq=fq, want_xhat=False, register_kernel=reg)
+        go = torch.randn_like(out)
+        ops.bn_pool_backward(go, idx, xhat, x.shape, w, b, rm, rv, 1e-5)
+        ops.bn_pool_backward(go, idx, None, x.shape, w, b, rm, rv, 1e-5, want_param_grads=False, grad_out2=go)
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 7, 7), (2, 16, 9, 11), (5, 8, 1, 1), (2, 512, 7, 7), (33, 4, 5, 3), (2, 1024, 2, 2),
+                                   (9, 16, 32, 32)])
+def test_residual_tail_and_pool_kernels_stay_in_bounds(guard, shape):
+    from ood_dfq_b200 import ops
+    c = shape[1]
+    x1 = rnd(shape, 5, relu=False).contiguous(memory_format=torch.channels_last)
+    r = rnd(shape, 6).contiguous(memory_format=torch.channels_last)
+    gy = rnd(shape, 7, relu=False).contiguous(memory_format=torch.channels_last)
+    ge = torch.randn(shape[:2], device=DEV)
+    bn1, bn2 = _bn(c, 8) + (1e-5,), _bn(c, 9) + (1e-5,)
+    lo, hi = torch.zeros(1, device=DEV), torch.ones(1, device=DEV) * 2
+    for b2 in (None, bn2):
+        y, e, mask = ops.res_tail_forward(x1, r, bn1, b2, fq=(4, lo, hi), want_energy=True, want_mask=True)
+        ops.res_tail_forward(x1, r, bn1, b2)
+        ops.res_tail_backward(gy, ge, x1, r, bn1, b2)
+        ops.res_tail_backward(gy, ge, x1, r if b2 is not None else None, bn1, b2, mask=mask, grad_y2=gy)
+        ops.res_tail_backward(gy, None, None, None, bn1, b2, want_param_grads=False, mask=mask)
+    if shape[2] * shape[3] > 1:
+        p = ops.global_avgpool_forward(r)
+        ops.global_avgpool_backward(torch.randn_like(p), r.shape)
+    _, m = ops.bn_eval_forward(x1, *bn1[:4], 1e-5, relu=True, fq=(4, lo, hi), want_mask=True)
+    if m is not None:                       # (a 1x1 plane is NCHW-contiguous too and takes the kernels without a mask)
+        ops.bn_eval_backward(None, gy, *bn1[:4], 1e-5, relu=True, want_param_grads=False, mask=m)
+
+
+@pytest.mark.parametrize("shape", [(3, 3, 32, 32), (2, 3, 224, 224), (5, 1, 28, 28), (2, 4, 10, 6)])
+def test_stem_relayout_stays_in_bounds(guard, shape):
+    from ood_dfq_b200 import ops
+    x = rnd(shape, 10, relu=False).contiguous(memory_format=torch.channels_last)
+    if not ops.s2d_stem_supported(x, 3):
+        pytest.skip("shape not taken by the re-layout kernel")
+    for cpad in (None, 16):
+        xs = ops.s2d_stem_forward(x, 3, cpad=cpad)
+        ops.s2d_stem_backward(torch.randn_like(xs), x.shape, 3)

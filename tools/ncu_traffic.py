@@ -31,8 +31,10 @@ def family(name):
         return "res_tail_bwd_kernel" if masked else "res_tail_bwd_kernel<no mask>"
     if plain.startswith("res_tail_fwd"):
         return "res_tail_fwd_kernel"
+    if plain.startswith("bn_pool_fwd_tma"):
+        return "bn_pool_fwd_kernel"                  # the default stem forward (TMA-staged ring)
     if plain.startswith("bn_pool_fwd"):
-        return "bn_pool_fwd_kernel"
+        return "bn_pool_fwd_kernel<register fallback>"
     if plain.startswith("bn_pool_bwd"):
         return "bn_pool_bwd_kernel"
     if plain.startswith("s2d_stem"):
