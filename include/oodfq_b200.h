@@ -216,6 +216,20 @@ int oodfq_channel_energy_forward(const float* x, float* e, int N, int C, long lo
 int oodfq_channel_energy_backward(const float* x, const float* grad_e, float* grad_x, int N, int C,
                                   long long HW, int flags, oodfq_stream_t stream);
 
+/* ---- deferred folds of the BatchNorm parameter-gradient reductions ----------------------------------------
+ * replaces: nothing in the reference -- launch bookkeeping behind `loss_S.backward()` (trainer_direct.py:350-356).
+ * oodfq_bn_eval_backward / oodfq_res_tail_backward / oodfq_bn_pool_backward with dwdb != NULL end in a small launch
+ * that folds the per-CTA (dW, dB) partials.  Between _begin and _end those calls write their partials into regions
+ * of `arena` (device memory, 256-byte aligned, caller-owned, must outlive _end) and the folds of ALL of them run
+ * as ONE launch at _flush / _end on `stream` (the stream the producing kernels ran on).  Until then every dwdb
+ * handed to a deferred call holds garbage and must neither be read nor freed.  A call that does not fit the arena
+ * folds immediately as usual.  Results are bit-identical to the immediate fold.  Process-wide state (one process
+ * per GPU), guarded by a mutex: the producing calls may come from autograd's backward thread. */
+int oodfq_defer_folds_begin(void* arena, size_t arena_bytes);
+int oodfq_defer_folds_flush(oodfq_stream_t stream);
+int oodfq_defer_folds_end(oodfq_stream_t stream);
+int oodfq_defer_folds_pending(void);
+
 /* ---- global average pool between the last QuantAct and Quant_Linear ------------------------------------
  * replaces: features.final_pool = AvgPool2d(7 | 8) over a plane of exactly that size (pytorchcv ResNet behind
  *           ptcv_get_model, main_direct.py:380-397; reference models.py avg_pool2d(out, 4)) and its backward

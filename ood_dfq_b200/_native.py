@@ -46,6 +46,10 @@ SIGNATURES = {
     "oodfq_bn_eval_forward": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp, _vp]),
     "oodfq_bn_pool_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_float, _i, _vp, _vp, _i, _vp]),
     "oodfq_bn_pool_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.c_float, _vp, _vp, _vp]),
+    "oodfq_defer_folds_begin": (_i, [_vp, C.c_size_t]),
+    "oodfq_defer_folds_flush": (_i, [_vp]),
+    "oodfq_defer_folds_end": (_i, [_vp]),
+    "oodfq_defer_folds_pending": (_i, []),
     "oodfq_global_avgpool_forward": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
     "oodfq_global_avgpool_backward": (_i, [_vp, _vp, _i, _i, _ll, _i, _vp]),
     "oodfq_channel_energy_scratch_floats": (C.c_size_t, [_i, _i]),

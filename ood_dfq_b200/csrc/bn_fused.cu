@@ -459,7 +459,7 @@ bn_nhwc_bwdx_tap_kernel(const float* __restrict__ x, const float* __restrict__ g
 template <bool RELU, bool REDUCE>
 __global__ void __launch_bounds__(kBThreads)
 bn_nhwc_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
-                    const NhwcGeom G, const BnParams P, Workspace* ws) {
+                    const NhwcGeom G, const BnParams P, double* __restrict__ part) {
     __shared__ __align__(16) float red[REDUCE ? 2 * kBThreads * 4 : 4];
     const int wcols = G.cols < kBThreads ? G.cols : kBThreads;
     const bool active = (int)threadIdx.x < G.lanes_r * wcols;
@@ -514,7 +514,7 @@ bn_nhwc_bwdx_kernel(const float* __restrict__ x, const float* __restrict__ gy, f
             if (on && rsub == 0) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    double* p = ws->bn_partial + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
+                    double* p = part + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
                     p[0] = (double)red[kBThreads * 4 + threadIdx.x * 4 + j] * (double)inv[j];
                     p[1] = (double)red[threadIdx.x * 4 + j];
                 }
@@ -621,16 +621,17 @@ extern "C" int oodfq_bn_eval_backward(const float* x, const float* grad_y, float
         const long long table = (long long)kMaxBnSplit * kMaxBnChannels / C;     // partial slots that fit
         if (reduce && cap > table) cap = table;
         const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
-        if (relu && reduce) bn_nhwc_bwdx_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, ws);
-        else if (relu) bn_nhwc_bwdx_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, ws);
-        else if (reduce) bn_nhwc_bwdx_kernel<false, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, ws);
-        else bn_nhwc_bwdx_kernel<false, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, ws);
+        // the per-CTA partials go to the workspace and are folded by a launch right behind this one, or -- while folds
+        // are deferred (fold.cu) -- to a region of their own, folded with everybody else's at the flush
+        double* part = reduce ? fold_target(ws->bn_partial, C, (int)grid) : nullptr;
+        if (relu && reduce) bn_nhwc_bwdx_kernel<true, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, part);
+        else if (relu) bn_nhwc_bwdx_kernel<true, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, part);
+        else if (reduce) bn_nhwc_bwdx_kernel<false, true><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, part);
+        else bn_nhwc_bwdx_kernel<false, false><<<grid, kBThreads, 0, st>>>(x, grad_y, grad_x, G, P, part);
         count_launch();
         int rc = check_launch("bn_eval_backward");
         if (rc != OODFQ_OK || !reduce) return rc;
-        bn_nhwc_fold_kernel<float><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
-        count_launch();
-        return check_launch("bn_eval_backward(fold)");
+        return fold_finish(part, ws->bn_partial, C, (int)grid, dwdb, st);
     }
     if (plane_ok(HW, vec_ok)) {
         static const int occ[4] = {resident_ctas(bn_plane_bwdx_kernel<false, false>, kBThreads),

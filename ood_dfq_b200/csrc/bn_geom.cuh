@@ -171,6 +171,11 @@ bn_nhwc_fold_kernel(const double* __restrict__ partial, int C, int nparts, OutT*
 
 
 // ---- host side ----------------------------------------------------------------------------
+// fold.cu: where a reducing kernel writes its per-CTA partials (the workspace, or its own arena region while folds
+// are deferred) and what happens behind it (an immediate fold launch, or a note for the deferred multi-tensor fold)
+double* fold_target(double* ws_partial, int C, int nparts);
+int fold_finish(double* target, double* ws_partial, int C, int nparts, float* out, cudaStream_t st);
+
 inline bool plane_ok(long long HW, bool vec_ok) { return vec_ok && HW >= kPlaneMin && (HW % 4) == 0; }
 
 // CTAs along the batch axis.  The grid is `base * split` CTAs of equal work, so it should fill the

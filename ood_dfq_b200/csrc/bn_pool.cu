@@ -222,7 +222,7 @@ template <bool REDUCE>
 __global__ void __launch_bounds__(kBThreads)
 bn_pool_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ gout2, const uint8_t* __restrict__ idx,
                    const float* __restrict__ xhat, float* __restrict__ gx, const PoolGeom G, const BnParams2 P,
-                   Workspace* ws) {
+                   double* __restrict__ part) {
     __shared__ float red[REDUCE ? 2 * kBThreads * 4 : 1];
     const bool active = (int)threadIdx.x < G.lanes_r * G.cols;
     const int col = threadIdx.x % G.cols, rsub = threadIdx.x / G.cols;
@@ -319,7 +319,7 @@ bn_pool_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ gou
                     tb += red[(l * G.cols + col) * 4 + j];
                     tw += red[kBThreads * 4 + (l * G.cols + col) * 4 + j];
                 }
-                double* q = ws->bn_partial + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
+                double* q = part + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
                 q[0] = (double)tw;      // dW: xhat already carries 1/sqrt(var+eps)
                 q[1] = (double)tb;      // dB
             }
@@ -350,7 +350,7 @@ template <bool REDUCE, bool TWO>
 __global__ void __launch_bounds__(kPbMaxThreads, 1)
 bn_pool_bwd_tma_kernel(const float* __restrict__ gout, const float* __restrict__ gout2, const uint8_t* __restrict__ idx,
                        const float* __restrict__ xhat, float* __restrict__ gx, const PoolGeom G, const PoolBwdPlan L,
-                       const BnParams2 P, Workspace* ws) {
+                       const BnParams2 P, double* __restrict__ part) {
     extern __shared__ __align__(128) unsigned char pb_smem[];
     __shared__ __align__(8) uint64_t full[kPbSlots];
     __shared__ float red[REDUCE ? 2 * kPbMaxThreads * 4 : 1];
@@ -501,7 +501,7 @@ bn_pool_bwd_tma_kernel(const float* __restrict__ gout, const float* __restrict__
                     tb += red[t2 * 4 + j];
                     tw += red[kPbMaxThreads * 4 + t2 * 4 + j];
                 }
-                double* qd = ws->bn_partial + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
+                double* qd = part + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
                 qd[0] = (double)tw;      // dW: xhat already carries 1/sqrt(var+eps)
                 qd[1] = (double)tb;      // dB
             }
@@ -650,16 +650,15 @@ extern "C" int oodfq_bn_pool_backward(const float* grad_out, const float* grad_o
         if (ok) {
             const long long items = (long long)N * L.nseg;
             const unsigned grid = (unsigned)(items < kNumSM ? items : kNumSM);
-            if (v == 0) bn_pool_bwd_tma_kernel<false, false><<<grid, threads, smem, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, L, P, ws);
-            else if (v == 1) bn_pool_bwd_tma_kernel<false, true><<<grid, threads, smem, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, L, P, ws);
-            else if (v == 2) bn_pool_bwd_tma_kernel<true, false><<<grid, threads, smem, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, L, P, ws);
-            else bn_pool_bwd_tma_kernel<true, true><<<grid, threads, smem, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, L, P, ws);
+            double* part = dwdb ? fold_target(ws->bn_partial, C, (int)grid) : nullptr;   // workspace, or its own region (fold.cu)
+            if (v == 0) bn_pool_bwd_tma_kernel<false, false><<<grid, threads, smem, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, L, P, part);
+            else if (v == 1) bn_pool_bwd_tma_kernel<false, true><<<grid, threads, smem, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, L, P, part);
+            else if (v == 2) bn_pool_bwd_tma_kernel<true, false><<<grid, threads, smem, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, L, P, part);
+            else bn_pool_bwd_tma_kernel<true, true><<<grid, threads, smem, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, L, P, part);
             count_launch();
             int rc = check_launch("bn_pool_backward(tma)");
             if (rc != OODFQ_OK || !dwdb) return rc;
-            bn_nhwc_fold_kernel<float><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
-            count_launch();
-            return check_launch("bn_pool_backward(fold)");
+            return fold_finish(part, ws->bn_partial, C, (int)grid, dwdb, st);
         }
     }
     static const int occ[2] = {resident_ctas(bn_pool_bwd_kernel<false>, kBThreads), resident_ctas(bn_pool_bwd_kernel<true>, kBThreads)};
@@ -668,12 +667,11 @@ extern "C" int oodfq_bn_pool_backward(const float* grad_out, const float* grad_o
     const long long table = (long long)kMaxBnSplit * kMaxBnChannels / C;
     if (dwdb && cap > table) cap = table;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    if (dwdb) bn_pool_bwd_kernel<true><<<grid, kBThreads, 0, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, P, ws);
-    else bn_pool_bwd_kernel<false><<<grid, kBThreads, 0, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, P, ws);
+    double* part = dwdb ? fold_target(ws->bn_partial, C, (int)grid) : nullptr;
+    if (dwdb) bn_pool_bwd_kernel<true><<<grid, kBThreads, 0, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, P, part);
+    else bn_pool_bwd_kernel<false><<<grid, kBThreads, 0, st>>>(grad_out, grad_out2, idx, xhat, grad_x, G, P, part);
     count_launch();
     int rc = check_launch("bn_pool_backward");
     if (rc != OODFQ_OK || !dwdb) return rc;
-    bn_nhwc_fold_kernel<float><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, dwdb);
-    count_launch();
-    return check_launch("bn_pool_backward(fold)");
+    return fold_finish(part, ws->bn_partial, C, (int)grid, dwdb, st);
 }

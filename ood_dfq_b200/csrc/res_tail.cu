@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kBThreads)
 res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2, const float* __restrict__ ge,
                     const float* __restrict__ x1, const float* __restrict__ r, const uint8_t* __restrict__ mask,
                     float* __restrict__ gx1, float* __restrict__ gr, const TailGeom G, const TailBn P1,
-                    const TailBn P2, float two_inv_hw, Workspace* ws) {
+                    const TailBn P2, float two_inv_hw, double* __restrict__ part) {
     constexpr bool NEED_X1 = ENERGY || REDUCE || !MASK;
     constexpr bool NEED_R = !MASK || (IDBN && REDUCE);
     __shared__ __align__(16) float red[REDUCE ? (IDBN ? 4 : 2) * kBThreads * 4 : 4];
@@ -276,7 +276,7 @@ res_tail_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ gy2,
                     const float tw = red[(2 * set + 1) * kBThreads * 4 + threadIdx.x * 4 + j];
                     const TailBn& P = set ? P2 : P1;
                     const float inv = __frcp_rn(__fsqrt_rn(__fadd_rn(__ldg(P.rv + 4 * col + j), P.eps)));
-                    double* p = ws->bn_partial + ((size_t)blockIdx.x * Ct + (size_t)set * G.C + 4 * col + j) * 2;
+                    double* p = part + ((size_t)blockIdx.x * Ct + (size_t)set * G.C + 4 * col + j) * 2;
                     p[0] = (double)tw * (double)inv;     // dW
                     p[1] = (double)tb;                   // dB
                 }
@@ -330,13 +330,13 @@ struct TailBwdArgs {
     TailGeom G;
     TailBn P1, P2;
     float two_inv_hw;
-    Workspace* ws;
+    double* part;
 };
 
 template <bool IDBN, bool ENERGY, bool REDUCE, bool MASK>
 static void tail_bwd_go(unsigned grid, cudaStream_t st, const TailBwdArgs& a) {
     res_tail_bwd_kernel<IDBN, ENERGY, REDUCE, MASK><<<grid, kBThreads, 0, st>>>(a.gy, a.gy2, a.ge, a.x1, a.r, a.mask, a.gx1,
-                                                                              a.gr, a.G, a.P1, a.P2, a.two_inv_hw, a.ws);
+                                                                              a.gr, a.G, a.P1, a.P2, a.two_inv_hw, a.part);
 }
 
 template <typename F>
@@ -427,8 +427,9 @@ extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2
     Workspace* ws = reinterpret_cast<Workspace*>(workspace);
     const long long items = (long long)N * G.chunks;
     const unsigned grid = (unsigned)(items < cap ? items : cap);
+    double* part = reduce ? fold_target(ws->bn_partial, Ct, (int)grid) : nullptr;     // workspace, or its own region (fold.cu)
     const TailBwdArgs args{grad_y, grad_y2, grad_energy, x1, r, relu_mask, grad_x1, grad_r, G,
-                           TailBn{w1, b1, rm1, rv1, eps1}, TailBn{w2, b2, rm2, rv2, eps2}, (float)(2.0 / (double)HW), ws};
+                           TailBn{w1, b1, rm1, rv1, eps1}, TailBn{w2, b2, rm2, rv2, eps2}, (float)(2.0 / (double)HW), part};
     tail_bwd_dispatch(idbn, energy, reduce, mask, [&](auto tag) {
         constexpr int v = decltype(tag)::value;
         tail_bwd_go<(v >> 3) & 1, (v >> 2) & 1, (v >> 1) & 1, v & 1>(grid, st, args);
@@ -438,7 +439,5 @@ extern "C" int oodfq_res_tail_backward(const float* grad_y, const float* grad_y2
     int rc = check_launch("res_tail_backward");
     if (rc != OODFQ_OK || !reduce) return rc;
     // dwdb[0 .. Ct) = dW (BN1 channels, then BN2), dwdb[Ct .. 2 Ct) = dB
-    bn_nhwc_fold_kernel<float><<<(Ct + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, Ct, (int)grid, dwdb);
-    count_launch();
-    return check_launch("res_tail_backward(fold)");
+    return fold_finish(part, ws->bn_partial, Ct, (int)grid, dwdb, st);
 }

@@ -76,6 +76,50 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+# ----------------------------------------------------------------------------- deferred parameter-gradient folds
+_DEFER_KEEP = None          # while folds are deferred: the dwdb buffers handed out, kept alive until the flush
+_FOLD_ARENAS = {}
+
+
+class deferred_folds:
+    """``with ops.deferred_folds(device):`` -- the BatchNorm parameter-gradient reductions launched inside (fused BN,
+    residual-tail and stem backward with parameter gradients) leave their per-CTA partials in an arena and are folded
+    by ONE launch when the block ends, instead of one small launch behind each of them (34-38 per QAT iteration).
+
+    Until the block ends the dW / dB tensors those backwards returned hold garbage: use it only around a sweep whose
+    results nothing reads before the block is left (``step.QATStep`` wraps each ``autograd.grad`` over the parameters).
+    Not re-entrant; bit-identical results."""
+
+    def __init__(self, device, arena_mb=96):
+        self.device, self.bytes = torch.device(device), int(arena_mb) << 20
+
+    def __enter__(self):
+        global _DEFER_KEEP
+        if self.device.type != "cuda":
+            raise RuntimeError("ood_dfq_b200: deferred_folds only exists on CUDA devices")
+        key = (self.device.index if self.device.index is not None else torch.cuda.current_device(), self.bytes)
+        arena = _FOLD_ARENAS.get(key)
+        if arena is None:
+            arena = _FOLD_ARENAS[key] = torch.empty(self.bytes, dtype=torch.uint8, device=self.device)
+        N.check(N.load().oodfq_defer_folds_begin(arena.data_ptr(), self.bytes), "defer_folds_begin")
+        _DEFER_KEEP = []
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFER_KEEP
+        rc = N.load().oodfq_defer_folds_end(_stream(self.device))
+        _DEFER_KEEP = None
+        if exc[0] is None:
+            N.check(rc, "defer_folds_end")
+        return False
+
+
+def _keep_until_flush(t):
+    if _DEFER_KEEP is not None and t is not None:
+        _DEFER_KEEP.append(t)
+    return t
+
+
 def workspace(device) -> torch.Tensor:
     """Zero-initialised scratch for the reducing kernels, one per (device, stream)."""
     device = torch.device(device)
@@ -414,7 +458,7 @@ def bn_eval_backward(x, grad_y, weight, bias, running_mean, running_var, eps, re
         gy = grad_y.contiguous(memory_format=torch.channels_last) if nhwc else grad_y.contiguous()
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
     gx = torch.empty_like(gy)
-    dwdb = torch.empty(2 * c, dtype=torch.float32, device=gy.device) if want_param_grads else None
+    dwdb = _keep_until_flush(torch.empty(2 * c, dtype=torch.float32, device=gy.device) if want_param_grads else None)
     ws = workspace(gy.device).data_ptr() if want_param_grads else None
     reads_x = (relu or want_param_grads) and not by_mask   # otherwise grad_x = grad_y * a_c and x is never touched
     with _Timed("bn_*_bwdx_kernel (fused BN backward, 12 B/elem; 8 without ReLU mask and parameter grads)",
@@ -642,7 +686,7 @@ def bn_pool_backward(grad_out, idx, xhat, in_shape, weight, bias, running_mean, 
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
     gx = torch.empty((n, c, h, w), dtype=torch.float32, device=grad_out.device, memory_format=torch.channels_last)
     need = want_param_grads and xhat is not None
-    dwdb = torch.empty(2 * c, dtype=torch.float32, device=grad_out.device) if need else None
+    dwdb = _keep_until_flush(torch.empty(2 * c, dtype=torch.float32, device=grad_out.device) if need else None)
     ws = workspace(grad_out.device).data_ptr() if need else None
     with _Timed("bn_pool_bwd_kernel (stem backward, 4 B/elem out + 1/4 size inputs)",
                 4 * gx.numel() + ((9 if need else 5) + (4 if go2 is not None else 0)) * go.numel()):
@@ -736,7 +780,7 @@ def res_tail_backward(grad_y, grad_energy, x1, r, bn1, bn2=None, want_param_grad
     p1, p2 = _tail_bn(bn1, c), _tail_bn(bn2, c)
     gx1, gr = torch.empty_like(gy), torch.empty_like(gy)
     ct = c * (2 if bn2 is not None else 1)
-    dwdb = torch.empty(2 * ct, dtype=torch.float32, device=gy.device) if want_param_grads else None
+    dwdb = _keep_until_flush(torch.empty(2 * ct, dtype=torch.float32, device=gy.device) if want_param_grads else None)
     ws = workspace(gy.device).data_ptr() if want_param_grads else None
     per_elem = 12 + (4 if gy2 is not None else 0) + (4 if reads_x1 else 0) + (4 if reads_r else 0) + (0.25 if mask is not None else 0)
     with _Timed("res_tail_bwd_kernel (ReLU mask + energy gradient + BN backward(s), 16.25 - 24 B/elem)",

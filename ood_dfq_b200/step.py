@@ -146,6 +146,17 @@ class FlatGrads:
             self.flat.div_(dist.get_world_size(group))
 
 
+def _deferred_folds(like):
+    """``ops.deferred_folds`` on the device of ``like`` when that is a GPU and the model uses this package's kernels,
+    else a no-op context (the CPU arm drives oracle / reference modules)."""
+    import contextlib
+    import os
+    if not like.is_cuda or os.environ.get("OODFQ_NO_DEFERRED_FOLDS"):        # (the switch is for A/B measurements)
+        return contextlib.nullcontext()
+    from . import ops
+    return ops.deferred_folds(like.device)
+
+
 def _multi_tensor_into(dst, src, add=False):
     """``dst[i].copy_(src[i])`` (or ``+=``) for every ``src[i]`` that is not None, as few launches as torch allows.
 
@@ -288,7 +299,10 @@ class QATStep:
             # parameter with its own launch (62 adds + 62 copies, 0.4 ms of the 224x224 step); a sweep per graph and two
             # multi-tensor launches give the same sums (g1 + g2, fp32 addition commutes) without them.
             for i, part in enumerate(parts):
-                got = torch.autograd.grad(part, self.grads.params, allow_unused=True)
+                # (on a GPU: the ~18 BatchNorm parameter-gradient reductions of a sweep fold their per-CTA partials with
+                # ONE launch when the sweep is over instead of a small launch behind each, ops.deferred_folds)
+                with _deferred_folds(self.grads.flat):
+                    got = torch.autograd.grad(part, self.grads.params, allow_unused=True)
                 _multi_tensor_into([p.grad for p in self.grads.params], got, add=i > 0)
         else:
             total.backward()
