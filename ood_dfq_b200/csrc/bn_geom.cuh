@@ -175,6 +175,7 @@ bn_nhwc_fold_kernel(const double* __restrict__ partial, int C, int nparts, OutT*
 // are deferred) and what happens behind it (an immediate fold launch, or a note for the deferred multi-tensor fold)
 double* fold_target(double* ws_partial, int C, int nparts);
 int fold_finish(double* target, double* ws_partial, int C, int nparts, float* out, cudaStream_t st);
+int fold_finish(double* target, double* ws_partial, int C, int nparts, double* out, cudaStream_t st);
 
 inline bool plane_ok(long long HW, bool vec_ok) { return vec_ok && HW >= kPlaneMin && (HW % 4) == 0; }
 

@@ -333,7 +333,7 @@ template <bool QUANT, int HEAD = 0>
 __global__ void __launch_bounds__(kBThreads)
 bn_nhwc_stats_kernel(const float* __restrict__ x, const NhwcGeom G, const float* __restrict__ shift,
                      float* __restrict__ y, const float* __restrict__ fq_lo, const float* __restrict__ fq_hi,
-                     int fq_k, Workspace* ws, const BnParams P = BnParams{nullptr, nullptr, nullptr, nullptr, 0.f}) {
+                     int fq_k, double* __restrict__ part, const BnParams P = BnParams{nullptr, nullptr, nullptr, nullptr, 0.f}) {
     __shared__ double dred[2 * kBThreads];
     __shared__ float lut[QUANT ? kLutMax : 1];
     QParams qp;
@@ -411,7 +411,7 @@ bn_nhwc_stats_kernel(const float* __restrict__ x, const NhwcGeom G, const float*
                 const int lc = threadIdx.x % wcols;
                 double t1 = 0.0, t2 = 0.0;
                 for (int l = 0; l < G.lanes_r; ++l) { t1 += dred[l * wcols + lc]; t2 += dred[kBThreads + l * wcols + lc]; }
-                double* p = ws->bn_partial + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
+                double* p = part + ((size_t)blockIdx.x * G.C + 4 * col + j) * 2;
                 p[0] = t1;
                 p[1] = t2;
             }
@@ -552,14 +552,13 @@ extern "C" int oodfq_bn_stats_forward(const float* x, int N, int C, long long HW
         const long long table = (long long)kMaxBnSplit * kMaxBnChannels / C;
         if (cap > table) cap = table;
         const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
-        if (y) bn_nhwc_stats_kernel<true><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws);
-        else bn_nhwc_stats_kernel<false><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws);
+        double* part = fold_target(ws->bn_partial, C, (int)grid);          // workspace, or its own region (fold.cu)
+        if (y) bn_nhwc_stats_kernel<true><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, part);
+        else bn_nhwc_stats_kernel<false><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, part);
         count_launch();
         int rc = check_launch("bn_stats_forward");
         if (rc != OODFQ_OK) return rc;
-        bn_nhwc_fold_kernel<double><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, sums);
-        count_launch();
-        return check_launch("bn_stats_forward(fold)");
+        return fold_finish(part, ws->bn_partial, C, (int)grid, sums, st);
     }
     if (plane_ok(HW, vec_ok)) {
         static const int per_sm_q = resident_ctas(bn_plane_stats_kernel<true>, kBThreads);
@@ -677,14 +676,13 @@ extern "C" int oodfq_bn_eval_stats_forward(const float* x, float* y, int N, int 
     const long long table = (long long)kMaxBnSplit * kMaxBnChannels / C;
     if (cap > table) cap = table;
     const unsigned grid = (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
-    if (quant && relu) bn_nhwc_stats_kernel<true, 2><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws, P);
-    else if (quant) bn_nhwc_stats_kernel<true, 1><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws, P);
-    else if (relu) bn_nhwc_stats_kernel<false, 2><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws, P);
-    else bn_nhwc_stats_kernel<false, 1><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, ws, P);
+    double* part = fold_target(ws->bn_partial, C, (int)grid);              // workspace, or its own region (fold.cu)
+    if (quant && relu) bn_nhwc_stats_kernel<true, 2><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, part, P);
+    else if (quant) bn_nhwc_stats_kernel<true, 1><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, part, P);
+    else if (relu) bn_nhwc_stats_kernel<false, 2><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, part, P);
+    else bn_nhwc_stats_kernel<false, 1><<<grid, kBThreads, 0, st>>>(x, G, shift, y, fq_lo, fq_hi, fq_k, part, P);
     count_launch();
     int rc = check_launch("bn_eval_stats_forward");
     if (rc != OODFQ_OK) return rc;
-    bn_nhwc_fold_kernel<double><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws->bn_partial, C, (int)grid, sums);
-    count_launch();
-    return check_launch("bn_eval_stats_forward(fold)");
+    return fold_finish(part, ws->bn_partial, C, (int)grid, sums, st);
 }

@@ -18,8 +18,8 @@ namespace oodfq {
 
 struct FoldDesc {
     const double* partial;   // [nparts][C][2]
-    float* out;              // [2C]
-    int C, nparts;
+    void* out;               // [2C] floats (parameter gradients) or doubles (BN-input statistics)
+    int C, nparts, out_is_double;
 };
 constexpr int kFoldBatchMax = 96;
 struct FoldBatch {
@@ -32,7 +32,9 @@ __global__ void __launch_bounds__(kBThreads) bn_fold_multi_kernel(const __grid_c
     int i = 0;
     while (i + 1 < B.n && (int)blockIdx.x >= B.first_cta[i + 1]) ++i;
     const int c = ((int)blockIdx.x - B.first_cta[i]) * (kBThreads / 32) + (threadIdx.x >> 5);
-    if (c < B.d[i].C) fold_partials(B.d[i].partial, B.d[i].C, c, B.d[i].nparts, threadIdx.x & 31, B.d[i].out);
+    if (c >= B.d[i].C) return;
+    if (B.d[i].out_is_double) fold_partials(B.d[i].partial, B.d[i].C, c, B.d[i].nparts, threadIdx.x & 31, static_cast<double*>(B.d[i].out));
+    else fold_partials(B.d[i].partial, B.d[i].C, c, B.d[i].nparts, threadIdx.x & 31, static_cast<float*>(B.d[i].out));
 }
 
 namespace {
@@ -74,15 +76,23 @@ double* fold_target(double* ws_partial, int C, int nparts) {
     return p;
 }
 
-int fold_finish(double* target, double* ws_partial, int C, int nparts, float* out, cudaStream_t st) {
+template <typename OutT>
+static int fold_finish_t(double* target, double* ws_partial, int C, int nparts, OutT* out, cudaStream_t st) {
     if (target == ws_partial) {
-        bn_nhwc_fold_kernel<float><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws_partial, C, nparts, out);
+        bn_nhwc_fold_kernel<OutT><<<(C + kBThreads / 32 - 1) / (kBThreads / 32), kBThreads, 0, st>>>(ws_partial, C, nparts, out);
         count_launch();
         return check_launch("fold");
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    g_pending.push_back(FoldDesc{target, out, C, nparts});
+    g_pending.push_back(FoldDesc{target, out, C, nparts, sizeof(OutT) == sizeof(double) ? 1 : 0});
     return OODFQ_OK;
+}
+
+int fold_finish(double* target, double* ws_partial, int C, int nparts, float* out, cudaStream_t st) {
+    return fold_finish_t(target, ws_partial, C, nparts, out, st);
+}
+int fold_finish(double* target, double* ws_partial, int C, int nparts, double* out, cudaStream_t st) {
+    return fold_finish_t(target, ws_partial, C, nparts, out, st);
 }
 
 }  // namespace oodfq

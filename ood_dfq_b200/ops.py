@@ -334,6 +334,7 @@ def bn_stats_forward(x, shift=None, sums=None, fq=None):
         sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
     elif sums.dtype != torch.float64 or sums.numel() != 2 * c or not sums.is_contiguous():
         raise RuntimeError("ood_dfq_b200: sums must be a contiguous float64 [2*C] tensor")
+    _keep_until_flush(sums)                 # (inside ops.deferred_folds the sums are written by the flush)
     y = lo = hi = None
     k = 0
     if fq is not None:
@@ -483,6 +484,7 @@ def bn_eval_stats_forward(x, weight, bias, running_mean, running_var, eps, shift
     pw, pb, prm, prv = _bn_ptrs(weight, bias, running_mean, running_var, c)
     if sums.dtype != torch.float64 or sums.numel() != 2 * c or not sums.is_contiguous():
         raise RuntimeError("ood_dfq_b200: sums must be a contiguous float64 [2*C] tensor")
+    _keep_until_flush(sums)
     y = torch.empty_like(xc)
     flags, k, lo, hi = (N.BN_RELU if relu else 0) | N.BN_NHWC, 0, None, None
     if fq is not None:

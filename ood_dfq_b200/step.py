@@ -456,7 +456,10 @@ class DistillStep:
         # backward() on the parameter itself (:270-271), but no AccumulateGrad node tied to the stream the
         # parameter was created on, so the iteration can be captured as a CUDA graph
         x = self.images.detach().requires_grad_(True)
-        out = self.teacher(self._augmented(x) if self.augment is not None else x)
+        # (on a GPU the ~20 statistics reductions of the forward fold their per-CTA partials with ONE launch when the
+        # forward is over, before the loss reads the sums: ops.deferred_folds)
+        with _deferred_folds(self.images):
+            out = self.teacher(self._augmented(x) if self.augment is not None else x)
         target = hard_sample_loss(out, self.labels, self.beta, self.gamma)
         total = self.stat.loss("distill") + target                   # mean/L + var/L + target, :259-265
         self.images.grad = torch.autograd.grad(total, [x])[0]

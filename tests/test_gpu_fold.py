@@ -117,3 +117,35 @@ def test_qat_step_with_and_without_deferred_folds_gives_the_same_update(monkeypa
         results.append([p.detach().clone() for p in s.parameters()])
     for a, b in zip(*results):
         assert torch.equal(a, b)
+
+
+def test_deferred_statistics_folds_equal_immediate_ones():
+    """The BN-input statistics (fp64 sums, ``bn_stats_forward`` / ``bn_eval_stats_forward``) go through the same deferral:
+    identical bits, one fold launch for all of them."""
+    from ood_dfq_b200 import _native, ops
+    shapes = [(8, 64, 14, 14), (4, 16, 32, 32), (16, 512, 7, 7), (2, 8, 5, 3)]
+    xs, bns = [], []
+    for i, shape in enumerate(shapes):
+        g = torch.Generator().manual_seed(200 + i)
+        xs.append((torch.randn(shape, generator=g) * 1.3 + 0.2).to(DEV).contiguous(memory_format=torch.channels_last))
+        bns.append(_bn(shape[1], 300 + i))
+
+    def run():
+        outs = []
+        for x, (w, b, rm, rv) in zip(xs, bns):
+            outs.append(ops.bn_stats_forward(x, rm))
+            sums = torch.empty(2 * x.shape[1], dtype=torch.float64, device=DEV)
+            ops.bn_eval_stats_forward(x, w, b, rm, rv, 1e-5, rm, sums, relu=True)
+            outs.append(sums)
+        return outs
+
+    ref = [o.cpu().numpy().view(np.int64).copy() for o in run()]
+    _native.reset_launch_count()
+    run()
+    immediate = _native.launch_count()
+    _native.reset_launch_count()
+    with ops.deferred_folds(DEV):
+        outs = run()
+    assert _native.launch_count() == immediate - 2 * len(shapes) + 1
+    for a, o in zip(ref, outs):
+        assert np.array_equal(a, o.cpu().numpy().view(np.int64))
