@@ -44,7 +44,7 @@ if has launches; then
   log "ncu launch list"
   timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'oodfq|fq_|bn_|res_tail|s2d|weight_fq|minmax|energy|crop_resize|gap_' \
       -c 4000 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-baselines --no-other-configs --graph off > gpurun_out/launches_run.log 2>&1
+      python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-baselines --no-other-configs --graph off > gpurun_out/launches_run.log 2>&1
   log "launch list exit $?"
   python tools/launch_list.py gpurun_out/launches.csv > gpurun_out/launches_summary.txt 2>&1 || true
 fi
