@@ -199,3 +199,49 @@ def test_graphed_step_refuses_to_replay_after_a_mode_change(monkeypatch):
     student.train()
     with pytest.raises(RuntimeError, match="mode flags"):
         g(torch.randn(2, 3, 32, 32))
+
+
+def test_multi_tensor_into_partitions_by_stride_and_keeps_the_sums():
+    """``step._multi_tensor_into``: pairs with equal strides go through one foreach call, a pair whose gradient is
+    strided differently from its destination (the 1x1 convolution weight: NCHW- vs channels_last-strided, same bytes)
+    is moved on its own -- and ``None`` gradients are skipped.  Copy then add gives g1 + g2 exactly."""
+    from ood_dfq_b200 import step
+    g = torch.Generator().manual_seed(0)
+    shapes = [(8,), (4, 3, 3, 3), (6, 5, 1, 1), (7, 2)]
+    flat = torch.zeros(sum(int(torch.tensor(s).prod()) for s in shapes))
+    dst, off = [], 0
+    for s in shapes:
+        n = int(torch.tensor(s).prod())
+        t = flat[off:off + n].view(s)
+        if len(s) == 4:                                     # parameters of a channels_last model: strides (C*H*W, 1, W*C, C)
+            t = torch.as_strided(flat, s, (s[1] * s[2] * s[3], 1, s[3] * s[1], s[1]), off)
+        dst.append(t)
+        off += n
+    g1 = [torch.randn(s, generator=g) for s in shapes]
+    g2 = [torch.randn(s, generator=g) for s in shapes]
+    g1[1] = g1[1].contiguous(memory_format=torch.channels_last)           # same strides as its destination
+    g2[1] = g2[1].contiguous(memory_format=torch.channels_last)
+    assert g1[2].stride() != dst[2].stride()                              # the odd one out
+    g2[3] = None
+    calls = []
+    real_copy, real_add = torch._foreach_copy_, torch._foreach_add_
+    try:
+        torch._foreach_copy_ = lambda d, s_: (calls.append(("copy", len(d))), real_copy(d, s_))[1]
+        torch._foreach_add_ = lambda d, s_: (calls.append(("add", len(d))), real_add(d, s_))[1]
+        step._multi_tensor_into(dst, g1, add=False)
+        step._multi_tensor_into(dst, g2, add=True)
+    finally:
+        torch._foreach_copy_, torch._foreach_add_ = real_copy, real_add
+    assert calls == [("copy", 3), ("add", 2)]
+    for d, a, b in zip(dst, g1, g2):
+        assert torch.equal(d, a if b is None else a + b)
+
+
+def test_deferred_folds_is_a_gpu_only_context():
+    import contextlib
+    from ood_dfq_b200 import ops, step
+    assert isinstance(step._deferred_folds(torch.zeros(1)), contextlib.nullcontext)
+    import pytest
+    with pytest.raises(RuntimeError):
+        with ops.deferred_folds("cpu"):
+            pass
