@@ -703,6 +703,8 @@ def main_ours(args):
                        "bn_relu_quant_fusion": not args.no_fuse,
                        "residual_tail_fusion": not (args.no_fuse or args.no_tail_fuse),
                        "stem_space_to_depth": not (args.no_fuse or args.no_s2d),
+                       "global_avgpool_kernel": not args.no_fuse,
+                       "deferred_param_grad_folds": not os.environ.get("OODFQ_NO_DEFERRED_FOLDS"),
                        "memory_format": "channels_last" if channels_last else "NCHW (as the reference)",
                        "cuda_graph": res["use_graph"], "graph_collective": res["graph_collective"],
                        **({"distill_batch": "global (BN statistics all-reduced)" if (args.distill_sync and world > 1)
