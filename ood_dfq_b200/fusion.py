@@ -656,16 +656,16 @@ class _FusedUnitMixin:
         xr = _pick_twin(x)                        # the producer's second handle, if it left one (see _twin_of)
         r = p.idconv(xr) if p.idconv is not None else xr
         bn1, bn2 = p.bn1, p.bn2
-        # BN-statistics taps on the two BatchNorms this path bypasses (the distillation loop hooks every BatchNorm)
-        x1 = _run_stat_taps(bn1, x1)
-        if bn2 is not None:
-            r = _run_stat_taps(bn2, r)
         if not ops.res_tail_supported(x1, r):
-            # (a convolution handed back another layout) finish with the ordinary modules
+            # (a convolution handed back another layout) finish with the ordinary modules; their own hooks fire as usual
             z = bn1(x1)
             for t in taps:
                 t._hook(p.hooked, (x,), z)
             return p.act(z + (bn2(r) if bn2 is not None else r))
+        # BN-statistics taps on the two BatchNorms this path bypasses (the distillation loop hooks every BatchNorm)
+        x1 = _run_stat_taps(bn1, x1)
+        if bn2 is not None:
+            r = _run_stat_taps(bn2, r)
         y, twin, e = _FusedTail.apply(x1, r, bn1.weight, bn1.bias, bn2.weight if bn2 is not None else None,
                                       bn2.bias if bn2 is not None else None, bn1, bn2, qact, bool(taps))
         setattr(y, _TWIN, twin)
